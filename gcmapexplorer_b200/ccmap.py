@@ -1,0 +1,275 @@
+"""CCMAP -- the data carrier the normalizers consume and emit.
+
+Behavioural mirror of ``gcMapExplorer/lib/ccmap.py`` for what the normalization path needs
+(reference lines in brackets): same attribute set [ccmap.py:125-140], same memmap lifecycle
+(make_readable / make_unreadable / make_writable / make_editable [:224-262]), ``copy(fill)`` creating a
+new temporary backing file next to the original [:264-300], ``gen_from_matrix`` [:188-221], the
+``.ccmap`` JSON + raw float32 ``.npbin[.gz]`` on-disk format [:302-567] (files written here load in
+the reference and vice versa) and ``checkCCMapObjectOrFile`` [:604-653] including its bare-``None`` return
+for a missing file.  Downsampling, smoothing, export and plotting are out of scope.
+
+If the real ``gcMapExplorer.lib.ccmap.CCMAP`` is importable, instances of it are accepted everywhere a
+CCMAP is expected (duck-typed on the attributes above).
+"""
+import gzip
+import json
+import logging
+import os
+import shutil
+import tempfile
+
+import numpy as np
+
+dtype_npBINarray = "float32"
+
+logger = logging.getLogger("ccmap")
+logger.setLevel(logging.INFO)
+
+_ATTRS = ("path2matrix", "xticks", "yticks", "binsize", "title", "xlabel", "ylabel", "shape", "minvalue",
+          "maxvalue", "bNoData", "bLog", "dtype", "matrix", "state")
+
+
+def _default_workdir():
+    return os.environ.get("GCX_WORKDIR") or tempfile.gettempdir()
+
+
+def gen_backup(path):
+    """Rename an existing file out of the way (``name`` -> ``name.bakN``) instead of overwriting it."""
+    if not os.path.exists(path):
+        return
+    k = 0
+    while os.path.exists(f"{path}.bak{k}"):
+        k += 1
+    os.rename(path, f"{path}.bak{k}")
+
+
+class CCMAP:
+    """Metadata + a float32 ``np.memmap`` backing file.  ``state`` is 'temporary', 'saved' or
+    'compressed'; temporary/compressed objects unlink their backing file when collected."""
+
+    def __init__(self, dtype=dtype_npBINarray):
+        self.path2matrix = ""
+        self.xticks = None
+        self.yticks = None
+        self.binsize = 0
+        self.title = None
+        self.xlabel = None
+        self.ylabel = None
+        self.shape = None
+        self.minvalue = 9e10
+        self.maxvalue = -9e10
+        self.bNoData = None
+        self.bLog = False
+        self.dtype = dtype
+        self.matrix = None
+        self.state = "temporary"
+
+    def __del__(self):
+        try:
+            mm = getattr(self, "matrix", None)
+            if mm is not None and getattr(mm, "_mmap", None) is not None:
+                mm._mmap.close()
+            self.matrix = None
+            if self.state in ("temporary", "compressed") and self.path2matrix and os.path.exists(self.path2matrix):
+                os.remove(self.path2matrix)
+        except Exception:
+            pass
+
+    # ---- ticks ----------------------------------------------------------------------------------
+    def get_ticks(self, binsize=None):
+        step = self.binsize if binsize is None else binsize
+        return (np.arange(self.xticks[0], self.xticks[1], step), np.arange(self.yticks[0], self.yticks[1], step))
+
+    # ---- backing file ---------------------------------------------------------------------------
+    def gen_matrix_file(self, workDir=None):
+        """Reserve a fresh temp file *name* (prefix gcx_npBinary_, like the reference) without keeping the file."""
+        fd, self.path2matrix = tempfile.mkstemp(prefix="gcx_npBinary_", suffix=".tmp", dir=workDir or _default_workdir())
+        os.close(fd)
+        if os.path.isfile(self.path2matrix):
+            os.remove(self.path2matrix)
+
+    def _map(self, mode):
+        self.matrix = None
+        self.matrix = np.memmap(self.path2matrix, dtype=self.dtype, mode=mode, shape=tuple(self.shape))
+
+    def make_readable(self):
+        self._map("r")
+
+    def make_editable(self):
+        self._map("r+")
+
+    def make_writable(self):
+        self.matrix = None
+        if os.path.exists(self.path2matrix):
+            gen_backup(self.path2matrix)
+        self._map("w+")
+
+    def make_unreadable(self):
+        self.matrix = None
+
+    # ---- construction ---------------------------------------------------------------------------
+    def gen_from_matrix(self, matrix, binsize, xlabel=None, ylabel=None, workDir=None):
+        if self.matrix is not None:
+            raise AssertionError("CCMAP object already contains a map.")
+        if self.path2matrix:
+            raise AssertionError("CCMAP object has already contains a memory mapped file")
+        self.gen_matrix_file(workDir=workDir)
+        self.shape = matrix.shape
+        self.dtype = matrix.dtype
+        self.binsize = binsize
+        self.make_writable()
+        self.matrix[:] = matrix
+        self.xlabel = xlabel if xlabel is not None else "unknown"
+        self.ylabel = ylabel if ylabel is not None else "unknown"
+        self.title = self.xlabel + "_vs_" + self.ylabel
+        self.xticks = [0, self.shape[0] * binsize]
+        self.yticks = [0, self.shape[1] * binsize]
+        self.maxvalue = np.max(self.matrix)
+        nz = np.ma.masked_equal(matrix, 0.0, copy=False)
+        self.minvalue = nz.min()
+
+    def _clone_meta(self):
+        other = CCMAP(dtype=self.dtype)
+        for key, val in self.__dict__.items():
+            other.__dict__[key] = val
+        other.matrix = None
+        other.state = "temporary"
+        other.gen_matrix_file(workDir=os.path.dirname(self.path2matrix) or None)
+        return other
+
+    def copy(self, fill=None):
+        """New temporary CCMAP with its own backing file in the same directory; values copied, or filled."""
+        other = self._clone_meta()
+        self.make_readable()
+        other.make_writable()
+        if fill is None:
+            other.matrix[:] = self.matrix[:]
+        else:
+            other.matrix.fill(fill)
+        other.matrix.flush()
+        self.make_unreadable()
+        other.make_unreadable()
+        return other
+
+    def new_like(self):
+        """New temporary CCMAP with an *uninitialised* writable backing file (the GPU result is downloaded
+        straight into it -- avoids the reference's extra n^2 memmap-to-memmap copy, lib/normalizer.py:561)."""
+        other = self._clone_meta()
+        other.make_writable()
+        return other
+
+
+def is_ccmap(obj):
+    return isinstance(obj, CCMAP) or all(hasattr(obj, a) for a in ("path2matrix", "shape", "make_readable", "bNoData", "state"))
+
+
+# ---- (de)serialisation ----------------------------------------------------------------------------
+def jsonify(ccMapObj):
+    """In-place conversion of attributes to JSON-safe strings (same encoding as the reference, ccmap.py:302-357)."""
+    if ccMapObj.bNoData is not None:
+        ccMapObj.bNoData = "".join("1" if b else "0" for b in np.asarray(ccMapObj.bNoData))
+    if ccMapObj.xticks is not None:
+        ccMapObj.xticks = [str(v) for v in ccMapObj.xticks]
+    if ccMapObj.yticks is not None:
+        ccMapObj.yticks = [str(v) for v in ccMapObj.yticks]
+    ccMapObj.minvalue = str(float(ccMapObj.minvalue))
+    ccMapObj.maxvalue = str(float(ccMapObj.maxvalue))
+    ccMapObj.shape = [str(v) for v in ccMapObj.shape]
+    if hasattr(ccMapObj, "binsize"):
+        ccMapObj.binsize = str(ccMapObj.binsize)
+    if isinstance(ccMapObj.dtype, np.dtype):
+        ccMapObj.dtype = ccMapObj.dtype.name
+
+
+def dejsonify(ccMapObj, json_dict=None):
+    if json_dict is not None:
+        ccMapObj.__dict__.update(json_dict)
+    if ccMapObj.bNoData is not None:
+        ccMapObj.bNoData = np.array([ch == "1" for ch in ccMapObj.bNoData], dtype=bool)
+    if ccMapObj.xticks is not None:
+        ccMapObj.xticks = [int(v) for v in ccMapObj.xticks]
+    if ccMapObj.yticks is not None:
+        ccMapObj.yticks = [int(v) for v in ccMapObj.yticks]
+    ccMapObj.minvalue = float(ccMapObj.minvalue)
+    ccMapObj.maxvalue = float(ccMapObj.maxvalue)
+    ccMapObj.shape = tuple(int(v) for v in ccMapObj.shape)
+    if hasattr(ccMapObj, "binsize"):
+        ccMapObj.binsize = int(ccMapObj.binsize)
+
+
+def save_ccmap(ccMapObj, outfile, compress=False, logHandler=None):
+    """Write ``<name>.ccmap`` (JSON) + ``<name>.npbin`` (raw float32, gzip'd when compress=True)."""
+    log = logging.getLogger("save_ccmap")
+    if logHandler is not None:
+        log.propagate = False
+        log.addHandler(logHandler)
+    log.setLevel(logging.INFO)
+    ccMapObj.make_unreadable()
+    if os.path.splitext(outfile)[1] != ".ccmap":
+        outfile = outfile + ".ccmap"
+    outpath = os.path.abspath(os.path.expanduser(outfile))
+    outdir = os.path.dirname(outpath)
+    npbin_name = os.path.splitext(os.path.basename(outfile))[0] + ".npbin"
+    npbin = os.path.join(outdir, npbin_name)
+    log.info(" Saving ccmap to file [{0}] and [{1}] ...".format(outfile, npbin))
+    if ccMapObj.path2matrix == npbin:
+        logging.warning("File {0} already exists !!!".format(ccMapObj.path2matrix))
+    else:
+        if os.path.exists(npbin):
+            gen_backup(npbin)
+        shutil.copy(ccMapObj.path2matrix, npbin)
+    if os.path.exists(outpath):
+        gen_backup(outpath)
+    keep_path, keep_state = ccMapObj.path2matrix, ccMapObj.state
+    ccMapObj.path2matrix = npbin_name
+    jsonify(ccMapObj)
+    ccMapObj.state = "compressed" if compress else "saved"
+    try:
+        with open(outpath, "w") as fout:
+            json.dump(ccMapObj.__dict__, fout, indent=4, separators=(",", ":"))   # matrix is None here
+        if compress:
+            if os.path.exists(npbin + ".gz"):
+                gen_backup(npbin + ".gz")
+            with open(npbin, "rb") as f_in, gzip.open(npbin + ".gz", "wb") as f_out:
+                shutil.copyfileobj(f_in, f_out)
+            if os.path.exists(npbin):
+                os.remove(npbin)
+    finally:
+        ccMapObj.path2matrix = keep_path
+        ccMapObj.state = "temporary" if keep_state == "temporary" else keep_state
+        dejsonify(ccMapObj)
+    log.info("       Finished!!!\n")
+
+
+def load_ccmap(infile, workDir=None):
+    with open(infile, "r") as fin:
+        jd = json.load(fin)
+    obj = CCMAP(dtype=np.dtype(jd["dtype"]))
+    dejsonify(obj, jd)
+    obj.matrix = None
+    indir = os.path.dirname(os.path.abspath(os.path.expanduser(infile)))
+    npbin = os.path.join(indir, obj.path2matrix)
+    if os.path.exists(npbin + ".gz"):
+        obj.gen_matrix_file(workDir=workDir)
+        try:
+            with gzip.open(npbin + ".gz", "rb") as f_in, open(obj.path2matrix, "wb") as f_out:
+                shutil.copyfileobj(f_in, f_out)
+        except (KeyboardInterrupt, SystemExit):
+            os.remove(obj.path2matrix)
+            raise
+        obj.state = "temporary"
+    else:
+        obj.path2matrix = npbin
+    return obj
+
+
+def checkCCMapObjectOrFile(ccMap, workDir=None):
+    """(CCMAP, 'Object' | 'File'); a missing file returns a bare None like the reference (ccmap.py:644-647),
+    so callers that tuple-unpack raise TypeError."""
+    if is_ccmap(ccMap):
+        return ccMap, "Object"
+    if not os.path.isfile(ccMap):
+        logger.info(" {0} file not found.".format(ccMap))
+        logger.info(" Not able to normalize.")
+        return None
+    return load_ccmap(ccMap, workDir=workDir), "File"

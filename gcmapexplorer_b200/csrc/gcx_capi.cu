@@ -1,0 +1,938 @@
+// gcx_capi.cu -- the C ABI declared in include/gcx_norm.h: context, residency, kernel drivers.
+// Host side is plain C++/CUDA runtime; no torch types cross this boundary.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gcx_norm.h"
+#include "gcx_kernels.cuh"
+
+using namespace gcx;
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) return fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+#define CKR(call)                  \
+    do {                           \
+        int r__ = (call);          \
+        if (r__ != 0) return r__;  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL through dlopen (torch bundles libnccl.so.2; the library itself has no link-time dependency)
+// ---------------------------------------------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclInt32 = 2, ncclUint32 = 3, ncclFloat32 = 7, ncclFloat64 = 8, ncclUint8 = 1 };
+enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.h) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return fail("cannot dlopen libnccl.so.2 (import torch first, or set LD_LIBRARY_PATH): %s", dlerror());
+#define SYM(f)                                                          \
+    *(void**)(&g_nccl.f) = dlsym(g_nccl.h, "nccl" #f);                   \
+    if (!g_nccl.f) return fail("libnccl: missing symbol nccl" #f);
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllGather) SYM(AllReduce) SYM(GetErrorString)
+#undef SYM
+    return 0;
+}
+#define NK(call)                                                                                           \
+    do {                                                                                                   \
+        int e__ = (call);                                                                                  \
+        if (e__ != 0) return fail("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, g_nccl.GetErrorString(e__)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+struct EvPair {
+    int cls;
+    cudaEvent_t a, b;
+};
+
+struct gcx_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    // map
+    int64_t n = 0, ld = 0, row0 = 0, nloc = 0, nv = 0;
+    float* A = nullptr;
+    float* Out = nullptr;
+    // vectors (float64, nv each) carved from one slab
+    double* slab = nullptr;
+    double *vz = nullptr, *vq = nullptr, *vB = nullptr, *vBd = nullptr, *vscale = nullptr, *vrowsum = nullptr, *vavg = nullptr;
+    KrVecs kr{};
+    float* csum32 = nullptr;
+    int32_t* zero_count = nullptr;
+    uint8_t* keep = nullptr;
+    bool have_mask = false, have_rowsum = false, have_scale = false;
+    // matvec workspace
+    double* ws = nullptr;
+    unsigned int* ticket = nullptr;
+    int mv_variant = 0;
+    // states
+    IcState* ic_state = nullptr;
+    KrState* kr_state = nullptr;
+    MinMax* mm = nullptr;
+    unsigned long long* csum_dev = nullptr;
+    void* h_state = nullptr;   // pinned, 4 KB
+    // staging
+    void* stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    // dist
+    int rank = 0, world = 1;
+    int64_t rpr = 0;   // rows per rank (allgather count)
+    ncclComm_t comm = nullptr;
+    // measurement
+    bool profile = false;
+    std::vector<EvPair> evs;
+    std::vector<cudaEvent_t> ev_pool;
+    int64_t prof_launches[GCX_NCLASS] = {0};
+    double prof_ms[GCX_NCLASS] = {0};
+    int64_t launches = 0;
+    cudaEvent_t run_a = nullptr, run_b = nullptr;
+    cudaEvent_t tm_a = nullptr, tm_b = nullptr;
+    double last_run_ms = 0;
+};
+
+static const size_t STAGE_BYTES = 64ull << 20;
+
+static int set_dev(gcx_ctx* c) {
+    CK(cudaSetDevice(c->device));
+    return 0;
+}
+
+static int prof_fold(gcx_ctx* c) {
+    if (c->evs.empty()) return 0;
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& p : c->evs) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, p.a, p.b));
+        c->prof_ms[p.cls] += ms;
+        c->prof_launches[p.cls] += 1;
+        c->ev_pool.push_back(p.a);
+        c->ev_pool.push_back(p.b);
+    }
+    c->evs.clear();
+    return 0;
+}
+
+static int ev_get(gcx_ctx* c, cudaEvent_t* e) {
+    if (!c->ev_pool.empty()) {
+        *e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+        return 0;
+    }
+    CK(cudaEventCreate(e));
+    return 0;
+}
+
+struct ProfScope {
+    gcx_ctx* c;
+    int cls;
+    bool on;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(gcx_ctx* c_, int cls_) : c(c_), cls(cls_), on(c_->profile) {
+        if (on) {
+            if (ev_get(c, &a) || ev_get(c, &b)) { on = false; return; }
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    ~ProfScope() {
+        c->launches += 1;
+        if (on) {
+            cudaEventRecord(b, c->stream);
+            c->evs.push_back({cls, a, b});
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// library / context
+// ---------------------------------------------------------------------------------------------------
+extern "C" const char* gcx_last_error(void) { return g_err.c_str(); }
+extern "C" int gcx_version(void) { return 100; }
+
+extern "C" int gcx_device_count(int* count) {
+    CK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
+    int cnt = 0;
+    CK(cudaGetDeviceCount(&cnt));
+    if (cnt <= 0) return fail("no CUDA device visible: libgcxnorm has no CPU fallback");
+    if (device < 0 || device >= cnt) return fail("device %d out of range (%d visible)", device, cnt);
+    gcx_ctx* c = new gcx_ctx();
+    c->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete c;
+        return fail("device %d is sm_%d%d; libgcxnorm is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    }
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&c->ic_state, sizeof(IcState)));
+    CK(cudaMalloc(&c->kr_state, sizeof(KrState)));
+    CK(cudaMalloc(&c->mm, sizeof(MinMax)));
+    CK(cudaMalloc(&c->csum_dev, sizeof(unsigned long long)));
+    CK(cudaMalloc(&c->ticket, sizeof(unsigned int)));
+    CK(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
+    CK(cudaMalloc(&c->ws, sizeof(double) * (size_t)c->sm_count * 8 * 2 * 16));
+    CK(cudaHostAlloc(&c->h_state, 4096, cudaHostAllocDefault));
+    CK(cudaEventCreate(&c->run_a));
+    CK(cudaEventCreate(&c->run_b));
+    CK(cudaEventCreate(&c->tm_a));
+    CK(cudaEventCreate(&c->tm_b));
+    const char* v = getenv("GCX_MATVEC_VARIANT");
+    if (v) c->mv_variant = atoi(v);
+    *out = c;
+    return 0;
+}
+
+static void free_map(gcx_ctx* c) {
+    cudaFree(c->A); c->A = nullptr;
+    cudaFree(c->Out); c->Out = nullptr;
+    cudaFree(c->slab); c->slab = nullptr;
+    cudaFree(c->csum32); c->csum32 = nullptr;
+    cudaFree(c->zero_count); c->zero_count = nullptr;
+    cudaFree(c->keep); c->keep = nullptr;
+    c->have_mask = c->have_rowsum = c->have_scale = false;
+}
+
+extern "C" int gcx_ctx_destroy(gcx_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    free_map(c);
+    for (auto& p : c->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->mm); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws);
+    cudaFreeHost(c->h_state);
+    for (int i = 0; i < 2; ++i) {
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+        if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+    }
+    cudaEventDestroy(c->run_a); cudaEventDestroy(c->run_b);
+    cudaEventDestroy(c->tm_a); cudaEventDestroy(c->tm_b);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int gcx_sync(gcx_ctx* c) {
+    CKR(set_dev(c));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gcx_device_info(gcx_ctx* c, int* sm_count, int64_t* hbm_total, int64_t* hbm_free) {
+    CKR(set_dev(c));
+    size_t f = 0, t = 0;
+    CK(cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = c->sm_count;
+    if (hbm_total) *hbm_total = (int64_t)t;
+    if (hbm_free) *hbm_free = (int64_t)f;
+    return 0;
+}
+
+extern "C" int gcx_host_alloc(int64_t bytes, void** ptr) {
+    CK(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return 0;
+}
+extern "C" int gcx_host_free(void* ptr) {
+    CK(cudaFreeHost(ptr));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// map residency
+// ---------------------------------------------------------------------------------------------------
+static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+extern "C" int gcx_map_create(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc) {
+    CKR(set_dev(c));
+    if (n <= 0 || nloc <= 0 || row0 < 0 || row0 + nloc > n) return fail("bad map geometry n=%lld row0=%lld nloc=%lld", (long long)n, (long long)row0, (long long)nloc);
+    if (n > 0x7ffffff0LL) return fail("n too large");
+    CK(cudaStreamSynchronize(c->stream));
+    free_map(c);
+    c->n = n; c->row0 = row0; c->nloc = nloc;
+    c->ld = round_up(n, 32);
+    c->rpr = (n + c->world - 1) / c->world;
+    c->nv = round_up(std::max<int64_t>(c->ld, c->rpr * c->world), 32) + 32;
+    CK(cudaMalloc(&c->A, sizeof(float) * (size_t)nloc * c->ld));
+    CK(cudaMemsetAsync(c->A, 0, sizeof(float) * (size_t)nloc * c->ld, c->stream));
+    const int NVEC = 15;
+    CK(cudaMalloc(&c->slab, sizeof(double) * (size_t)c->nv * NVEC));
+    CK(cudaMemsetAsync(c->slab, 0, sizeof(double) * (size_t)c->nv * NVEC, c->stream));
+    double* p = c->slab;
+    auto take = [&]() { double* r = p; p += c->nv; return r; };
+    c->vz = take(); c->vq = take(); c->vB = take(); c->vBd = take(); c->vscale = take(); c->vrowsum = take(); c->vavg = take();
+    c->kr.x = take(); c->kr.v = take(); c->kr.rk = take(); c->kr.y = take(); c->kr.Z = take(); c->kr.p = take(); c->kr.w = take();
+    c->kr.z = c->vz;
+    CK(cudaMalloc(&c->csum32, sizeof(float) * (size_t)c->nv));
+    CK(cudaMemsetAsync(c->csum32, 0, sizeof(float) * (size_t)c->nv, c->stream));
+    CK(cudaMalloc(&c->zero_count, sizeof(int32_t) * (size_t)c->nv));
+    CK(cudaMemsetAsync(c->zero_count, 0, sizeof(int32_t) * (size_t)c->nv, c->stream));
+    CK(cudaMalloc(&c->keep, (size_t)c->nv));
+    CK(cudaMemsetAsync(c->keep, 0, (size_t)c->nv, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int need_map(gcx_ctx* c) {
+    if (!c || !c->A) return fail("no resident map: call gcx_map_create first");
+    return set_dev(c);
+}
+
+static int ensure_out(gcx_ctx* c) {
+    if (!c->Out) CK(cudaMalloc(&c->Out, sizeof(float) * (size_t)c->nloc * c->ld));
+    return 0;
+}
+
+static int ensure_stage(gcx_ctx* c) {
+    if (c->stage[0]) return 0;
+    c->stage_bytes = STAGE_BYTES;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaHostAlloc(&c->stage[i], c->stage_bytes, cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static void par_copy_rows(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, int64_t rows) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = (int)std::min<int64_t>(std::max(1u, std::min(hw, 8u)), rows);
+    if ((size_t)rows * width < (4u << 20)) T = 1;
+    auto work = [=](int t) {
+        const int64_t a = rows * t / T, b = rows * (t + 1) / T;
+        for (int64_t r = a; r < b; ++r) memcpy(dst + r * dpitch, src + r * spitch, width);
+    };
+    if (T == 1) { work(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
+extern "C" int gcx_map_upload(gcx_ctx* c, const float* host, int64_t host_ld) {
+    CKR(need_map(c));
+    if (host_ld < c->n) return fail("host_ld < n");
+    const size_t width = sizeof(float) * (size_t)c->n;
+    if (is_pinned(host)) {
+        CK(cudaMemcpy2DAsync(c->A, sizeof(float) * c->ld, host, sizeof(float) * host_ld, width, (size_t)c->nloc, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    CKR(ensure_stage(c));
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t)(c->stage_bytes / width));
+    int64_t r0 = 0;
+    int it = 0;
+    while (r0 < c->nloc) {
+        const int b = it & 1;
+        const int64_t rows = std::min(rows_per, c->nloc - r0);
+        if (it >= 2) CK(cudaEventSynchronize(c->stage_ev[b]));
+        par_copy_rows((char*)c->stage[b], width, (const char*)(host + r0 * host_ld), sizeof(float) * host_ld, width, rows);
+        CK(cudaMemcpy2DAsync(c->A + r0 * c->ld, sizeof(float) * c->ld, c->stage[b], width, width, (size_t)rows, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(c->stage_ev[b], c->stream));
+        r0 += rows;
+        ++it;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gcx_map_download(gcx_ctx* c, int which, float* host, int64_t host_ld) {
+    CKR(need_map(c));
+    const float* src = which == 0 ? c->A : c->Out;
+    if (!src) return fail("no output map resident");
+    if (host_ld < c->n) return fail("host_ld < n");
+    const size_t width = sizeof(float) * (size_t)c->n;
+    if (is_pinned(host)) {
+        CK(cudaMemcpy2DAsync(host, sizeof(float) * host_ld, src, sizeof(float) * c->ld, width, (size_t)c->nloc, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    CKR(ensure_stage(c));
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t)(c->stage_bytes / width));
+    int64_t r0 = 0, prev_r0 = -1, prev_rows = 0;
+    int it = 0;
+    while (r0 < c->nloc || prev_r0 >= 0) {
+        const int b = it & 1;
+        int64_t rows = 0;
+        if (r0 < c->nloc) {
+            rows = std::min(rows_per, c->nloc - r0);
+            CK(cudaMemcpy2DAsync(c->stage[b], width, src + r0 * c->ld, sizeof(float) * c->ld, width, (size_t)rows, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaEventRecord(c->stage_ev[b], c->stream));
+        }
+        if (prev_r0 >= 0) {
+            CK(cudaEventSynchronize(c->stage_ev[b ^ 1]));
+            par_copy_rows((char*)(host + prev_r0 * host_ld), sizeof(float) * host_ld, (const char*)c->stage[b ^ 1], width, width, prev_rows);
+        }
+        if (rows > 0) { prev_r0 = r0; prev_rows = rows; r0 += rows; } else { prev_r0 = -1; }
+        ++it;
+    }
+    return 0;
+}
+
+static int grid_rows(gcx_ctx* c) { return (int)std::min<int64_t>(c->nloc, (int64_t)c->sm_count * 8); }
+
+extern "C" int gcx_map_synth(gcx_ctx* c, uint64_t seed, double scale, double alpha, double empty_frac) {
+    CKR(need_map(c));
+    const unsigned int thresh = (unsigned int)(std::min(1.0, std::max(0.0, empty_frac)) * 16777216.0);
+    {
+        ProfScope ps(c, 7);
+        k_synth<<<grid_rows(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, (int)c->n, (int)c->row0, seed, (float)scale, (float)alpha, thresh);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_rowsum = false;
+    return 0;
+}
+
+static int clamp_scale(gcx_ctx* c, int hmin, float vmin, int hmax, float vmax, int hs, float s) {
+    const long long total4 = (long long)c->nloc * c->ld / 4;
+    {
+        ProfScope ps(c, 7);
+        k_clamp_scale<<<c->sm_count * 8, MV_THREADS, 0, c->stream>>>(c->A, total4, hmin, vmin, hmax, vmax, hs, s);
+    }
+    CK(cudaGetLastError());
+    c->have_rowsum = false;
+    return 0;
+}
+
+extern "C" int gcx_map_clamp(gcx_ctx* c, int has_vmin, float vmin, int has_vmax, float vmax) {
+    CKR(need_map(c));
+    if (!has_vmin && !has_vmax) return 0;
+    return clamp_scale(c, has_vmin, vmin, has_vmax, vmax, 0, 1.f);
+}
+
+extern "C" int gcx_map_scale(gcx_ctx* c, float factor) {
+    CKR(need_map(c));
+    return clamp_scale(c, 0, 0.f, 0, 0.f, 1, factor);
+}
+
+extern "C" int gcx_map_swap(gcx_ctx* c) {
+    CKR(need_map(c));
+    if (!c->Out) return fail("no output map resident");
+    std::swap(c->A, c->Out);
+    c->have_rowsum = false;
+    return 0;
+}
+
+extern "C" int gcx_map_checksum(gcx_ctx* c, int which, uint64_t* sum) {
+    CKR(need_map(c));
+    const float* src = which == 0 ? c->A : c->Out;
+    if (!src) return fail("no output map resident");
+    CK(cudaMemsetAsync(c->csum_dev, 0, sizeof(unsigned long long), c->stream));
+    k_checksum<<<grid_rows(c), MV_THREADS, 0, c->stream>>>(src, c->ld, (int)c->nloc, (int)c->n, (int)c->row0, c->csum_dev);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    CK(cudaMemcpyAsync(c->h_state, c->csum_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *sum = *(uint64_t*)c->h_state;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// collectives (no-ops on a single rank)
+// ---------------------------------------------------------------------------------------------------
+static int allgather_f64(gcx_ctx* c, double* vec) {
+    if (c->world == 1) return 0;
+    NK(g_nccl.AllGather(vec + c->rank * c->rpr, vec, (size_t)c->rpr, ncclFloat64, c->comm, c->stream));
+    return 0;
+}
+static int allgather_i32(gcx_ctx* c, int32_t* vec) {
+    if (c->world == 1) return 0;
+    NK(g_nccl.AllGather(vec + c->rank * c->rpr, vec, (size_t)c->rpr, ncclInt32, c->comm, c->stream));
+    return 0;
+}
+
+extern "C" int gcx_dist_unique_id(void* id128) {
+    CKR(nccl_load());
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+extern "C" int gcx_dist_init(gcx_ctx* c, int rank, int world, const void* id128) {
+    CKR(set_dev(c));
+    if (c->A) return fail("gcx_dist_init must precede gcx_map_create");
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank/world");
+    c->rank = rank; c->world = world;
+    if (world == 1) return 0;
+    CKR(nccl_load());
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NK(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// mask
+// ---------------------------------------------------------------------------------------------------
+static int run_row_stats(gcx_ctx* c) {
+    if (c->have_rowsum) return 0;
+    {
+        ProfScope ps(c, 3);
+        k_row_stats<<<grid_rows(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, (int)c->n, c->vrowsum + c->row0, c->zero_count + c->row0);
+    }
+    CK(cudaGetLastError());
+    CKR(allgather_f64(c, c->vrowsum));
+    CKR(allgather_i32(c, c->zero_count));
+    c->have_rowsum = true;
+    return 0;
+}
+
+extern "C" int gcx_row_stats(gcx_ctx* c, double* rowsum, int32_t* zero_count) {
+    CKR(need_map(c));
+    CKR(run_row_stats(c));
+    if (rowsum) CK(cudaMemcpyAsync(rowsum, c->vrowsum, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->stream));
+    if (zero_count) CK(cudaMemcpyAsync(zero_count, c->zero_count, sizeof(int32_t) * c->n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gcx_set_mask(gcx_ctx* c, const uint8_t* keep) {
+    CKR(need_map(c));
+    CK(cudaMemsetAsync(c->keep, 0, (size_t)c->nv, c->stream));
+    CK(cudaMemcpyAsync(c->keep, keep, (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_mask = true;
+    c->have_scale = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// matvec dispatch
+// ---------------------------------------------------------------------------------------------------
+template <int R, int OCC>
+static void launch_mv(gcx_ctx* c, const double* z, double* q, const int* done) {
+    k_matvec<R, OCC><<<c->sm_count * OCC, MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, (int)(c->ld / 4), z, q + c->row0, c->ws, c->ticket, done);
+}
+
+static int matvec(gcx_ctx* c, int variant, const double* z, double* q, const int* done) {
+    {
+        ProfScope ps(c, 0);
+        switch (variant) {
+            case 0: launch_mv<8, 2>(c, z, q, done); break;
+            case 1: launch_mv<8, 3>(c, z, q, done); break;
+            case 2: launch_mv<4, 4>(c, z, q, done); break;
+            case 3: launch_mv<4, 6>(c, z, q, done); break;
+            case 4: launch_mv<16, 1>(c, z, q, done); break;
+            case 5: launch_mv<2, 8>(c, z, q, done); break;
+            case 6: launch_mv<8, 4>(c, z, q, done); break;
+            default: return fail("unknown matvec variant %d", variant);
+        }
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gcx_bench_matvec(gcx_ctx* c, int variant, int iters, double* ms_total) {
+    CKR(need_map(c));
+    if (variant < 0) variant = c->mv_variant;
+    // z = ones on the real columns
+    std::vector<double> ones((size_t)c->nv, 0.0);
+    for (int64_t i = 0; i < c->n; ++i) ones[i] = 1.0;
+    CK(cudaMemcpyAsync(c->vz, ones.data(), sizeof(double) * c->nv, cudaMemcpyHostToDevice, c->stream));
+    CKR(matvec(c, variant, c->vz, c->vq, nullptr));   // warm
+    CK(cudaEventRecord(c->run_a, c->stream));
+    for (int i = 0; i < iters; ++i) CKR(matvec(c, variant, c->vz, c->vq, nullptr));
+    CK(cudaEventRecord(c->run_b, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->run_a, c->run_b));
+    *ms_total = ms;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// iteration drivers: chunks of (matvec, allgather, vector step) are enqueued one chunk ahead of the
+// host's convergence check, so the GPU never waits for the host; launches after convergence exit at once.
+// ---------------------------------------------------------------------------------------------------
+static int chunk_len(gcx_ctx* c) {
+    const double est_ms = 4.0 * (double)c->nloc * (double)c->ld / 5.0e9;   // ~5 TB/s
+    int ch = (int)(0.25 / std::max(est_ms, 1e-4)) + 1;
+    return std::max(2, std::min(ch, 16));
+}
+
+template <typename State, typename StepFn>
+static int iterate(gcx_ctx* c, State* dev_state, int max_matvecs, StepFn step, State* final_state) {
+    const int CH = chunk_len(c);
+    State* hs = (State*)c->h_state;   // two pinned slots
+    static_assert(sizeof(State) <= 1024, "state too large");
+    State* slot[2] = {hs, (State*)((char*)c->h_state + 2048)};
+    cudaEvent_t ev[2];
+    CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    CK(cudaEventRecord(c->run_a, c->stream));
+    int issued = 0, rc = 0;
+    auto enqueue_chunk = [&](int b) -> int {
+        for (int i = 0; i < CH; ++i) CKR(step());
+        issued += CH;
+        CK(cudaMemcpyAsync(slot[b], dev_state, sizeof(State), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaEventRecord(ev[b], c->stream));
+        return 0;
+    };
+    rc = enqueue_chunk(0);
+    int cur = 0;
+    while (rc == 0) {
+        rc = enqueue_chunk(cur ^ 1);
+        if (rc) break;
+        cudaError_t e = cudaEventSynchronize(ev[cur]);
+        if (e != cudaSuccess) { rc = fail("cudaEventSynchronize: %s", cudaGetErrorString(e)); break; }
+        if (slot[cur]->done) break;
+        if (issued > max_matvecs + 2 * CH) { rc = fail("iteration did not terminate within %d matrix passes", max_matvecs); break; }
+        cur ^= 1;
+    }
+    cudaError_t e2 = cudaEventRecord(c->run_b, c->stream);
+    cudaError_t e3 = cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (rc) return rc;
+    CK(e2);
+    CK(e3);
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->run_a, c->run_b));
+    c->last_run_ms = ms;
+    CK(cudaMemcpy(final_state, dev_state, sizeof(State), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, int* passes, double* last_l1, int* matvecs) {
+    CKR(need_map(c));
+    if (!c->have_mask) return fail("gcx_ic_run: call gcx_set_mask first");
+    const int n = (int)c->n;
+    k_ic_init<<<1, EP_THREADS, 0, c->stream>>>(c->ic_state, (int)c->nv, c->keep, c->vz, c->vB, c->vBd, tol, iteration);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    auto step = [&]() -> int {
+        CKR(matvec(c, c->mv_variant, c->vz, c->vq, &c->ic_state->done));
+        CKR(allgather_f64(c, c->vq));
+        {
+            ProfScope ps(c, 6);
+            k_ic_epilogue<<<1, EP_THREADS, 0, c->stream>>>(c->ic_state, n, c->keep, c->vq, c->vz, c->vB, c->vBd);
+        }
+        CK(cudaGetLastError());
+        return 0;
+    };
+    IcState fin;
+    CKR(iterate<IcState>(c, c->ic_state, iteration + 3, step, &fin));
+    k_ic_scale<<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>((int)c->nv, n, c->keep, c->vB, c->vscale);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    c->have_scale = true;
+    if (bias) CK(cudaMemcpyAsync(bias, c->vB, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (passes) *passes = fin.pass;
+    if (last_l1) *last_l1 = fin.l1;
+    if (matvecs) *matvecs = fin.matvecs;
+    return 0;
+}
+
+extern "C" int gcx_kr_run(gcx_ctx* c, double tol, double delta, double Delta, double* x, int* outer, int* mvp, double* rout) {
+    CKR(need_map(c));
+    if (!c->have_mask) return fail("gcx_kr_run: call gcx_set_mask first");
+    const int n = (int)c->n;
+    k_kr_init<<<1, EP_THREADS, 0, c->stream>>>(c->kr_state, (int)c->nv, c->keep, c->kr, tol, delta, Delta);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    auto step = [&]() -> int {
+        CKR(matvec(c, c->mv_variant, c->vz, c->vq, &c->kr_state->done));
+        CKR(allgather_f64(c, c->vq));
+        {
+            ProfScope ps(c, 6);
+            k_kr_step<<<1, EP_THREADS, 0, c->stream>>>(c->kr_state, n, c->keep, c->vq, c->kr);
+        }
+        CK(cudaGetLastError());
+        return 0;
+    };
+    KrState fin;
+    CKR(iterate<KrState>(c, c->kr_state, 20000, step, &fin));
+    CK(cudaMemcpyAsync(c->vscale, c->kr.x, sizeof(double) * c->nv, cudaMemcpyDeviceToDevice, c->stream));
+    c->have_scale = true;
+    if (x) CK(cudaMemcpyAsync(x, c->kr.x, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (outer) *outer = fin.outer;
+    if (mvp) *mvp = fin.mvp;
+    if (rout) *rout = fin.rout;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// elementwise passes
+// ---------------------------------------------------------------------------------------------------
+static int mm_begin(gcx_ctx* c) {
+    MinMax init{0xffffffffu, 0u};
+    memcpy(c->h_state, &init, sizeof init);
+    CK(cudaMemcpyAsync(c->mm, c->h_state, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+static int mm_end(gcx_ctx* c, float* minv, float* maxv) {
+    if (c->world > 1) {
+        NK(g_nccl.AllReduce(&c->mm->min_nz, &c->mm->min_nz, 1, ncclUint32, ncclMin, c->comm, c->stream));
+        NK(g_nccl.AllReduce(&c->mm->max_all, &c->mm->max_all, 1, ncclUint32, ncclMax, c->comm, c->stream));
+    }
+    CK(cudaMemcpyAsync(c->h_state, c->mm, sizeof(MinMax), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    MinMax r;
+    memcpy(&r, c->h_state, sizeof r);
+    const float nanv = __builtin_nanf("");
+    if (minv) *minv = r.min_nz == 0xffffffffu ? nanv : ord2f(r.min_nz);
+    if (maxv) *maxv = r.max_all == 0u ? nanv : ord2f(r.max_all);
+    return 0;
+}
+
+static const int EW_R = 4;
+static int ew_grid(gcx_ctx* c) { return c->sm_count * 3; }
+
+extern "C" int gcx_apply_sym_scale(gcx_ctx* c, const double* s, int masked_mode, int in_place, float* minv, float* maxv) {
+    CKR(need_map(c));
+    if (!c->have_mask) return fail("gcx_apply_sym_scale: call gcx_set_mask first");
+    if (s) {
+        CK(cudaMemsetAsync(c->vscale, 0, sizeof(double) * c->nv, c->stream));
+        CK(cudaMemcpyAsync(c->vscale, s, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+        c->have_scale = true;
+    }
+    if (!c->have_scale) return fail("gcx_apply_sym_scale: no scale vector (pass s or run gcx_ic_run / gcx_kr_run)");
+    float* out = c->A;
+    if (!in_place) { CKR(ensure_out(c)); out = c->Out; }
+    CKR(mm_begin(c));
+    {
+        ProfScope ps(c, 1);
+        k_apply_sym<EW_R><<<ew_grid(c), MV_THREADS, 0, c->stream>>>(c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->row0, c->vscale, c->keep, masked_mode, c->mm);
+    }
+    CK(cudaGetLastError());
+    if (in_place) c->have_rowsum = false;
+    return mm_end(c, minv, maxv);
+}
+
+__global__ void k_f64_to_f32(int nv, const double* __restrict__ a, float* __restrict__ b) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) b[i] = (float)a[i];
+}
+
+extern "C" int gcx_vc_run(gcx_ctx* c, int sqroot, int in_place, float* minv, float* maxv, float* csum) {
+    CKR(need_map(c));
+    if (!c->have_mask) return fail("gcx_vc_run: call gcx_set_mask first");
+    CKR(run_row_stats(c));
+    // csum = np.sum(A, axis=1) is float32 in the reference (lib/normalizeCore.pyx:72)
+    k_f64_to_f32<<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>((int)c->nv, c->vrowsum, c->csum32);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    float* out = c->A;
+    if (!in_place) { CKR(ensure_out(c)); out = c->Out; }
+    CKR(mm_begin(c));
+    {
+        ProfScope ps(c, 2);
+        k_vc_apply<EW_R><<<ew_grid(c), MV_THREADS, 0, c->stream>>>(c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->csum32, c->keep, sqroot, c->mm);
+    }
+    CK(cudaGetLastError());
+    if (csum) CK(cudaMemcpyAsync(csum, c->csum32, sizeof(float) * c->n, cudaMemcpyDeviceToHost, c->stream));
+    if (in_place) c->have_rowsum = false;
+    return mm_end(c, minv, maxv);
+}
+
+static dim3 diag_grid(gcx_ctx* c) {
+    return dim3((unsigned)((c->n + MV_THREADS - 1) / MV_THREADS), (unsigned)((c->nloc + DIAG_RB - 1) / DIAG_RB));
+}
+
+static int diag_mean(gcx_ctx* c) {
+    const int n = (int)c->n, nbands = (int)((c->nloc + DIAG_RB - 1) / DIAG_RB);
+    double* psum = nullptr;
+    int* pcnt = nullptr;
+    double* sumcnt = nullptr;     // [2][nv]
+    CK(cudaMalloc(&psum, sizeof(double) * (size_t)nbands * n));
+    CK(cudaMalloc(&pcnt, sizeof(int) * (size_t)nbands * n));
+    CK(cudaMalloc(&sumcnt, sizeof(double) * 2 * (size_t)c->nv));
+    int rc = 0;
+    do {
+        {
+            ProfScope ps(c, 4);
+            k_diag_mean_partial<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, psum, pcnt);
+        }
+        k_diag_mean_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(nbands, n, (int)c->row0, psum, pcnt, sumcnt, sumcnt + c->nv);
+        c->launches += 1;
+        if (c->world > 1) {
+            int e = g_nccl.AllReduce(sumcnt, sumcnt, 2 * (size_t)c->nv, ncclFloat64, ncclSum, c->comm, c->stream);
+            if (e) { rc = fail("ncclAllReduce: %s", g_nccl.GetErrorString(e)); break; }
+        }
+        k_diag_mean_final<<<(n + 255) / 256, 256, 0, c->stream>>>(n, sumcnt, sumcnt + c->nv, c->vavg);
+        c->launches += 1;
+        cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(c->stream);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail("diag mean: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    } while (0);
+    cudaFree(psum); cudaFree(pcnt); cudaFree(sumcnt);
+    return rc;
+}
+
+static int diag_median(gcx_ctx* c) {
+    const int n = (int)c->n;
+    DiagSel S{};
+    unsigned int* small = nullptr;     // prefix, krem, cnt, need, next
+    CK(cudaMalloc(&S.hist, sizeof(unsigned int) * 256 * (size_t)n));
+    CK(cudaMalloc(&small, sizeof(unsigned int) * 5 * (size_t)n));
+    S.prefix = small; S.krem = small + n; S.cnt = small + 2 * (size_t)n; S.need = small + 3 * (size_t)n; S.next = small + 4 * (size_t)n;
+    int rc = 0;
+    do {
+        cudaMemsetAsync(S.hist, 0, sizeof(unsigned int) * 256 * (size_t)n, c->stream);
+        cudaMemsetAsync(small, 0, sizeof(unsigned int) * 5 * (size_t)n, c->stream);
+        for (int pass = 0; pass < 4 && rc == 0; ++pass) {
+            {
+                ProfScope ps(c, 4);
+                k_diag_hist<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, pass, S);
+            }
+            if (c->world > 1) {
+                int e = g_nccl.AllReduce(S.hist, S.hist, 256 * (size_t)n, ncclUint32, ncclSum, c->comm, c->stream);
+                if (e) { rc = fail("ncclAllReduce: %s", g_nccl.GetErrorString(e)); break; }
+            }
+            k_diag_select<<<(int)(((long long)n * 32 + MV_THREADS - 1) / MV_THREADS), MV_THREADS, 0, c->stream>>>(n, pass, S);
+            c->launches += 1;
+        }
+        if (rc) break;
+        {
+            ProfScope ps(c, 4);
+            k_diag_next<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, S);
+        }
+        if (c->world > 1) {
+            int e = g_nccl.AllReduce(S.next, S.next, (size_t)n, ncclUint32, ncclMin, c->comm, c->stream);
+            if (e) { rc = fail("ncclAllReduce: %s", g_nccl.GetErrorString(e)); break; }
+        }
+        k_diag_median_final<<<(n + 255) / 256, 256, 0, c->stream>>>(n, S, c->vavg);
+        c->launches += 1;
+        cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(c->stream);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail("diag median: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    } while (0);
+    cudaFree(S.hist); cudaFree(small);
+    return rc;
+}
+
+extern "C" int gcx_diag_stats(gcx_ctx* c, int median, double* avg) {
+    CKR(need_map(c));
+    CK(cudaMemsetAsync(c->vavg, 0, sizeof(double) * c->nv, c->stream));
+    CKR(median ? diag_median(c) : diag_mean(c));
+    if (avg) CK(cudaMemcpyAsync(avg, c->vavg, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gcx_diag_apply(gcx_ctx* c, const double* avg, int subtract, int in_place, float* minv, float* maxv) {
+    CKR(need_map(c));
+    if (avg) {
+        CK(cudaMemsetAsync(c->vavg, 0, sizeof(double) * c->nv, c->stream));
+        CK(cudaMemcpyAsync(c->vavg, avg, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));
+    }
+    float* out = c->A;
+    if (!in_place) { CKR(ensure_out(c)); out = c->Out; }
+    CKR(mm_begin(c));
+    {
+        ProfScope ps(c, 5);
+        k_diag_apply<EW_R><<<ew_grid(c), MV_THREADS, 0, c->stream>>>(c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->vavg, subtract, c->mm);
+    }
+    CK(cudaGetLastError());
+    if (in_place) c->have_rowsum = false;
+    return mm_end(c, minv, maxv);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// measurement
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gcx_profile(gcx_ctx* c, int enable) {
+    CKR(set_dev(c));
+    CKR(prof_fold(c));
+    c->profile = enable != 0;
+    return 0;
+}
+
+extern "C" int gcx_profile_read(gcx_ctx* c, int reset, int64_t launches[GCX_NCLASS], double ms[GCX_NCLASS]) {
+    CKR(set_dev(c));
+    CKR(prof_fold(c));
+    for (int i = 0; i < GCX_NCLASS; ++i) {
+        launches[i] = c->prof_launches[i];
+        ms[i] = c->prof_ms[i];
+        if (reset) { c->prof_launches[i] = 0; c->prof_ms[i] = 0; }
+    }
+    return 0;
+}
+
+extern "C" int gcx_timer_start(gcx_ctx* c) {
+    CKR(set_dev(c));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->tm_a, c->stream));
+    return 0;
+}
+
+extern "C" int gcx_timer_stop(gcx_ctx* c, double* ms) {
+    CKR(set_dev(c));
+    CK(cudaEventRecord(c->tm_b, c->stream));
+    CK(cudaEventSynchronize(c->tm_b));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, c->tm_a, c->tm_b));
+    *ms = f;
+    return 0;
+}
+
+extern "C" int gcx_map_invalidate(gcx_ctx* c) {
+    c->have_rowsum = false;
+    return 0;
+}
+
+extern "C" int gcx_last_run_ms(gcx_ctx* c, double* ms) {
+    *ms = c->last_run_ms;
+    return 0;
+}
+
+extern "C" int gcx_launch_count(gcx_ctx* c, int64_t* launches) {
+    *launches = c->launches;
+    return 0;
+}

@@ -1,0 +1,999 @@
+// gcx_kernels.cuh -- hand-written sm_100a kernels for the contact-map normalization hot path.
+//
+// Data layout in HBM: the rank's row block of the dense float32 n x n map, row-major, row pitch `ld`
+// floats (ld % 32 == 0, so every row starts on a 128-byte line and 128-bit loads are always aligned;
+// pad columns are zero).  All O(n) vectors are float64, length >= ld, zero padded.
+//
+// Every matrix pass uses the same decomposition: the block is cut into bands of R rows and chunks of
+// MV_THREADS float4 columns; the flattened (band, chunk) unit list is split evenly over a persistent
+// grid of (SM count x occupancy) CTAs, so no CTA has more than one unit more than another.  A thread
+// keeps the column-vector entries for its float4 in registers and reuses them across the R rows of the
+// band, which cuts L2 traffic for the vector to 1/R of the matrix traffic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gcx {
+
+constexpr int MV_THREADS = 256;   // threads per CTA for matrix passes
+constexpr int EP_THREADS = 1024;  // threads of the single-CTA vector epilogues
+
+// ---------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    // streaming 128-bit load: read-only path, do not allocate in L1 (the map is read once per pass)
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block reductions (fixed tree).  `sm` holds >= 32 doubles.  All threads get the result.
+enum { RED_SUM = 0, RED_MIN = 1, RED_MAX = 2 };
+template <int OP>
+__device__ __forceinline__ double block_reduce(double v, double* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = OP == RED_SUM ? warp_sum(v) : (OP == RED_MIN ? warp_min(v) : warp_max(v));
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        const double ident = OP == RED_SUM ? 0.0 : (OP == RED_MIN ? __longlong_as_double(0x7ff0000000000000LL)
+                                                                   : __longlong_as_double(0xfff0000000000000LL));
+        double x = lane < nw ? sm[lane] : ident;
+        x = OP == RED_SUM ? warp_sum(x) : (OP == RED_MIN ? warp_min(x) : warp_max(x));
+        if (lane == 0) sm[0] = x;
+    }
+    __syncthreads();
+    const double r = sm[0];
+    __syncthreads();
+    return r;
+}
+
+// order-preserving float <-> uint32 encoding for atomicMin/atomicMax on floats of either sign
+__device__ __forceinline__ unsigned int f2ord(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(unsigned int u) {
+    unsigned int b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// Even split of U work units over G CTAs: CTA c owns [c*U/G, (c+1)*U/G).
+__device__ __forceinline__ long long unit_begin(long long c, long long U, long long G) { return c * U / G; }
+__device__ __forceinline__ long long unit_owner(long long u, long long U, long long G) {
+    long long c = ((u + 1) * G - 1) / U;
+    while (c + 1 < G && unit_begin(c + 1, U, G) <= u) ++c;
+    while (c > 0 && unit_begin(c, U, G) > u) --c;
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2/K3: q[row0 + r] = sum_j A[r][j] * z[j]   (float32 map, float64 vector, float64 accumulation)
+// Replaces np.sum(matrix, axis=0) of lib/normalizeCore.pyx:42 (symmetric map: column sums = row sums
+// of the bias-scaled map) and np.dot(A, x) of lib/normalizeKnightRuiz.pyx:120, 139, 169.
+// Algorithmic HBM bytes per launch: 4 * nloc * n (one read of the block).
+// Bands that straddle two CTAs' unit ranges leave partial sums in `ws`; the last CTA to finish folds them
+// in CTA order, so the result is bitwise reproducible for a given grid size.
+// ---------------------------------------------------------------------------------------------------
+template <int R, int OCC>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
+k_matvec(const float* __restrict__ A, long long ld, int nloc, int n4, const double* __restrict__ z,
+         double* __restrict__ q, double* ws, unsigned int* ticket, const int* __restrict__ done) {
+    if (done != nullptr && *done) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
+    long long u = unit_begin(c, U, G);
+    const long long u1 = unit_begin(c + 1, U, G);
+    const int bfirst = (int)(u / nch);
+    __shared__ double red[MV_THREADS / 32][R];
+    const double2* __restrict__ z2 = reinterpret_cast<const double2*>(z);
+
+    while (u < u1) {
+        const int b = (int)(u / nch);
+        const int k0 = (int)(u - (long long)b * nch);
+        const long long rem = u1 - u;
+        const int k1 = (int)(((long long)(nch - k0) < rem) ? nch : (k0 + rem));
+        const float4* rowp[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            int r = b * R + rr;
+            r = r < nloc ? r : nloc - 1;
+            rowp[rr] = reinterpret_cast<const float4*>(A + (long long)r * ld);
+        }
+        double acc[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) acc[rr] = 0.0;
+
+        for (int k = k0; k < k1; ++k) {
+            const int c4 = k * MV_THREADS + tid;
+            if (c4 < n4) {
+                float4 a[R];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) a[rr] = ld_stream_f4(rowp[rr] + c4);
+                const double2 za = __ldg(z2 + 2 * c4), zb = __ldg(z2 + 2 * c4 + 1);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    acc[rr] = fma((double)a[rr].x, za.x, acc[rr]);
+                    acc[rr] = fma((double)a[rr].y, za.y, acc[rr]);
+                    acc[rr] = fma((double)a[rr].z, zb.x, acc[rr]);
+                    acc[rr] = fma((double)a[rr].w, zb.y, acc[rr]);
+                }
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) acc[rr] = warp_sum(acc[rr]);
+        if (lane == 0) {
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) red[warp][rr] = acc[rr];
+        }
+        __syncthreads();
+        if (tid < R) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < MV_THREADS / 32; ++w) s += red[w][tid];
+            const int r = b * R + tid;
+            if (k0 == 0 && k1 == nch) {
+                if (r < nloc) q[r] = s;
+            } else {
+                ws[((long long)c * 2 + (b == bfirst ? 0 : 1)) * R + tid] = s;
+            }
+        }
+        __syncthreads();
+        u += (k1 - k0);
+    }
+
+    // ---- last-arriving CTA folds the split bands ----
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned int)(G - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int b = tid; b < nb; b += MV_THREADS) {
+        const long long ub0 = (long long)b * nch;
+        const long long cf = unit_owner(ub0, U, G), cl = unit_owner(ub0 + nch - 1, U, G);
+        if (cf == cl) continue;   // one CTA had the whole band and wrote it directly
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            double s = 0.0;
+            for (long long cc = cf; cc <= cl; ++cc) {
+                const int bfc = (int)(unit_begin(cc, U, G) / nch);
+                s += __ldcg(ws + (cc * 2 + (b == bfc ? 0 : 1)) * R + rr);
+            }
+            const int r = b * R + rr;
+            if (r < nloc) q[r] = s;
+        }
+    }
+    if (tid == 0) *ticket = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1 row statistics: float64 row sum + int32 count of zeros over the n real columns.
+// Replaces the loop of lib/ccmapHelpers.pyx:190-201.  Algorithmic bytes: 4 * nloc * n.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MV_THREADS)
+k_row_stats(const float* __restrict__ A, long long ld, int nloc, int n, double* __restrict__ rowsum,
+            int* __restrict__ zero_count) {
+    __shared__ double sm[32];
+    const int n4 = (int)(ld / 4);
+    const int pad = (int)ld - n;
+    for (int r = blockIdx.x; r < nloc; r += gridDim.x) {
+        const float4* rp = reinterpret_cast<const float4*>(A + (long long)r * ld);
+        double s = 0.0;
+        int zc = 0;
+        for (int c4 = threadIdx.x; c4 < n4; c4 += 4 * MV_THREADS) {
+            float4 a[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int cc = c4 + k * MV_THREADS;
+                a[k] = cc < n4 ? ld_stream_f4(rp + cc) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int cc = c4 + k * MV_THREADS;
+                if (cc < n4) {
+                    s += ((double)a[k].x + (double)a[k].y) + ((double)a[k].z + (double)a[k].w);
+                    zc += (a[k].x == 0.f) + (a[k].y == 0.f) + (a[k].z == 0.f) + (a[k].w == 0.f);
+                }
+            }
+        }
+        const double S = block_reduce<RED_SUM>(s, sm);
+        const double Z = block_reduce<RED_SUM>((double)zc, sm);   // exact: counts < 2^53
+        if (threadIdx.x == 0) {
+            rowsum[r] = S;
+            // raw count of zeros among the n real columns; the host applies lib/ccmapHelpers.pyx:192-195
+            // (a row whose sum is 0.0 records a zero count of 0)
+            zero_count[r] = (int)Z - pad;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// elementwise passes: same (band, chunk) decomposition, column-vector entries held in registers
+// ---------------------------------------------------------------------------------------------------
+struct MinMax {
+    unsigned int min_nz;   // f2ord-encoded min over non-zero entries (init 0xffffffff)
+    unsigned int max_all;  // f2ord-encoded max (init 0)
+};
+
+__device__ __forceinline__ void mm_update(float v, unsigned int& mn, unsigned int& mx) {
+    const unsigned int o = f2ord(v);
+    if (v != 0.f && o < mn) mn = o;
+    if (o > mx) mx = o;
+}
+
+__device__ __forceinline__ void mm_commit(unsigned int mn, unsigned int mx, MinMax* out) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mn != 0xffffffffu) atomicMin(&out->min_nz, mn);
+        atomicMax(&out->max_all, mx);
+    }
+}
+
+// K4: out_ij = f32((s_lo * A_ij) * s_hi) for kept i,j (lo/hi by global index), else 0 or pass-through.
+// Replaces GenNormMatrixRAM (lib/normalizeKnightRuiz.pyx:207-227) and the net effect of
+// lib/normalizeCore.pyx:48-53 + the write-back of lib/normalizer.py:601-613.
+// Algorithmic bytes: 8 * nloc * n.  min/max over the kept x kept block only.
+template <int R>
+__global__ void __launch_bounds__(MV_THREADS, 3)
+k_apply_sym(const float* __restrict__ A, float* __restrict__ Out, long long ld, int nloc, int n4, int row0,
+            const double* __restrict__ s, const uint8_t* __restrict__ keep, int passthrough, MinMax* mm) {
+    const int tid = threadIdx.x;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
+    const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
+    unsigned int mn = 0xffffffffu, mx = 0u;
+    const double2* __restrict__ s2 = reinterpret_cast<const double2*>(s);
+    const uchar4* __restrict__ k4 = reinterpret_cast<const uchar4*>(keep);
+    for (long long u = u0; u < u1; ++u) {
+        const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
+        const int c4 = k * MV_THREADS + tid;
+        if (c4 >= n4) continue;
+        const double2 sa = __ldg(s2 + 2 * c4), sb = __ldg(s2 + 2 * c4 + 1);
+        const uchar4 kc = __ldg(k4 + c4);
+        const double sc[4] = {sa.x, sa.y, sb.x, sb.y};
+        const unsigned char kcol[4] = {kc.x, kc.y, kc.z, kc.w};
+        const int j0 = 4 * c4;
+        float4 a[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r < nloc) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(A + (long long)r * ld) + c4);
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r >= nloc) continue;
+            const int i = row0 + r;
+            const double si = __ldg(s + i);
+            const bool ki = __ldg(keep + i) != 0;
+            const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + e;
+                if (ki && kcol[e]) {
+                    const double lo = j < i ? sc[e] : si, hi = j < i ? si : sc[e];
+                    o[e] = (float)((lo * (double)in[e]) * hi);
+                    mm_update(o[e], mn, mx);
+                } else {
+                    o[e] = passthrough ? in[e] : 0.f;
+                }
+            }
+            st_stream_f4(reinterpret_cast<float4*>(Out + (long long)r * ld) + c4, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+    mm_commit(mn, mx, mm);
+}
+
+// K5: vanilla coverage in the reference's fp32 arithmetic (lib/normalizeCore.pyx:72-86):
+// out = A; kept row i: out = fl32(out / c_i); kept column j: out = fl32(out / c_j); optional sqrt.
+// Algorithmic bytes: 8 * nloc * n (+ the row-sum pass of k_row_stats = 12 n^2 in total).
+template <int R>
+__global__ void __launch_bounds__(MV_THREADS, 3)
+k_vc_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld, int nloc, int n4, int n, int row0,
+           const float* __restrict__ csum, const uint8_t* __restrict__ keep, int sqroot, MinMax* mm) {
+    const int tid = threadIdx.x;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
+    const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
+    unsigned int mn = 0xffffffffu, mx = 0u;
+    const float4* __restrict__ c4v = reinterpret_cast<const float4*>(csum);
+    const uchar4* __restrict__ k4 = reinterpret_cast<const uchar4*>(keep);
+    for (long long u = u0; u < u1; ++u) {
+        const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
+        const int c4 = k * MV_THREADS + tid;
+        if (c4 >= n4) continue;
+        const float4 cs = __ldg(c4v + c4);
+        const uchar4 kc = __ldg(k4 + c4);
+        const float cc[4] = {cs.x, cs.y, cs.z, cs.w};
+        const unsigned char kcol[4] = {kc.x, kc.y, kc.z, kc.w};
+        const int j0 = 4 * c4;
+        float4 a[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r < nloc) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(A + (long long)r * ld) + c4);
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r >= nloc) continue;
+            const int i = row0 + r;
+            const float ci = __ldg(csum + i);
+            const bool ki = __ldg(keep + i) != 0;
+            const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float v = in[e];
+                if (ki) v = __fdiv_rn(v, ci);
+                if (kcol[e]) v = __fdiv_rn(v, cc[e]);
+                if (sqroot) v = __fsqrt_rn(v);
+                o[e] = v;
+                if (j0 + e < n) mm_update(v, mn, mx);
+            }
+            st_stream_f4(reinterpret_cast<float4*>(Out + (long long)r * ld) + c4, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+    mm_commit(mn, mx, mm);
+}
+
+// K7: distance-frequency apply (lib/normalizeCore.pyx:91-170): divide or subtract by avg[|i-j|].
+// Algorithmic bytes: 8 * nloc * n.
+template <int R>
+__global__ void __launch_bounds__(MV_THREADS, 3)
+k_diag_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld, int nloc, int n4, int n, int row0,
+             const double* __restrict__ avg, int subtract, MinMax* mm) {
+    const int tid = threadIdx.x;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
+    const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
+    unsigned int mn = 0xffffffffu, mx = 0u;
+    for (long long u = u0; u < u1; ++u) {
+        const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
+        const int c4 = k * MV_THREADS + tid;
+        if (c4 >= n4) continue;
+        const int j0 = 4 * c4;
+        float4 a[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r < nloc) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(A + (long long)r * ld) + c4);
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r >= nloc) continue;
+            const int i = row0 + r;
+            const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + e;
+                float v = in[e];
+                if (j < n) {
+                    const int d = i > j ? i - j : j - i;
+                    const double av = __ldg(avg + d);
+                    if (av != 0.0) {
+                        if (!subtract) {
+                            v = (float)((double)in[e] / av);                       // :105-108, :114-117
+                        } else {
+                            double t = (double)in[e] - av;                         // :138
+                            if (t < 0.0) t = 1.0;                                  // :139-141
+                            if (in[e] == 0.f) t = 0.0;                             // :142-144
+                            v = (float)t;
+                        }
+                    }
+                    mm_update(v, mn, mx);
+                }
+                o[e] = v;
+            }
+            st_stream_f4(reinterpret_cast<float4*>(Out + (long long)r * ld) + c4, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+    mm_commit(mn, mx, mm);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K6: per-diagonal statistics of the non-zero entries (lib/cmstats.py:569-605).
+// Only the lower triangle is read (the reference gathers rows[d:], cols[:-d], lib/util.py:95-96).
+// Traversal: CTA (x = chunk of 256 diagonals, y = band of DIAG_RB rows); thread t owns diagonal
+// d = 256*x + t and walks the band's rows i, reading A[i][i-d] -- per row a warp reads 32 consecutive
+// floats (coalesced, descending).  Algorithmic bytes: 2 * n^2 per traversal (half the map).
+// ---------------------------------------------------------------------------------------------------
+constexpr int DIAG_RB = 64;
+
+// mean: per-(band, diagonal) partial sum/count, then a fixed-order reduction over bands (deterministic)
+__global__ void __launch_bounds__(MV_THREADS)
+k_diag_mean_partial(const float* __restrict__ A, long long ld, int nloc, int n, int row0, double* __restrict__ psum,
+                    int* __restrict__ pcnt) {
+    const int band = blockIdx.y, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
+    const int imax = row0 + r1 - 1;
+    if ((int)(blockIdx.x * MV_THREADS) > imax) return;
+    const int d = blockIdx.x * MV_THREADS + threadIdx.x;
+    if (d > imax || d >= n) return;
+    double s = 0.0;
+    int c = 0;
+    const int rs = max(r0, d - row0);
+#pragma unroll 8
+    for (int r = rs; r < r1; ++r) {
+        const float v = __ldg(A + (long long)r * ld + (row0 + r - d));
+        if (v != 0.f) {
+            s += (double)v;
+            ++c;
+        }
+    }
+    psum[(long long)band * n + d] = s;
+    pcnt[(long long)band * n + d] = c;
+}
+
+__global__ void k_diag_mean_reduce(int nbands, int n, int row0, const double* __restrict__ psum, const int* __restrict__ pcnt,
+                                   double* __restrict__ sum, double* __restrict__ cnt) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    double s = 0.0, c = 0.0;
+    const int b0 = max(0, d - row0) / DIAG_RB;
+    for (int b = b0; b < nbands; ++b) {
+        s += psum[(long long)b * n + d];
+        c += (double)pcnt[(long long)b * n + d];
+    }
+    sum[d] = s;
+    cnt[d] = c;
+}
+
+__global__ void k_diag_mean_final(int n, const double* __restrict__ sum, const double* __restrict__ cnt, double* __restrict__ avg) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) avg[d] = cnt[d] > 0.0 ? sum[d] / cnt[d] : 0.0;      // lib/cmstats.py:598, :602-603
+}
+
+// median: 4-pass MSB-first radix select on the order-preserving uint32 encoding of the floats, one
+// 256-bin histogram per diagonal (global atomics; lanes of a warp hit 32 different diagonals).
+struct DiagSel {
+    unsigned int* hist;     // [n][256]
+    unsigned int* prefix;   // [n] high bytes fixed so far
+    unsigned int* krem;     // [n] rank still to skip inside the current prefix group
+    unsigned int* cnt;      // [n] number of non-zero entries
+    unsigned int* need;     // [n] 1 if the upper middle value is the next distinct key
+    unsigned int* next;     // [n] min key > vlo
+};
+
+__global__ void __launch_bounds__(MV_THREADS)
+k_diag_hist(const float* __restrict__ A, long long ld, int nloc, int n, int row0, int pass, DiagSel S) {
+    const int band = blockIdx.y, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
+    const int imax = row0 + r1 - 1;
+    if ((int)(blockIdx.x * MV_THREADS) > imax) return;
+    const int d = blockIdx.x * MV_THREADS + threadIdx.x;
+    if (d > imax || d >= n) return;
+    const unsigned int pre = pass ? S.prefix[d] : 0u;
+    const int sh_hi = 32 - 8 * pass, sh = 24 - 8 * pass;
+    unsigned int* h = S.hist + (long long)d * 256;
+    const int rs = max(r0, d - row0);
+    int run_bin = -1;
+    unsigned int run = 0;
+#pragma unroll 8
+    for (int r = rs; r < r1; ++r) {
+        const float v = __ldg(A + (long long)r * ld + (row0 + r - d));
+        if (v != 0.f) {
+            const unsigned int key = f2ord(v);
+            if (pass == 0 || (key >> sh_hi) == pre) {
+                const int bin = (key >> sh) & 255;
+                if (bin == run_bin) {
+                    ++run;
+                } else {
+                    if (run) atomicAdd(h + run_bin, run);
+                    run_bin = bin;
+                    run = 1;
+                }
+            }
+        }
+    }
+    if (run) atomicAdd(h + run_bin, run);
+}
+
+// one warp per diagonal: find the bin holding rank krem, descend into it, clear the histogram row
+__global__ void __launch_bounds__(MV_THREADS)
+k_diag_select(int n, int pass, DiagSel S) {
+    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (d >= n) return;
+    unsigned int* h = S.hist + (long long)d * 256;
+    unsigned int c[8], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        c[k] = h[lane * 8 + k];
+        tot += c[k];
+        h[lane * 8 + k] = 0u;
+    }
+    unsigned int incl = tot;     // inclusive prefix over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned int kr;
+    if (pass == 0) {
+        if (lane == 0) S.cnt[d] = total;
+        kr = total ? (total - 1) / 2 : 0;      // lower middle rank (np.median: mean of the two middles when even)
+    } else {
+        kr = S.krem[d];
+    }
+    if (total == 0) {
+        if (lane == 0) { S.prefix[d] = 0u; S.krem[d] = 0u; S.need[d] = 0u; }
+        return;
+    }
+    const unsigned int excl = incl - tot;
+    const bool mine = kr >= excl && kr < incl;
+    if (mine) {
+        unsigned int run = excl;
+        int bin = 0;
+        unsigned int hb = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (kr >= run && kr < run + c[k]) { bin = lane * 8 + k; hb = c[k]; break; }
+            run += c[k];
+        }
+        const unsigned int pre = pass ? S.prefix[d] : 0u;
+        S.prefix[d] = (pre << 8) | (unsigned int)bin;
+        const unsigned int kin = kr - run;      // rank inside the chosen bin
+        S.krem[d] = kin;
+        if (pass == 3) {
+            const unsigned int cn = S.cnt[d];
+            S.need[d] = ((cn & 1u) == 0u && kin + 1 >= hb) ? 1u : 0u;
+            S.next[d] = 0xffffffffu;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(MV_THREADS)
+k_diag_next(const float* __restrict__ A, long long ld, int nloc, int n, int row0, DiagSel S) {
+    const int band = blockIdx.y, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
+    const int imax = row0 + r1 - 1;
+    if ((int)(blockIdx.x * MV_THREADS) > imax) return;
+    const int d = blockIdx.x * MV_THREADS + threadIdx.x;
+    if (d > imax || d >= n) return;
+    if (!S.need[d]) return;
+    const unsigned int vlo = S.prefix[d];
+    unsigned int best = 0xffffffffu;
+    const int rs = max(r0, d - row0);
+#pragma unroll 8
+    for (int r = rs; r < r1; ++r) {
+        const float v = __ldg(A + (long long)r * ld + (row0 + r - d));
+        if (v != 0.f) {
+            const unsigned int key = f2ord(v);
+            if (key > vlo && key < best) best = key;
+        }
+    }
+    if (best != 0xffffffffu) atomicMin(S.next + d, best);
+}
+
+__global__ void k_diag_median_final(int n, DiagSel S, double* __restrict__ avg) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    if (S.cnt[d] == 0u) { avg[d] = 0.0; return; }                        // lib/cmstats.py:602-603
+    const double lo = (double)ord2f(S.prefix[d]);
+    const double hi = S.need[d] ? (double)ord2f(S.next[d]) : lo;
+    avg[d] = ((S.cnt[d] & 1u) == 0u) ? (lo + hi) / 2.0 : lo;             // np.median semantics
+}
+
+// vmin/vmax clamp + scale, in place (lib/normalizer.py:567-569, 832-834)
+__global__ void __launch_bounds__(MV_THREADS)
+k_clamp_scale(float* __restrict__ A, long long total4, int has_vmin, float vmin, int has_vmax, float vmax, int has_scale,
+              float scale) {
+    float4* p = reinterpret_cast<float4*>(A);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = p[i];
+        float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (has_vmin && e[k] <= vmin) e[k] = 0.f;
+            if (has_vmax && e[k] >= vmax) e[k] = 0.f;
+            if (has_scale) e[k] = e[k] * scale;
+        }
+        p[i] = make_float4(e[0], e[1], e[2], e[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// synthetic map: value is a pure function of (seed, min(i,j), max(i,j)) so any row block
+// can be generated on any rank.  Poisson(lambda(d)), lambda = scale * (d+1)^-alpha.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool synth_empty(uint64_t seed, int i, unsigned int thresh24) {
+    return (unsigned int)(mix64(seed * 0x2545F4914F6CDD1Dull + 0x5851F42D4C957F2Dull * (uint64_t)(i + 1)) >> 40) < thresh24;
+}
+
+__device__ __forceinline__ float synth_value(uint64_t seed, int i, int j, float scale, float alpha, unsigned int thresh24) {
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    if (synth_empty(seed, lo, thresh24) || synth_empty(seed, hi, thresh24)) return 0.f;
+    const uint64_t h = mix64(mix64(seed ^ ((uint64_t)lo << 32 | (uint64_t)hi)) + seed);
+    const float u1 = ((unsigned int)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((unsigned int)((h >> 16) & 0xffffffu) + 0.5f) * (1.0f / 16777216.0f);
+    const float lam = scale * __powf((float)(hi - lo + 1), -alpha);
+    float kf;
+    if (lam < 24.f) {
+        float p = __expf(-lam), F = p;
+        int k = 0;
+        while (u1 > F && k < 128) {
+            ++k;
+            p *= lam / (float)k;
+            F += p;
+        }
+        kf = (float)k;
+    } else {
+        const float zn = sqrtf(-2.f * __logf(u1)) * __cosf(6.2831853f * u2);
+        kf = floorf(lam + sqrtf(lam) * zn + 0.5f);
+        if (kf < 0.f) kf = 0.f;
+    }
+    if (lo == hi && kf < 1.f) kf = 1.f;
+    return kf;
+}
+
+__global__ void __launch_bounds__(MV_THREADS)
+k_synth(float* __restrict__ A, long long ld, int nloc, int n, int row0, uint64_t seed, float scale, float alpha,
+        unsigned int thresh24) {
+    const int n4 = (int)(ld / 4);
+    for (int r = blockIdx.x; r < nloc; r += gridDim.x) {
+        const int i = row0 + r;
+        float4* rp = reinterpret_cast<float4*>(A + (long long)r * ld);
+        for (int c4 = threadIdx.x; c4 < n4; c4 += MV_THREADS) {
+            float e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = 4 * c4 + k;
+                e[k] = j < n ? synth_value(seed, i, j, scale, alpha, thresh24) : 0.f;
+            }
+            rp[c4] = make_float4(e[0], e[1], e[2], e[3]);
+        }
+    }
+}
+
+// order-independent checksum: sum over entries of mix64(bits ^ (i*n+j)) (sharded parity checks)
+__global__ void __launch_bounds__(MV_THREADS)
+k_checksum(const float* __restrict__ A, long long ld, int nloc, int n, int row0, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (int r = blockIdx.x; r < nloc; r += gridDim.x) {
+        const float* rp = A + (long long)r * ld;
+        const uint64_t base = (uint64_t)(row0 + r) * (uint64_t)n;
+        for (int j = threadIdx.x; j < n; j += MV_THREADS) {
+            const unsigned int bits = __float_as_uint(rp[j]);
+            if (bits & 0x7fffffffu) acc += mix64((uint64_t)bits ^ ((base + j) << 32));
+        }
+    }
+    acc = (unsigned long long)warp_sum_ll((long long)acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// IC vector epilogue -- the O(n) part of lib/normalizeCore.pyx:42-60, one launch per matvec.
+//
+// With w = 1/B_k the reference's pass k+1 is: dBraw = w o (A w); dB = dBraw/mean(dBraw[!=0]) (0 -> 1);
+// v = w/dB; S' = v'Av; B_{k+1} = B_k dB sqrt(S'/cc); next dBraw = (cc/S') v o (A v).  So matvec m (t = A v)
+// closes pass m and opens pass m+1.  Single CTA, fixed reduction tree -> every rank that
+// runs this on the same gathered vector gets bitwise identical state.
+// ---------------------------------------------------------------------------------------------------
+struct IcState {
+    double cc, S, l1, mean, tol;
+    int pass, done, cnt, max_iter, matvecs;
+};
+
+__global__ void __launch_bounds__(EP_THREADS)
+k_ic_init(IcState* st, int nv, const uint8_t* __restrict__ keep, double* v, double* B, double* Bd, double tol, int max_iter) {
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const double k = keep[i] ? 1.0 : 0.0;
+        v[i] = k;
+        B[i] = 1.0;
+        Bd[i] = 1.0;
+    }
+    if (threadIdx.x == 0) {
+        st->cc = 0; st->S = 0; st->l1 = 0; st->mean = 0; st->tol = tol;
+        st->pass = 0; st->done = 0; st->cnt = 0; st->max_iter = max_iter; st->matvecs = 0;
+    }
+}
+
+__global__ void __launch_bounds__(EP_THREADS)
+k_ic_epilogue(IcState* st, int n, const uint8_t* __restrict__ keep, const double* __restrict__ t, double* v, double* B,
+              double* Bd) {
+    __shared__ double sm[32];
+    if (st->done) return;
+    const int m = st->matvecs;
+    const double cc_prev = st->cc, tol = st->tol;
+    const int max_iter = st->max_iter;
+    __syncthreads();
+    // phase A: S' = sum v_i t_i, cnt = #non-zero terms  (cc on the first launch, lib/normalizeCore.pyx:36)
+    double s = 0.0, cn = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (keep[i]) {
+            const double p = v[i] * t[i];
+            s += p;
+            cn += (p != 0.0) ? 1.0 : 0.0;
+        }
+    }
+    const double S = block_reduce<RED_SUM>(s, sm);
+    const double C = block_reduce<RED_SUM>(cn, sm);
+    const double cc = (m == 0) ? S : cc_prev;
+    const double f = (m == 0) ? 1.0 : sqrt(S / cc);     // :52
+    const double g = (m == 0) ? 1.0 : cc / S;           // :53
+    // phase B: B_{k+1} = (B_k dB) f (:51-52), L1 change (:56), sum of next raw column sums
+    double l1 = 0.0, sd = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (keep[i]) {
+            if (m > 0) {
+                const double bn = Bd[i] * f;
+                l1 += fabs(B[i] - bn);
+                B[i] = bn;
+            }
+            const double d = g * (v[i] * t[i]);
+            if (d != 0.0) sd += d;
+        }
+    }
+    const double L1 = block_reduce<RED_SUM>(l1, sm);
+    const double SD = block_reduce<RED_SUM>(sd, sm);
+    const bool done = (m >= 2) && (L1 < tol || (m - 1) > max_iter);   // :55-57 (count = pass-1)
+    const double mean = SD / C;                                       // :44
+    if (!done) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (keep[i]) {
+                const double d = g * (v[i] * t[i]);
+                const double dB = (d != 0.0) ? d / mean : 1.0;        // :44-45
+                const double bd = B[i] * dB;
+                Bd[i] = bd;
+                v[i] = 1.0 / bd;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        st->cc = cc; st->S = S; st->l1 = L1; st->mean = mean; st->cnt = (int)C;
+        st->pass = m; st->matvecs = m + 1; st->done = done ? 1 : 0;
+    }
+}
+
+// s_i = keep_i ? 1/B_i : 0 -- the symmetric scale for the final apply
+__global__ void k_ic_scale(int nv, int n, const uint8_t* __restrict__ keep, const double* __restrict__ B, double* s) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x)
+        s[i] = (i < n && keep[i]) ? 1.0 / B[i] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// KR vector step -- everything of lib/normalizeKnightRuiz.pyx:106-191, 271-286 except the matvec.
+// One launch per matvec; `phase` says what the matvec just produced: 0 -> q = A x (init or outer Newton
+// step), 1 -> q = A (x o p) (inner CG step).  The kernel advances the reference's control flow up to the
+// next matvec and leaves its input in z.
+// ---------------------------------------------------------------------------------------------------
+struct KrState {
+    double tol, delta, Delta, rt, stop_tol, g, etamax;
+    double eta, rho_km1, rho_km2, rout, rold, innertol;
+    int phase, init, k, outer, mvp, matvecs, done, pad;
+};
+
+struct KrVecs {
+    double *x, *v, *rk, *y, *Z, *p, *w, *z;
+};
+
+__global__ void __launch_bounds__(EP_THREADS)
+k_kr_init(KrState* st, int nv, const uint8_t* __restrict__ keep, KrVecs V, double tol, double delta, double Delta) {
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const double k = keep[i] ? 1.0 : 0.0;
+        V.x[i] = k;       // x = e (:111, :118)
+        V.z[i] = k;
+        V.v[i] = 0; V.rk[i] = 0; V.y[i] = k; V.Z[i] = 0; V.p[i] = 0; V.w[i] = 0;
+    }
+    if (threadIdx.x == 0) {
+        st->tol = tol; st->delta = delta; st->Delta = Delta;
+        st->rt = tol * tol;            // :119
+        st->stop_tol = tol * 0.5;      // :116
+        st->g = 0.9; st->etamax = 0.1; // :113-114
+        st->eta = 0.1;                 // :115
+        st->rho_km1 = 0; st->rho_km2 = 0; st->rout = 0; st->rold = 0; st->innertol = 0;
+        st->phase = 0; st->init = 1; st->k = 0; st->outer = 0; st->mvp = 0; st->matvecs = 0; st->done = 0; st->pad = 0;
+    }
+}
+
+__global__ void __launch_bounds__(EP_THREADS)
+k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __restrict__ q, KrVecs V) {
+    __shared__ double sm[32];
+    if (st->done) return;
+    KrState s = *st;
+    __syncthreads();
+    const int tid = threadIdx.x, nt = blockDim.x;
+    bool to_outer = false;
+
+    if (s.phase == 0) {
+        // v = x.*(A*x); rk = 1 - v; rho_km1 = rk'*rk   (:120-122 / :169-171)
+        double acc = 0.0;
+        for (int i = tid; i < n; i += nt) {
+            if (keep[i]) {
+                const double vi = V.x[i] * q[i];
+                const double r = 1.0 - vi;
+                V.v[i] = vi;
+                V.rk[i] = r;
+                V.y[i] = 1.0;      // y = e for the next outer iteration (:278)
+                acc += r * r;
+            }
+        }
+        const double rho = block_reduce<RED_SUM>(acc, sm);
+        s.rho_km1 = rho;
+        if (s.init) {
+            s.rout = rho; s.rold = rho; s.init = 0;          // :123-124
+        } else {
+            s.rout = rho;                                     // :172
+            s.mvp += s.k + 1;                                 // :173
+            const double rat = s.rout / s.rold;               // :176
+            s.rold = s.rout;
+            const double res_norm = sqrt(s.rout);
+            const double eta_o = s.eta;
+            s.eta = s.g * rat;                                // :180
+            if (s.g * eta_o * eta_o > 0.1) s.eta = fmax(s.eta, s.g * eta_o * eta_o);        // :184-185
+            s.eta = fmax(fmin(s.eta, s.etamax), s.stop_tol / res_norm);                     // :187
+        }
+        if (!(s.rout > s.rt)) {                               // :275
+            s.done = 1;
+            s.matvecs += 1;
+            if (tid == 0) *st = s;
+            return;
+        }
+        s.outer += 1;                                         // :276
+        s.k = 0;
+        s.innertol = fmax(s.eta * s.eta * s.rout, s.rt);      // :279
+    } else {
+        // w = x.*(A*(x.*p)) + v.*p ; alpha = rho_km1/(p'*w)   (:139-140)
+        double acc = 0.0;
+        for (int i = tid; i < n; i += nt) {
+            if (keep[i]) {
+                const double pi = V.p[i];
+                const double wi = V.x[i] * q[i] + V.v[i] * pi;
+                V.w[i] = wi;
+                acc += pi * wi;
+            }
+        }
+        const double pw = block_reduce<RED_SUM>(acc, sm);
+        const double alpha = s.rho_km1 / pw;
+        // ynew = y + ap ; distance to the cone boundary (:144-158)
+        double mn = __longlong_as_double(0x7ff0000000000000LL), mx = __longlong_as_double(0xfff0000000000000LL);
+        for (int i = tid; i < n; i += nt) {
+            if (keep[i]) {
+                const double yn = V.y[i] + alpha * V.p[i];
+                mn = fmin(mn, yn);
+                mx = fmax(mx, yn);
+            }
+        }
+        mn = block_reduce<RED_MIN>(mn, sm);
+        mx = block_reduce<RED_MAX>(mx, sm);
+        if (mn <= s.delta) {
+            if (s.delta != 0.0) {
+                double gm = __longlong_as_double(0x7ff0000000000000LL);
+                for (int i = tid; i < n; i += nt) {
+                    if (keep[i]) {
+                        const double ap = alpha * V.p[i];
+                        if (ap < 0.0) gm = fmin(gm, (s.delta - V.y[i]) / ap);          // :150-151
+                    }
+                }
+                const double gamma = block_reduce<RED_MIN>(gm, sm);
+                for (int i = tid; i < n; i += nt)
+                    if (keep[i]) V.y[i] = V.y[i] + gamma * (alpha * V.p[i]);           // :152
+            }
+            to_outer = true;
+        } else if (mx >= s.Delta) {
+            double gm = __longlong_as_double(0x7ff0000000000000LL);
+            for (int i = tid; i < n; i += nt) {
+                if (keep[i]) {
+                    const double ap = alpha * V.p[i];
+                    const double yn = V.y[i] + ap;
+                    if (yn > s.Delta) gm = fmin(gm, (s.Delta - V.y[i]) / ap);          // :155-156
+                }
+            }
+            const double gamma = block_reduce<RED_MIN>(gm, sm);
+            for (int i = tid; i < n; i += nt)
+                if (keep[i]) V.y[i] = V.y[i] + gamma * (alpha * V.p[i]);               // :157
+            to_outer = true;
+        } else {
+            // y = ynew; rk = rk - alpha*w; Z = rk./v; rho_km1 = rk'*Z   (:159-163)
+            double a2 = 0.0;
+            for (int i = tid; i < n; i += nt) {
+                if (keep[i]) {
+                    V.y[i] = V.y[i] + alpha * V.p[i];
+                    const double r = V.rk[i] - alpha * V.w[i];
+                    const double Zi = r / V.v[i];
+                    V.rk[i] = r;
+                    V.Z[i] = Zi;
+                    a2 += r * Zi;
+                }
+            }
+            s.rho_km2 = s.rho_km1;
+            s.rho_km1 = block_reduce<RED_SUM>(a2, sm);
+        }
+    }
+
+    // ---- inner-loop test (:281) and preparation of the next matvec input ----
+    if (!to_outer && s.rho_km1 > s.innertol) {
+        s.k += 1;                                                                       // :127
+        if (s.k == 1) {
+            double acc = 0.0;
+            for (int i = tid; i < n; i += nt) {
+                if (keep[i]) {
+                    const double Zi = V.rk[i] / V.v[i];                                 // :130
+                    V.Z[i] = Zi;
+                    V.p[i] = Zi;                                                        // :131
+                    V.z[i] = V.x[i] * Zi;
+                    acc += V.rk[i] * Zi;
+                }
+            }
+            s.rho_km1 = block_reduce<RED_SUM>(acc, sm);                                 // :132
+        } else {
+            const double beta = s.rho_km1 / s.rho_km2;                                  // :134
+            for (int i = tid; i < n; i += nt) {
+                if (keep[i]) {
+                    const double pn = V.Z[i] + beta * V.p[i];                           // :135
+                    V.p[i] = pn;
+                    V.z[i] = V.x[i] * pn;
+                }
+            }
+        }
+        s.phase = 1;
+    } else {
+        for (int i = tid; i < n; i += nt) {
+            if (keep[i]) {
+                const double xn = V.x[i] * V.y[i];                                      // :168
+                V.x[i] = xn;
+                V.z[i] = xn;
+            }
+        }
+        s.phase = 0;
+    }
+    s.matvecs += 1;
+    __syncthreads();
+    if (tid == 0) *st = s;
+}
+
+}  // namespace gcx

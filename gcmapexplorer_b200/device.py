@@ -1,0 +1,241 @@
+"""DeviceMap: one resident contact map (or one rank's row block of it) on a B200, driven through the
+C ABI of libgcxnorm.so.  This is the only module that touches ctypes pointers; the reference-shaped
+modules (normalizeCore, normalizeKnightRuiz, ccmapHelpers, cmstats, normalizer) are written on top."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import GcxError, check, lib
+
+
+def default_device():
+    for key in ("GCX_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(key):
+            return int(os.environ[key])
+    return 0
+
+
+def _as_f32_matrix(matrix):
+    m = matrix
+    if not isinstance(m, np.ndarray) or m.dtype != np.float32 or m.ndim != 2 or m.strides[1] != 4 or m.strides[0] % 4 != 0:
+        m = np.ascontiguousarray(matrix, dtype=np.float32)
+    return m
+
+
+class PinnedArray:
+    """float32 2-D array in CUDA pinned host memory (full-speed PCIe copies)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.shape = tuple(shape)
+        nbytes = int(np.prod(self.shape)) * np.dtype(dtype).itemsize
+        self._ptr = C.c_void_p()
+        check(lib().gcx_host_alloc(nbytes, C.byref(self._ptr)))
+        buf = (C.c_char * nbytes).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(self.shape)
+
+    def free(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            lib().gcx_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceMap:
+    def __init__(self, n, row0=0, nloc=None, device=None, dist=None):
+        """dist: None or (rank, world, id128 bytes) for row-block sharding over NCCL."""
+        self._ctx = C.c_void_p()
+        self.n = int(n)
+        self.row0 = int(row0)
+        self.nloc = int(self.n - self.row0 if nloc is None else nloc)
+        self.device = default_device() if device is None else int(device)
+        check(lib().gcx_ctx_create(self.device, C.byref(self._ctx)))
+        try:
+            if dist is not None:
+                rank, world, id128 = dist
+                buf = C.create_string_buffer(bytes(id128), 128)
+                check(lib().gcx_dist_init(self._ctx, int(rank), int(world), buf))
+            check(lib().gcx_map_create(self._ctx, self.n, self.row0, self.nloc))
+        except Exception:
+            self.close()
+            raise
+
+    # ---- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if self._ctx is not None and self._ctx.value:
+            lib().gcx_ctx_destroy(self._ctx)
+        self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- residency ------------------------------------------------------------------------------
+    @classmethod
+    def from_host(cls, matrix, device=None):
+        m = _as_f32_matrix(matrix)
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("contact map must be square")
+        dm = cls(m.shape[0], device=device)
+        dm.upload(m)
+        return dm
+
+    def upload(self, rows):
+        """rows: float32 [nloc, n] (the local row block; the whole map on one GPU)."""
+        m = _as_f32_matrix(rows)
+        if m.shape != (self.nloc, self.n):
+            raise ValueError(f"expected shape {(self.nloc, self.n)}, got {m.shape}")
+        check(lib().gcx_map_upload(self._ctx, C.c_void_p(m.ctypes.data), m.strides[0] // 4))
+
+    def download(self, which=1, out=None):
+        if out is None:
+            out = np.empty((self.nloc, self.n), dtype=np.float32)
+        if out.dtype != np.float32 or out.shape != (self.nloc, self.n) or out.strides[1] != 4:
+            raise ValueError("out must be float32 [nloc, n] with unit column stride")
+        check(lib().gcx_map_download(self._ctx, int(which), C.c_void_p(out.ctypes.data), out.strides[0] // 4))
+        return out
+
+    def synth(self, seed, scale=200.0, alpha=1.0, empty_frac=0.01):
+        check(lib().gcx_map_synth(self._ctx, int(seed), float(scale), float(alpha), float(empty_frac)))
+
+    def clamp(self, vmin=None, vmax=None):
+        check(lib().gcx_map_clamp(self._ctx, vmin is not None, 0.0 if vmin is None else float(vmin),
+                                  vmax is not None, 0.0 if vmax is None else float(vmax)))
+
+    def scale(self, factor):
+        check(lib().gcx_map_scale(self._ctx, float(factor)))
+
+    def swap(self):
+        check(lib().gcx_map_swap(self._ctx))
+
+    def checksum(self, which=0):
+        s = C.c_uint64(0)
+        check(lib().gcx_map_checksum(self._ctx, int(which), C.byref(s)))
+        return s.value
+
+    def sync(self):
+        check(lib().gcx_sync(self._ctx))
+
+    def info(self):
+        sm, tot, free = C.c_int(0), C.c_int64(0), C.c_int64(0)
+        check(lib().gcx_device_info(self._ctx, C.byref(sm), C.byref(tot), C.byref(free)))
+        return dict(sm_count=sm.value, hbm_total=tot.value, hbm_free=free.value)
+
+    # ---- mask -----------------------------------------------------------------------------------
+    def row_stats(self, force=False):
+        """(rowsum float64[n], raw zero_count int32[n]).  Cached on the device until the map changes;
+        force=True re-reads the map (benchmark steps)."""
+        if force:
+            check(lib().gcx_map_invalidate(self._ctx))
+        rs = np.empty(self.n, dtype=np.float64)
+        zc = np.empty(self.n, dtype=np.int32)
+        check(lib().gcx_row_stats(self._ctx, rs.ctypes.data_as(_lib._c_f64p), zc.ctypes.data_as(_lib._c_i32p)))
+        return rs, zc
+
+    def set_mask(self, keep):
+        k = np.ascontiguousarray(np.asarray(keep, dtype=bool).astype(np.uint8))
+        if k.shape != (self.n,):
+            raise ValueError("mask must have n entries")
+        check(lib().gcx_set_mask(self._ctx, k.ctypes.data_as(_lib._c_u8p)))
+
+    # ---- solvers --------------------------------------------------------------------------------
+    def ic(self, tol=1e-4, iteration=500):
+        bias = np.empty(self.n, dtype=np.float64)
+        passes, mv, l1 = C.c_int(0), C.c_int(0), C.c_double(0)
+        check(lib().gcx_ic_run(self._ctx, float(tol), int(iteration), bias.ctypes.data_as(_lib._c_f64p),
+                               C.byref(passes), C.byref(l1), C.byref(mv)))
+        return dict(bias=bias, passes=passes.value, l1=l1.value, matvecs=mv.value, ms=self.last_run_ms())
+
+    def kr(self, tol=1e-12, delta=0.1, Delta=3.0):
+        x = np.empty(self.n, dtype=np.float64)
+        outer, mvp, rout = C.c_int(0), C.c_int(0), C.c_double(0)
+        check(lib().gcx_kr_run(self._ctx, float(tol), float(delta), float(Delta), x.ctypes.data_as(_lib._c_f64p),
+                               C.byref(outer), C.byref(mvp), C.byref(rout)))
+        return dict(x=x, outer=outer.value, MVP=mvp.value, rout=rout.value, ms=self.last_run_ms())
+
+    # ---- elementwise passes ---------------------------------------------------------------------
+    def apply_sym(self, s=None, masked_mode=0, in_place=False):
+        mn, mx = C.c_float(0), C.c_float(0)
+        sp = None
+        if s is not None:
+            s = np.ascontiguousarray(s, dtype=np.float64)
+            if s.shape != (self.n,):
+                raise ValueError("scale vector must have n entries")
+            sp = s.ctypes.data_as(_lib._c_f64p)
+        check(lib().gcx_apply_sym_scale(self._ctx, sp, int(masked_mode), int(bool(in_place)), C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
+    def vc(self, sqroot=False, in_place=False):
+        mn, mx = C.c_float(0), C.c_float(0)
+        csum = np.empty(self.n, dtype=np.float32)
+        check(lib().gcx_vc_run(self._ctx, int(bool(sqroot)), int(bool(in_place)), C.byref(mn), C.byref(mx),
+                               csum.ctypes.data_as(_lib._c_f32p)))
+        return mn.value, mx.value, csum
+
+    def diag_stats(self, stats="median"):
+        avg = np.empty(self.n, dtype=np.float64)
+        check(lib().gcx_diag_stats(self._ctx, 1 if stats == "median" else 0, avg.ctypes.data_as(_lib._c_f64p)))
+        return avg
+
+    def diag_apply(self, avg, subtract=False, in_place=False):
+        mn, mx = C.c_float(0), C.c_float(0)
+        ap = None
+        if avg is not None:
+            avg = np.ascontiguousarray(avg, dtype=np.float64)
+            ap = avg.ctypes.data_as(_lib._c_f64p)
+        check(lib().gcx_diag_apply(self._ctx, ap, int(bool(subtract)), int(bool(in_place)), C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
+    # ---- measurement ----------------------------------------------------------------------------
+    def profile(self, enable=True):
+        check(lib().gcx_profile(self._ctx, int(bool(enable))))
+
+    def profile_read(self, reset=True):
+        la = (C.c_int64 * _lib.NCLASS)()
+        ms = (C.c_double * _lib.NCLASS)()
+        check(lib().gcx_profile_read(self._ctx, int(bool(reset)), la, ms))
+        return {name: dict(launches=int(la[i]), ms=float(ms[i])) for i, name in enumerate(_lib.KERNEL_CLASSES)}
+
+    def timer_start(self):
+        check(lib().gcx_timer_start(self._ctx))
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        check(lib().gcx_timer_stop(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def last_run_ms(self):
+        ms = C.c_double(0)
+        check(lib().gcx_last_run_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        check(lib().gcx_launch_count(self._ctx, C.byref(n)))
+        return n.value
+
+    def bench_matvec(self, iters=20, variant=-1):
+        ms = C.c_double(0)
+        check(lib().gcx_bench_matvec(self._ctx, int(variant), int(iters), C.byref(ms)))
+        return ms.value / iters
+
+
+def dist_unique_id():
+    buf = C.create_string_buffer(128)
+    check(lib().gcx_dist_unique_id(buf))
+    return buf.raw

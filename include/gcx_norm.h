@@ -1,0 +1,131 @@
+/* gcx_norm.h -- C ABI of libgcxnorm.so: B200-native (sm_100a) contact-map normalization.
+ *
+ * This is the drop-in boundary for the hot path of rjdkmr/gcMapExplorer's normalizer.  The reference
+ * has no FFI layer: its seam is the three Cython modules lib/normalizeCore.pyx, lib/normalizeKnightRuiz.pyx,
+ * lib/ccmapHelpers.pyx plus lib/cmstats.py:getAvgContactByDistance, called from lib/normalizer.py.
+ * Each entry point below names the reference interface (file:line, relative to
+ * /root/reference/gcMapExplorer/) it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are HOST pointers unless stated otherwise;
+ *   - every function returns 0 on success, non-zero on failure; gcx_last_error() gives the message
+ *     (thread-local);
+ *   - a gcx_ctx owns one CUDA device, one stream, one resident map (the rank's row block of the dense
+ *     float32 n x n matrix, pitch padded to 128 B), an optional output map and all O(n) vectors;
+ *   - nothing here falls back to the CPU: without a CUDA device every call fails.
+ */
+#ifndef GCX_NORM_H
+#define GCX_NORM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gcx_ctx gcx_ctx;
+
+/* ---- library / context ------------------------------------------------------------------------ */
+const char* gcx_last_error(void);
+int gcx_version(void);
+int gcx_device_count(int* count);
+int gcx_ctx_create(int device, gcx_ctx** out);
+int gcx_ctx_destroy(gcx_ctx* ctx);
+int gcx_sync(gcx_ctx* ctx);
+/* device properties the benchmark reports: SM count, total/free HBM bytes */
+int gcx_device_info(gcx_ctx* ctx, int* sm_count, int64_t* hbm_total, int64_t* hbm_free);
+
+/* pinned host memory for callers that want full-speed PCIe copies (bench.py e2e leg) */
+int gcx_host_alloc(int64_t bytes, void** ptr);
+int gcx_host_free(void* ptr);
+
+/* ---- map residency ----------------------------------------------------------------------------
+ * Replaces the CCMAP memmap copies of lib/normalizer.py:308, 561, 842, 1117 (ccMapObj.copy()) and the
+ * compaction matrix[bNZ,:][:,bNZ] (lib/normalizer.py:329, 589) / remove_zeros (lib/ccmapHelpers.pyx:241-301):
+ * the map is uploaded once, never compacted -- masked bins are handled by zeroing vector entries.
+ * n = global number of bins, [row0, row0+nloc) = the row block this context owns (single GPU: 0, n). */
+int gcx_map_create(gcx_ctx* ctx, int64_t n, int64_t row0, int64_t nloc);
+int gcx_map_upload(gcx_ctx* ctx, const float* host_rows, int64_t host_ld);          /* host_rows -> first local row */
+int gcx_map_download(gcx_ctx* ctx, int which, float* host_rows, int64_t host_ld);   /* which: 0 input, 1 output */
+/* device-side synthetic map: symmetric Poisson(scale*(d+1)^-alpha), empty bins, diag >= 1 */
+int gcx_map_synth(gcx_ctx* ctx, uint64_t seed, double scale, double alpha, double empty_frac);
+/* vmin/vmax clamp, lib/normalizer.py:299-301, 567-569, 827-829, 1105-1107: x<=vmin or x>=vmax -> 0 */
+int gcx_map_clamp(gcx_ctx* ctx, int has_vmin, float vmin, int has_vmax, float vmax);
+/* scaleUpInput, lib/normalizer.py:832-834: matrix *= factor (float32) */
+int gcx_map_scale(gcx_ctx* ctx, float factor);
+/* make the output map the new input (used to chain normalizations without a host round trip) */
+int gcx_map_swap(gcx_ctx* ctx);
+
+/* ---- mask -------------------------------------------------------------------------------------
+ * Replaces the row loop of ccmapHelpers.get_nonzeros_index (lib/ccmapHelpers.pyx:190-201): per row the
+ * float64 row sum and the int32 number of zero entries.  Outputs are the FULL n-vectors (allgathered when
+ * sharded).  The empty-row rule (:192-195) and the percentile / occupancy comparisons (:204-237) are
+ * integer work on n values and stay on the host (NumPy itself) so the mask is bit-exact. */
+int gcx_row_stats(gcx_ctx* ctx, double* rowsum /* n, may be NULL */, int32_t* zero_count /* n, may be NULL */);
+int gcx_set_mask(gcx_ctx* ctx, const uint8_t* keep /* n; 1 = bin takes part */);
+
+/* ---- Iterative correction ---------------------------------------------------------------------
+ * Replaces normalizeCore.performIterativeCorrection(matrix, tol, iteration) (lib/normalizeCore.pyx:34-60).
+ * One fused matvec per pass, fp64 accumulation; the matrix is not rewritten (see gcx_apply_sym_scale).
+ * bias: n doubles (entries of masked bins are 1).  passes: number of reference passes (502 at the cap of
+ * iteration=500).  matvecs = passes + 1. */
+int gcx_ic_run(gcx_ctx* ctx, double tol, int iteration, double* bias, int* passes, double* last_l1, int* matvecs);
+
+/* ---- Knight-Ruiz ------------------------------------------------------------------------------
+ * Replaces KnightRuizNorm.__init__/run_for_RAM (lib/normalizeKnightRuiz.pyx:74-191, 271-286) with
+ * identical control flow, device-resident.  x: n doubles (masked bins 0). */
+int gcx_kr_run(gcx_ctx* ctx, double tol, double delta, double Delta, double* x, int* outer, int* mvp, double* rout);
+
+/* ---- final apply ------------------------------------------------------------------------------
+ * out_ij = f32((s_lo * A_ij) * s_hi) on kept x kept, lo/hi = min/max(i,j): GenNormMatrixRAM
+ * (lib/normalizeKnightRuiz.pyx:207-227) and the accumulated effect of lib/normalizeCore.pyx:48-53.
+ * s: n doubles on the host, or NULL to use the vector left resident by the last gcx_ic_run (1/bias) or
+ * gcx_kr_run (x).  masked_mode: 0 -> masked rows/cols are 0 (KR, lib/normalizer.py:308),
+ * 1 -> masked rows/cols keep the input value (IC write-back quirk, lib/normalizer.py:601-613).
+ * minv/maxv: min non-zero / max over the kept x kept block (lib/normalizer.py:596-598, .pyx:214-216). */
+int gcx_apply_sym_scale(gcx_ctx* ctx, const double* s, int masked_mode, int in_place, float* minv, float* maxv);
+
+/* ---- Vanilla coverage -------------------------------------------------------------------------
+ * Replaces normalizeCore.performVCNormalization (lib/normalizeCore.pyx:63-89) in its fp32 arithmetic.
+ * Needs gcx_row_stats + gcx_set_mask first.  csum: n floats out (may be NULL). */
+int gcx_vc_run(gcx_ctx* ctx, int sqroot, int in_place, float* minv, float* maxv, float* csum);
+
+/* ---- distance-frequency (MCFS) ----------------------------------------------------------------
+ * gcx_diag_stats replaces cmstats.getAvgContactByDistance (lib/cmstats.py:569-605) for one map:
+ * median != 0 -> per-diagonal median of non-zero entries, else mean; avg: n doubles.
+ * gcx_diag_apply replaces normalizeByAvgContactByDivision / BySubtraction (lib/normalizeCore.pyx:91-170). */
+int gcx_diag_stats(gcx_ctx* ctx, int median, double* avg);
+int gcx_diag_apply(gcx_ctx* ctx, const double* avg, int subtract, int in_place, float* minv, float* maxv);
+
+/* ---- multi-GPU (row-block sharding; one context per rank) ------------------------------------
+ * nccl_unique_id: the 128-byte ncclUniqueId from gcx_dist_unique_id on rank 0, broadcast by the host
+ * (torch.distributed / any store).  After init, ic/kr/row_stats/diag_stats exchange their n-vectors with
+ * one NCCL allgather per matrix pass on the context's stream. */
+int gcx_dist_unique_id(void* id128);
+int gcx_dist_init(gcx_ctx* ctx, int rank, int world, const void* id128);
+
+/* ---- measurement ------------------------------------------------------------------------------
+ * gcx_profile enables CUDA-event pairs around every matrix-pass kernel on the context's stream;
+ * gcx_profile_read returns launches and summed device milliseconds per kernel class since the last reset.
+ * classes: 0 matvec, 1 apply_sym, 2 vc_apply, 3 row_stats, 4 diag_reduce, 5 diag_apply, 6 vector epilogue */
+#define GCX_NCLASS 8
+int gcx_profile(gcx_ctx* ctx, int enable);
+int gcx_profile_read(gcx_ctx* ctx, int reset, int64_t launches[GCX_NCLASS], double ms[GCX_NCLASS]);
+/* CUDA-event stopwatch on the context's stream (bench.py brackets its timed region with it) */
+int gcx_timer_start(gcx_ctx* ctx);
+int gcx_timer_stop(gcx_ctx* ctx, double* ms);
+/* forget cached row statistics so the next mask / VC call re-reads the map (benchmark steps) */
+int gcx_map_invalidate(gcx_ctx* ctx);
+/* device time (ms, CUDA events) of the last ic/kr run: matrix resident -> final vector */
+int gcx_last_run_ms(gcx_ctx* ctx, double* ms);
+/* total kernel launches issued by this context since creation */
+int gcx_launch_count(gcx_ctx* ctx, int64_t* launches);
+/* micro-benchmark: `iters` back-to-back matvec launches (variant: 0 = default), device ms total */
+int gcx_bench_matvec(gcx_ctx* ctx, int variant, int iters, double* ms_total);
+/* 64-bit checksum of the selected map (order-independent sum of hashed entries; sharded parity checks) */
+int gcx_map_checksum(gcx_ctx* ctx, int which, uint64_t* sum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCX_NORM_H */

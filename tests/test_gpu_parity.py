@@ -1,0 +1,368 @@
+"""GPU parity tests (pytest -m gpu): every call goes through the C ABI of libgcxnorm.so and is compared with
+the oracle (oracle/oracle_np.py) and the golden vectors produced by the real reference.
+
+Tolerances (north_star: bias 1e-6, fp32 matrices 1e-4 -- asserted much tighter here):
+  BIAS_RTOL   bias / KR x vectors vs fp64 oracle
+  MAT_RTOL    fp32 matrices vs fp64 oracle rounded to fp32 (a couple of fp32 ulps)
+  ASIS_RTOL   fp32 matrices vs the as-is fp32 reference IC (its own noise floor)
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, rel_err
+from oracle import oracle_np as onp
+from oracle import ref_loader as rl
+
+pytestmark = pytest.mark.gpu
+
+BIAS_RTOL = 1e-9
+MAT_RTOL = 3e-7
+ASIS_RTOL = 5e-5
+
+
+@pytest.fixture(scope="module")
+def gx():
+    from gcmapexplorer_b200 import device
+    assert device._lib.device_count() >= 1
+    return device
+
+
+def _ic_device(gx, A, tol, iteration, keep):
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.set_mask(keep)
+        r = dm.ic(tol, iteration)
+        mn, mx = dm.apply_sym(None, masked_mode=1, in_place=False)
+        r["matrix"] = dm.download(1)
+        r["min"], r["max"] = mn, mx
+    return r
+
+
+@pytest.mark.parametrize("n", [5, 33, 97, 256, 1000, 1025])
+def test_upload_download_roundtrip_and_checksum(gx, n):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)).astype(np.float32)
+    with gx.DeviceMap.from_host(A) as dm:
+        assert np.array_equal(dm.download(0), A)
+        c0 = dm.checksum(0)
+        # strided (non-contiguous rows) host view
+        big = np.zeros((n, n + 7), dtype=np.float32)
+        big[:, :n] = A
+        dm.upload(big[:, :n])
+        assert np.array_equal(dm.download(0), A)
+        assert dm.checksum(0) == c0
+
+
+@pytest.mark.parametrize("n,seed", [(64, 1), (97, 2), (482, 3), (1500, 4)])
+def test_row_stats_and_mask(gx, n, seed):
+    A = onp.synth_map(n, seed=seed, scale=30.0, alpha=1.3, empty_frac=0.03)
+    from gcmapexplorer_b200 import ccmapHelpers as cmh
+    with gx.DeviceMap.from_host(A) as dm:
+        rs, zc = dm.row_stats()
+    np.testing.assert_array_equal(rs, A.astype(np.float64).sum(axis=1))      # integer counts: exact
+    np.testing.assert_array_equal(zc, (A == 0).sum(axis=1))
+    for kw in (dict(), dict(threshold_percentile=90), dict(threshold_percentile=50), dict(threshold_data_occup=0.3),
+               dict(threshold_data_occup=0.05)):
+        try:
+            exp = onp.get_nonzeros_index(A, kw.get("threshold_percentile"), kw.get("threshold_data_occup"))
+        except ValueError:
+            with pytest.raises(ValueError):            # same error when the filter leaves nothing
+                cmh.get_nonzeros_index(A, **kw)
+            continue
+        got = cmh.get_nonzeros_index(A, **kw)
+        assert got.dtype == bool and np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("name", golden_names("MASK"))
+def test_mask_golden(gx, name):
+    from gcmapexplorer_b200 import ccmapHelpers as cmh
+    g = load_golden(name)
+    keep = cmh.get_nonzeros_index(g["input"], threshold_percentile=g["kwargs"].get("percentile_threshold_no_data"),
+                                  threshold_data_occup=g["kwargs"].get("threshold_data_occup"))
+    assert np.array_equal(keep, g["keep"])
+
+
+def test_mask_errors(gx):
+    from gcmapexplorer_b200 import ccmapHelpers as cmh
+    A = onp.synth_map(40, seed=3)
+    with pytest.raises(AssertionError):
+        cmh.get_nonzeros_index(A, 90, 0.5)
+    with pytest.raises(ValueError):
+        cmh.get_nonzeros_index(A, None, 1.5)
+
+
+@pytest.mark.parametrize("n,seed", [(5, 0), (31, 1), (300, 2), (1031, 3), (2048, 4)])
+def test_ic_vs_fp64_oracle(gx, n, seed):
+    A = onp.synth_map(n, seed=seed) if n > 5 else load_golden("kat5_ic")["input"]
+    M64, B, passes, l1 = onp.ic_fp64(A, 1e-4, 500)
+    r = _ic_device(gx, A, 1e-4, 500, np.ones(n, dtype=bool))
+    assert r["passes"] == passes and r["matvecs"] == passes + 1
+    np.testing.assert_allclose(r["bias"], B, rtol=BIAS_RTOL)
+    assert rel_err(r["matrix"], M64.astype(np.float32)) < MAT_RTOL
+    assert abs(r["l1"] - l1[-1]) <= 1e-6 * max(l1[-1], 1e-30) + 1e-15
+    nzv = M64.astype(np.float32)
+    assert r["max"] == pytest.approx(float(nzv.max()), rel=MAT_RTOL)
+    assert r["min"] == pytest.approx(float(nzv[nzv != 0].min()), rel=MAT_RTOL)
+
+
+@pytest.mark.parametrize("name", golden_names("IC"))
+def test_ic_golden_dropin(gx, name):
+    """normalizeCCMapByIC through CCMAP objects vs (a) the real reference's as-is output (loose, its own
+    fp32 noise) and (b) the fp64 oracle (tight), incl. mask, quirks, min/max and pass count."""
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz
+    g = load_golden(name)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(g["input"], 100000, xlabel="chrS", ylabel="chrS")
+    c.make_unreadable()
+    out = nz.normalizeCCMapByIC(c, **g["kwargs"])
+    assert out is not None and out.matrix is not None and c.matrix is None      # states: lib/normalizer.py:583
+    got = np.array(out.matrix)
+    assert np.array_equal(out.bNoData, g["bNoData"])                             # bit-exact mask
+    assert rel_err(got, g["matrix"]) < ASIS_RTOL
+    ref = onp.normalize_ic(g["input"], fp64=True, **g["kwargs"])
+    assert rel_err(got, ref["matrix"]) < MAT_RTOL
+    assert nz.last_run_info["passes"] == ref["passes"]
+    np.testing.assert_allclose(nz.last_run_info["bias"][ref["keep"]], ref["bias"], rtol=BIAS_RTOL)
+    assert out.minvalue == pytest.approx(ref["minvalue"], rel=MAT_RTOL)
+    assert out.maxvalue == pytest.approx(ref["maxvalue"], rel=MAT_RTOL)
+    assert out.minvalue == pytest.approx(float(g["minvalue"]), rel=ASIS_RTOL)
+
+
+@pytest.mark.parametrize("name", golden_names("KR"))
+def test_kr_golden_dropin(gx, name):
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz
+    g = load_golden(name)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(g["input"], 100000, xlabel="chrS", ylabel="chrS")
+    c.make_unreadable()
+    out = nz.normalizeCCMapByKR(c, **g["kwargs"])
+    assert out.matrix is None and c.matrix is None                               # lib/normalizer.py:359-360
+    out.make_readable()
+    got = np.array(out.matrix)
+    assert np.array_equal(out.bNoData, g["bNoData"])
+    assert (nz.last_run_info["outer"], nz.last_run_info["MVP"]) == (int(g["outer"]), int(g["MVP"]))
+    assert rel_err(got, g["matrix"]) < MAT_RTOL                                  # vs the REAL reference output
+    assert out.minvalue == pytest.approx(float(g["minvalue"]), rel=MAT_RTOL)
+    assert out.maxvalue == pytest.approx(float(g["maxvalue"]), rel=MAT_RTOL)
+    kept = ~g["bNoData"]
+    assert np.all(got[~kept] == 0) and np.all(got[:, ~kept] == 0)
+
+
+@pytest.mark.parametrize("name", golden_names("KR"))
+def test_kr_x_vs_reference(gx, name):
+    g = load_golden(name)
+    T = onp.clamp(g["input"], g["kwargs"].get("vmin"), g["kwargs"].get("vmax"))
+    keep = ~g["bNoData"]
+    with gx.DeviceMap.from_host(T) as dm:
+        dm.set_mask(keep)
+        r = dm.kr(g["kwargs"].get("tol", 1e-12), 0.1, 3)
+    np.testing.assert_allclose(r["x"][keep], g["x"], rtol=BIAS_RTOL)
+    assert np.all(r["x"][~keep] == 0)
+    assert (r["outer"], r["MVP"]) == (int(g["outer"]), int(g["MVP"]))
+
+
+@pytest.mark.parametrize("name", golden_names("VC"))
+def test_vc_golden_dropin(gx, name):
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz
+    g = load_golden(name)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(g["input"], 100000, xlabel="chrS", ylabel="chrS")
+    c.make_unreadable()
+    out = nz.normalizeCCMapByVCNorm(c, **g["kwargs"])
+    assert out.matrix is not None
+    got = np.array(out.matrix)
+    assert np.array_equal(out.bNoData, g["bNoData"])
+    assert np.array_equal(got, g["matrix"])                                      # integer counts: bit-exact fp32
+    assert np.float32(out.minvalue) == np.float32(g["minvalue"])
+    assert np.float32(out.maxvalue) == np.float32(g["maxvalue"])
+
+
+def test_inner_seam_functions(gx):
+    """The normalizeCore / normalizeKnightRuiz shims keep the reference's calling conventions."""
+    from gcmapexplorer_b200 import normalizeCore as core, normalizeKnightRuiz as krn
+    A = onp.synth_map(211, seed=5)
+    keep = onp.get_nonzeros_index(A)
+    sub = np.ascontiguousarray(A[keep][:, keep])
+    M = sub.copy()
+    assert core.performIterativeCorrection(M, 1e-4, 500) is None                 # in place, returns None
+    M64, B, passes, _ = onp.ic_fp64(sub, 1e-4, 500)
+    assert rel_err(M, M64.astype(np.float32)) < MAT_RTOL and core.last_ic_info["passes"] == passes
+    out = A.copy()
+    assert core.performVCNormalization(A, Out=out, sqroot=False, bNoData=~keep) is None
+    assert np.array_equal(out, onp.vc(A, bNoData=~keep, out=A.copy())[0])
+    ret = core.performVCNormalization(A, sqroot=True, bNoData=~keep)
+    exp = onp.vc(A, bNoData=~keep, sqroot=True, out=np.zeros_like(A))[0]
+    assert np.array_equal(ret, exp)
+    K = krn.KnightRuizNorm(sub, tol=1e-12, delta=0.1, Delta=3)
+    O = np.zeros_like(A)
+    mn, mx = K.run(sub, 0, O, ~keep)
+    r = onp.kr(sub)
+    assert (K.i, K.MVP) == (r["outer"], r["MVP"]) and K.x.shape == (sub.shape[0], 1)
+    np.testing.assert_allclose(K.x[:, 0], r["x"], rtol=BIAS_RTOL)
+    exp = onp.scatter_symmetric(onp.kr_matrix(sub, r["x"]), ~keep, np.zeros_like(A))
+    assert rel_err(O, exp) < MAT_RTOL
+    with pytest.raises(ValueError):
+        krn.KnightRuizNorm(sub, memory="TAPE")
+
+
+@pytest.mark.skipif(not rl.have_cores(), reason="oracle/_ref not built")
+def test_ic_kr_vs_live_reference_cores(gx):
+    """n=1200 through the reference's own compiled cores (oracle/_ref) on the same map."""
+    core, krmod, cmh = rl.load_cores()
+    A = onp.synth_map(1200, seed=12)
+    keep = onp.get_nonzeros_index(A)
+    sub = np.ascontiguousarray(A[keep][:, keep])
+    M = sub.copy()
+    core.performIterativeCorrection(M, 1e-4, 500)
+    r = _ic_device(gx, sub, 1e-4, 500, np.ones(sub.shape[0], dtype=bool))
+    assert rel_err(r["matrix"], M) < ASIS_RTOL
+
+    class F(np.ndarray):
+        def flush(self):
+            pass
+    K = krmod.KnightRuizNorm(sub, tol=1e-12, delta=0.1, Delta=3)
+    O = np.zeros_like(A).view(F)
+    K.run(sub, 0, O, ~keep)
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.set_mask(keep)
+        k = dm.kr(1e-12, 0.1, 3)
+        dm.apply_sym(None, masked_mode=0, in_place=False)
+        got = dm.download(1)
+    assert (k["outer"], k["MVP"]) == (K.i, K.MVP)
+    np.testing.assert_allclose(k["x"][keep], np.asarray(K.x)[:, 0], rtol=BIAS_RTOL)
+    assert rel_err(got, np.asarray(O)) < MAT_RTOL
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 6])
+def test_matvec_variants_agree(gx, variant, monkeypatch):
+    """Every compiled (rows-per-band, occupancy) variant of k_matvec gives the same IC result."""
+    monkeypatch.setenv("GCX_MATVEC_VARIANT", str(variant))
+    A = onp.synth_map(777, seed=21)
+    M64, B, passes, _ = onp.ic_fp64(A, 1e-4, 500)
+    r = _ic_device(gx, A, 1e-4, 500, np.ones(777, dtype=bool))
+    assert r["passes"] == passes
+    np.testing.assert_allclose(r["bias"], B, rtol=BIAS_RTOL)
+
+
+def test_device_synth_properties_and_full_size_invariants(gx):
+    """Device-generated map at a size the oracle cannot reach quickly (n=12000): symmetry, empty bins,
+    and size-independent invariants of the normalizations."""
+    n = 12000
+    with gx.DeviceMap(n) as dm:
+        dm.synth(seed=110, scale=200.0, alpha=1.0, empty_frac=0.01)
+        rs, zc = dm.row_stats()
+        A_rows = dm.download(0)
+        assert np.array_equal(A_rows[:200, :], A_rows[:, :200].T)                 # symmetric
+        empty = rs == 0
+        assert 0.005 * n < empty.sum() < 0.02 * n
+        keep = ~empty
+        dm.set_mask(np.ones(n, dtype=bool))
+        r = dm.ic(1e-4, 500)
+        assert 10 < r["passes"] < 200
+        dm.apply_sym(None, masked_mode=1, in_place=False)
+        dm.swap()
+        rs_ic, _ = dm.row_stats()
+        # IC invariants: total conserved, kept row sums all equal (lib/normalizeCore.pyx:36,53)
+        assert abs(rs_ic.sum() - rs.sum()) < 1e-6 * rs.sum()
+        k = rs_ic[keep]
+        assert (k.max() - k.min()) / k.mean() < 1e-3
+        dm.swap()
+        dm.set_mask(keep)
+        kk = dm.kr(1e-12, 0.1, 3)
+        assert kk["rout"] <= 1e-24 and kk["MVP"] < 200
+        dm.apply_sym(None, masked_mode=0, in_place=False)
+        dm.swap()
+        rs_kr, _ = dm.row_stats()
+        assert np.max(np.abs(rs_kr[keep] - 1.0)) < 1e-5 and np.all(rs_kr[~keep] == 0)   # fp32 storage
+
+
+# --------------------------------------------------------------------------------------------------
+# distance-frequency (MCFS)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,seed,dense", [(5, 0, True), (64, 1, True), (97, 2, False), (300, 3, True), (1111, 4, False)])
+@pytest.mark.parametrize("stats", ["median", "mean"])
+def test_diag_stats_vs_oracle(gx, n, seed, dense, stats):
+    if n == 5:
+        A = load_golden("kat5_ic")["input"]
+    else:
+        A = onp.synth_map(n, seed=seed) if dense else onp.synth_map(n, seed=seed, scale=30.0, alpha=1.3, empty_frac=0.03)
+    exp = onp.avg_contact_by_distance(A, stats)
+    with gx.DeviceMap.from_host(A) as dm:
+        got = dm.diag_stats(stats)
+    if stats == "median":
+        assert np.array_equal(got, exp)                      # selection: bit-exact
+    else:
+        np.testing.assert_allclose(got, exp, rtol=1e-13, atol=0)
+
+
+def test_diag_median_non_integer_and_negative(gx):
+    """Median select on arbitrary floats (already-normalized maps, negative o-e values, duplicates)."""
+    rng = np.random.default_rng(5)
+    n = 257
+    L = rng.standard_normal((n, n)).astype(np.float32)
+    L[rng.random((n, n)) < 0.3] = 0.0
+    L[rng.random((n, n)) < 0.2] = np.float32(0.5)          # many duplicates
+    A = np.tril(L) + np.tril(L, -1).T
+    exp = onp.avg_contact_by_distance(A, "median")
+    with gx.DeviceMap.from_host(A) as dm:
+        got = dm.diag_stats("median")
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("name", golden_names("MCFS"))
+def test_mcfs_golden_dropin(gx, name):
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz
+    g = load_golden(name)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(g["input"], 100000, xlabel="chrS", ylabel="chrS")
+    c.make_unreadable()
+    out = nz.normalizeCCMapByMCFS(c, **g["kwargs"])
+    assert out is not None and out.matrix is not None and c.matrix is not None     # lib/normalizer.py:851-857
+    got = np.array(out.matrix)
+    assert np.array_equal(out.bNoData, g["bNoData"])
+    if "avg" in g:
+        if g["kwargs"].get("stats", "median") == "median":
+            assert np.array_equal(nz.last_run_info["avg"], g["avg"])
+        else:
+            np.testing.assert_allclose(nz.last_run_info["avg"], g["avg"], rtol=1e-13)
+    assert rel_err(got, g["matrix"]) < MAT_RTOL
+    assert out.minvalue == pytest.approx(float(g["minvalue"]), rel=MAT_RTOL)
+    assert out.maxvalue == pytest.approx(float(g["maxvalue"]), rel=MAT_RTOL)
+
+
+def test_mcfs_bad_stype_and_inner_seam(gx):
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz, normalizeCore as core, cmstats
+    A = onp.synth_map(150, seed=9)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(A, 100000)
+    assert nz.normalizeCCMapByMCFS(c, stype="bogus") is None
+    c.make_readable()
+    avg = cmstats.getAvgContactByDistance(c, stats="mean")
+    np.testing.assert_allclose(avg, onp.avg_contact_by_distance(A, "mean"), rtol=1e-13)
+    assert rel_err(core.normalizeByAvgContactByDivision(A, avg), onp.mcfs_divide(A, avg)) < MAT_RTOL
+    out = np.zeros_like(A)
+    assert core.normalizeByAvgContactBySubtraction(A, avg, Out=out) is None
+    assert rel_err(out, onp.mcfs_subtract(A, avg)) < MAT_RTOL
+    with pytest.raises(NotImplementedError):
+        cmstats.getAvgContactByDistance([c, c])
+    with pytest.raises(TypeError):
+        cmstats.getAvgContactByDistance(A)
+
+
+def test_ccmap_save_load_roundtrip_with_outfile(gx, tmp_path):
+    """outFile= path: result saved as .ccmap + gz npbin (lib/normalizer.py:621-622), loads back identically."""
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz
+    A = onp.synth_map(120, seed=4)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(A, 50000, xlabel="chr9", ylabel="chr9", workDir=str(tmp_path))
+    c.make_unreadable()
+    assert nz.normalizeCCMapByIC(c, outFile=str(tmp_path / "n_ic")) is None
+    direct = nz.normalizeCCMapByIC(c)
+    loaded = cmp.load_ccmap(str(tmp_path / "n_ic.ccmap"), workDir=str(tmp_path))
+    loaded.make_readable()
+    assert np.array_equal(np.array(loaded.matrix), np.array(direct.matrix))
+    assert np.array_equal(loaded.bNoData, direct.bNoData) and loaded.binsize == 50000 and loaded.xlabel == "chr9"
+    # a path instead of an object, and a missing file (lib/ccmap.py:644-647 -> TypeError at the unpack)
+    again = nz.normalizeCCMapByKR(str(tmp_path / "n_ic.ccmap"), workDir=str(tmp_path))
+    assert again is not None
+    with pytest.raises(TypeError):
+        nz.normalizeCCMapByIC(str(tmp_path / "missing.ccmap"))
