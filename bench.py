@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- the driver-facing benchmark of the normalization hot path.
+
+  python bench.py --gpus N --steps K --warmup W                  # this repo's sm_100a path
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path, same metric
+
+Workload (BASELINE.json): N=1 -> configs[1], synthetic chr1 @ 10 kb (n = 24,926, 2.485 GB fp32 dense), IC + VC.
+N>1 -> the same pipeline on a row-sharded map with the per-GPU block held at 2.485 GB (n = 24,926*sqrt(N):
+weak scaling), one NCCL allgather of the n-vector per IC pass.  `--workload chr1_1kb` runs BASELINE
+configs[4] (n = 249,251, needs >= 2 GPUs), `--workload chr1_5kb_kr` runs configs[2] (KR on one GPU).
+
+A "step" = one complete pass of the hot path over the resident map:
+    row statistics/mask (4n^2 B) + IC to convergence (matvecs x 4n^2 B) + final apply (8n^2 B) + VC apply (8n^2 B).
+metric  = algorithmic bytes of the step / step time, in GB/s (whole job, all ranks) -- BASELINE's "per-iteration HBM
+          GB/s"; the time-to-converge BASELINE also names is carried in `time_to_converge_s` / `ms_per_step`.
+e2e     = the same metric for the C-ABI call sequence on HOST buffers: pinned-host upload + mask + IC + apply +
+          download + VC + download, all copies inside the timed region.
+roofline= the dominant kernel (k_matvec): 4*nloc*n bytes per launch / mean CUDA-event duration of the launches inside
+          the timed region, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline = the reference's own compiled Cython cores (oracle/_ref, kind "reference") -- or the NumPy port when
+          they are absent -- timed on this box's host cores on a bounded sample of the same map.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_CHR1_10KB = 24926     # hg19 chr1 length 249,250,621 // 10,000 + 1  (lib/importer.py:1695-1707 shape rule)
+N_CHR1_5KB = 49851
+N_CHR1_1KB = 249251
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+IC_TOL, IC_ITER = 1e-4, 500    # API defaults, lib/normalizer.py:505
+REF_IC_CAP_PASSES = IC_ITER + 2
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def step_bytes(n, nloc_total, matvecs):
+    """Algorithmic HBM bytes of one step: mask 4, IC 4/matvec, apply 8, VC apply 8 -- times rows x n."""
+    return (4.0 * (1 + matvecs) + 16.0) * nloc_total * n
+
+
+# ======================================================================================================
+# this repo's arm
+# ======================================================================================================
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    dist = None
+    tdist = None
+    if world > 1:
+        import torch
+        import torch.distributed as tdist
+        torch.cuda.set_device(local)
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from gcmapexplorer_b200 import device as gx
+
+    if args.workload == "chr1_1kb":
+        n = args.n or N_CHR1_1KB
+        wl = "synthetic chr1 @ 1 kb (n=%d), IC + VC, row-sharded" % n
+    elif args.workload == "chr1_5kb_kr":
+        n = args.n or N_CHR1_5KB
+        wl = "synthetic chr1 @ 5 kb (n=%d), KR" % n
+    else:
+        n = args.n or int(round(N_CHR1_10KB * math.sqrt(world)))
+        wl = ("synthetic chr1 @ 10 kb (n=%d), IC + VC" % n) if world == 1 else \
+             ("synthetic chr1-like map, n=%d (2.485 GB fp32 per GPU), IC + VC, row-sharded" % n)
+    rpr = (n + world - 1) // world
+    row0 = rank * rpr
+    nloc = max(0, min(rpr, n - row0))
+    if world > 1:
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(gx.dist_unique_id()), dtype=torch.uint8, device="cuda")
+        tdist.broadcast(idt, 0)
+        dist = (rank, world, bytes(idt.cpu().tolist()))
+    dm = gx.DeviceMap(n, row0, nloc, device=local, dist=dist)
+    dm.synth(seed=args.seed, scale=200.0, alpha=1.0, empty_frac=0.01)
+    peak, peak_kind = measured_peak()
+    kr_mode = args.workload == "chr1_5kb_kr"
+
+    def barrier():
+        dm.sync()
+        if tdist is not None:
+            tdist.barrier()
+
+    def max_over_ranks(x):
+        if tdist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    ones = np.ones(n, dtype=bool)
+    info = {}
+
+    def step():
+        rs, zc = dm.row_stats(force=True)                 # K1: mask pass
+        keep = rs != 0.0
+        if kr_mode:
+            dm.set_mask(keep)
+            r = dm.kr(1e-12, 0.1, 3.0)
+            dm.apply_sym(None, masked_mode=0, in_place=False)
+            info.update(matvecs=r["MVP"] + 1, outer=r["outer"], converge_ms=r["ms"], passes=r["MVP"])
+        else:
+            dm.set_mask(ones)                             # IC without filter runs on the whole map (normalizer.py:592)
+            r = dm.ic(IC_TOL, IC_ITER)                    # K2 x passes + vector epilogues
+            dm.apply_sym(None, masked_mode=1, in_place=False)   # K4
+            dm.set_mask(keep)
+            dm.vc(False, in_place=False)                  # K5 (row sums reused from the mask pass)
+            info.update(matvecs=r["matvecs"], passes=r["passes"], converge_ms=r["ms"], l1=r["l1"])
+
+    for _ in range(args.warmup):
+        step()
+    # ---- timed region: device-resident ---------------------------------------------------------------
+    dm.profile(True)
+    dm.profile_read(reset=True)
+    l0 = dm.launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    dm.timer_start()
+    conv_ms = []
+    for _ in range(args.steps):
+        step()
+        conv_ms.append(info["converge_ms"])
+    ms_total = dm.timer_stop()
+    barrier()
+    ms_total = max_over_ranks(ms_total)
+    prof = dm.profile_read(reset=True)
+    dm.profile(False)
+    launches = dm.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    mv = info["matvecs"]
+    if kr_mode:
+        bytes_step = (4.0 * (1 + mv) + 8.0) * n * n
+    else:
+        bytes_step = step_bytes(n, n, mv)
+    value = bytes_step / (ms_per_step * 1e-3) / 1e9
+
+    # roofline of the dominant kernel: mean duration over the *effective* launches (launches after the
+    # device-side convergence flag exit immediately; their few microseconds stay in the sum)
+    mv_ms = max_over_ranks(prof["matvec"]["ms"]) / max(1, args.steps * mv)
+    mv_bytes = 4.0 * rpr * n
+    achieved = mv_bytes / (mv_ms * 1e-3) / 1e9
+    roofline = {"kernel": "k_matvec", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "bytes_per_launch": mv_bytes, "us_per_launch": round(mv_ms * 1e3, 2),
+                "launches_timed": args.steps * mv,
+                "other_kernels_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if k != "matvec" and v["launches"]}}
+
+    # ---- e2e: the same pipeline through the C ABI with HOST (pinned) buffers ------------------------------
+    e2e = None
+    if not args.no_e2e and nloc * n * 8 < 0.4 * psutil_avail():
+        hin = gx.PinnedArray((nloc, n))
+        hout = gx.PinnedArray((nloc, n))
+        dm.download(0, out=hin.array)
+
+        def e2e_step():
+            dm.upload(hin.array)                           # H2D 4*nloc*n
+            rs, zc = dm.row_stats(force=True)
+            keep = rs != 0.0
+            if kr_mode:
+                dm.set_mask(keep)
+                dm.kr(1e-12, 0.1, 3.0)
+                dm.apply_sym(None, masked_mode=0, in_place=False)
+                dm.download(1, out=hout.array)             # D2H 4*nloc*n
+                return 1
+            dm.set_mask(ones)
+            dm.ic(IC_TOL, IC_ITER)
+            dm.apply_sym(None, masked_mode=1, in_place=False)
+            dm.download(1, out=hout.array)                 # D2H: IC result
+            dm.set_mask(keep)
+            dm.vc(False, in_place=False)
+            dm.download(1, out=hout.array)                 # D2H: VC result
+            return 2
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(1, min(args.steps, 5))
+        for _ in range(ke):
+            nd = e2e_step()
+        dm.sync()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / ke)
+        barrier()
+        e2e = {"value": round(bytes_step / e2e_s / 1e9, 2), "unit": "GB/s", "seconds_per_step": round(e2e_s, 4),
+               "h2d_bytes_per_step": int(4 * nloc * n), "d2h_bytes_per_step": int(4 * nloc * n * nd),
+               "path": "gcx_map_upload(pinned) -> row_stats -> ic_run -> apply -> gcx_map_download [-> vc_run -> download]"}
+        host_map = hin.array if (rank == 0 and world == 1) else None
+    else:
+        host_map = None
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and host_map is not None and not kr_mode:
+        cpu = cpu_reference_sample(host_map, mv - 1, budget_s=args.cpu_budget)
+
+    if rank == 0:
+        line = {
+            "metric": "IC+VC normalization throughput, chr1 10 kb (algorithmic HBM GB/s over the whole step; time-to-converge alongside)"
+                      if not kr_mode else "KR normalization throughput, chr1 5 kb (algorithmic HBM GB/s)",
+            "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 accumulate / f32 storage", "data": "synthetic (device-generated Poisson power-law map, 1% empty bins)",
+            "config": {"workload": wl, "n": n, "rows_per_gpu": rpr, "map_bytes_per_gpu": int(4 * rpr * n), "l2": "inputs larger than L2 (no flush needed)",
+                       "tol": IC_TOL if not kr_mode else 1e-12, "parallelism": "row-block x%d, NCCL allgather of the n-vector per pass" % world if world > 1 else "single GPU"},
+            "time_to_converge_s": round(float(np.median(conv_ms)) * 1e-3, 5), "passes": info["passes"], "matvecs": mv,
+            "algorithmic_bytes_per_step": bytes_step,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clk,
+        }
+        print(json.dumps(line))
+    dm.close()
+    if tdist is not None:
+        tdist.destroy_process_group()
+
+
+def psutil_avail():
+    try:
+        import psutil
+        return psutil.virtual_memory().available
+    except Exception:
+        return 64 << 30
+
+
+# ======================================================================================================
+# CPU reference: bounded sample of the same workload
+# ======================================================================================================
+def _load_reference():
+    from oracle import ref_loader as rl
+    if rl.have_cores():
+        core, _, cmh = rl.load_cores()
+        return "reference", core.performIterativeCorrection, core.performVCNormalization, cmh.get_nonzeros_index
+    from oracle import oracle_np as onp          # NumPy port of the same lines (kind "port")
+
+    def ic(M, tol, it):
+        onp._ic_recurrence(M, tol, it, np.float32)
+
+    def vc(A, Out=None, sqroot=False, bNoData=None):
+        onp.vc(A, bNoData=bNoData, sqroot=sqroot, out=Out)
+    return "port", ic, vc, onp.get_nonzeros_index
+
+
+def cpu_reference_sample(host_map, passes_same_work, budget_s=25.0):
+    """Times the reference's IC core for exactly 2 passes (iteration=0 -> lib/normalizeCore.pyx:55-57 breaks at
+    the second pass) on the full map, and its VC + mask on a leading principal block, then scales:
+    IC by passes, VC/mask by (n/n_s)^2."""
+    kind, ic, vc, mask = _load_reference()
+    n = host_map.shape[0]
+    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    M = np.array(host_map, dtype=np.float32, copy=True)
+    t0 = time.perf_counter()
+    ic(M, IC_TOL, 0)
+    t_pass = (time.perf_counter() - t0) / 2.0
+    del M
+    ns = min(n, 3000)
+    sub = np.ascontiguousarray(host_map[:ns, :ns])
+    t0 = time.perf_counter()
+    keep = mask(sub)
+    t_mask = (time.perf_counter() - t0) * (n / ns) ** 2
+    out = sub.copy()
+    t0 = time.perf_counter()
+    vc(sub, Out=out, sqroot=False, bNoData=~np.asarray(keep, dtype=bool))
+    t_vc = (time.perf_counter() - t0) * (n / ns) ** 2
+    t_cap = t_mask + REF_IC_CAP_PASSES * t_pass + t_vc
+    t_same = t_mask + passes_same_work * t_pass + t_vc
+    b_cap = step_bytes(n, n, REF_IC_CAP_PASSES + 1)
+    b_same = step_bytes(n, n, passes_same_work + 1)
+    return {"value": round(b_same / t_same / 1e9, 4), "unit": "GB/s", "cores": 1, "host_cores_available": os.cpu_count(), "blas_threads": threads,
+            "kind": kind, "seconds_per_step_same_passes": round(t_same, 1), "seconds_per_step_at_reference_cap": round(t_cap, 1),
+            "value_at_reference_cap": round(b_cap / t_cap / 1e9, 4), "s_per_ic_pass": round(t_pass, 3), "s_mask_scaled": round(t_mask, 2), "s_vc_scaled": round(t_vc, 2),
+            "sample": f"IC: 2 passes of the reference core on the full n={n} map (single-threaded NumPy), scaled to {passes_same_work} passes "
+                      f"(the fp64-converged count; the as-is fp32 reference stalls above tol and runs {REF_IC_CAP_PASSES} = its cap, SURVEY.md fact 3); "
+                      f"mask + VC: reference cores on the leading {ns}x{ns} block, scaled by (n/{ns})^2"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on this box's host cores, same metric/unit/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_np as onp
+    n = args.n or N_CHR1_10KB
+    # the same synthetic law as the device generator, drawn with the host RNG on a band-limited budget:
+    # the reference's cost per pass does not depend on the values, only on n.
+    rng = np.random.default_rng(args.seed)
+    t_gen = time.perf_counter()
+    A = np.zeros((n, n), dtype=np.float32)
+    blk = 2048
+    idx = np.arange(n)
+    for r0 in range(0, n, blk):
+        r1 = min(n, r0 + blk)
+        d = np.abs(idx[r0:r1, None] - idx[None, :]).astype(np.float32)
+        A[r0:r1] = rng.poisson(200.0 / (d + 1.0)).astype(np.float32)
+    A = np.triu(A)
+    A = A + np.triu(A, 1).T
+    empty = rng.choice(n, size=max(2, round(0.01 * n)), replace=False)
+    A[empty, :] = 0
+    A[:, empty] = 0
+    t_gen = time.perf_counter() - t_gen
+    samples = []
+    cpu = None
+    for i in range(args.warmup + args.steps):
+        cpu = cpu_reference_sample(A, args.ref_passes, budget_s=args.cpu_budget)
+        if i >= args.warmup:
+            samples.append(cpu)
+        if sum(s["s_per_ic_pass"] * 2 for s in samples) > 240:     # keep the whole run within a few minutes
+            break
+    val = float(np.median([s["value"] for s in samples]))
+    sec = float(np.median([s["seconds_per_step_same_passes"] for s in samples]))
+    cpu = dict(samples[-1], value=round(val, 4))
+    line = {"impl": "reference", "metric": "IC+VC normalization throughput, chr1 10 kb (algorithmic HBM GB/s over the whole step; time-to-converge alongside)",
+            "value": round(val, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": len(samples), "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (reference as-is)", "data": "synthetic (host-generated Poisson power-law map)",
+            "config": {"workload": "synthetic chr1 @ 10 kb (n=%d), IC + VC" % n, "n": n, "passes_assumed": args.ref_passes},
+            "cpu_baseline": cpu,
+            "e2e": {"value": round(val, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "chr1_10kb", "chr1_5kb_kr", "chr1_1kb"])
+    ap.add_argument("--n", type=int, default=0, help="override the number of bins (quick checks)")
+    ap.add_argument("--seed", type=int, default=110)
+    ap.add_argument("--ref-passes", type=int, default=60, help="IC passes the reference sample is scaled to (fp64-converged count)")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

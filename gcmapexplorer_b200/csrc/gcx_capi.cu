@@ -106,7 +106,7 @@ struct gcx_ctx {
     // matvec workspace
     double* ws = nullptr;
     unsigned int* ticket = nullptr;
-    int mv_variant = 0;
+    int mv_variant = 2;   // R=4 rows per band, 4 CTAs/SM: best of the sweep in profiles/r01_matvec_variants.txt
     // states
     IcState* ic_state = nullptr;
     KrState* kr_state = nullptr;
@@ -653,7 +653,7 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
     CKR(need_map(c));
     if (!c->have_mask) return fail("gcx_ic_run: call gcx_set_mask first");
     const int n = (int)c->n;
-    k_ic_init<<<1, EP_THREADS, 0, c->stream>>>(c->ic_state, (int)c->nv, c->keep, c->vz, c->vB, c->vBd, tol, iteration);
+    k_ic_init<<<32, EP_THREADS, 0, c->stream>>>(c->ic_state, (int)c->nv, c->keep, c->vz, c->vB, tol, iteration);
     CK(cudaGetLastError());
     c->launches += 1;
     auto step = [&]() -> int {
@@ -661,7 +661,7 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         CKR(allgather_f64(c, c->vq));
         {
             ProfScope ps(c, 6);
-            k_ic_epilogue<<<1, EP_THREADS, 0, c->stream>>>(c->ic_state, n, c->keep, c->vq, c->vz, c->vB, c->vBd);
+            k_ic_epilogue<<<EP_CL, EP_THREADS, 0, c->stream>>>(c->ic_state, n, c->keep, c->vq, c->vz, c->vB);
         }
         CK(cudaGetLastError());
         return 0;
@@ -684,7 +684,7 @@ extern "C" int gcx_kr_run(gcx_ctx* c, double tol, double delta, double Delta, do
     CKR(need_map(c));
     if (!c->have_mask) return fail("gcx_kr_run: call gcx_set_mask first");
     const int n = (int)c->n;
-    k_kr_init<<<1, EP_THREADS, 0, c->stream>>>(c->kr_state, (int)c->nv, c->keep, c->kr, tol, delta, Delta);
+    k_kr_init<<<32, EP_THREADS, 0, c->stream>>>(c->kr_state, (int)c->nv, c->keep, c->kr, tol, delta, Delta);
     CK(cudaGetLastError());
     c->launches += 1;
     auto step = [&]() -> int {
@@ -692,7 +692,7 @@ extern "C" int gcx_kr_run(gcx_ctx* c, double tol, double delta, double Delta, do
         CKR(allgather_f64(c, c->vq));
         {
             ProfScope ps(c, 6);
-            k_kr_step<<<1, EP_THREADS, 0, c->stream>>>(c->kr_state, n, c->keep, c->vq, c->kr);
+            k_kr_step<<<EP_CL, EP_THREADS, 0, c->stream>>>(c->kr_state, n, c->keep, c->vq, c->kr);
         }
         CK(cudaGetLastError());
         return 0;

@@ -10,13 +10,15 @@
 // keeps the column-vector entries for its float4 in registers and reuses them across the R rows of the
 // band, which cuts L2 traffic for the vector to 1/R of the matrix traffic.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace gcx {
 
 constexpr int MV_THREADS = 256;   // threads per CTA for matrix passes
-constexpr int EP_THREADS = 1024;  // threads of the single-CTA vector epilogues
+constexpr int EP_THREADS = 1024;  // threads per CTA of the vector-step kernels
+constexpr int EP_CL = 8;          // CTAs per thread-block cluster running a vector step (8 SMs, DSMEM reductions)
 
 // ---------------------------------------------------------------------------------------------------
 // small device helpers
@@ -76,6 +78,66 @@ __device__ __forceinline__ double block_reduce(double v, double* sm) {
     __syncthreads();
     return r;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Team: one thread-block cluster (EP_CL CTAs x EP_THREADS threads) that runs a vector step.  Element i is
+// always handled by the same thread (i = gtid + k*nthreads), so successive elementwise phases need no
+// synchronisation; only reductions do.  A reduction is: fixed-tree block reduce -> one slot in this CTA's
+// shared memory -> cluster barrier -> warp 0 reads the EP_CL slots through distributed shared memory and
+// folds them in rank order.  Every CTA folds the same values in the same order, so all CTAs (and all ranks
+// running the same step on the same gathered vector) hold bitwise identical scalars.
+// ---------------------------------------------------------------------------------------------------
+struct Team {
+    cooperative_groups::cluster_group cl;
+    double* slots;   // shared, [2][4]: double-buffered so one cluster barrier per reduction is enough
+    double* sm;      // shared, [32]: block-reduce scratch
+    int par;
+    unsigned int nb, gtid, nthreads;
+    __device__ Team(double* slots_, double* sm_)
+        : cl(cooperative_groups::this_cluster()), slots(slots_), sm(sm_), par(0) {
+        nb = cl.num_blocks();
+        gtid = cl.block_rank() * blockDim.x + threadIdx.x;
+        nthreads = nb * blockDim.x;
+    }
+    template <int OP, int K>
+    __device__ __forceinline__ void reduce(double (&v)[K]) {
+        static_assert(K <= 4, "at most 4 values per reduction");
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = block_reduce<OP>(v[k], sm);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) slots[par * 4 + k] = v[k];
+        }
+        cl.sync();
+        if (threadIdx.x < 32) {
+            const unsigned int lane = threadIdx.x;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double x = 0.0;
+                if (lane < nb) x = *cl.map_shared_rank(&slots[par * 4 + k], lane);
+                double acc = __shfl_sync(0xffffffffu, x, 0);
+                for (unsigned int r = 1; r < nb; ++r) {
+                    const double y = __shfl_sync(0xffffffffu, x, r);
+                    acc = OP == RED_SUM ? acc + y : (OP == RED_MIN ? fmin(acc, y) : fmax(acc, y));
+                }
+                if (lane == 0) sm[k] = acc;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = sm[k];
+        __syncthreads();
+        par ^= 1;
+    }
+    template <int OP>
+    __device__ __forceinline__ double reduce1(double v) {
+        double a[1] = {v};
+        reduce<OP, 1>(a);
+        return a[0];
+    }
+    // no CTA may exit while a peer can still read its shared memory
+    __device__ __forceinline__ void finish() { cl.sync(); }
+};
 
 // order-preserving float <-> uint32 encoding for atomicMin/atomicMax on floats of either sign
 __device__ __forceinline__ unsigned int f2ord(float f) {
@@ -194,19 +256,36 @@ k_matvec(const float* __restrict__ A, long long ld, int nloc, int n4, const doub
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int b = tid; b < nb; b += MV_THREADS) {
-        const long long ub0 = (long long)b * nch;
-        const long long cf = unit_owner(ub0, U, G), cl = unit_owner(ub0 + nch - 1, U, G);
-        if (cf == cl) continue;   // one CTA had the whole band and wrote it directly
+    // One thread per CTA boundary (G-1 of them) instead of one per band: a band is split only where a
+    // boundary falls strictly inside it.  The thread of the first such boundary folds the partials of
+    // every CTA that touched the band, in CTA order.
+    for (long long cb = 1 + tid; cb < G; cb += MV_THREADS) {
+        const long long ub = unit_begin(cb, U, G);
+        const int b = (int)(ub / nch);
+        const long long band0 = (long long)b * nch, band1 = band0 + nch;
+        if (ub == band0 || ub >= U) continue;                       // boundary on a band edge
+        const long long ubp = unit_begin(cb - 1, U, G);
+        if (ubp > band0) continue;                                   // an earlier boundary owns this band
+        double s[R];
+        {
+            const int slot = (b == (int)(ubp / nch)) ? 0 : 1;        // CTA cb-1: band b is its last band
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) s[rr] = __ldcg(ws + ((cb - 1) * 2 + slot) * R + rr);
+        }
+        long long cc = cb, ucc = ub;
+        while (cc < G && ucc < band1) {
+            const long long unext = unit_begin(cc + 1, U, G);
+            if (unext > ucc) {                                       // non-empty CTA: band b is its first band
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) s[rr] += __ldcg(ws + (cc * 2) * R + rr);
+            }
+            ++cc;
+            ucc = unext;
+        }
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
-            double s = 0.0;
-            for (long long cc = cf; cc <= cl; ++cc) {
-                const int bfc = (int)(unit_begin(cc, U, G) / nch);
-                s += __ldcg(ws + (cc * 2 + (b == bfc ? 0 : 1)) * R + rr);
-            }
             const int r = b * R + rr;
-            if (r < nloc) q[r] = s;
+            if (r < nloc) q[r] = s[rr];
         }
     }
     if (tid == 0) *ticket = 0u;
@@ -378,9 +457,11 @@ k_vc_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld, i
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 float v = in[e];
-                if (ki) v = __fdiv_rn(v, ci);
-                if (kcol[e]) v = __fdiv_rn(v, cc[e]);
-                if (sqroot) v = __fsqrt_rn(v);
+                if (v != 0.f) {     // 0/c = 0 exactly; skipping keeps zeros (most of a Hi-C map) off fdiv's slow path
+                    if (ki) v = __fdiv_rn(v, ci);
+                    if (kcol[e]) v = __fdiv_rn(v, cc[e]);
+                    if (sqroot) v = __fsqrt_rn(v);
+                }
                 o[e] = v;
                 if (j0 + e < n) mm_update(v, mn, mx);
             }
@@ -427,7 +508,7 @@ k_diag_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld,
                 if (j < n) {
                     const int d = i > j ? i - j : j - i;
                     const double av = __ldg(avg + d);
-                    if (av != 0.0) {
+                    if (av != 0.0 && (subtract || in[e] != 0.f)) {     // 0/avg = 0: zeros skip the fp64 divide
                         if (!subtract) {
                             v = (float)((double)in[e] / av);                       // :105-108, :114-117
                         } else {
@@ -729,74 +810,65 @@ struct IcState {
 };
 
 __global__ void __launch_bounds__(EP_THREADS)
-k_ic_init(IcState* st, int nv, const uint8_t* __restrict__ keep, double* v, double* B, double* Bd, double tol, int max_iter) {
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-        const double k = keep[i] ? 1.0 : 0.0;
-        v[i] = k;
+k_ic_init(IcState* st, int nv, const uint8_t* __restrict__ keep, double* v, double* B, double tol, int max_iter) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+        v[i] = keep[i] ? 1.0 : 0.0;
         B[i] = 1.0;
-        Bd[i] = 1.0;
     }
-    if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->cc = 0; st->S = 0; st->l1 = 0; st->mean = 0; st->tol = tol;
         st->pass = 0; st->done = 0; st->cnt = 0; st->max_iter = max_iter; st->matvecs = 0;
     }
 }
 
-__global__ void __launch_bounds__(EP_THREADS)
-k_ic_epilogue(IcState* st, int n, const uint8_t* __restrict__ keep, const double* __restrict__ t, double* v, double* B,
-              double* Bd) {
+// State per bin: B_k and v = 1/(B_k dB_{k+1}) (the matvec input).  Two phases per launch:
+//   A: S' = sum v_i t_i and the number of non-zero terms            (one cluster reduction)
+//   B: B_{k+1} = f / v  (= B_k dB f, :51-52), L1 change (:56), next v (one cluster reduction for the L1)
+// mean(dBraw[!=0]) (:44) of the next pass is (cc/S') S' / cnt -- the sum of the raw column sums is S' itself.
+__global__ void __cluster_dims__(EP_CL, 1, 1) __launch_bounds__(EP_THREADS)
+k_ic_epilogue(IcState* st, int n, const uint8_t* __restrict__ keep, const double* __restrict__ t, double* v, double* B) {
     __shared__ double sm[32];
+    __shared__ double slots[8];
     if (st->done) return;
+    Team T(slots, sm);
     const int m = st->matvecs;
     const double cc_prev = st->cc, tol = st->tol;
     const int max_iter = st->max_iter;
-    __syncthreads();
-    // phase A: S' = sum v_i t_i, cnt = #non-zero terms  (cc on the first launch, lib/normalizeCore.pyx:36)
-    double s = 0.0, cn = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double a[2] = {0.0, 0.0};
+    for (int i = T.gtid; i < n; i += T.nthreads) {
         if (keep[i]) {
             const double p = v[i] * t[i];
-            s += p;
-            cn += (p != 0.0) ? 1.0 : 0.0;
+            a[0] += p;
+            a[1] += (p != 0.0) ? 1.0 : 0.0;
         }
     }
-    const double S = block_reduce<RED_SUM>(s, sm);
-    const double C = block_reduce<RED_SUM>(cn, sm);
-    const double cc = (m == 0) ? S : cc_prev;
+    T.reduce<RED_SUM, 2>(a);
+    const double S = a[0], C = a[1];
+    const double cc = (m == 0) ? S : cc_prev;           // contact_count, :36
     const double f = (m == 0) ? 1.0 : sqrt(S / cc);     // :52
     const double g = (m == 0) ? 1.0 : cc / S;           // :53
-    // phase B: B_{k+1} = (B_k dB) f (:51-52), L1 change (:56), sum of next raw column sums
-    double l1 = 0.0, sd = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double mean = g * S / C;                      // :44
+    double l1 = 0.0;
+    for (int i = T.gtid; i < n; i += T.nthreads) {
         if (keep[i]) {
+            const double vi = v[i];
+            const double d = g * (vi * t[i]);           // next pass's raw column sum, :42
+            double bn = B[i];
             if (m > 0) {
-                const double bn = Bd[i] * f;
-                l1 += fabs(B[i] - bn);
+                bn = f / vi;                            // (B dB) sqrt(S'/cc), :51-52
+                l1 += fabs(B[i] - bn);                  // :56
                 B[i] = bn;
             }
-            const double d = g * (v[i] * t[i]);
-            if (d != 0.0) sd += d;
+            v[i] = (d != 0.0) ? mean / (bn * d) : 1.0 / bn;   // 1/(B dB), dB = d/mean or 1 (:44-45)
         }
     }
-    const double L1 = block_reduce<RED_SUM>(l1, sm);
-    const double SD = block_reduce<RED_SUM>(sd, sm);
+    const double L1 = T.reduce1<RED_SUM>(l1);
     const bool done = (m >= 2) && (L1 < tol || (m - 1) > max_iter);   // :55-57 (count = pass-1)
-    const double mean = SD / C;                                       // :44
-    if (!done) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            if (keep[i]) {
-                const double d = g * (v[i] * t[i]);
-                const double dB = (d != 0.0) ? d / mean : 1.0;        // :44-45
-                const double bd = B[i] * dB;
-                Bd[i] = bd;
-                v[i] = 1.0 / bd;
-            }
-        }
-    }
-    if (threadIdx.x == 0) {
+    if (T.gtid == 0) {
         st->cc = cc; st->S = S; st->l1 = L1; st->mean = mean; st->cnt = (int)C;
         st->pass = m; st->matvecs = m + 1; st->done = done ? 1 : 0;
     }
+    T.finish();
 }
 
 // s_i = keep_i ? 1/B_i : 0 -- the symmetric scale for the final apply
@@ -823,13 +895,13 @@ struct KrVecs {
 
 __global__ void __launch_bounds__(EP_THREADS)
 k_kr_init(KrState* st, int nv, const uint8_t* __restrict__ keep, KrVecs V, double tol, double delta, double Delta) {
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
         const double k = keep[i] ? 1.0 : 0.0;
         V.x[i] = k;       // x = e (:111, :118)
         V.z[i] = k;
         V.v[i] = 0; V.rk[i] = 0; V.y[i] = k; V.Z[i] = 0; V.p[i] = 0; V.w[i] = 0;
     }
-    if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->tol = tol; st->delta = delta; st->Delta = Delta;
         st->rt = tol * tol;            // :119
         st->stop_tol = tol * 0.5;      // :116
@@ -840,13 +912,14 @@ k_kr_init(KrState* st, int nv, const uint8_t* __restrict__ keep, KrVecs V, doubl
     }
 }
 
-__global__ void __launch_bounds__(EP_THREADS)
+__global__ void __cluster_dims__(EP_CL, 1, 1) __launch_bounds__(EP_THREADS)
 k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __restrict__ q, KrVecs V) {
     __shared__ double sm[32];
+    __shared__ double slots[8];
     if (st->done) return;
+    Team T(slots, sm);
     KrState s = *st;
-    __syncthreads();
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = T.gtid, nt = T.nthreads;
     bool to_outer = false;
 
     if (s.phase == 0) {
@@ -862,7 +935,7 @@ k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __
                 acc += r * r;
             }
         }
-        const double rho = block_reduce<RED_SUM>(acc, sm);
+        const double rho = T.reduce1<RED_SUM>(acc);
         s.rho_km1 = rho;
         if (s.init) {
             s.rout = rho; s.rold = rho; s.init = 0;          // :123-124
@@ -880,6 +953,7 @@ k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __
         if (!(s.rout > s.rt)) {                               // :275
             s.done = 1;
             s.matvecs += 1;
+            T.finish();                 // every CTA has read *st (all passed the reduction above)
             if (tid == 0) *st = s;
             return;
         }
@@ -897,7 +971,7 @@ k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __
                 acc += pi * wi;
             }
         }
-        const double pw = block_reduce<RED_SUM>(acc, sm);
+        const double pw = T.reduce1<RED_SUM>(acc);
         const double alpha = s.rho_km1 / pw;
         // ynew = y + ap ; distance to the cone boundary (:144-158)
         double mn = __longlong_as_double(0x7ff0000000000000LL), mx = __longlong_as_double(0xfff0000000000000LL);
@@ -908,8 +982,8 @@ k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __
                 mx = fmax(mx, yn);
             }
         }
-        mn = block_reduce<RED_MIN>(mn, sm);
-        mx = block_reduce<RED_MAX>(mx, sm);
+        mn = T.reduce1<RED_MIN>(mn);
+        mx = T.reduce1<RED_MAX>(mx);
         if (mn <= s.delta) {
             if (s.delta != 0.0) {
                 double gm = __longlong_as_double(0x7ff0000000000000LL);
@@ -919,7 +993,7 @@ k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __
                         if (ap < 0.0) gm = fmin(gm, (s.delta - V.y[i]) / ap);          // :150-151
                     }
                 }
-                const double gamma = block_reduce<RED_MIN>(gm, sm);
+                const double gamma = T.reduce1<RED_MIN>(gm);
                 for (int i = tid; i < n; i += nt)
                     if (keep[i]) V.y[i] = V.y[i] + gamma * (alpha * V.p[i]);           // :152
             }
@@ -933,7 +1007,7 @@ k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __
                     if (yn > s.Delta) gm = fmin(gm, (s.Delta - V.y[i]) / ap);          // :155-156
                 }
             }
-            const double gamma = block_reduce<RED_MIN>(gm, sm);
+            const double gamma = T.reduce1<RED_MIN>(gm);
             for (int i = tid; i < n; i += nt)
                 if (keep[i]) V.y[i] = V.y[i] + gamma * (alpha * V.p[i]);               // :157
             to_outer = true;
@@ -951,7 +1025,7 @@ k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __
                 }
             }
             s.rho_km2 = s.rho_km1;
-            s.rho_km1 = block_reduce<RED_SUM>(a2, sm);
+            s.rho_km1 = T.reduce1<RED_SUM>(a2);
         }
     }
 
@@ -969,7 +1043,7 @@ k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __
                     acc += V.rk[i] * Zi;
                 }
             }
-            s.rho_km1 = block_reduce<RED_SUM>(acc, sm);                                 // :132
+            s.rho_km1 = T.reduce1<RED_SUM>(acc);                                 // :132
         } else {
             const double beta = s.rho_km1 / s.rho_km2;                                  // :134
             for (int i = tid; i < n; i += nt) {
@@ -992,7 +1066,7 @@ k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __
         s.phase = 0;
     }
     s.matvecs += 1;
-    __syncthreads();
+    T.finish();
     if (tid == 0) *st = s;
 }
 

@@ -1,0 +1,61 @@
+"""Host-side plumbing for row-block sharding over several B200s (one process per GPU).
+
+The data path stays in libgcxnorm.so (NCCL allgather of the n-vector after every matrix pass, on the
+context's stream); this module only (a) defines the partition, (b) moves the 128-byte ncclUniqueId between
+ranks with torch.distributed, (c) builds the per-rank DeviceMap.
+"""
+import numpy as np
+
+
+def rows_per_rank(n, world):
+    """ceil(n / world): every rank's allgather slot has this many entries (the last rank's tail is padding)."""
+    return (int(n) + int(world) - 1) // int(world)
+
+
+def row_partition(n, world, rank):
+    """(row0, nloc) of the contiguous row block owned by `rank`."""
+    rpr = rows_per_rank(n, world)
+    row0 = min(int(n), rank * rpr)
+    return row0, max(0, min(rpr, int(n) - row0))
+
+
+def padded_length(n, world):
+    return rows_per_rank(n, world) * int(world)
+
+
+def allgather_padded(local, n, world, rank, all_gather_fn):
+    """Reference semantics of the in-library exchange: `local` holds this rank's nloc results; returns the full
+    n-vector assembled from equal-size padded slots.  all_gather_fn(list_of_out_arrays, in_array) is the
+    collective (torch.distributed.all_gather on CPU tensors in the gloo tests)."""
+    rpr = rows_per_rank(n, world)
+    slot = np.zeros(rpr, dtype=local.dtype)
+    slot[: local.shape[0]] = local
+    outs = [np.zeros(rpr, dtype=local.dtype) for _ in range(world)]
+    all_gather_fn(outs, slot)
+    return np.concatenate(outs)[:n]
+
+
+def broadcast_unique_id(rank, device=None):
+    """ncclUniqueId created on rank 0 and broadcast with torch.distributed (any initialised backend)."""
+    import torch
+    import torch.distributed as tdist
+    from .device import dist_unique_id
+    backend = tdist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t = torch.tensor(list(dist_unique_id()), dtype=torch.uint8, device=dev)
+    tdist.broadcast(t, 0)
+    return bytes(t.cpu().tolist())
+
+
+def sharded_device_map(n, device=None):
+    """DeviceMap for this rank's row block, wired to the other ranks (torch.distributed must be initialised)."""
+    import torch.distributed as tdist
+    from .device import DeviceMap
+    rank, world = tdist.get_rank(), tdist.get_world_size()
+    row0, nloc = row_partition(n, world, rank)
+    if nloc == 0:
+        raise ValueError("more ranks than row blocks")
+    dist = (rank, world, broadcast_unique_id(rank)) if world > 1 else None
+    return DeviceMap(n, row0, nloc, device=device, dist=dist)

@@ -1,0 +1,82 @@
+"""CPU, world_size 2 over gloo: the host-side sharding logic (partition, padded allgather) and the sharded
+formulation of IC -- local row-block matvec, allgather of the n-vector, identical vector step on every rank
+ -- give the oracle's result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as tdist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gcmapexplorer_b200 import dist as gd      # noqa: E402
+from oracle import oracle_np as onp            # noqa: E402
+
+
+@pytest.mark.parametrize("n,world", [(10, 1), (10, 2), (11, 2), (24926, 8), (249251, 8), (5, 8)])
+def test_row_partition_covers_everything(n, world):
+    seen = 0
+    for r in range(world):
+        row0, nloc = gd.row_partition(n, world, r)
+        assert row0 == seen or nloc == 0
+        assert nloc <= gd.rows_per_rank(n, world)
+        seen += nloc
+    assert seen == n and gd.padded_length(n, world) >= n
+
+
+def _sharded_ic(rank, world, port, n, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        A = onp.synth_map(n, seed=17).astype(np.float64)
+        row0, nloc = gd.row_partition(n, world, rank)
+        Aloc = A[row0:row0 + nloc]
+
+        def ag(outs, slot):
+            touts = [torch.zeros(slot.shape[0], dtype=torch.float64) for _ in outs]
+            tdist.all_gather(touts, torch.from_numpy(slot))
+            for o, t in zip(outs, touts):
+                o[:] = t.numpy()
+
+        # the one-matvec-per-pass recurrence of k_ic_epilogue, with the matvec sharded by rows
+        v = np.ones(n)
+        B = np.ones(n)
+        cc = None
+        m = 0
+        while True:
+            t = gd.allgather_padded(Aloc @ v, n, world, rank, ag)
+            p = v * t
+            S, C = p.sum(), np.count_nonzero(p)
+            if m == 0:
+                cc, f, g = S, 1.0, 1.0
+            else:
+                f, g = np.sqrt(S / cc), cc / S
+            mean = g * S / C
+            d = g * p
+            bn = B if m == 0 else f / v
+            l1 = np.abs(B - bn).sum()
+            B = bn
+            v = np.where(d != 0, mean / (bn * np.where(d != 0, d, 1.0)), 1.0 / bn)
+            if m >= 2 and (l1 < 1e-4 or (m - 1) > 500):
+                break
+            m += 1
+        ret[rank] = (m, B)
+    finally:
+        tdist.destroy_process_group()
+
+
+def test_sharded_ic_world2_gloo_matches_oracle():
+    n, world = 203, 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_sharded_ic, args=(world, port, n, ret), nprocs=world, join=True)
+    A = onp.synth_map(n, seed=17)
+    _, Bo, passes, _ = onp.ic_fp64(A, 1e-4, 500)
+    (m0, B0), (m1, B1) = ret[0], ret[1]
+    assert m0 == m1 == passes
+    assert np.array_equal(B0, B1)                       # ranks hold bitwise identical state
+    np.testing.assert_allclose(B0, Bo, rtol=1e-10)
