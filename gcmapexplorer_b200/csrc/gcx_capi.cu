@@ -106,6 +106,9 @@ struct gcx_ctx {
     // matvec workspace
     double* ws = nullptr;
     unsigned int* ticket = nullptr;
+    double* part = nullptr;      // per-CTA partials of the fused IC pass (3 x grid)
+    int ic_fused = 1;            // 1: one cooperative launch per IC pass (k_ic_pass); 0: k_matvec + k_ic_epilogue
+    int ic_grid = 0;
     int mv_variant = 2;   // R=4 rows per band, 4 CTAs/SM: best of the sweep in profiles/r01_matvec_variants.txt
     // states
     IcState* ic_state = nullptr;
@@ -219,6 +222,16 @@ extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
     CK(cudaMalloc(&c->ticket, sizeof(unsigned int)));
     CK(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
     CK(cudaMalloc(&c->ws, sizeof(double) * (size_t)c->sm_count * 8 * 2 * 16));
+    CK(cudaMalloc(&c->part, sizeof(double) * 3 * (size_t)c->sm_count * 8));
+    {
+        int occ = 0, coop = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ic_pass<4, 4>, MV_THREADS, 0));
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        c->ic_grid = c->sm_count * std::min(occ, 4);
+        if (!coop || occ < 1) c->ic_fused = 0;
+        const char* f = getenv("GCX_IC_FUSED");
+        if (f) c->ic_fused = atoi(f) && coop && occ >= 1;
+    }
     CK(cudaHostAlloc(&c->h_state, 4096, cudaHostAllocDefault));
     CK(cudaEventCreate(&c->run_a));
     CK(cudaEventCreate(&c->run_b));
@@ -248,7 +261,7 @@ extern "C" int gcx_ctx_destroy(gcx_ctx* c) {
     free_map(c);
     for (auto& p : c->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
-    cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->mm); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws);
+    cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->mm); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws); cudaFree(c->part);
     cudaFreeHost(c->h_state);
     for (int i = 0; i < 2; ++i) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
@@ -656,7 +669,8 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
     k_ic_init<<<32, EP_THREADS, 0, c->stream>>>(c->ic_state, (int)c->nv, c->keep, c->vz, c->vB, tol, iteration);
     CK(cudaGetLastError());
     c->launches += 1;
-    auto step = [&]() -> int {
+    int n4 = (int)(c->ld / 4), nloc = (int)c->nloc, row0 = (int)c->row0;
+    auto step_split = [&]() -> int {
         CKR(matvec(c, c->mv_variant, c->vz, c->vq, &c->ic_state->done));
         CKR(allgather_f64(c, c->vq));
         {
@@ -666,8 +680,19 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         CK(cudaGetLastError());
         return 0;
     };
+    auto step_fused = [&]() -> int {
+        void* args[] = {(void*)&c->A, (void*)&c->ld, (void*)&nloc, (void*)&n4, (void*)&n, (void*)&row0, (void*)&c->keep, (void*)&c->vq,
+                        (void*)&c->vz, (void*)&c->vB, (void*)&c->ws, (void*)&c->ticket, (void*)&c->ic_state, (void*)&c->part};
+        {
+            ProfScope ps(c, 0);
+            CK(cudaLaunchCooperativeKernel((void*)k_ic_pass<4, 4>, dim3(c->ic_grid), dim3(MV_THREADS), args, 0, c->stream));
+        }
+        CKR(allgather_f64(c, c->vq));
+        return 0;
+    };
+    auto step = [&]() -> int { return c->ic_fused ? step_fused() : step_split(); };
     IcState fin;
-    CKR(iterate<IcState>(c, c->ic_state, iteration + 3, step, &fin));
+    CKR(iterate<IcState>(c, c->ic_state, iteration + 4, step, &fin));
     k_ic_scale<<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>((int)c->nv, n, c->keep, c->vB, c->vscale);
     CK(cudaGetLastError());
     c->launches += 1;

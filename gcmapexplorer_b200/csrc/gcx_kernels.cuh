@@ -871,6 +871,195 @@ k_ic_epilogue(IcState* st, int n, const uint8_t* __restrict__ keep, const double
     T.finish();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused IC pass: ONE cooperative launch per iteration = [vector step that closes pass m-1] + [matvec m].
+//   P1  p_i = v_i t_i ; per-CTA partial (S', count)                      -> grid barrier
+//   P2  every CTA folds the partials in CTA order (bitwise identical scalars everywhere), then for its
+//       bins: B_{k+1} = f / v, L1 change, next v ; per-CTA partial L1     -> grid barrier (v complete)
+//   P3  fold the L1 partials; converged -> record state, whole grid exits
+//   P4  the matvec main loop of k_matvec with z = v ; last CTA folds split bands and bumps the counter
+// Multi-GPU: the host enqueues one NCCL allgather of t after each launch; P1..P3 then run redundantly on
+// every rank on the same gathered vector with the same grid, so all ranks stay bitwise identical.
+// `part` holds 3 x gridDim.x doubles.
+// ---------------------------------------------------------------------------------------------------
+template <int R, int OCC>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
+k_ic_pass(const float* __restrict__ A, long long ld, int nloc, int n4, int n, int row0, const uint8_t* __restrict__ keep,
+          double* t, double* v, double* B, double* ws, unsigned int* ticket, IcState* st, double* part) {
+    namespace cg = cooperative_groups;
+    if (st->done) return;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[32];
+    __shared__ double red[MV_THREADS / 32][R];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int m = st->matvecs;                  // matvecs completed so far; t holds the result of matvec m-1
+    const int gth = bid * MV_THREADS + tid, nth = G * MV_THREADS;
+
+    if (m > 0) {
+        const int mm = m - 1;
+        const double cc_prev = st->cc, tol = st->tol;
+        const int max_iter = st->max_iter;
+        // ---- P1 ----
+        double s = 0.0, c = 0.0;
+        for (int i = gth; i < n; i += nth) {
+            if (keep[i]) {
+                const double p = v[i] * t[i];
+                s += p;
+                c += (p != 0.0) ? 1.0 : 0.0;
+            }
+        }
+        s = block_reduce<RED_SUM>(s, sm);
+        c = block_reduce<RED_SUM>(c, sm);
+        if (tid == 0) {
+            part[bid] = s;
+            part[G + bid] = c;
+        }
+        grid.sync();
+        // ---- P2 ----
+        double a0 = 0.0, a1 = 0.0;
+        for (int b = tid; b < G; b += MV_THREADS) {
+            a0 += __ldcg(part + b);
+            a1 += __ldcg(part + G + b);
+        }
+        const double S = block_reduce<RED_SUM>(a0, sm), C = block_reduce<RED_SUM>(a1, sm);
+        const double cc = (mm == 0) ? S : cc_prev;          // contact_count, lib/normalizeCore.pyx:36
+        const double f = (mm == 0) ? 1.0 : sqrt(S / cc);    // :52
+        const double g = (mm == 0) ? 1.0 : cc / S;          // :53
+        const double mean = g * S / C;                      // :44
+        double l1 = 0.0;
+        for (int i = gth; i < n; i += nth) {
+            if (keep[i]) {
+                const double vi = v[i];
+                const double d = g * (vi * t[i]);           // next pass's raw column sum, :42
+                double bn = B[i];
+                if (mm > 0) {
+                    bn = f / vi;                            // (B dB) sqrt(S'/cc), :51-52
+                    l1 += fabs(B[i] - bn);                  // :56
+                    B[i] = bn;
+                }
+                v[i] = (d != 0.0) ? mean / (bn * d) : 1.0 / bn;     // 1/(B dB), :44-45
+            }
+        }
+        l1 = block_reduce<RED_SUM>(l1, sm);
+        if (tid == 0) part[2 * G + bid] = l1;
+        grid.sync();
+        // ---- P3 ----
+        double a2 = 0.0;
+        for (int b = tid; b < G; b += MV_THREADS) a2 += __ldcg(part + 2 * G + b);
+        const double L1 = block_reduce<RED_SUM>(a2, sm);
+        const bool done = (mm >= 2) && (L1 < tol || (mm - 1) > max_iter);       // :55-57
+        if (bid == 0 && tid == 0) {
+            st->cc = cc; st->S = S; st->l1 = L1; st->mean = mean; st->cnt = (int)C;
+            st->pass = mm; st->done = done ? 1 : 0;
+        }
+        if (done) return;
+    }
+
+    // ---- P4: matvec (same decomposition and arithmetic as k_matvec; z = v is read with coherent loads
+    //      because this kernel wrote it before the grid barrier) ----
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, GG = G, cta = bid;
+    long long u = unit_begin(cta, U, GG);
+    const long long u1 = unit_begin(cta + 1, U, GG);
+    const int bfirst = (int)(u / nch);
+    const double2* z2 = reinterpret_cast<const double2*>(v);
+    double* q = t + row0;
+    while (u < u1) {
+        const int b = (int)(u / nch);
+        const int k0 = (int)(u - (long long)b * nch);
+        const long long rem = u1 - u;
+        const int k1 = (int)(((long long)(nch - k0) < rem) ? nch : (k0 + rem));
+        const float4* rowp[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            int r = b * R + rr;
+            r = r < nloc ? r : nloc - 1;
+            rowp[rr] = reinterpret_cast<const float4*>(A + (long long)r * ld);
+        }
+        double acc[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) acc[rr] = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            const int c4 = k * MV_THREADS + tid;
+            if (c4 < n4) {
+                float4 a[R];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) a[rr] = ld_stream_f4(rowp[rr] + c4);
+                const double2 za = z2[2 * c4], zb = z2[2 * c4 + 1];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    acc[rr] = fma((double)a[rr].x, za.x, acc[rr]);
+                    acc[rr] = fma((double)a[rr].y, za.y, acc[rr]);
+                    acc[rr] = fma((double)a[rr].z, zb.x, acc[rr]);
+                    acc[rr] = fma((double)a[rr].w, zb.y, acc[rr]);
+                }
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) acc[rr] = warp_sum(acc[rr]);
+        if (lane == 0) {
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) red[warp][rr] = acc[rr];
+        }
+        __syncthreads();
+        if (tid < R) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < MV_THREADS / 32; ++w) s += red[w][tid];
+            const int r = b * R + tid;
+            if (k0 == 0 && k1 == nch) {
+                if (r < nloc) q[r] = s;
+            } else {
+                ws[((long long)cta * 2 + (b == bfirst ? 0 : 1)) * R + tid] = s;
+            }
+        }
+        __syncthreads();
+        u += (k1 - k0);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned int)(G - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (long long cb = 1 + tid; cb < GG; cb += MV_THREADS) {
+        const long long ub = unit_begin(cb, U, GG);
+        const int b = (int)(ub / nch);
+        const long long band0 = (long long)b * nch, band1 = band0 + nch;
+        if (ub == band0 || ub >= U) continue;
+        const long long ubp = unit_begin(cb - 1, U, GG);
+        if (ubp > band0) continue;
+        double s[R];
+        {
+            const int slot = (b == (int)(ubp / nch)) ? 0 : 1;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) s[rr] = __ldcg(ws + ((cb - 1) * 2 + slot) * R + rr);
+        }
+        long long cc2 = cb, ucc = ub;
+        while (cc2 < GG && ucc < band1) {
+            const long long unext = unit_begin(cc2 + 1, U, GG);
+            if (unext > ucc) {
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) s[rr] += __ldcg(ws + (cc2 * 2) * R + rr);
+            }
+            ++cc2;
+            ucc = unext;
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r < nloc) q[r] = s[rr];
+        }
+    }
+    if (tid == 0) {
+        *ticket = 0u;
+        st->matvecs = m + 1;
+    }
+}
+
 // s_i = keep_i ? 1/B_i : 0 -- the symmetric scale for the final apply
 __global__ void k_ic_scale(int nv, int n, const uint8_t* __restrict__ keep, const double* __restrict__ B, double* s) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x)
