@@ -759,8 +759,21 @@ static int mm_end(gcx_ctx* c, float* minv, float* maxv) {
     return 0;
 }
 
-static const int EW_R = 4;
-static int ew_grid(gcx_ctx* c) { return c->sm_count * 3; }
+// elementwise kernels: (rows per band, CTAs per SM) variants, selectable with GCX_EW_VARIANT for sweeps
+static int ew_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GCX_EW_VARIANT"); v = e ? atoi(e) : 3; }   // default R=4, 4 CTAs/SM (profiles/r01_ew_variants.txt)
+    return v;
+}
+#define EW_DISPATCH(KERNEL, ...)                                                                                   \
+    switch (ew_variant()) {                                                                                        \
+        case 1: KERNEL<8, 2><<<c->sm_count * 2, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;                    \
+        case 2: KERNEL<8, 3><<<c->sm_count * 3, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;                    \
+        case 3: KERNEL<4, 4><<<c->sm_count * 4, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;                    \
+        case 4: KERNEL<4, 6><<<c->sm_count * 6, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;                    \
+        case 5: KERNEL<2, 8><<<c->sm_count * 8, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;                    \
+        default: KERNEL<4, 3><<<c->sm_count * 3, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;                   \
+    }
 
 extern "C" int gcx_apply_sym_scale(gcx_ctx* c, const double* s, int masked_mode, int in_place, float* minv, float* maxv) {
     CKR(need_map(c));
@@ -776,7 +789,7 @@ extern "C" int gcx_apply_sym_scale(gcx_ctx* c, const double* s, int masked_mode,
     CKR(mm_begin(c));
     {
         ProfScope ps(c, 1);
-        k_apply_sym<EW_R><<<ew_grid(c), MV_THREADS, 0, c->stream>>>(c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->row0, c->vscale, c->keep, masked_mode, c->mm);
+        EW_DISPATCH(k_apply_sym, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->row0, c->vscale, c->keep, masked_mode, c->mm)
     }
     CK(cudaGetLastError());
     if (in_place) c->have_rowsum = false;
@@ -800,7 +813,7 @@ extern "C" int gcx_vc_run(gcx_ctx* c, int sqroot, int in_place, float* minv, flo
     CKR(mm_begin(c));
     {
         ProfScope ps(c, 2);
-        k_vc_apply<EW_R><<<ew_grid(c), MV_THREADS, 0, c->stream>>>(c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->csum32, c->keep, sqroot, c->mm);
+        EW_DISPATCH(k_vc_apply, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->csum32, c->keep, sqroot, c->mm)
     }
     CK(cudaGetLastError());
     if (csum) CK(cudaMemcpyAsync(csum, c->csum32, sizeof(float) * c->n, cudaMemcpyDeviceToHost, c->stream));
@@ -902,7 +915,7 @@ extern "C" int gcx_diag_apply(gcx_ctx* c, const double* avg, int subtract, int i
     CKR(mm_begin(c));
     {
         ProfScope ps(c, 5);
-        k_diag_apply<EW_R><<<ew_grid(c), MV_THREADS, 0, c->stream>>>(c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->vavg, subtract, c->mm);
+        EW_DISPATCH(k_diag_apply, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->vavg, subtract, c->mm)
     }
     CK(cudaGetLastError());
     if (in_place) c->have_rowsum = false;

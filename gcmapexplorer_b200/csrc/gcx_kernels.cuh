@@ -340,13 +340,18 @@ struct MinMax {
     unsigned int max_all;  // f2ord-encoded max (init 0)
 };
 
-__device__ __forceinline__ void mm_update(float v, unsigned int& mn, unsigned int& mx) {
-    const unsigned int o = f2ord(v);
-    if (v != 0.f && o < mn) mn = o;
-    if (o > mx) mx = o;
+// per-thread tracking stays in the float domain (one FMNMX each); the order-preserving encoding is applied
+// once per thread at commit.  mn starts at +inf (no non-zero seen), mx at -inf (nothing seen).
+#define GCX_PINF __int_as_float(0x7f800000)
+#define GCX_NINF __int_as_float(0xff800000)
+__device__ __forceinline__ void mm_update(float v, float& mn, float& mx) {
+    if (v != 0.f) mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
 }
 
-__device__ __forceinline__ void mm_commit(unsigned int mn, unsigned int mx, MinMax* out) {
+__device__ __forceinline__ void mm_commit(float fmn, float fmx, MinMax* out) {
+    unsigned int mn = fmn == GCX_PINF ? 0xffffffffu : f2ord(fmn);
+    unsigned int mx = fmx == GCX_NINF ? 0u : f2ord(fmx);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -362,8 +367,8 @@ __device__ __forceinline__ void mm_commit(unsigned int mn, unsigned int mx, MinM
 // Replaces GenNormMatrixRAM (lib/normalizeKnightRuiz.pyx:207-227) and the net effect of
 // lib/normalizeCore.pyx:48-53 + the write-back of lib/normalizer.py:601-613.
 // Algorithmic bytes: 8 * nloc * n.  min/max over the kept x kept block only.
-template <int R>
-__global__ void __launch_bounds__(MV_THREADS, 3)
+template <int R, int OCC>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
 k_apply_sym(const float* __restrict__ A, float* __restrict__ Out, long long ld, int nloc, int n4, int row0,
             const double* __restrict__ s, const uint8_t* __restrict__ keep, int passthrough, MinMax* mm) {
     const int tid = threadIdx.x;
@@ -371,28 +376,28 @@ k_apply_sym(const float* __restrict__ A, float* __restrict__ Out, long long ld, 
     const int nb = (nloc + R - 1) / R;
     const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
     const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
-    unsigned int mn = 0xffffffffu, mx = 0u;
+    float mn = GCX_PINF, mx = GCX_NINF;
     const double2* __restrict__ s2 = reinterpret_cast<const double2*>(s);
     const uchar4* __restrict__ k4 = reinterpret_cast<const uchar4*>(keep);
     for (long long u = u0; u < u1; ++u) {
         const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
         const int c4 = k * MV_THREADS + tid;
         if (c4 >= n4) continue;
-        const double2 sa = __ldg(s2 + 2 * c4), sb = __ldg(s2 + 2 * c4 + 1);
-        const uchar4 kc = __ldg(k4 + c4);
-        const double sc[4] = {sa.x, sa.y, sb.x, sb.y};
-        const unsigned char kcol[4] = {kc.x, kc.y, kc.z, kc.w};
-        const int j0 = 4 * c4;
         float4 a[R];
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             const int r = b * R + rr;
             if (r < nloc) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(A + (long long)r * ld) + c4);
         }
+        const double2 sa = __ldg(s2 + 2 * c4), sb = __ldg(s2 + 2 * c4 + 1);
+        const uchar4 kc = __ldg(k4 + c4);
+        const double sc[4] = {sa.x, sa.y, sb.x, sb.y};
+        const unsigned char kcol[4] = {kc.x, kc.y, kc.z, kc.w};
+        const int j0 = 4 * c4;
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             const int r = b * R + rr;
-            if (r >= nloc) continue;
+            if (r >= nloc) break;
             const int i = row0 + r;
             const double si = __ldg(s + i);
             const bool ki = __ldg(keep + i) != 0;
@@ -402,8 +407,12 @@ k_apply_sym(const float* __restrict__ A, float* __restrict__ Out, long long ld, 
             for (int e = 0; e < 4; ++e) {
                 const int j = j0 + e;
                 if (ki && kcol[e]) {
-                    const double lo = j < i ? sc[e] : si, hi = j < i ? si : sc[e];
-                    o[e] = (float)((lo * (double)in[e]) * hi);
+                    if (in[e] != 0.f) {     // (lo*0)*hi = 0: zeros (most of a Hi-C map) skip the fp64 work
+                        const double lo = j < i ? sc[e] : si, hi = j < i ? si : sc[e];
+                        o[e] = (float)((lo * (double)in[e]) * hi);
+                    } else {
+                        o[e] = in[e];
+                    }
                     mm_update(o[e], mn, mx);
                 } else {
                     o[e] = passthrough ? in[e] : 0.f;
@@ -418,8 +427,8 @@ k_apply_sym(const float* __restrict__ A, float* __restrict__ Out, long long ld, 
 // K5: vanilla coverage in the reference's fp32 arithmetic (lib/normalizeCore.pyx:72-86):
 // out = A; kept row i: out = fl32(out / c_i); kept column j: out = fl32(out / c_j); optional sqrt.
 // Algorithmic bytes: 8 * nloc * n (+ the row-sum pass of k_row_stats = 12 n^2 in total).
-template <int R>
-__global__ void __launch_bounds__(MV_THREADS, 3)
+template <int R, int OCC>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
 k_vc_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld, int nloc, int n4, int n, int row0,
            const float* __restrict__ csum, const uint8_t* __restrict__ keep, int sqroot, MinMax* mm) {
     const int tid = threadIdx.x;
@@ -427,28 +436,28 @@ k_vc_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld, i
     const int nb = (nloc + R - 1) / R;
     const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
     const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
-    unsigned int mn = 0xffffffffu, mx = 0u;
+    float mn = GCX_PINF, mx = GCX_NINF;
     const float4* __restrict__ c4v = reinterpret_cast<const float4*>(csum);
     const uchar4* __restrict__ k4 = reinterpret_cast<const uchar4*>(keep);
     for (long long u = u0; u < u1; ++u) {
         const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
         const int c4 = k * MV_THREADS + tid;
         if (c4 >= n4) continue;
-        const float4 cs = __ldg(c4v + c4);
-        const uchar4 kc = __ldg(k4 + c4);
-        const float cc[4] = {cs.x, cs.y, cs.z, cs.w};
-        const unsigned char kcol[4] = {kc.x, kc.y, kc.z, kc.w};
-        const int j0 = 4 * c4;
         float4 a[R];
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             const int r = b * R + rr;
             if (r < nloc) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(A + (long long)r * ld) + c4);
         }
+        const float4 cs = __ldg(c4v + c4);
+        const uchar4 kc = __ldg(k4 + c4);
+        const float cc[4] = {cs.x, cs.y, cs.z, cs.w};
+        const unsigned char kcol[4] = {kc.x, kc.y, kc.z, kc.w};
+        const int j0 = 4 * c4;
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             const int r = b * R + rr;
-            if (r >= nloc) continue;
+            if (r >= nloc) break;
             const int i = row0 + r;
             const float ci = __ldg(csum + i);
             const bool ki = __ldg(keep + i) != 0;
@@ -473,8 +482,8 @@ k_vc_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld, i
 
 // K7: distance-frequency apply (lib/normalizeCore.pyx:91-170): divide or subtract by avg[|i-j|].
 // Algorithmic bytes: 8 * nloc * n.
-template <int R>
-__global__ void __launch_bounds__(MV_THREADS, 3)
+template <int R, int OCC>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
 k_diag_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld, int nloc, int n4, int n, int row0,
              const double* __restrict__ avg, int subtract, MinMax* mm) {
     const int tid = threadIdx.x;
@@ -482,22 +491,22 @@ k_diag_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld,
     const int nb = (nloc + R - 1) / R;
     const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
     const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
-    unsigned int mn = 0xffffffffu, mx = 0u;
+    float mn = GCX_PINF, mx = GCX_NINF;
     for (long long u = u0; u < u1; ++u) {
         const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
         const int c4 = k * MV_THREADS + tid;
         if (c4 >= n4) continue;
-        const int j0 = 4 * c4;
         float4 a[R];
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             const int r = b * R + rr;
             if (r < nloc) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(A + (long long)r * ld) + c4);
         }
+        const int j0 = 4 * c4;
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             const int r = b * R + rr;
-            if (r >= nloc) continue;
+            if (r >= nloc) break;
             const int i = row0 + r;
             const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
             float o[4];
@@ -506,9 +515,10 @@ k_diag_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld,
                 const int j = j0 + e;
                 float v = in[e];
                 if (j < n) {
+                    // a zero entry stays zero in both modes (0/avg = 0; :142-144 forces 0 for o-e): skip the lookup
                     const int d = i > j ? i - j : j - i;
-                    const double av = __ldg(avg + d);
-                    if (av != 0.0 && (subtract || in[e] != 0.f)) {     // 0/avg = 0: zeros skip the fp64 divide
+                    const double av = in[e] != 0.f ? __ldg(avg + d) : 0.0;
+                    if (av != 0.0) {
                         if (!subtract) {
                             v = (float)((double)in[e] / av);                       // :105-108, :114-117
                         } else {
