@@ -144,7 +144,7 @@ def run_b200(args):
     dm = gx.DeviceMap(n, row0, nloc, device=local, dist=dist)
     dm.synth(seed=args.seed, scale=200.0, alpha=1.0, empty_frac=0.01)
     peak, peak_kind = measured_peak()
-    kr_mode = args.workload == "chr1_5kb_kr"
+    kr_mode = args.workload == "chr1_5kb_kr" or args.kr
 
     def barrier():
         dm.sync()
@@ -267,7 +267,7 @@ def run_b200(args):
     if rank == 0:
         line = {
             "metric": "IC+VC normalization throughput, chr1 10 kb (algorithmic HBM GB/s over the whole step; time-to-converge alongside)"
-                      if not kr_mode else "KR normalization throughput, chr1 5 kb (algorithmic HBM GB/s)",
+                      if not kr_mode else "KR normalization throughput (algorithmic HBM GB/s over the whole step)",
             "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 accumulate / f32 storage", "data": "synthetic (device-generated Poisson power-law map, 1% empty bins)",
@@ -281,6 +281,57 @@ def run_b200(args):
     dm.close()
     if tdist is not None:
         tdist.destroy_process_group()
+
+
+WG_25KB_BINS = [9971, 9728, 7921, 7647, 7237, 6845, 6366, 5855, 5649, 5422, 5401, 5355, 4607, 4294, 4102, 3615, 3248,
+                3124, 2366, 2522, 1926, 2053, 6211, 2375]     # hg19 chr1..22, X, Y at 25 kb
+
+
+def run_mcfs_wg(args):
+    """BASELINE configs[3]: distance-frequency (MCFS o/e) over the 24 whole-genome maps at 25 kb on one GPU.
+    Maps are device-generated and resident; a step = per-diagonal stats + apply for all 24 maps."""
+    from gcmapexplorer_b200 import device as gx
+    stats = args.mcfs_stats
+    maps = []
+    for k, n in enumerate(WG_25KB_BINS):
+        dm = gx.DeviceMap(n, device=int(os.environ.get("LOCAL_RANK", "0")))
+        dm.synth(seed=25000 + k, scale=200.0, alpha=1.0, empty_frac=0.01)
+        maps.append(dm)
+    peak, peak_kind = measured_peak()
+
+    def step():
+        for dm in maps:
+            dm.diag_stats(stats)
+            dm.diag_apply(None, subtract=False, in_place=False)
+    for _ in range(args.warmup):
+        step()
+    for dm in maps:
+        dm.profile(True); dm.profile_read(True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    for dm in maps:
+        dm.sync()
+    sec = (time.perf_counter() - t0) / args.steps
+    red_ms = app_ms = 0.0
+    launches = 0
+    for dm in maps:
+        p = dm.profile_read(True)
+        red_ms += p["diag_reduce"]["ms"] / args.steps
+        app_ms += p["diag_apply"]["ms"] / args.steps
+    nn = float(sum(n * n for n in WG_25KB_BINS))
+    traversals = 5 if stats == "median" else 1
+    bytes_step = (2.0 * traversals + 8.0) * nn
+    line = {"metric": "MCFS (distance-frequency o/e, stats=%s) throughput, whole genome @ 25 kb, 24 maps (algorithmic GB/s)" % stats,
+            "value": round(bytes_step / sec / 1e9, 1), "unit": "GB/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 stats / f32 storage",
+            "data": "synthetic (device-generated)", "config": {"workload": "24 maps, sum n^2*4 = %.3f GB" % (4 * nn / 1e9), "stats": stats},
+            "kernel_ms_per_step": {"diag_reduce": round(red_ms, 3), "diag_apply": round(app_ms, 3)},
+            "roofline": {"kernel": "k_diag_apply", "bound": "hbm", "achieved": round(8.0 * nn / (app_ms * 1e-3) / 1e9, 1), "peak": peak, "peak_kind": peak_kind,
+                         "unit": "GB/s", "frac": round(8.0 * nn / (app_ms * 1e-3) / 1e9 / peak, 4), "traffic": None}}
+    print(json.dumps(line))
+    for dm in maps:
+        dm.close()
 
 
 def psutil_avail():
@@ -392,16 +443,20 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "chr1_10kb", "chr1_5kb_kr", "chr1_1kb"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "chr1_10kb", "chr1_5kb_kr", "chr1_1kb", "wg_25kb_mcfs"])
+    ap.add_argument("--mcfs-stats", default="median", choices=["median", "mean"])
     ap.add_argument("--n", type=int, default=0, help="override the number of bins (quick checks)")
     ap.add_argument("--seed", type=int, default=110)
     ap.add_argument("--ref-passes", type=int, default=60, help="IC passes the reference sample is scaled to (fp64-converged count)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kr", action="store_true", help="run KR instead of IC + VC on the selected workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "wg_25kb_mcfs":
+        run_mcfs_wg(args)
     else:
         run_b200(args)
 

@@ -106,6 +106,8 @@ struct gcx_ctx {
     // matvec workspace
     double* ws = nullptr;
     unsigned int* ticket = nullptr;
+    void* scratch = nullptr;     // grow-only arena for the per-diagonal statistics (avoids cudaMalloc/cudaFree per call)
+    size_t scratch_bytes = 0;
     double* part = nullptr;      // per-CTA partials of the fused IC pass (3 x grid)
     int ic_fused = 1;            // 1: one cooperative launch per IC pass (k_ic_pass); 0: k_matvec + k_ic_epilogue
     int ic_grid = 0;
@@ -261,7 +263,7 @@ extern "C" int gcx_ctx_destroy(gcx_ctx* c) {
     free_map(c);
     for (auto& p : c->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
-    cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->mm); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws); cudaFree(c->part);
+    cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->mm); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws); cudaFree(c->part); cudaFree(c->scratch);
     cudaFreeHost(c->h_state);
     for (int i = 0; i < 2; ++i) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
@@ -341,6 +343,17 @@ static int need_map(gcx_ctx* c) {
 
 static int ensure_out(gcx_ctx* c) {
     if (!c->Out) CK(cudaMalloc(&c->Out, sizeof(float) * (size_t)c->nloc * c->ld));
+    return 0;
+}
+
+static int ensure_scratch(gcx_ctx* c, size_t bytes) {
+    if (bytes <= c->scratch_bytes) return 0;
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->scratch) CK(cudaFree(c->scratch));
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
+    CK(cudaMalloc(&c->scratch, bytes));
+    c->scratch_bytes = bytes;
     return 0;
 }
 
@@ -825,74 +838,61 @@ static dim3 diag_grid(gcx_ctx* c) {
     return dim3((unsigned)((c->n + MV_THREADS - 1) / MV_THREADS), (unsigned)((c->nloc + DIAG_RB - 1) / DIAG_RB));
 }
 
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
 static int diag_mean(gcx_ctx* c) {
     const int n = (int)c->n, nbands = (int)((c->nloc + DIAG_RB - 1) / DIAG_RB);
-    double* psum = nullptr;
-    int* pcnt = nullptr;
-    double* sumcnt = nullptr;     // [2][nv]
-    CK(cudaMalloc(&psum, sizeof(double) * (size_t)nbands * n));
-    CK(cudaMalloc(&pcnt, sizeof(int) * (size_t)nbands * n));
-    CK(cudaMalloc(&sumcnt, sizeof(double) * 2 * (size_t)c->nv));
-    int rc = 0;
-    do {
-        {
-            ProfScope ps(c, 4);
-            k_diag_mean_partial<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, psum, pcnt);
-        }
-        k_diag_mean_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(nbands, n, (int)c->row0, psum, pcnt, sumcnt, sumcnt + c->nv);
-        c->launches += 1;
-        if (c->world > 1) {
-            int e = g_nccl.AllReduce(sumcnt, sumcnt, 2 * (size_t)c->nv, ncclFloat64, ncclSum, c->comm, c->stream);
-            if (e) { rc = fail("ncclAllReduce: %s", g_nccl.GetErrorString(e)); break; }
-        }
-        k_diag_mean_final<<<(n + 255) / 256, 256, 0, c->stream>>>(n, sumcnt, sumcnt + c->nv, c->vavg);
-        c->launches += 1;
-        cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(c->stream);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail("diag mean: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    } while (0);
-    cudaFree(psum); cudaFree(pcnt); cudaFree(sumcnt);
-    return rc;
+    const size_t b_psum = align256(sizeof(double) * (size_t)nbands * n), b_pcnt = align256(sizeof(int) * (size_t)nbands * n),
+                 b_sc = align256(sizeof(double) * 2 * (size_t)c->nv);
+    CKR(ensure_scratch(c, b_psum + b_pcnt + b_sc));
+    double* psum = (double*)c->scratch;
+    int* pcnt = (int*)((char*)c->scratch + b_psum);
+    double* sumcnt = (double*)((char*)c->scratch + b_psum + b_pcnt);     // [2][nv]
+    {
+        ProfScope ps(c, 4);
+        k_diag_mean_partial<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, psum, pcnt);
+    }
+    CK(cudaGetLastError());
+    k_diag_mean_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(nbands, n, (int)c->row0, psum, pcnt, sumcnt, sumcnt + c->nv);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    if (c->world > 1) NK(g_nccl.AllReduce(sumcnt, sumcnt, 2 * (size_t)c->nv, ncclFloat64, ncclSum, c->comm, c->stream));
+    k_diag_mean_final<<<(n + 255) / 256, 256, 0, c->stream>>>(n, sumcnt, sumcnt + c->nv, c->vavg);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    return 0;
 }
 
 static int diag_median(gcx_ctx* c) {
     const int n = (int)c->n;
+    const size_t b_hist = align256(sizeof(unsigned int) * 256 * (size_t)n), b_small = align256(sizeof(unsigned int) * 5 * (size_t)n);
+    CKR(ensure_scratch(c, b_hist + b_small));
     DiagSel S{};
-    unsigned int* small = nullptr;     // prefix, krem, cnt, need, next
-    CK(cudaMalloc(&S.hist, sizeof(unsigned int) * 256 * (size_t)n));
-    CK(cudaMalloc(&small, sizeof(unsigned int) * 5 * (size_t)n));
+    S.hist = (unsigned int*)c->scratch;
+    unsigned int* small = (unsigned int*)((char*)c->scratch + b_hist);     // prefix, krem, cnt, need, next
     S.prefix = small; S.krem = small + n; S.cnt = small + 2 * (size_t)n; S.need = small + 3 * (size_t)n; S.next = small + 4 * (size_t)n;
-    int rc = 0;
-    do {
-        cudaMemsetAsync(S.hist, 0, sizeof(unsigned int) * 256 * (size_t)n, c->stream);
-        cudaMemsetAsync(small, 0, sizeof(unsigned int) * 5 * (size_t)n, c->stream);
-        for (int pass = 0; pass < 4 && rc == 0; ++pass) {
-            {
-                ProfScope ps(c, 4);
-                k_diag_hist<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, pass, S);
-            }
-            if (c->world > 1) {
-                int e = g_nccl.AllReduce(S.hist, S.hist, 256 * (size_t)n, ncclUint32, ncclSum, c->comm, c->stream);
-                if (e) { rc = fail("ncclAllReduce: %s", g_nccl.GetErrorString(e)); break; }
-            }
-            k_diag_select<<<(int)(((long long)n * 32 + MV_THREADS - 1) / MV_THREADS), MV_THREADS, 0, c->stream>>>(n, pass, S);
-            c->launches += 1;
-        }
-        if (rc) break;
+    CK(cudaMemsetAsync(c->scratch, 0, b_hist + b_small, c->stream));
+    for (int pass = 0; pass < 4; ++pass) {
         {
             ProfScope ps(c, 4);
-            k_diag_next<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, S);
+            k_diag_hist<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, pass, S);
         }
-        if (c->world > 1) {
-            int e = g_nccl.AllReduce(S.next, S.next, (size_t)n, ncclUint32, ncclMin, c->comm, c->stream);
-            if (e) { rc = fail("ncclAllReduce: %s", g_nccl.GetErrorString(e)); break; }
-        }
-        k_diag_median_final<<<(n + 255) / 256, 256, 0, c->stream>>>(n, S, c->vavg);
+        CK(cudaGetLastError());
+        if (c->world > 1) NK(g_nccl.AllReduce(S.hist, S.hist, 256 * (size_t)n, ncclUint32, ncclSum, c->comm, c->stream));
+        k_diag_select<<<(int)(((long long)n * 32 + MV_THREADS - 1) / MV_THREADS), MV_THREADS, 0, c->stream>>>(n, pass, S);
+        CK(cudaGetLastError());
         c->launches += 1;
-        cudaError_t e1 = cudaGetLastError(), e2 = cudaStreamSynchronize(c->stream);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail("diag median: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    } while (0);
-    cudaFree(S.hist); cudaFree(small);
-    return rc;
+    }
+    {
+        ProfScope ps(c, 4);
+        k_diag_next<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, S);
+    }
+    CK(cudaGetLastError());
+    if (c->world > 1) NK(g_nccl.AllReduce(S.next, S.next, (size_t)n, ncclUint32, ncclMin, c->comm, c->stream));
+    k_diag_median_final<<<(n + 255) / 256, 256, 0, c->stream>>>(n, S, c->vavg);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    return 0;
 }
 
 extern "C" int gcx_diag_stats(gcx_ctx* c, int median, double* avg) {
