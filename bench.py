@@ -261,8 +261,11 @@ def run_b200(args):
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and host_map is not None and not kr_mode:
-        cpu = cpu_reference_sample(host_map, mv - 1, budget_s=args.cpu_budget)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and host_map is not None:
+        if kr_mode:
+            cpu = cpu_reference_sample_kr(host_map, mv, bytes_step)
+        else:
+            cpu = cpu_reference_sample(host_map, mv - 1, budget_s=args.cpu_budget)
 
     if rank == 0:
         line = {
@@ -329,6 +332,10 @@ def run_mcfs_wg(args):
             "kernel_ms_per_step": {"diag_reduce": round(red_ms, 3), "diag_apply": round(app_ms, 3)},
             "roofline": {"kernel": "k_diag_apply", "bound": "hbm", "achieved": round(8.0 * nn / (app_ms * 1e-3) / 1e9, 1), "peak": peak, "peak_kind": peak_kind,
                          "unit": "GB/s", "frac": round(8.0 * nn / (app_ms * 1e-3) / 1e9 / peak, 4), "traffic": None}}
+    if not args.no_cpu_baseline:
+        cpu = cpu_reference_sample_mcfs(stats, nn)
+        cpu["value"] = round(bytes_step / cpu["seconds_per_step"] / 1e9, 4)
+        line["cpu_baseline"] = cpu
     print(json.dumps(line))
     for dm in maps:
         dm.close()
@@ -391,6 +398,51 @@ def cpu_reference_sample(host_map, passes_same_work, budget_s=25.0):
             "sample": f"IC: 2 passes of the reference core on the full n={n} map (single-threaded NumPy), scaled to {passes_same_work} passes "
                       f"(the fp64-converged count; the as-is fp32 reference stalls above tol and runs {REF_IC_CAP_PASSES} = its cap, SURVEY.md fact 3); "
                       f"mask + VC: reference cores on the leading {ns}x{ns} block, scaled by (n/{ns})^2"}
+
+
+def cpu_reference_sample_kr(host_map, matvecs, bytes_step):
+    """KR on the CPU is np.dot(float32 A, float64 x) per matrix-vector product (lib/normalizeKnightRuiz.pyx:120,139,169),
+    which NumPy evaluates by materialising a float64 copy of A and calling OpenBLAS dgemv.  Times 2 products on the full
+    map after one warm-up and scales by the product count (lower bound: compaction, vector algebra and
+    GenNormMatrixRAM's temp files are left out)."""
+    n = host_map.shape[0]
+    x = np.ones((n, 1))
+    np.dot(host_map[:64], x)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        y = np.dot(host_map, x)
+    t_mvp = (time.perf_counter() - t0) / 2
+    total = t_mvp * matvecs
+    return {"value": round(bytes_step / total / 1e9, 4), "unit": "GB/s", "cores": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
+            "kind": "reference", "s_per_matvec": round(t_mvp, 3), "seconds_per_step_same_matvecs": round(total, 1),
+            "sample": f"2 x np.dot(float32 A[{n}x{n}], float64 x) (the reference's matrix-vector product, OpenBLAS threads as available), scaled to {matvecs} "
+                      "products; compaction, O(n) algebra and the final matrix generation not included (lower bound)"}
+
+
+def cpu_reference_sample_mcfs(stats, nn_total):
+    """getAvgContactByDistance (lib/cmstats.py:569-605, pure Python: NumPy port in oracle_np) + the reference's compiled
+    normalizeByAvgContactByDivision on one 2,366-bin map (chrY @ 25 kb shape), scaled by sum(n^2)/2366^2."""
+    from oracle import oracle_np as onp
+    from oracle import ref_loader as rl
+    n = 2366
+    A = onp.synth_map(n, seed=25023)
+    t0 = time.perf_counter()
+    avg = onp.avg_contact_by_distance(A, stats)
+    t_stats = time.perf_counter() - t0
+    out = np.zeros_like(A)
+    t0 = time.perf_counter()
+    if rl.have_cores():
+        rl.load_cores()[0].normalizeByAvgContactByDivision(A, avg, Out=out)
+        kind = "reference (apply) + port (stats)"
+    else:
+        out = onp.mcfs_divide(A, avg)
+        kind = "port"
+    t_apply = time.perf_counter() - t0
+    scale = nn_total / float(n * n)
+    total = (t_stats + t_apply) * scale
+    return {"value": None, "unit": "GB/s", "cores": 1, "kind": kind, "seconds_per_step": round(total, 1),
+            "s_stats_one_map": round(t_stats, 2), "s_apply_one_map": round(t_apply, 2),
+            "sample": f"one {n}-bin map (stats={stats}) through the reference's per-diagonal Python loops, scaled by sum(n^2)/{n}^2 = {scale:.1f}"}
 
 
 def run_reference(args):
