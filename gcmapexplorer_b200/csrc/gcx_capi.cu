@@ -91,6 +91,9 @@ struct EvPair {
 struct gcx_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // async D2H of results, overlapped with compute
+    cudaEvent_t ev_ready = nullptr, ev_copied = nullptr;
+    bool copy_pending = false;
     // map
     int64_t n = 0, ld = 0, row0 = 0, nloc = 0, nv = 0;
     float* A = nullptr;
@@ -217,6 +220,9 @@ extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
     }
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
     CK(cudaMalloc(&c->ic_state, sizeof(IcState)));
     CK(cudaMalloc(&c->kr_state, sizeof(KrState)));
     CK(cudaMalloc(&c->mm, sizeof(MinMax)));
@@ -234,7 +240,7 @@ extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
         const char* f = getenv("GCX_IC_FUSED");
         if (f) c->ic_fused = atoi(f) && coop && occ >= 1;
     }
-    CK(cudaHostAlloc(&c->h_state, 4096, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&c->h_state, 4096, cudaHostAllocMapped));     // UVA: the same pointer is valid on the device
     CK(cudaEventCreate(&c->run_a));
     CK(cudaEventCreate(&c->run_b));
     CK(cudaEventCreate(&c->tm_a));
@@ -271,6 +277,9 @@ extern "C" int gcx_ctx_destroy(gcx_ctx* c) {
     }
     cudaEventDestroy(c->run_a); cudaEventDestroy(c->run_b);
     cudaEventDestroy(c->tm_a); cudaEventDestroy(c->tm_b);
+    cudaStreamSynchronize(c->copy_stream);
+    cudaEventDestroy(c->ev_ready); cudaEventDestroy(c->ev_copied);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -341,6 +350,8 @@ static int need_map(gcx_ctx* c) {
     return set_dev(c);
 }
 
+static int fence_copy(gcx_ctx* c);
+
 static int ensure_out(gcx_ctx* c) {
     if (!c->Out) CK(cudaMalloc(&c->Out, sizeof(float) * (size_t)c->nloc * c->ld));
     return 0;
@@ -391,10 +402,14 @@ static void par_copy_rows(char* dst, size_t dpitch, const char* src, size_t spit
 
 extern "C" int gcx_map_upload(gcx_ctx* c, const float* host, int64_t host_ld) {
     CKR(need_map(c));
+    CKR(fence_copy(c));
     if (host_ld < c->n) return fail("host_ld < n");
     const size_t width = sizeof(float) * (size_t)c->n;
     if (is_pinned(host)) {
-        CK(cudaMemcpy2DAsync(c->A, sizeof(float) * c->ld, host, sizeof(float) * host_ld, width, (size_t)c->nloc, cudaMemcpyHostToDevice, c->stream));
+        if (host_ld == c->ld)
+            CK(cudaMemcpyAsync(c->A, host, sizeof(float) * (size_t)c->nloc * c->ld, cudaMemcpyHostToDevice, c->stream));
+        else
+            CK(cudaMemcpy2DAsync(c->A, sizeof(float) * c->ld, host, sizeof(float) * host_ld, width, (size_t)c->nloc, cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return 0;
     }
@@ -423,7 +438,10 @@ extern "C" int gcx_map_download(gcx_ctx* c, int which, float* host, int64_t host
     if (host_ld < c->n) return fail("host_ld < n");
     const size_t width = sizeof(float) * (size_t)c->n;
     if (is_pinned(host)) {
-        CK(cudaMemcpy2DAsync(host, sizeof(float) * host_ld, src, sizeof(float) * c->ld, width, (size_t)c->nloc, cudaMemcpyDeviceToHost, c->stream));
+        if (host_ld == c->ld)
+            CK(cudaMemcpyAsync(host, src, sizeof(float) * (size_t)c->nloc * c->ld, cudaMemcpyDeviceToHost, c->stream));
+        else
+            CK(cudaMemcpy2DAsync(host, sizeof(float) * host_ld, src, sizeof(float) * c->ld, width, (size_t)c->nloc, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return 0;
     }
@@ -449,10 +467,45 @@ extern "C" int gcx_map_download(gcx_ctx* c, int which, float* host, int64_t host
     return 0;
 }
 
+extern "C" int gcx_map_download_async(gcx_ctx* c, int which, float* host, int64_t host_ld) {
+    CKR(need_map(c));
+    const float* src = which == 0 ? c->A : c->Out;
+    if (!src) return fail("no output map resident");
+    if (host_ld < c->n) return fail("host_ld < n");
+    if (!is_pinned(host)) return fail("gcx_map_download_async needs pinned host memory (gcx_host_alloc)");
+    CK(cudaEventRecord(c->ev_ready, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_ready, 0));
+    if (host_ld == c->ld) {     // same pitch on both sides: one contiguous DMA transfer (pad columns travel too)
+        CK(cudaMemcpyAsync(host, src, sizeof(float) * (size_t)c->nloc * c->ld, cudaMemcpyDeviceToHost, c->copy_stream));
+    } else {
+        CK(cudaMemcpy2DAsync(host, sizeof(float) * host_ld, src, sizeof(float) * c->ld, sizeof(float) * (size_t)c->n, (size_t)c->nloc,
+                             cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    CK(cudaEventRecord(c->ev_copied, c->copy_stream));
+    c->copy_pending = true;
+    return 0;
+}
+
+extern "C" int gcx_download_wait(gcx_ctx* c) {
+    CKR(set_dev(c));
+    if (c->copy_pending) {
+        CK(cudaEventSynchronize(c->ev_copied));
+        c->copy_pending = false;
+    }
+    return 0;
+}
+
+// kernels that are about to overwrite a map buffer wait (on the device) for an in-flight async download of it
+static int fence_copy(gcx_ctx* c) {
+    if (c->copy_pending) CK(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
+    return 0;
+}
+
 static int grid_rows(gcx_ctx* c) { return (int)std::min<int64_t>(c->nloc, (int64_t)c->sm_count * 8); }
 
 extern "C" int gcx_map_synth(gcx_ctx* c, uint64_t seed, double scale, double alpha, double empty_frac) {
     CKR(need_map(c));
+    CKR(fence_copy(c));
     const unsigned int thresh = (unsigned int)(std::min(1.0, std::max(0.0, empty_frac)) * 16777216.0);
     {
         ProfScope ps(c, 7);
@@ -465,6 +518,7 @@ extern "C" int gcx_map_synth(gcx_ctx* c, uint64_t seed, double scale, double alp
 }
 
 static int clamp_scale(gcx_ctx* c, int hmin, float vmin, int hmax, float vmax, int hs, float s) {
+    CKR(fence_copy(c));
     const long long total4 = (long long)c->nloc * c->ld / 4;
     {
         ProfScope ps(c, 7);
@@ -632,11 +686,19 @@ static int chunk_len(gcx_ctx* c) {
     return std::max(2, std::min(ch, 16));
 }
 
+// The host's convergence check reads the device state through MAPPED pinned memory written by this tiny kernel,
+// not through a D2H memcpy: a copy-engine transfer would queue behind any large async download in flight on the
+// copy stream (head-of-line blocking) and stall the look-ahead loop.
+__global__ void k_publish_state(const int* __restrict__ src, volatile int* dst, int words) {
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+
 template <typename State, typename StepFn>
 static int iterate(gcx_ctx* c, State* dev_state, int max_matvecs, StepFn step, State* final_state) {
     const int CH = chunk_len(c);
     State* hs = (State*)c->h_state;   // two pinned slots
-    static_assert(sizeof(State) <= 1024, "state too large");
+    static_assert(sizeof(State) <= 1024 && sizeof(State) % 4 == 0, "state too large / not word sized");
     State* slot[2] = {hs, (State*)((char*)c->h_state + 2048)};
     cudaEvent_t ev[2];
     CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
@@ -646,7 +708,8 @@ static int iterate(gcx_ctx* c, State* dev_state, int max_matvecs, StepFn step, S
     auto enqueue_chunk = [&](int b) -> int {
         for (int i = 0; i < CH; ++i) CKR(step());
         issued += CH;
-        CK(cudaMemcpyAsync(slot[b], dev_state, sizeof(State), cudaMemcpyDeviceToHost, c->stream));
+        k_publish_state<<<1, 64, 0, c->stream>>>((const int*)dev_state, (volatile int*)slot[b], (int)(sizeof(State) / 4));
+        CK(cudaGetLastError());
         CK(cudaEventRecord(ev[b], c->stream));
         return 0;
     };
@@ -662,6 +725,7 @@ static int iterate(gcx_ctx* c, State* dev_state, int max_matvecs, StepFn step, S
         cur ^= 1;
     }
     cudaError_t e2 = cudaEventRecord(c->run_b, c->stream);
+    k_publish_state<<<1, 64, 0, c->stream>>>((const int*)dev_state, (volatile int*)slot[0], (int)(sizeof(State) / 4));
     cudaError_t e3 = cudaStreamSynchronize(c->stream);
     cudaEventDestroy(ev[0]);
     cudaEventDestroy(ev[1]);
@@ -671,7 +735,7 @@ static int iterate(gcx_ctx* c, State* dev_state, int max_matvecs, StepFn step, S
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->run_a, c->run_b));
     c->last_run_ms = ms;
-    CK(cudaMemcpy(final_state, dev_state, sizeof(State), cudaMemcpyDeviceToHost));
+    memcpy(final_state, slot[0], sizeof(State));
     return 0;
 }
 
@@ -790,6 +854,7 @@ static int ew_variant() {
 
 extern "C" int gcx_apply_sym_scale(gcx_ctx* c, const double* s, int masked_mode, int in_place, float* minv, float* maxv) {
     CKR(need_map(c));
+    CKR(fence_copy(c));
     if (!c->have_mask) return fail("gcx_apply_sym_scale: call gcx_set_mask first");
     if (s) {
         CK(cudaMemsetAsync(c->vscale, 0, sizeof(double) * c->nv, c->stream));
@@ -815,6 +880,7 @@ __global__ void k_f64_to_f32(int nv, const double* __restrict__ a, float* __rest
 
 extern "C" int gcx_vc_run(gcx_ctx* c, int sqroot, int in_place, float* minv, float* maxv, float* csum) {
     CKR(need_map(c));
+    CKR(fence_copy(c));
     if (!c->have_mask) return fail("gcx_vc_run: call gcx_set_mask first");
     CKR(run_row_stats(c));
     // csum = np.sum(A, axis=1) is float32 in the reference (lib/normalizeCore.pyx:72)
@@ -906,6 +972,7 @@ extern "C" int gcx_diag_stats(gcx_ctx* c, int median, double* avg) {
 
 extern "C" int gcx_diag_apply(gcx_ctx* c, const double* avg, int subtract, int in_place, float* minv, float* maxv) {
     CKR(need_map(c));
+    CKR(fence_copy(c));
     if (avg) {
         CK(cudaMemsetAsync(c->vavg, 0, sizeof(double) * c->nv, c->stream));
         CK(cudaMemcpyAsync(c->vavg, avg, sizeof(double) * c->n, cudaMemcpyHostToDevice, c->stream));

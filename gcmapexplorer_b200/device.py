@@ -24,20 +24,32 @@ def _as_f32_matrix(matrix):
     return m
 
 
-class PinnedArray:
-    """float32 2-D array in CUDA pinned host memory (full-speed PCIe copies)."""
+def device_pitch(n):
+    """Row pitch (in floats) of the resident map: n rounded up to 32 floats = 128 bytes."""
+    return (int(n) + 31) // 32 * 32
 
-    def __init__(self, shape, dtype=np.float32):
+
+class PinnedArray:
+    """float32 2-D array in CUDA pinned host memory (full-speed PCIe copies).  With pitched=True the rows use
+    the device's own pitch, so uploads/downloads are one contiguous DMA transfer (and overlap with kernels);
+    `.array` is the [rows, cols] view either way."""
+
+    def __init__(self, shape, dtype=np.float32, pitched=False):
         self.shape = tuple(shape)
-        nbytes = int(np.prod(self.shape)) * np.dtype(dtype).itemsize
+        rows, cols = self.shape
+        ld = device_pitch(cols) if pitched else cols
+        nbytes = int(rows) * int(ld) * np.dtype(dtype).itemsize
         self._ptr = C.c_void_p()
         check(lib().gcx_host_alloc(nbytes, C.byref(self._ptr)))
         buf = (C.c_char * nbytes).from_address(self._ptr.value)
-        self.array = np.frombuffer(buf, dtype=dtype).reshape(self.shape)
+        self.full = np.frombuffer(buf, dtype=dtype).reshape(rows, ld)
+        self.full[:, cols:] = 0
+        self.array = self.full[:, :cols]
 
     def free(self):
         if self._ptr is not None and self._ptr.value:
             self.array = None
+            self.full = None
             lib().gcx_host_free(self._ptr)
             self._ptr = None
 
@@ -109,6 +121,15 @@ class DeviceMap:
             raise ValueError("out must be float32 [nloc, n] with unit column stride")
         check(lib().gcx_map_download(self._ctx, int(which), C.c_void_p(out.ctypes.data), out.strides[0] // 4))
         return out
+
+    def download_async(self, which, out):
+        """Start a device->host copy into a pinned array on the copy stream; pair with download_wait()."""
+        if out.dtype != np.float32 or out.shape != (self.nloc, self.n) or out.strides[1] != 4:
+            raise ValueError("out must be float32 [nloc, n] with unit column stride")
+        check(lib().gcx_map_download_async(self._ctx, int(which), C.c_void_p(out.ctypes.data), out.strides[0] // 4))
+
+    def download_wait(self):
+        check(lib().gcx_download_wait(self._ctx))
 
     def synth(self, seed, scale=200.0, alpha=1.0, empty_frac=0.01):
         check(lib().gcx_map_synth(self._ctx, int(seed), float(scale), float(alpha), float(empty_frac)))

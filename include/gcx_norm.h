@@ -47,6 +47,11 @@ int gcx_host_free(void* ptr);
 int gcx_map_create(gcx_ctx* ctx, int64_t n, int64_t row0, int64_t nloc);
 int gcx_map_upload(gcx_ctx* ctx, const float* host_rows, int64_t host_ld);          /* host_rows -> first local row */
 int gcx_map_download(gcx_ctx* ctx, int which, float* host_rows, int64_t host_ld);   /* which: 0 input, 1 output */
+/* asynchronous download into PINNED host memory on the context's copy stream: returns at once, overlaps with
+ * kernels enqueued afterwards (e.g. the VC result streams out while IC iterates); gcx_download_wait blocks until
+ * the last async download has landed.  Kernels that later overwrite the source buffer wait for it on the device. */
+int gcx_map_download_async(gcx_ctx* ctx, int which, float* pinned_host_rows, int64_t host_ld);
+int gcx_download_wait(gcx_ctx* ctx);
 /* device-side synthetic map: symmetric Poisson(scale*(d+1)^-alpha), empty bins, diag >= 1 */
 int gcx_map_synth(gcx_ctx* ctx, uint64_t seed, double scale, double alpha, double empty_frac);
 /* vmin/vmax clamp, lib/normalizer.py:299-301, 567-569, 827-829, 1105-1107: x<=vmin or x>=vmax -> 0 */

@@ -366,3 +366,83 @@ def test_ccmap_save_load_roundtrip_with_outfile(gx, tmp_path):
     assert again is not None
     with pytest.raises(TypeError):
         nz.normalizeCCMapByIC(str(tmp_path / "missing.ccmap"))
+
+
+# --------------------------------------------------------------------------------------------------
+# edge cases: tiny / ragged sizes, error conventions, residency variants
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 31, 32, 33, 255, 257])
+def test_tiny_and_ragged_sizes(gx, n):
+    rng = np.random.default_rng(100 + n)
+    U = np.triu(rng.integers(1, 50, size=(n, n)).astype(np.float32))
+    A = U + np.triu(U, 1).T                     # dense, positive: every pad / tail path, no empty rows
+    keep = np.ones(n, dtype=bool)
+    r = _ic_device(gx, A, 1e-6, 500, keep)
+    M64, B, passes, _ = onp.ic_fp64(A, 1e-6, 500)
+    assert r["passes"] == passes
+    np.testing.assert_allclose(r["bias"], B, rtol=BIAS_RTOL)
+    assert rel_err(r["matrix"], M64.astype(np.float32)) < MAT_RTOL
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.set_mask(keep)
+        k = dm.kr(1e-12, 0.1, 3)
+        dm.apply_sym(None, 0, False)
+        D = dm.download(1)
+        mn, mx, csum = dm.vc(False, False)
+        V = dm.download(1)
+        med = dm.diag_stats("median")
+        mean = dm.diag_stats("mean")
+    ko = onp.kr(A)
+    assert (k["outer"], k["MVP"]) == (ko["outer"], ko["MVP"])
+    np.testing.assert_allclose(k["x"], ko["x"], rtol=BIAS_RTOL)
+    assert rel_err(D, onp.scatter_symmetric(onp.kr_matrix(A, ko["x"]), ~keep, np.zeros_like(A))) < MAT_RTOL
+    assert np.array_equal(V, onp.vc(A)[0])
+    assert np.array_equal(med, onp.avg_contact_by_distance(A, "median"))
+    np.testing.assert_allclose(mean, onp.avg_contact_by_distance(A, "mean"), rtol=1e-13)
+
+
+def test_error_conventions(gx, caplog):
+    """IC swallows non-device errors and returns None (lib/normalizer.py:642-647); KR logs and re-raises (:390-395)."""
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz
+    A = onp.synth_map(60, seed=8)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(A, 100000)
+    c.make_unreadable()
+    assert nz.normalizeCCMapByIC(c, percentile_threshold_no_data=90, threshold_data_occup=0.5) is None     # AssertionError inside
+    assert nz.normalizeCCMapByIC(c, threshold_data_occup=1.5) is None                                     # ValueError inside
+    with pytest.raises(AssertionError):
+        nz.normalizeCCMapByKR(c, percentile_threshold_no_data=90, threshold_data_occup=0.5)
+    with pytest.raises(ValueError):
+        nz.normalizeCCMapByKR(c, memory="TAPE")
+    assert nz.normalizeCCMapByVCNorm(c, threshold_data_occup=1.5) is None
+    assert nz.normalizeCCMapByMCFS(c, threshold_data_occup=1.5) is None
+    with pytest.raises(NotImplementedError):
+        nz.normalizeGCMapByIC("in.gcmap", "out.gcmap")
+
+
+def test_non_float32_and_non_contiguous_inputs(gx):
+    A = onp.synth_map(90, seed=2)
+    with gx.DeviceMap.from_host(A.astype(np.float64)) as dm:         # converted on the host
+        assert np.array_equal(dm.download(0), A)
+    F = np.asfortranarray(A)
+    with gx.DeviceMap.from_host(F) as dm:
+        assert np.array_equal(dm.download(0), A)
+
+
+def test_in_place_equals_out_of_place_and_async_download(gx):
+    A = onp.synth_map(500, seed=6)
+    keep = onp.get_nonzeros_index(A)
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.set_mask(keep)
+        dm.kr(1e-12, 0.1, 3)
+        m1 = dm.apply_sym(None, 0, in_place=False)
+        out = dm.download(1)
+        pin = gx.PinnedArray((500, 500))
+        dm.download_async(1, pin.array)
+        dm.vc(False, in_place=False)              # overwrites Out: must wait for the async copy on the device
+        dm.download_wait()
+        assert np.array_equal(pin.array, out)
+        m2 = dm.apply_sym(None, 0, in_place=True)
+        assert m1 == m2 and np.array_equal(dm.download(0), out)
+        with pytest.raises(gx.GcxError):
+            dm.download_async(0, np.empty((500, 500), dtype=np.float32))     # pageable memory is refused
+        pin.free()
