@@ -1,0 +1,161 @@
+"""CPU: the C-ABI library loads, exports every symbol include/gcx_norm.h declares, fails loudly without a GPU,
+and the host-side logic (mask rules, CCMAP carrier, util) matches the oracle / the reference's file format."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names, load_golden
+from oracle import oracle_np as onp
+
+HEADER = os.path.join(ROOT, "include", "gcx_norm.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gcmapexplorer_b200 import _lib
+    assert os.path.isfile(_lib.LIB_PATH), "libgcxnorm.so not built: run __graft_entry__.build()"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(_lib.EXPORTS) == set(declared), set(_lib.EXPORTS) ^ set(declared)
+    assert _lib.lib().gcx_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a CUDA device every entry point that needs one raises (no silent CPU path)."""
+    from gcmapexplorer_b200 import _lib, device
+    try:
+        ngpu = _lib.device_count()
+    except _lib.GcxError:
+        ngpu = 0
+    if ngpu > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(_lib.GcxError):
+        device.DeviceMap(16)
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz, normalizeCore, ccmapHelpers
+    A = onp.synth_map(20, seed=1)
+    with pytest.raises(_lib.GcxError):
+        normalizeCore.performIterativeCorrection(A.copy(), 1e-4, 10)
+    with pytest.raises(_lib.GcxError):
+        ccmapHelpers.get_nonzeros_index(A)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(A, 1000)
+    with pytest.raises(_lib.GcxError):       # IC swallows ordinary errors, never a missing device
+        nz.normalizeCCMapByIC(c)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "gcmapexplorer_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("oracle/", ""), fn     # docstrings may cite the directory only
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_host_mask_rules_match_oracle(seed):
+    """ccmapHelpers.mask_from_row_stats (host half of get_nonzeros_index) vs the oracle, from true row statistics."""
+    from gcmapexplorer_b200 import ccmapHelpers as cmh
+    n = 150 + 17 * seed
+    A = onp.synth_map(n, seed=seed, scale=25.0, alpha=1.2, empty_frac=0.04)
+    rowsum = A.astype(np.float64).sum(axis=1)
+    raw_zc = (A == 0).sum(axis=1).astype(np.int32)
+    for pct, occ in [(None, None), (99, None), (80, None), (50, None), (None, 0.2), (None, 0.35)]:
+        try:
+            exp = onp.get_nonzeros_index(A, pct, occ)
+        except ValueError:
+            with pytest.raises(ValueError):
+                cmh.mask_from_row_stats(rowsum, raw_zc, n, pct, occ)
+            continue
+        assert np.array_equal(cmh.mask_from_row_stats(rowsum, raw_zc, n, pct, occ), exp)
+    with pytest.raises(AssertionError):
+        cmh.mask_from_row_stats(rowsum, raw_zc, n, 90, 0.5)
+
+
+@pytest.mark.parametrize("name", golden_names("MASK"))
+def test_host_mask_rules_golden(name):
+    from gcmapexplorer_b200 import ccmapHelpers as cmh
+    g = load_golden(name)
+    A = g["input"]
+    got = cmh.mask_from_row_stats(A.astype(np.float64).sum(axis=1), (A == 0).sum(axis=1), A.shape[0],
+                                  g["kwargs"].get("percentile_threshold_no_data"), g["kwargs"].get("threshold_data_occup"))
+    assert np.array_equal(got, g["keep"])
+
+
+def test_ccmap_lifecycle_and_file_format(tmp_path):
+    from gcmapexplorer_b200 import ccmap as cmp
+    A = onp.synth_map(50, seed=3)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(A, 40000, xlabel="chr7", ylabel="chr7", workDir=str(tmp_path))
+    assert c.state == "temporary" and os.path.basename(c.path2matrix).startswith("gcx_npBinary_")
+    assert c.shape == (50, 50) and c.xticks == [0, 2000000] and c.title == "chr7_vs_chr7"
+    assert float(c.minvalue) == float(A[A != 0].min()) and float(c.maxvalue) == float(A.max())
+    c.bNoData = ~onp.get_nonzeros_index(A)
+    d = c.copy()
+    assert d.path2matrix != c.path2matrix and os.path.dirname(d.path2matrix) == os.path.dirname(c.path2matrix)
+    assert c.matrix is None and d.matrix is None                       # copy() leaves both unreadable (lib/ccmap.py:296-297)
+    d.make_readable()
+    assert np.array_equal(np.array(d.matrix), A) and not d.matrix.flags.writeable
+    z = c.copy(fill=0.0)
+    z.make_editable()
+    assert not z.matrix.any()
+    z.matrix[0, 0] = 5
+    z.make_unreadable()
+    # save: JSON with stringified fields + gzip'd raw float32 (lib/ccmap.py:302-505)
+    cmp.save_ccmap(c, str(tmp_path / "m"), compress=True)
+    jd = json.load(open(tmp_path / "m.ccmap"))
+    assert jd["shape"] == ["50", "50"] and jd["binsize"] == "40000" and jd["state"] == "compressed" and jd["dtype"] == "float32"
+    assert jd["bNoData"] == "".join("1" if b else "0" for b in c.bNoData) and jd["path2matrix"] == "m.npbin" and jd["matrix"] is None
+    assert os.path.isfile(tmp_path / "m.npbin.gz") and not os.path.exists(tmp_path / "m.npbin")
+    assert c.state == "temporary" and isinstance(c.shape, tuple) and c.bNoData.dtype == bool      # object restored after save
+    e = cmp.load_ccmap(str(tmp_path / "m.ccmap"), workDir=str(tmp_path))
+    e.make_readable()
+    assert np.array_equal(np.array(e.matrix), A) and e.state == "temporary" and np.array_equal(e.bNoData, c.bNoData)
+    cmp.save_ccmap(c, str(tmp_path / "u.ccmap"), compress=False)
+    f = cmp.load_ccmap(str(tmp_path / "u.ccmap"))
+    assert f.state == "saved" and f.path2matrix == str(tmp_path / "u.npbin")
+    path = f.path2matrix
+    del f
+    assert os.path.exists(path)                                        # saved maps are never unlinked
+    tmpfile = d.path2matrix
+    del d
+    assert not os.path.exists(tmpfile)                                 # temporary ones are (lib/ccmap.py:141-148)
+    assert cmp.checkCCMapObjectOrFile(c)[1] == "Object"
+    assert cmp.checkCCMapObjectOrFile(str(tmp_path / "u.ccmap"))[1] == "File"
+    assert cmp.checkCCMapObjectOrFile(str(tmp_path / "nope.ccmap")) is None
+
+
+def test_reference_reads_our_ccmap_files(tmp_path):
+    """File-format interchange with the real reference (only where /root/reference exists)."""
+    from oracle import ref_loader as rl
+    if not rl.have_full():
+        pytest.skip("full reference not available")
+    import sys
+    rl.load_full()
+    rcmp = sys.modules["gcMapExplorer.lib.ccmap"]
+    from gcmapexplorer_b200 import ccmap as cmp
+    A = onp.synth_map(40, seed=9)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(A, 5000, xlabel="chr2", ylabel="chr2", workDir=str(tmp_path))
+    c.bNoData = ~onp.get_nonzeros_index(A)
+    cmp.save_ccmap(c, str(tmp_path / "ours"), compress=True)
+    r = rcmp.load_ccmap(str(tmp_path / "ours.ccmap"), workDir=str(tmp_path))
+    r.make_readable()
+    assert np.array_equal(np.array(r.matrix), A) and r.binsize == 5000 and np.array_equal(r.bNoData, c.bNoData)
+    r.make_unreadable()
+    rcmp.save_ccmap(r, str(tmp_path / "theirs"), compress=True)
+    o = cmp.load_ccmap(str(tmp_path / "theirs.ccmap"), workDir=str(tmp_path))
+    o.make_readable()
+    assert np.array_equal(np.array(o.matrix), A) and o.xlabel == "chr2"
