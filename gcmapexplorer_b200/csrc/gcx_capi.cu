@@ -113,8 +113,8 @@ struct gcx_ctx {
     size_t scratch_bytes = 0;
     double* part = nullptr;      // per-CTA partials of the fused IC pass (3 x grid)
     int ic_fused = 1;            // 1: one cooperative launch per IC pass (k_ic_pass); 0: k_matvec + k_ic_epilogue
-    int ic_grid = 0;
-    int mv_variant = 2;   // R=4 rows per band, 4 CTAs/SM: best of the sweep in profiles/r01_matvec_variants.txt
+    int ic_grid = 0, ic_grid_tma = 0;
+    int mv_variant = 7;   // TMA-bulk, R=4 rows per band, 6 stages, 2 CTAs/SM: best of profiles/r01_matvec_variants.txt
     // states
     IcState* ic_state = nullptr;
     KrState* kr_state = nullptr;
@@ -238,7 +238,17 @@ extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
         c->ic_grid = c->sm_count * std::min(occ, 4);
         if (!coop || occ < 1) c->ic_fused = 0;
         const char* f = getenv("GCX_IC_FUSED");
-        if (f) c->ic_fused = atoi(f) && coop && occ >= 1;
+        if (f) c->ic_fused = atoi(f) && coop && occ >= 1;     // 0 split, 1 fused LDG, 2 fused TMA-bulk (default)
+        if (c->ic_fused) {
+            const int smem = 6 * 4 * MV_THREADS * (int)sizeof(float4);
+            CK(cudaFuncSetAttribute(k_ic_pass_tma<4, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int occ2 = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_ic_pass_tma<4, 6, 2>, TMA_THREADS, smem));
+            c->ic_grid_tma = c->sm_count * std::min(occ2, 2);
+            if (!f) c->ic_fused = occ2 >= 1 ? 2 : 1;
+            else if (atoi(f) == 2 && occ2 < 1) c->ic_fused = 1;
+            else if (atoi(f) == 2) c->ic_fused = 2;
+        }
     }
     CK(cudaHostAlloc(&c->h_state, 4096, cudaHostAllocMapped));     // UVA: the same pointer is valid on the device
     CK(cudaEventCreate(&c->run_a));
@@ -640,6 +650,19 @@ static void launch_mv(gcx_ctx* c, const double* z, double* q, const int* done) {
     k_matvec<R, OCC><<<c->sm_count * OCC, MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, (int)(c->ld / 4), z, q + c->row0, c->ws, c->ticket, done);
 }
 
+template <int R, int STAGES, int OCC>
+static int launch_mv_tma(gcx_ctx* c, const double* z, double* q, const int* done) {
+    const size_t smem = (size_t)STAGES * R * MV_THREADS * sizeof(float4);
+    static bool configured = false;
+    if (!configured) {
+        CK(cudaFuncSetAttribute(k_matvec_tma<R, STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    k_matvec_tma<R, STAGES, OCC><<<c->sm_count * OCC, TMA_THREADS, smem, c->stream>>>(c->A, c->ld, (int)c->nloc, (int)(c->ld / 4), z, q + c->row0, c->ws,
+                                                                                      c->ticket, done);
+    return 0;
+}
+
 static int matvec(gcx_ctx* c, int variant, const double* z, double* q, const int* done) {
     {
         ProfScope ps(c, 0);
@@ -651,6 +674,17 @@ static int matvec(gcx_ctx* c, int variant, const double* z, double* q, const int
             case 4: launch_mv<16, 1>(c, z, q, done); break;
             case 5: launch_mv<2, 8>(c, z, q, done); break;
             case 6: launch_mv<8, 4>(c, z, q, done); break;
+            case 7: CKR((launch_mv_tma<4, 6, 2>(c, z, q, done))); break;      // 96 KB/CTA, 2 CTAs/SM
+            case 8: CKR((launch_mv_tma<4, 12, 1>(c, z, q, done))); break;     // 192 KB/CTA, 1 CTA/SM
+            case 9: CKR((launch_mv_tma<8, 6, 1>(c, z, q, done))); break;      // 192 KB/CTA, 1 CTA/SM, 8-row bands
+            case 10: CKR((launch_mv_tma<4, 4, 3>(c, z, q, done))); break;     // 64 KB/CTA, 3 CTAs/SM
+            case 11: CKR((launch_mv_tma<2, 8, 3>(c, z, q, done))); break;     // 64 KB/CTA, 3 CTAs/SM, 2-row bands
+            case 12: CKR((launch_mv_tma<4, 7, 2>(c, z, q, done))); break;     // 112 KB/CTA, 2 CTAs/SM
+            case 13: CKR((launch_mv_tma<8, 3, 2>(c, z, q, done))); break;     // 96 KB/CTA, 2 CTAs/SM, 8-row bands
+            case 14: CKR((launch_mv_tma<2, 12, 2>(c, z, q, done))); break;    // 96 KB/CTA, 2 CTAs/SM, 2-row bands
+            case 15: CKR((launch_mv_tma<4, 5, 2>(c, z, q, done))); break;     // 80 KB/CTA, 2 CTAs/SM
+            case 16: CKR((launch_mv_tma<2, 14, 2>(c, z, q, done))); break;    // 112 KB/CTA, 2 CTAs/SM, 2-row bands
+            case 17: CKR((launch_mv_tma<1, 24, 2>(c, z, q, done))); break;    // 96 KB/CTA, 2 CTAs/SM, single rows
             default: return fail("unknown matvec variant %d", variant);
         }
     }
@@ -762,7 +796,11 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
                         (void*)&c->vz, (void*)&c->vB, (void*)&c->ws, (void*)&c->ticket, (void*)&c->ic_state, (void*)&c->part};
         {
             ProfScope ps(c, 0);
-            CK(cudaLaunchCooperativeKernel((void*)k_ic_pass<4, 4>, dim3(c->ic_grid), dim3(MV_THREADS), args, 0, c->stream));
+            if (c->ic_fused == 2)
+                CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_tma<4, 6, 2>, dim3(c->ic_grid_tma), dim3(TMA_THREADS), args,
+                                               6 * 4 * MV_THREADS * sizeof(float4), c->stream));
+            else
+                CK(cudaLaunchCooperativeKernel((void*)k_ic_pass<4, 4>, dim3(c->ic_grid), dim3(MV_THREADS), args, 0, c->stream));
         }
         CKR(allgather_f64(c, c->vq));
         return 0;

@@ -292,6 +292,219 @@ k_matvec(const float* __restrict__ A, long long ld, int nloc, int n4, const doub
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K2/K3, TMA-bulk variant: the same (band, chunk) decomposition and arithmetic as k_matvec, but the map is
+// staged through shared memory by the bulk async-copy engine (cp.async.bulk = SASS UBLKCP) instead of
+// per-thread LDG.128: one producer lane keeps STAGES x R row segments (R x 4 KB per stage) in flight behind
+// mbarriers, 8 consumer warps read them back with conflict-free LDS.128.  Bytes in flight no longer depend on
+// registers or occupancy.  Selected with GCX_MATVEC_VARIANT >= 7; see profiles/ for the measured comparison.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned int parity) {
+    unsigned int ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned int parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int TMA_CONSUMERS = MV_THREADS;          // 8 consumer warps
+constexpr int TMA_THREADS = MV_THREADS + 32;       // + 1 producer warp
+
+// Split bands: one thread per CTA boundary folds the partial sums of every CTA that touched the band, in CTA
+// order (bitwise reproducible for a given grid).  Called by the last CTA to finish.
+template <int R>
+__device__ __forceinline__ void fold_split_bands(double* q, const double* ws, long long U, long long G, int nch, int nloc, int nthreads) {
+    for (long long cb = 1 + threadIdx.x; cb < G; cb += nthreads) {
+        const long long ub = unit_begin(cb, U, G);
+        const int b = (int)(ub / nch);
+        const long long band0 = (long long)b * nch, band1 = band0 + nch;
+        if (ub == band0 || ub >= U) continue;                        // boundary on a band edge
+        const long long ubp = unit_begin(cb - 1, U, G);
+        if (ubp > band0) continue;                                   // an earlier boundary owns this band
+        double s[R];
+        {
+            const int slot = (b == (int)(ubp / nch)) ? 0 : 1;        // CTA cb-1: band b is its last band
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) s[rr] = __ldcg(ws + ((cb - 1) * 2 + slot) * R + rr);
+        }
+        long long cc = cb, ucc = ub;
+        while (cc < G && ucc < band1) {
+            const long long unext = unit_begin(cc + 1, U, G);
+            if (unext > ucc) {                                       // non-empty CTA: band b is its first band
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) s[rr] += __ldcg(ws + (cc * 2) * R + rr);
+            }
+            ++cc;
+            ucc = unext;
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r < nloc) q[r] = s[rr];
+        }
+    }
+}
+
+// The producer/consumer main loop.  ZNC: read z through the non-coherent path (allowed only when this kernel
+// never writes z).  Ends with every thread past a CTA-wide barrier.
+template <int R, int STAGES, bool ZNC>
+__device__ __forceinline__ void matvec_tma_core(const float* __restrict__ A, long long ld, int nloc, int n4, const double* z, double* q,
+                                                double* ws, float4* tiles, uint64_t* full_bar, uint64_t* empty_bar,
+                                                double (*red)[R]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
+    const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], MV_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == MV_THREADS / 32) {
+        // ---------------- producer: one lane drives the bulk-copy engine ----------------
+        if (lane == 0) {
+            int stage = 0;
+            unsigned int phase = 0;
+            for (long long u = u0; u < u1; ++u) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
+                const int c0 = k * MV_THREADS;
+                const int nf4 = min(MV_THREADS, n4 - c0);
+                const unsigned int row_bytes = (unsigned int)nf4 * 16u;
+                mbar_expect_tx(&full_bar[stage], row_bytes * R);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    int r = b * R + rr;
+                    r = r < nloc ? r : nloc - 1;
+                    bulk_g2s(tiles + ((size_t)stage * R + rr) * MV_THREADS, A + (long long)r * ld + 4LL * c0, row_bytes, &full_bar[stage]);
+                }
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ---------------- consumers ----------------
+        const double2* z2 = reinterpret_cast<const double2*>(z);
+        const int bfirst = (int)(u0 / nch);
+        int stage = 0;
+        unsigned int phase = 0;
+        long long u = u0;
+        while (u < u1) {
+            const int b = (int)(u / nch);
+            const int k0 = (int)(u - (long long)b * nch);
+            const long long rem = u1 - u;
+            const int k1 = (int)(((long long)(nch - k0) < rem) ? nch : (k0 + rem));
+            double acc[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) acc[rr] = 0.0;
+            for (int k = k0; k < k1; ++k) {
+                const int c4 = k * MV_THREADS + tid;
+                double2 za = make_double2(0.0, 0.0), zb = za;
+                if (c4 < n4) {
+                    if (ZNC) {
+                        za = __ldg(z2 + 2 * c4);
+                        zb = __ldg(z2 + 2 * c4 + 1);
+                    } else {
+                        za = z2[2 * c4];
+                        zb = z2[2 * c4 + 1];
+                    }
+                }
+                mbar_wait(&full_bar[stage], phase);
+                if (c4 < n4) {
+                    float4 a[R];
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) a[rr] = tiles[((size_t)stage * R + rr) * MV_THREADS + tid];
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        acc[rr] = fma((double)a[rr].x, za.x, acc[rr]);
+                        acc[rr] = fma((double)a[rr].y, za.y, acc[rr]);
+                        acc[rr] = fma((double)a[rr].z, zb.x, acc[rr]);
+                        acc[rr] = fma((double)a[rr].w, zb.y, acc[rr]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) acc[rr] = warp_sum(acc[rr]);
+            if (lane == 0) {
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) red[warp][rr] = acc[rr];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");
+            if (tid < R) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < MV_THREADS / 32; ++w) s += red[w][tid];
+                const int r = b * R + tid;
+                if (k0 == 0 && k1 == nch) {
+                    if (r < nloc) q[r] = s;
+                } else {
+                    ws[((long long)c * 2 + (b == bfirst ? 0 : 1)) * R + tid] = s;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TMA_CONSUMERS) : "memory");
+            u += (k1 - k0);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+}
+
+template <int R, int STAGES, int OCC>
+__global__ void __launch_bounds__(TMA_THREADS, OCC)
+k_matvec_tma(const float* __restrict__ A, long long ld, int nloc, int n4, const double* __restrict__ z, double* __restrict__ q,
+             double* ws, unsigned int* ticket, const int* __restrict__ done) {
+    if (done != nullptr && *done) return;
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ double red[MV_THREADS / 32][R];
+    __shared__ int s_last;
+    matvec_tma_core<R, STAGES, true>(A, ld, nloc, n4, z, q, ws, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, red);
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const long long U = (long long)((nloc + R - 1) / R) * nch, G = gridDim.x;
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned int)(G - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    fold_split_bands<R>(q, ws, U, G, nch, nloc, TMA_THREADS);
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K1 row statistics: float64 row sum + int32 count of zeros over the n real columns.
 // Replaces the loop of lib/ccmapHelpers.pyx:190-201.  Algorithmic bytes: 4 * nloc * n.
 // ---------------------------------------------------------------------------------------------------
@@ -1064,6 +1277,97 @@ k_ic_pass(const float* __restrict__ A, long long ld, int nloc, int n4, int n, in
             if (r < nloc) q[r] = s[rr];
         }
     }
+    if (tid == 0) {
+        *ticket = 0u;
+        st->matvecs = m + 1;
+    }
+}
+
+// Fused IC pass with the TMA-bulk main loop (same P1..P4 structure as k_ic_pass; all 288 threads take part in
+// the vector phases).
+template <int R, int STAGES, int OCC>
+__global__ void __launch_bounds__(TMA_THREADS, OCC)
+k_ic_pass_tma(const float* __restrict__ A, long long ld, int nloc, int n4, int n, int row0, const uint8_t* __restrict__ keep, double* t,
+              double* v, double* B, double* ws, unsigned int* ticket, IcState* st, double* part) {
+    namespace cg = cooperative_groups;
+    if (st->done) return;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ double red[MV_THREADS / 32][R];
+    __shared__ double sm[32];
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int m = st->matvecs;
+    const int gth = bid * TMA_THREADS + tid, nth = G * TMA_THREADS;
+
+    if (m > 0) {
+        const int mm = m - 1;
+        const double cc_prev = st->cc, tol = st->tol;
+        const int max_iter = st->max_iter;
+        double s = 0.0, c = 0.0;
+        for (int i = gth; i < n; i += nth) {
+            if (keep[i]) {
+                const double p = v[i] * t[i];
+                s += p;
+                c += (p != 0.0) ? 1.0 : 0.0;
+            }
+        }
+        s = block_reduce<RED_SUM>(s, sm);
+        c = block_reduce<RED_SUM>(c, sm);
+        if (tid == 0) {
+            part[bid] = s;
+            part[G + bid] = c;
+        }
+        grid.sync();
+        double a0 = 0.0, a1 = 0.0;
+        for (int b = tid; b < G; b += TMA_THREADS) {
+            a0 += __ldcg(part + b);
+            a1 += __ldcg(part + G + b);
+        }
+        const double S = block_reduce<RED_SUM>(a0, sm), C = block_reduce<RED_SUM>(a1, sm);
+        const double cc = (mm == 0) ? S : cc_prev;          // contact_count, lib/normalizeCore.pyx:36
+        const double f = (mm == 0) ? 1.0 : sqrt(S / cc);    // :52
+        const double g = (mm == 0) ? 1.0 : cc / S;          // :53
+        const double mean = g * S / C;                      // :44
+        double l1 = 0.0;
+        for (int i = gth; i < n; i += nth) {
+            if (keep[i]) {
+                const double vi = v[i];
+                const double d = g * (vi * t[i]);
+                double bn = B[i];
+                if (mm > 0) {
+                    bn = f / vi;                            // :51-52
+                    l1 += fabs(B[i] - bn);                  // :56
+                    B[i] = bn;
+                }
+                v[i] = (d != 0.0) ? mean / (bn * d) : 1.0 / bn;     // :44-45
+            }
+        }
+        l1 = block_reduce<RED_SUM>(l1, sm);
+        if (tid == 0) part[2 * G + bid] = l1;
+        grid.sync();
+        double a2 = 0.0;
+        for (int b = tid; b < G; b += TMA_THREADS) a2 += __ldcg(part + 2 * G + b);
+        const double L1 = block_reduce<RED_SUM>(a2, sm);
+        const bool done = (mm >= 2) && (L1 < tol || (mm - 1) > max_iter);       // :55-57
+        if (bid == 0 && tid == 0) {
+            st->cc = cc; st->S = S; st->l1 = L1; st->mean = mean; st->cnt = (int)C;
+            st->pass = mm; st->done = done ? 1 : 0;
+        }
+        if (done) return;
+    }
+
+    matvec_tma_core<R, STAGES, false>(A, ld, nloc, n4, v, t + row0, ws, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, red);
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const long long U = (long long)((nloc + R - 1) / R) * nch;
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == (unsigned int)(G - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    fold_split_bands<R>(t + row0, ws, U, G, nch, nloc, TMA_THREADS);
     if (tid == 0) {
         *ticket = 0u;
         st->matvecs = m + 1;
