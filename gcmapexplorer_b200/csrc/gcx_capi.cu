@@ -94,6 +94,7 @@ struct gcx_ctx {
     cudaStream_t copy_stream = nullptr;          // async D2H of results, overlapped with compute
     cudaEvent_t ev_ready = nullptr, ev_copied = nullptr;
     bool copy_pending = false;
+    bool last_sym = false;       // the last ic/kr run used the upper-triangle passes
     // map
     int64_t n = 0, ld = 0, row0 = 0, nloc = 0, nv = 0;
     float* A = nullptr;
@@ -109,6 +110,16 @@ struct gcx_ctx {
     // matvec workspace
     double* ws = nullptr;
     unsigned int* ticket = nullptr;
+    // symmetric (upper-triangle) passes: single rank, exactly symmetric map
+    int sym_enable = 1;          // GCX_SYM=0 disables
+    int sym_state = -1;          // -1 unknown, 0 not symmetric, 1 symmetric
+    double* rowpart = nullptr;   // [nch * SYM_NG][ld]
+    double* colpart = nullptr;   // [grid][nslots][SYM_NG][1024]
+    long long* sym_cta_u0 = nullptr;
+    int* sym_cta_kf = nullptr;
+    int* sym_panel_cta = nullptr;
+    int* sym_panel_cta_hi = nullptr;
+    int sym_slots = 0, sym_grid = 0;
     void* scratch = nullptr;     // grow-only arena for the per-diagonal statistics (avoids cudaMalloc/cudaFree per call)
     size_t scratch_bytes = 0;
     double* part = nullptr;      // per-CTA partials of the fused IC pass (3 x grid)
@@ -193,6 +204,24 @@ struct ProfScope {
     }
 };
 
+// Small device->host reads (convergence state, min/max, counters) go through MAPPED pinned memory written by this
+// tiny kernel, never through a D2H memcpy: a copy-engine transfer would queue behind any large async download in
+// flight on the copy stream (head-of-line blocking) and stall the caller for its whole duration.
+__global__ void k_publish_state(const int* __restrict__ src, volatile int* dst, int words) {
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+
+static int read_small(gcx_ctx* c, const void* dev, size_t bytes, void* host_dst) {
+    if (bytes > 1024 || bytes % 4) return fail("read_small: bad size");
+    volatile int* slot = (volatile int*)((char*)c->h_state + 3072);
+    k_publish_state<<<1, 64, 0, c->stream>>>((const int*)dev, slot, (int)(bytes / 4));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    memcpy(host_dst, (const void*)slot, bytes);
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // library / context
 // ---------------------------------------------------------------------------------------------------
@@ -257,6 +286,18 @@ extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
     CK(cudaEventCreate(&c->tm_b));
     const char* v = getenv("GCX_MATVEC_VARIANT");
     if (v) c->mv_variant = atoi(v);
+    const char* sy = getenv("GCX_SYM");
+    if (sy) c->sym_enable = atoi(sy);
+    if (c->ic_fused != 2) c->sym_enable = c->sym_enable && (c->ic_fused != 1);   // the fused LDG pass has no symmetric twin
+    {
+        const int smem = 6 * SYM_R * MV_THREADS * (int)sizeof(float4);
+        CK(cudaFuncSetAttribute(k_matvec_sym_tma<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k_ic_pass_sym_tma<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ3 = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_ic_pass_sym_tma<6, 2>, TMA_THREADS, smem));
+        c->sym_grid = c->sm_count * std::min(occ3, 2);
+        if (occ3 < 1) c->sym_enable = 0;
+    }
     *out = c;
     return 0;
 }
@@ -264,6 +305,13 @@ extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
 static void free_map(gcx_ctx* c) {
     cudaFree(c->A); c->A = nullptr;
     cudaFree(c->Out); c->Out = nullptr;
+    cudaFree(c->rowpart); c->rowpart = nullptr;
+    cudaFree(c->colpart); c->colpart = nullptr;
+    cudaFree(c->sym_cta_u0); c->sym_cta_u0 = nullptr;
+    cudaFree(c->sym_cta_kf); c->sym_cta_kf = nullptr;
+    cudaFree(c->sym_panel_cta); c->sym_panel_cta = nullptr;
+    cudaFree(c->sym_panel_cta_hi); c->sym_panel_cta_hi = nullptr;
+    c->sym_state = -1;
     cudaFree(c->slab); c->slab = nullptr;
     cudaFree(c->csum32); c->csum32 = nullptr;
     cudaFree(c->zero_count); c->zero_count = nullptr;
@@ -413,6 +461,7 @@ static void par_copy_rows(char* dst, size_t dpitch, const char* src, size_t spit
 extern "C" int gcx_map_upload(gcx_ctx* c, const float* host, int64_t host_ld) {
     CKR(need_map(c));
     CKR(fence_copy(c));
+    c->sym_state = -1;
     if (host_ld < c->n) return fail("host_ld < n");
     const size_t width = sizeof(float) * (size_t)c->n;
     if (is_pinned(host)) {
@@ -516,6 +565,7 @@ static int grid_rows(gcx_ctx* c) { return (int)std::min<int64_t>(c->nloc, (int64
 extern "C" int gcx_map_synth(gcx_ctx* c, uint64_t seed, double scale, double alpha, double empty_frac) {
     CKR(need_map(c));
     CKR(fence_copy(c));
+    c->sym_state = -1;
     const unsigned int thresh = (unsigned int)(std::min(1.0, std::max(0.0, empty_frac)) * 16777216.0);
     {
         ProfScope ps(c, 7);
@@ -529,6 +579,7 @@ extern "C" int gcx_map_synth(gcx_ctx* c, uint64_t seed, double scale, double alp
 
 static int clamp_scale(gcx_ctx* c, int hmin, float vmin, int hmax, float vmax, int hs, float s) {
     CKR(fence_copy(c));
+    c->sym_state = -1;
     const long long total4 = (long long)c->nloc * c->ld / 4;
     {
         ProfScope ps(c, 7);
@@ -555,6 +606,7 @@ extern "C" int gcx_map_swap(gcx_ctx* c) {
     if (!c->Out) return fail("no output map resident");
     std::swap(c->A, c->Out);
     c->have_rowsum = false;
+    c->sym_state = -1;
     return 0;
 }
 
@@ -566,9 +618,7 @@ extern "C" int gcx_map_checksum(gcx_ctx* c, int which, uint64_t* sum) {
     k_checksum<<<grid_rows(c), MV_THREADS, 0, c->stream>>>(src, c->ld, (int)c->nloc, (int)c->n, (int)c->row0, c->csum_dev);
     CK(cudaGetLastError());
     c->launches += 1;
-    CK(cudaMemcpyAsync(c->h_state, c->csum_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    *sum = *(uint64_t*)c->h_state;
+    CKR(read_small(c, c->csum_dev, sizeof(unsigned long long), sum));
     return 0;
 }
 
@@ -645,6 +695,86 @@ extern "C" int gcx_set_mask(gcx_ctx* c, const uint8_t* keep) {
 // ---------------------------------------------------------------------------------------------------
 // matvec dispatch
 // ---------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------
+// symmetric (upper-triangle) passes
+// ---------------------------------------------------------------------------------------------------
+static int64_t sym_bytes_per_pass(gcx_ctx* c) {
+    const int n = (int)c->n, n4 = (int)(c->ld / 4), nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    int64_t bytes = 0;
+    for (int k = 0; k < nch; ++k) {
+        const int64_t rows = (k < nch - 1) ? (int64_t)(k + 1) * 1024 : ((int64_t)(n + SYM_R - 1) / SYM_R) * SYM_R;
+        const int64_t width = std::min<int64_t>(1024, c->ld - (int64_t)k * 1024);
+        bytes += rows * width * 4;
+    }
+    return bytes;
+}
+
+// decides (and caches) whether the resident map can use the upper-triangle passes
+static int sym_ready(gcx_ctx* c, bool* ok) {
+    *ok = false;
+    if (!c->sym_enable || c->world != 1 || c->row0 != 0 || c->nloc != c->n || c->n < 2048) return 0;
+    if (c->sym_state < 0) {
+        CK(cudaMemsetAsync(c->csum_dev, 0, sizeof(unsigned long long), c->stream));
+        k_count_asym<<<c->sm_count * 8, 256, 0, c->stream>>>(c->A, c->ld, (int)c->n, c->csum_dev);
+        CK(cudaGetLastError());
+        c->launches += 1;
+        unsigned long long bad = 0;
+        CKR(read_small(c, c->csum_dev, sizeof bad, &bad));
+        c->sym_state = bad == 0 ? 1 : 0;
+    }
+    if (c->sym_state != 1) return 0;
+    if (!c->rowpart) {
+        // every CTA's share of the panel-major unit list, computed once per map (the kernels do no 64-bit divisions)
+        const int n4 = (int)(c->ld / 4), nch = (n4 + MV_THREADS - 1) / MV_THREADS, G = c->sym_grid;
+        const long long U = sym_total_units((int)c->n, nch);
+        std::vector<long long> u0((size_t)G + 1);
+        std::vector<int> kf((size_t)G, 0), pc((size_t)nch, G), ph((size_t)nch, -1);
+        if (U < G) return 0;          // tiny maps: not every CTA would get a unit (n >= 2048 guarantees U >= 262k/...); keep the dense pass
+        for (int g = 0; g <= G; ++g) u0[g] = (long long)g * U / G;
+        int slots = 1;
+        for (int g = 0; g < G; ++g) {
+            if (u0[g + 1] <= u0[g]) continue;
+            kf[g] = sym_panel_of(u0[g], nch);
+            const int kl = sym_panel_of(u0[g + 1] - 1, nch);
+            slots = std::max(slots, kl - kf[g] + 1);
+            for (int k = kf[g]; k <= kl; ++k) { pc[k] = std::min(pc[k], g); ph[k] = std::max(ph[k], g); }
+        }
+        c->sym_slots = slots;
+        CK(cudaMalloc(&c->sym_cta_u0, sizeof(long long) * ((size_t)G + 1)));
+        CK(cudaMalloc(&c->sym_cta_kf, sizeof(int) * (size_t)G));
+        CK(cudaMalloc(&c->sym_panel_cta, sizeof(int) * (size_t)nch));
+        CK(cudaMalloc(&c->sym_panel_cta_hi, sizeof(int) * (size_t)nch));
+        CK(cudaMemcpy(c->sym_panel_cta_hi, ph.data(), sizeof(int) * (size_t)nch, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->sym_cta_u0, u0.data(), sizeof(long long) * ((size_t)G + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->sym_cta_kf, kf.data(), sizeof(int) * (size_t)G, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->sym_panel_cta, pc.data(), sizeof(int) * (size_t)nch, cudaMemcpyHostToDevice));
+        const size_t rp_bytes = sizeof(double) * (size_t)nch * SYM_NG * c->ld;
+        const size_t cp_bytes = sizeof(double) * (size_t)G * slots * SYM_NG * 1024;
+        CK(cudaMalloc(&c->rowpart, rp_bytes));
+        CK(cudaMalloc(&c->colpart, cp_bytes));
+        // rowpart must start from zero: a (panel, band) is written by one consumer group only, the fold adds both
+        CK(cudaMemsetAsync(c->rowpart, 0, rp_bytes, c->stream));
+        CK(cudaMemsetAsync(c->colpart, 0, cp_bytes, c->stream));
+    }
+    *ok = true;
+    return 0;
+}
+
+static SymTab sym_tab(gcx_ctx* c) { return SymTab{c->sym_cta_u0, c->sym_cta_kf, c->sym_panel_cta, c->sym_panel_cta_hi, c->sym_slots}; }
+
+static int matvec_sym(gcx_ctx* c, const double* z, double* q, const int* done) {
+    const size_t smem = (size_t)6 * SYM_R * MV_THREADS * sizeof(float4);
+    const int n = (int)c->n, n4 = (int)(c->ld / 4);
+    {
+        ProfScope ps(c, 0);
+        k_matvec_sym_tma<6, 2><<<c->sym_grid, TMA_THREADS, smem, c->stream>>>(c->A, c->ld, n, n4, z, c->rowpart, c->colpart, sym_tab(c), done);
+        k_sym_fold<<<(n * 8 + 255) / 256, 256, 0, c->stream>>>(n, n4, c->sym_grid, c->rowpart, c->colpart, sym_tab(c), q, done);
+    }
+    c->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <int R, int OCC>
 static void launch_mv(gcx_ctx* c, const double* z, double* q, const int* done) {
     k_matvec<R, OCC><<<c->sm_count * OCC, MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, (int)(c->ld / 4), z, q + c->row0, c->ws, c->ticket, done);
@@ -664,6 +794,7 @@ static int launch_mv_tma(gcx_ctx* c, const double* z, double* q, const int* done
 }
 
 static int matvec(gcx_ctx* c, int variant, const double* z, double* q, const int* done) {
+    if (variant == 100) return matvec_sym(c, z, q, done);
     {
         ProfScope ps(c, 0);
         switch (variant) {
@@ -695,6 +826,11 @@ static int matvec(gcx_ctx* c, int variant, const double* z, double* q, const int
 extern "C" int gcx_bench_matvec(gcx_ctx* c, int variant, int iters, double* ms_total) {
     CKR(need_map(c));
     if (variant < 0) variant = c->mv_variant;
+    if (variant == 100) {
+        bool ok = false;
+        CKR(sym_ready(c, &ok));
+        if (!ok) return fail("symmetric pass not available for this map (GCX_SYM=0, sharded, n < 2048 or asymmetric)");
+    }
     // z = ones on the real columns
     std::vector<double> ones((size_t)c->nv, 0.0);
     for (int64_t i = 0; i < c->n; ++i) ones[i] = 1.0;
@@ -718,14 +854,6 @@ static int chunk_len(gcx_ctx* c) {
     const double est_ms = 4.0 * (double)c->nloc * (double)c->ld / 5.0e9;   // ~5 TB/s
     int ch = (int)(0.25 / std::max(est_ms, 1e-4)) + 1;
     return std::max(2, std::min(ch, 16));
-}
-
-// The host's convergence check reads the device state through MAPPED pinned memory written by this tiny kernel,
-// not through a D2H memcpy: a copy-engine transfer would queue behind any large async download in flight on the
-// copy stream (head-of-line blocking) and stall the look-ahead loop.
-__global__ void k_publish_state(const int* __restrict__ src, volatile int* dst, int words) {
-    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-    __threadfence_system();
 }
 
 template <typename State, typename StepFn>
@@ -805,7 +933,33 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         CKR(allgather_f64(c, c->vq));
         return 0;
     };
-    auto step = [&]() -> int { return c->ic_fused ? step_fused() : step_split(); };
+    bool sym = false;
+    CKR(sym_ready(c, &sym));
+    c->last_sym = sym;
+    auto step_split_sym = [&]() -> int {
+        CKR(matvec_sym(c, c->vz, c->vq, &c->ic_state->done));
+        {
+            ProfScope ps(c, 6);
+            k_ic_epilogue<<<EP_CL, EP_THREADS, 0, c->stream>>>(c->ic_state, n, c->keep, c->vq, c->vz, c->vB);
+        }
+        CK(cudaGetLastError());
+        return 0;
+    };
+    auto step_fused_sym = [&]() -> int {
+        SymTab tab = sym_tab(c);
+        void* args[] = {(void*)&c->A, (void*)&c->ld, (void*)&n, (void*)&n4, (void*)&c->keep, (void*)&c->vq, (void*)&c->vz, (void*)&c->vB,
+                        (void*)&c->rowpart, (void*)&c->colpart, (void*)&tab, (void*)&c->ticket, (void*)&c->ic_state, (void*)&c->part};
+        {
+            ProfScope ps(c, 0);
+            CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_sym_tma<6, 2>, dim3(c->sym_grid), dim3(TMA_THREADS), args,
+                                           6 * SYM_R * MV_THREADS * sizeof(float4), c->stream));
+        }
+        return 0;
+    };
+    auto step = [&]() -> int {
+        if (sym) return c->ic_fused ? step_fused_sym() : step_split_sym();
+        return c->ic_fused ? step_fused() : step_split();
+    };
     IcState fin;
     CKR(iterate<IcState>(c, c->ic_state, iteration + 4, step, &fin));
     k_ic_scale<<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>((int)c->nv, n, c->keep, c->vB, c->vscale);
@@ -827,8 +981,11 @@ extern "C" int gcx_kr_run(gcx_ctx* c, double tol, double delta, double Delta, do
     k_kr_init<<<32, EP_THREADS, 0, c->stream>>>(c->kr_state, (int)c->nv, c->keep, c->kr, tol, delta, Delta);
     CK(cudaGetLastError());
     c->launches += 1;
+    bool sym = false;
+    CKR(sym_ready(c, &sym));
+    c->last_sym = sym;
     auto step = [&]() -> int {
-        CKR(matvec(c, c->mv_variant, c->vz, c->vq, &c->kr_state->done));
+        CKR(matvec(c, sym ? 100 : c->mv_variant, c->vz, c->vq, &c->kr_state->done));
         CKR(allgather_f64(c, c->vq));
         {
             ProfScope ps(c, 6);
@@ -864,10 +1021,8 @@ static int mm_end(gcx_ctx* c, float* minv, float* maxv) {
         NK(g_nccl.AllReduce(&c->mm->min_nz, &c->mm->min_nz, 1, ncclUint32, ncclMin, c->comm, c->stream));
         NK(g_nccl.AllReduce(&c->mm->max_all, &c->mm->max_all, 1, ncclUint32, ncclMax, c->comm, c->stream));
     }
-    CK(cudaMemcpyAsync(c->h_state, c->mm, sizeof(MinMax), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
     MinMax r;
-    memcpy(&r, c->h_state, sizeof r);
+    CKR(read_small(c, c->mm, sizeof r, &r));
     const float nanv = __builtin_nanf("");
     if (minv) *minv = r.min_nz == 0xffffffffu ? nanv : ord2f(r.min_nz);
     if (maxv) *maxv = r.max_all == 0u ? nanv : ord2f(r.max_all);
@@ -908,7 +1063,7 @@ extern "C" int gcx_apply_sym_scale(gcx_ctx* c, const double* s, int masked_mode,
         EW_DISPATCH(k_apply_sym, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->row0, c->vscale, c->keep, masked_mode, c->mm)
     }
     CK(cudaGetLastError());
-    if (in_place) c->have_rowsum = false;
+    if (in_place) { c->have_rowsum = false; c->sym_state = -1; }
     return mm_end(c, minv, maxv);
 }
 
@@ -934,7 +1089,7 @@ extern "C" int gcx_vc_run(gcx_ctx* c, int sqroot, int in_place, float* minv, flo
     }
     CK(cudaGetLastError());
     if (csum) CK(cudaMemcpyAsync(csum, c->csum32, sizeof(float) * c->n, cudaMemcpyDeviceToHost, c->stream));
-    if (in_place) c->have_rowsum = false;
+    if (in_place) { c->have_rowsum = false; c->sym_state = -1; }
     return mm_end(c, minv, maxv);
 }
 
@@ -1023,7 +1178,7 @@ extern "C" int gcx_diag_apply(gcx_ctx* c, const double* avg, int subtract, int i
         EW_DISPATCH(k_diag_apply, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->vavg, subtract, c->mm)
     }
     CK(cudaGetLastError());
-    if (in_place) c->have_rowsum = false;
+    if (in_place) { c->have_rowsum = false; c->sym_state = -1; }
     return mm_end(c, minv, maxv);
 }
 
@@ -1067,6 +1222,13 @@ extern "C" int gcx_timer_stop(gcx_ctx* c, double* ms) {
 
 extern "C" int gcx_map_invalidate(gcx_ctx* c) {
     c->have_rowsum = false;
+    return 0;
+}
+
+extern "C" int gcx_pass_bytes(gcx_ctx* c, int64_t* bytes, int* symmetric) {
+    CKR(need_map(c));
+    if (symmetric) *symmetric = c->last_sym ? 1 : 0;
+    *bytes = c->last_sym ? sym_bytes_per_pass(c) : (int64_t)4 * c->nloc * c->n;
     return 0;
 }
 

@@ -505,6 +505,308 @@ k_matvec_tma(const float* __restrict__ A, long long ld, int nloc, int n4, const 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K2/K3, symmetric variant: t = A z for a SYMMETRIC map, reading only the upper triangle of the dense
+// layout (north_star: "...or as the upper triangle, since the map is symmetric").  HBM bytes per launch:
+// ~2 n (n + 1024) instead of 4 n^2.
+//
+// Units are (panel k of 1024 columns, band b of 4 rows) with rows <= last column of the panel, enumerated
+// panel-major so that a CTA's contiguous share stays inside a few panels.  The 8 consumer warps form NG groups
+// that take the CTA's units round-robin; a thread of a group owns 4*NG columns of the panel:
+//   column part  y_j += A_ij z_i  (j > i)  accumulates in registers across all bands of the panel and is flushed
+//                once per (CTA, panel, group) into colpart;
+//   row part     x_i += A_ij z_j  (j >= i) is reduced over the warp's columns with a 6-shuffle butterfly and
+//                stored as one partial per (panel, warp-in-group, row) in rowpart -- no CTA-wide barrier, no atomics.
+// The fold adds, in a fixed order, the row partials of the panels right of i and the column partials of the
+// CTAs that walked i's panel.  Everything is deterministic for a given grid.  Tables with every CTA's share
+// (SymTab) are computed once per map on the host, so the kernels do no 64-bit divisions.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SYM_R = 4;
+constexpr int SYM_BPP = 1024 / SYM_R;        // bands per 1024 rows
+constexpr int SYM_NG = 2;                    // consumer groups per CTA (4 warps each, 8 columns per thread)
+
+struct SymTab {
+    const long long* cta_u0;   // [G + 1] first unit of every CTA's share
+    const int* cta_kf;         // [G] panel of that unit
+    const int* panel_cta;      // [nch] first CTA whose (non-empty) share intersects the panel
+    const int* panel_cta_hi;   // [nch] last such CTA; every CTA in between has a non-empty share inside the panel
+    int nslots;                // panels a share may touch (sizes colpart)
+};
+
+__host__ __device__ __forceinline__ long long sym_panel_begin(int k) { return (long long)(SYM_BPP / 2) * k * (k + 1); }
+__host__ __device__ __forceinline__ long long sym_total_units(int n, int nch) {
+    return sym_panel_begin(nch - 1) + (n + SYM_R - 1) / SYM_R;
+}
+__host__ __device__ __forceinline__ int sym_panel_of(long long u, int nch) {
+    int k = (int)((sqrt(1.0 + (double)u / (SYM_BPP / 8)) - 1.0) * 0.5);
+    if (k > nch - 1) k = nch - 1;
+    if (k < 0) k = 0;
+    while (k > 0 && sym_panel_begin(k) > u) --k;
+    while (k < nch - 1 && sym_panel_begin(k + 1) <= u) ++k;
+    return k;
+}
+
+template <int NG, int STAGES, bool ZNC>
+__device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, long long ld, int n, int n4, const double* z,
+                                                double* rowpart, double* colpart, SymTab T, float4* tiles, uint64_t* full_bar,
+                                                uint64_t* empty_bar, double* gred) {
+    constexpr int R = SYM_R;
+    constexpr int WPG = (MV_THREADS / 32) / NG;      // warps per group
+    constexpr int TG = MV_THREADS / NG;              // threads per group
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const long long U = sym_total_units(n, nch), c = blockIdx.x;
+    const long long u0 = T.cta_u0[c], u1 = T.cta_u0[c + 1];
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], WPG);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (u0 >= u1) return;
+    const int kfirst = T.cta_kf[c];
+
+    if (warp == MV_THREADS / 32) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            int stage = 0;
+            unsigned int phase = 0;
+            int k = kfirst;
+            long long pbeg = sym_panel_begin(k);
+            long long pend = (k < nch - 1) ? sym_panel_begin(k + 1) : U;
+            for (long long u = u0; u < u1; ++u) {
+                if (u >= pend) {
+                    ++k;
+                    pbeg = pend;
+                    pend = (k < nch - 1) ? sym_panel_begin(k + 1) : U;
+                }
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                const int b = (int)(u - pbeg);
+                const int c0 = k * MV_THREADS;
+                const int nf4 = min(MV_THREADS, n4 - c0);
+                const unsigned int row_bytes = (unsigned int)nf4 * 16u;
+                mbar_expect_tx(&full_bar[stage], row_bytes * R);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    int r = b * R + rr;
+                    r = r < n ? r : n - 1;
+                    bulk_g2s(tiles + ((size_t)stage * R + rr) * MV_THREADS, A + (long long)r * ld + 4LL * c0, row_bytes, &full_bar[stage]);
+                }
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: group g takes units u0+g, u0+g+NG, ... ----------------
+    const int g = warp / WPG, wig = warp % WPG, tig = tid - g * TG;
+    const double2* z2 = reinterpret_cast<const double2*>(z);
+    const long long rp_ld = (long long)n4 * 4;
+    int k = kfirst;
+    long long pbeg = sym_panel_begin(k);
+    long long pend = (k < nch - 1) ? sym_panel_begin(k + 1) : U;
+    double cacc[NG][4], zc[NG][4];
+    auto load_zc = [&](int kk) {
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+            const int c4 = kk * MV_THREADS + q * TG + tig;
+            double2 za = make_double2(0.0, 0.0), zb = za;
+            if (c4 < n4) {
+                if (ZNC) { za = __ldg(z2 + 2 * c4); zb = __ldg(z2 + 2 * c4 + 1); }
+                else { za = z2[2 * c4]; zb = z2[2 * c4 + 1]; }
+            }
+            zc[q][0] = za.x; zc[q][1] = za.y; zc[q][2] = zb.x; zc[q][3] = zb.y;
+        }
+    };
+    auto flush = [&](int kk) {
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+            double2* dst = reinterpret_cast<double2*>(colpart + (((size_t)c * T.nslots + (kk - kfirst)) * NG + g) * 1024) + 2 * (q * TG + tig);
+            dst[0] = make_double2(cacc[q][0], cacc[q][1]);
+            dst[1] = make_double2(cacc[q][2], cacc[q][3]);
+            cacc[q][0] = cacc[q][1] = cacc[q][2] = cacc[q][3] = 0.0;
+        }
+    };
+#pragma unroll
+    for (int q = 0; q < NG; ++q) cacc[q][0] = cacc[q][1] = cacc[q][2] = cacc[q][3] = 0.0;
+    load_zc(k);
+    for (long long u = u0 + g; u < u1; u += NG) {
+        while (u >= pend) {
+            flush(k);
+            ++k;
+            pbeg = pend;
+            pend = (k < nch - 1) ? sym_panel_begin(k + 1) : U;
+            load_zc(k);
+        }
+        const int it = (int)(u - u0);
+        const int stage = it % STAGES;
+        const unsigned int phase = (unsigned int)(it / STAGES) & 1u;
+        const int i0 = (int)(u - pbeg) * R;
+        // z of the band's rows (broadcast loads); rows past n read the zero padding of z
+        double2 zr01, zr23;
+        if (ZNC) { zr01 = __ldg(z2 + (i0 >> 1)); zr23 = __ldg(z2 + (i0 >> 1) + 1); }
+        else { zr01 = z2[i0 >> 1]; zr23 = z2[(i0 >> 1) + 1]; }
+        const double zr[4] = {zr01.x, zr01.y, zr23.x, zr23.y};
+        mbar_wait(&full_bar[stage], phase);
+        double rp[R] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+            const int cl = q * TG + tig;                    // float4 column inside the panel
+            const int c4 = k * MV_THREADS + cl;
+            // j0 and i0 are multiples of 4: a thread's 4x4 block is entirely above the diagonal (delta > 0), entirely
+            // below it (delta < 0: nothing to do) or the diagonal block itself (delta == 0, one thread per unit)
+            const int delta = 4 * c4 - i0;
+            if (c4 < n4 && delta >= 0) {
+                float4 a[R];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) a[rr] = tiles[((size_t)stage * R + rr) * MV_THREADS + cl];
+                if (delta > 0) {
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        const double x0 = (double)a[rr].x, x1 = (double)a[rr].y, x2 = (double)a[rr].z, x3 = (double)a[rr].w;
+                        rp[rr] = fma(x0, zc[q][0], rp[rr]); rp[rr] = fma(x1, zc[q][1], rp[rr]);
+                        rp[rr] = fma(x2, zc[q][2], rp[rr]); rp[rr] = fma(x3, zc[q][3], rp[rr]);
+                        cacc[q][0] = fma(x0, zr[rr], cacc[q][0]); cacc[q][1] = fma(x1, zr[rr], cacc[q][1]);
+                        cacc[q][2] = fma(x2, zr[rr], cacc[q][2]); cacc[q][3] = fma(x3, zr[rr], cacc[q][3]);
+                    }
+                } else {
+                    // diagonal 4x4 block: row part takes j >= i, column part j > i
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        const float av[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const double x = (double)av[e];
+                            if (e >= rr) rp[rr] = fma(x, zc[q][e], rp[rr]);
+                            if (e > rr) cacc[q][e] = fma(x, zr[rr], cacc[q][e]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        // butterfly: 4 row partials x 32 lanes -> lanes {0,8,16,24} hold the warp sums of rows {0,1,2,3}
+        {
+            const bool hi16 = lane & 16, hi8 = lane & 8;
+            double k0 = hi16 ? rp[2] : rp[0], k1 = hi16 ? rp[3] : rp[1];
+            const double s0 = hi16 ? rp[0] : rp[2], s1 = hi16 ? rp[1] : rp[3];
+            k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            double y = hi8 ? k1 : k0;
+            const double sy = hi8 ? k0 : k1;
+            y += __shfl_xor_sync(0xffffffffu, sy, 8);
+            y += __shfl_xor_sync(0xffffffffu, y, 4);
+            y += __shfl_xor_sync(0xffffffffu, y, 2);
+            y += __shfl_xor_sync(0xffffffffu, y, 1);
+            // join the group's WPG warps through shared memory (double-buffered by unit parity: one named barrier per
+            // unit), fixed order -> one partial per (panel, group, row)
+            const int par = (it / NG) & 1;
+            if ((lane & 7) == 0) gred[((par * NG + g) * WPG + wig) * R + (lane >> 3)] = y;
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + g), "n"(TG) : "memory");
+            if (wig == 0 && lane < R) {
+                double ssum = 0.0;
+#pragma unroll
+                for (int w = 0; w < WPG; ++w) ssum += gred[((par * NG + g) * WPG + w) * R + lane];
+                const int i = i0 + lane;
+                if (i < n) rowpart[((long long)k * NG + g) * rp_ld + i] = ssum;
+            }
+        }
+    }
+    // every group flushes every panel the CTA's share touches (groups that saw no unit of a panel flush zeros)
+    const int klast = sym_panel_of(u1 - 1, nch);
+    while (true) {
+        flush(k);
+        if (k >= klast) break;
+        ++k;
+    }
+}
+
+template <int STAGES, int OCC>
+__global__ void __launch_bounds__(TMA_THREADS, OCC)
+k_matvec_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, const double* __restrict__ z, double* rowpart,
+                 double* colpart, SymTab T, const int* __restrict__ done) {
+    if (done != nullptr && *done) return;
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ double gred[2 * (MV_THREADS / 32) * SYM_R];
+    matvec_sym_core<SYM_NG, STAGES, true>(A, ld, n, n4, z, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred);
+}
+
+// t_i, computed by 8 cooperating lanes: lane j sums the row partials of (group, warp-in-group) pair j over the panels
+// k >= i/1024 (a unit of a panel belongs to exactly one group, the other group's slot for that band holds a stale or
+// zero value -- so every (panel, band) is written by ONE group; both slots are zero-initialised and only the owner's
+// is ever written, hence summing both is exact), lane 0 also adds the column partials, then a fixed 3-step shuffle
+// tree joins them.  Must be called by all 8 lanes of an aligned group; every lane returns t_i.
+__device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n, int n4, int G, const double* rowpart, const double* colpart,
+                                                  SymTab T) {
+    const int j = threadIdx.x & 7;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const long long rp_ld = (long long)n4 * 4;
+    double s = 0.0;
+    if (valid) {
+        const int ki = i >> 10;
+        // lane j: consumer group j % NG, panels ki + j / NG, + 8/NG, ...  (a (panel, band) is written by ONE group; the
+        // other group's entry keeps its initial zero, so adding both is exact)
+#pragma unroll 4
+        for (int k = ki + j / SYM_NG; k < nch; k += 8 / SYM_NG) s += __ldcg(rowpart + ((long long)k * SYM_NG + (j % SYM_NG)) * rp_ld + i);
+        // column partials: the CTAs [panel_cta[ki], panel_cta_hi[ki]] walked panel ki; lane j takes every 8th of them
+        const int clo = T.panel_cta[ki], chi = T.panel_cta_hi[ki];
+#pragma unroll 2
+        for (int c = clo + j; c <= chi; c += 8) {
+            const double* cp = colpart + ((size_t)c * T.nslots + (ki - T.cta_kf[c])) * SYM_NG * 1024 + (i & 1023);
+#pragma unroll
+            for (int gg = 0; gg < SYM_NG; ++gg) s += __ldcg(cp + gg * 1024);
+        }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+k_sym_fold(int n, int n4, int G, const double* rowpart, const double* colpart, SymTab T, double* __restrict__ t,
+           const int* __restrict__ done) {
+    if (done != nullptr && *done) return;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const double ti = sym_fold_group8(i, i < n, n, n4, G, rowpart, colpart, T);
+    if (i < n && (threadIdx.x & 7) == 0) t[i] = ti;
+}
+
+// Exact symmetry test: number of (i, j), i < j, with A_ij != A_ji (bitwise on the float values; +0 == -0).
+// One read of the map (32 x 32 tiles, the mirror tile transposed through shared memory).
+__global__ void __launch_bounds__(256)
+k_count_asym(const float* __restrict__ A, long long ld, int n, unsigned long long* count) {
+    __shared__ float tile[32][33];
+    const int nt = (n + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    unsigned int bad = 0;
+    for (long long p = blockIdx.x; p < (long long)nt * nt; p += gridDim.x) {
+        const int bi = (int)(p / nt), bj = (int)(p % nt);
+        if (bj < bi) continue;
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {            // mirror tile (bj, bi)
+            const int i = bj * 32 + r, j = bi * 32 + tx;
+            tile[r][tx] = (i < n && j < n) ? A[(long long)i * ld + j] : 0.f;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int i = bi * 32 + r, j = bj * 32 + tx;
+            if (i < n && j < n && i < j) bad += (A[(long long)i * ld + j] != tile[tx][r]);
+        }
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if (tx == 0 && bad) atomicAdd(count, (unsigned long long)bad);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K1 row statistics: float64 row sum + int32 count of zeros over the n real columns.
 // Replaces the loop of lib/ccmapHelpers.pyx:190-201.  Algorithmic bytes: 4 * nloc * n.
 // ---------------------------------------------------------------------------------------------------
@@ -1371,6 +1673,98 @@ k_ic_pass_tma(const float* __restrict__ A, long long ld, int nloc, int n4, int n
     if (tid == 0) {
         *ticket = 0u;
         st->matvecs = m + 1;
+    }
+}
+
+// Fused IC pass on the upper triangle: P1 folds t_i from the partials of the previous launch's symmetric
+// matvec on the fly, P2/P3 as in k_ic_pass, then the symmetric TMA main loop with z = v.
+template <int STAGES, int OCC>
+__global__ void __launch_bounds__(TMA_THREADS, OCC)
+k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, const uint8_t* __restrict__ keep, double* t, double* v,
+                  double* B, double* rowpart, double* colpart, SymTab T, unsigned int* ticket, IcState* st, double* part) {
+    namespace cg = cooperative_groups;
+    if (st->done) return;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ double sm[32];
+    __shared__ double gred[2 * (MV_THREADS / 32) * SYM_R];
+    const int tid = threadIdx.x;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int m = st->matvecs;
+    const int gth = bid * TMA_THREADS + tid, nth = G * TMA_THREADS;
+
+    if (m > 0) {
+        const int mm = m - 1;
+        const double cc_prev = st->cc, tol = st->tol;
+        const int max_iter = st->max_iter;
+        double s = 0.0, c = 0.0;
+        // t_i is folded by groups of 8 lanes (TMA_THREADS = 288 is a multiple of 8); lane 0 of a group owns bin i
+        for (int base = 0; base < n; base += nth / 8) {
+            const int i = base + (gth >> 3);
+            const double ti = sym_fold_group8(i, i < n, n, n4, G, rowpart, colpart, T);
+            if (i < n && (tid & 7) == 0) {
+                t[i] = ti;
+                if (keep[i]) {
+                    const double p = v[i] * ti;
+                    s += p;
+                    c += (p != 0.0) ? 1.0 : 0.0;
+                }
+            }
+        }
+        s = block_reduce<RED_SUM>(s, sm);
+        c = block_reduce<RED_SUM>(c, sm);
+        if (tid == 0) {
+            part[bid] = s;
+            part[G + bid] = c;
+        }
+        grid.sync();
+        double a0 = 0.0, a1 = 0.0;
+        for (int b = tid; b < G; b += TMA_THREADS) {
+            a0 += __ldcg(part + b);
+            a1 += __ldcg(part + G + b);
+        }
+        const double S = block_reduce<RED_SUM>(a0, sm), C = block_reduce<RED_SUM>(a1, sm);
+        const double cc = (mm == 0) ? S : cc_prev;          // contact_count, lib/normalizeCore.pyx:36
+        const double f = (mm == 0) ? 1.0 : sqrt(S / cc);    // :52
+        const double g = (mm == 0) ? 1.0 : cc / S;          // :53
+        const double mean = g * S / C;                      // :44
+        double l1 = 0.0;
+        for (int i = gth; i < n; i += nth) {
+            if (keep[i]) {
+                const double vi = v[i];
+                const double d = g * (vi * t[i]);
+                double bn = B[i];
+                if (mm > 0) {
+                    bn = f / vi;                            // :51-52
+                    l1 += fabs(B[i] - bn);                  // :56
+                    B[i] = bn;
+                }
+                v[i] = (d != 0.0) ? mean / (bn * d) : 1.0 / bn;     // :44-45
+            }
+        }
+        l1 = block_reduce<RED_SUM>(l1, sm);
+        if (tid == 0) part[2 * G + bid] = l1;
+        grid.sync();
+        double a2 = 0.0;
+        for (int b = tid; b < G; b += TMA_THREADS) a2 += __ldcg(part + 2 * G + b);
+        const double L1 = block_reduce<RED_SUM>(a2, sm);
+        const bool done = (mm >= 2) && (L1 < tol || (mm - 1) > max_iter);       // :55-57
+        if (bid == 0 && tid == 0) {
+            st->cc = cc; st->S = S; st->l1 = L1; st->mean = mean; st->cnt = (int)C;
+            st->pass = mm; st->done = done ? 1 : 0;
+        }
+        if (done) return;
+    }
+    // the previous launch's partials have been consumed by every CTA (grid barriers above, or m == 0)
+    matvec_sym_core<SYM_NG, STAGES, false>(A, ld, n, n4, v, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred);
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == (unsigned int)(G - 1)) {       // last CTA to issue its work: safe to bump the counter
+            *ticket = 0u;
+            st->matvecs = m + 1;
+        }
     }
 }
 

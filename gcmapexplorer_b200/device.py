@@ -180,14 +180,16 @@ class DeviceMap:
         passes, mv, l1 = C.c_int(0), C.c_int(0), C.c_double(0)
         check(lib().gcx_ic_run(self._ctx, float(tol), int(iteration), bias.ctypes.data_as(_lib._c_f64p),
                                C.byref(passes), C.byref(l1), C.byref(mv)))
-        return dict(bias=bias, passes=passes.value, l1=l1.value, matvecs=mv.value, ms=self.last_run_ms())
+        pb, sym = self.pass_bytes()
+        return dict(bias=bias, passes=passes.value, l1=l1.value, matvecs=mv.value, ms=self.last_run_ms(), pass_bytes=pb, symmetric=sym)
 
     def kr(self, tol=1e-12, delta=0.1, Delta=3.0):
         x = np.empty(self.n, dtype=np.float64)
         outer, mvp, rout = C.c_int(0), C.c_int(0), C.c_double(0)
         check(lib().gcx_kr_run(self._ctx, float(tol), float(delta), float(Delta), x.ctypes.data_as(_lib._c_f64p),
                                C.byref(outer), C.byref(mvp), C.byref(rout)))
-        return dict(x=x, outer=outer.value, MVP=mvp.value, rout=rout.value, ms=self.last_run_ms())
+        pb, sym = self.pass_bytes()
+        return dict(x=x, outer=outer.value, MVP=mvp.value, rout=rout.value, ms=self.last_run_ms(), pass_bytes=pb, symmetric=sym)
 
     # ---- elementwise passes ---------------------------------------------------------------------
     def apply_sym(self, s=None, masked_mode=0, in_place=False):
@@ -239,6 +241,12 @@ class DeviceMap:
         ms = C.c_double(0)
         check(lib().gcx_timer_stop(self._ctx, C.byref(ms)))
         return ms.value
+
+    def pass_bytes(self):
+        """(HBM bytes per matrix pass of the last ic/kr run, used_upper_triangle)."""
+        b, sym = C.c_int64(0), C.c_int(0)
+        check(lib().gcx_pass_bytes(self._ctx, C.byref(b), C.byref(sym)))
+        return b.value, bool(sym.value)
 
     def last_run_ms(self):
         ms = C.c_double(0)

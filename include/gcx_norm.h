@@ -121,6 +121,9 @@ int gcx_timer_start(gcx_ctx* ctx);
 int gcx_timer_stop(gcx_ctx* ctx, double* ms);
 /* forget cached row statistics so the next mask / VC call re-reads the map (benchmark steps) */
 int gcx_map_invalidate(gcx_ctx* ctx);
+/* HBM bytes one matrix pass of the last ic/kr run read: 4*nloc*n for the dense pass, ~2*n*(n+1024) when the
+ * upper-triangle pass was used (single rank, exactly symmetric map, n >= 2048; GCX_SYM=0 disables it) */
+int gcx_pass_bytes(gcx_ctx* ctx, int64_t* bytes, int* symmetric);
 /* device time (ms, CUDA events) of the last ic/kr run: matrix resident -> final vector */
 int gcx_last_run_ms(gcx_ctx* ctx, double* ms);
 /* total kernel launches issued by this context since creation */

@@ -446,3 +446,43 @@ def test_in_place_equals_out_of_place_and_async_download(gx):
         with pytest.raises(gx.GcxError):
             dm.download_async(0, np.empty((500, 500), dtype=np.float32))     # pageable memory is refused
         pin.free()
+
+
+# --------------------------------------------------------------------------------------------------
+# upper-triangle (symmetric) passes
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [2048, 3000, 4099, 6145])
+def test_symmetric_pass_matches_dense_pass(gx, n, monkeypatch):
+    """IC and KR through the upper-triangle matvec vs the dense matvec on the same device-generated map."""
+    res = {}
+    for sym in ("1", "0"):
+        monkeypatch.setenv("GCX_SYM", sym)
+        with gx.DeviceMap(n) as dm:
+            dm.synth(seed=77, scale=150.0, alpha=1.0, empty_frac=0.01)
+            rs, _ = dm.row_stats()
+            keep = rs != 0
+            dm.set_mask(np.ones(n, dtype=bool))
+            ic = dm.ic(1e-4, 500)
+            dm.set_mask(keep)
+            kr = dm.kr(1e-12, 0.1, 3)
+            res[sym] = (ic, kr, keep)
+    (ic1, kr1, keep), (ic0, kr0, _) = res["1"], res["0"]
+    assert ic1["symmetric"] and kr1["symmetric"] and not ic0["symmetric"]
+    assert ic1["pass_bytes"] < (0.5 + 0.5 * 1024.0 / n + 0.03) * ic0["pass_bytes"]      # half + the 1024-column diagonal panels
+    assert ic1["passes"] == ic0["passes"] and (kr1["outer"], kr1["MVP"]) == (kr0["outer"], kr0["MVP"])
+    np.testing.assert_allclose(ic1["bias"], ic0["bias"], rtol=1e-12)
+    np.testing.assert_allclose(kr1["x"][keep], kr0["x"][keep], rtol=1e-11)
+
+
+def test_symmetric_pass_vs_oracle_and_asymmetric_fallback(gx):
+    n = 2100
+    A = onp.synth_map(n, seed=31)
+    M64, B, passes, _ = onp.ic_fp64(A, 1e-4, 500)
+    r = _ic_device(gx, A, 1e-4, 500, np.ones(n, dtype=bool))
+    assert r["symmetric"] and r["passes"] == passes
+    np.testing.assert_allclose(r["bias"], B, rtol=BIAS_RTOL)
+    assert rel_err(r["matrix"], M64.astype(np.float32)) < MAT_RTOL
+    A2 = A.copy()
+    A2[5, 1900] += 1.0                       # break the symmetry in one entry
+    r2 = _ic_device(gx, A2, 1e-4, 500, np.ones(n, dtype=bool))
+    assert not r2["symmetric"]               # dense pass: row sums of the stored matrix, like every other dense run
