@@ -131,9 +131,16 @@ def run_b200(args):
         n = args.n or int(round(N_CHR1_10KB * math.sqrt(world)))
         wl = ("synthetic chr1 @ 10 kb (n=%d), IC + VC" % n) if world == 1 else \
              ("synthetic chr1-like map, n=%d (2.485 GB fp32 per GPU), IC + VC, row-sharded" % n)
+    from gcmapexplorer_b200 import dist as gd
     rpr = (n + world - 1) // world
-    row0 = rank * rpr
-    nloc = max(0, min(rpr, n - row0))
+    options = {}
+    if world > 1 and args.partition == "equal_area":
+        # equal shares of the upper triangle per rank (panel-aligned cuts): the IC/KR passes read the upper triangle only.
+        # The synthetic map is symmetric by construction, which a rank cannot verify locally -> assume_symmetric.
+        row0, nloc = gd.row_partition_equal_area(n, world, rank)
+        options = {"exchange_allreduce": 1, "assume_symmetric": 1}
+    else:
+        row0, nloc = gd.row_partition(n, world, rank)
     if world > 1:
         import torch
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -141,7 +148,7 @@ def run_b200(args):
             idt = torch.tensor(list(gx.dist_unique_id()), dtype=torch.uint8, device="cuda")
         tdist.broadcast(idt, 0)
         dist = (rank, world, bytes(idt.cpu().tolist()))
-    dm = gx.DeviceMap(n, row0, nloc, device=local, dist=dist)
+    dm = gx.DeviceMap(n, row0, nloc, device=local, dist=dist, options=options)
     dm.synth(seed=args.seed, scale=200.0, alpha=1.0, empty_frac=0.01)
     peak, peak_kind = measured_peak()
     kr_mode = args.workload == "chr1_5kb_kr" or args.kr
@@ -157,6 +164,14 @@ def run_b200(args):
         import torch
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if tdist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
         return float(t.item())
 
     ones = np.ones(n, dtype=bool)
@@ -204,7 +219,7 @@ def run_b200(args):
     mv = info["matvecs"]
     # bytes the step actually has to move: mask 4n^2 + matvecs x (bytes of one pass over the resident layout:
     # 4n^2 dense, ~2n(n+1024) when the upper-triangle pass is used) + apply 8n^2 (+ VC apply 8n^2)
-    pass_bytes_all = float(info["pass_bytes"]) * (1 if info["symmetric"] else world)
+    pass_bytes_all = sum_over_ranks(float(info["pass_bytes"]))
     bytes_step = 4.0 * n * n + mv * pass_bytes_all + (8.0 if kr_mode else 16.0) * n * n
     dense_equiv = (4.0 * (1 + mv) + (8.0 if kr_mode else 16.0)) * n * n
     value = bytes_step / (ms_per_step * 1e-3) / 1e9
@@ -212,7 +227,7 @@ def run_b200(args):
     # roofline of the dominant kernel: mean duration over the *effective* launches (launches after the
     # device-side convergence flag exit immediately; their few microseconds stay in the sum)
     mv_ms = max_over_ranks(prof["matvec"]["ms"]) / max(1, args.steps * mv)
-    mv_bytes = float(info["pass_bytes"])
+    mv_bytes = max_over_ranks(float(info["pass_bytes"]))      # the most loaded rank's share of one pass
     achieved = mv_bytes / (mv_ms * 1e-3) / 1e9
     kname = ("k_matvec_sym_tma+k_sym_fold" if kr_mode else "k_ic_pass_sym_tma") if info["symmetric"] else ("k_matvec_tma" if kr_mode else "k_ic_pass_tma")
     roofline = {"kernel": kname, "layout": "dense fp32, upper triangle read (symmetric pass)" if info["symmetric"] else "dense fp32, all rows read", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
@@ -279,8 +294,8 @@ def run_b200(args):
             "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 accumulate / f32 storage", "data": "synthetic (device-generated Poisson power-law map, 1% empty bins)",
-            "config": {"workload": wl, "n": n, "rows_per_gpu": rpr, "map_bytes_per_gpu": int(4 * rpr * n), "l2": "inputs larger than L2 (no flush needed)",
-                       "tol": IC_TOL if not kr_mode else 1e-12, "parallelism": "row-block x%d, NCCL allgather of the n-vector per pass" % world if world > 1 else "single GPU"},
+            "config": {"workload": wl, "n": n, "rows_this_rank": nloc, "map_bytes_per_gpu_mean": int(4 * rpr * n), "partition": (args.partition if world > 1 else "single"), "l2": "inputs larger than L2 (no flush needed)",
+                       "tol": IC_TOL if not kr_mode else 1e-12, "parallelism": ("row-block x%d (%s), one NCCL %s of the n-vector per pass" % (world, args.partition, "allreduce" if info["symmetric"] else "allgather")) if world > 1 else "single GPU"},
             "time_to_converge_s": round(float(np.median(conv_ms)) * 1e-3, 5), "passes": info["passes"], "matvecs": mv,
             "hbm_bytes_per_step": bytes_step, "dense_equivalent_bytes_per_step": dense_equiv,
             "value_dense_equivalent": round(dense_equiv / (ms_per_step * 1e-3) / 1e9, 1),
@@ -509,6 +524,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--partition", default="equal_area", choices=["equal_area", "rows"],
+                    help="N>1: equal_area = equal upper-triangle shares per rank + symmetric passes; rows = equal row blocks + dense passes")
     ap.add_argument("--kr", action="store_true", help="run KR instead of IC + VC on the selected workload")
     args = ap.parse_args()
     if args.impl == "reference":

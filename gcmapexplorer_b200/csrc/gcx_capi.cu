@@ -115,10 +115,12 @@ struct gcx_ctx {
     int sym_state = -1;          // -1 unknown, 0 not symmetric, 1 symmetric
     double* rowpart = nullptr;   // [nch * SYM_NG][ld]
     double* colpart = nullptr;   // [grid][nslots][SYM_NG][1024]
-    long long* sym_cta_u0 = nullptr;
-    int* sym_cta_kf = nullptr;
-    int* sym_panel_cta = nullptr;
-    int* sym_panel_cta_hi = nullptr;
+    long long* sym_tab_ll = nullptr;      // panel_u0 [nch+1] | cta_u0 [G+1]
+    int* sym_tab_i = nullptr;             // cta_kf [G] | cta_kl [G] | panel_cta [nch] | panel_cta_hi [nch]
+    int sym_nch = 0;
+    int64_t sym_bytes = 0;
+    int assume_symmetric = 0;             // sharded runs cannot test symmetry locally: the caller vouches for it
+    int exchange_allreduce = 0;           // custom (unequal) row partition: vectors are exchanged by zero-fill + allreduce
     int sym_slots = 0, sym_grid = 0;
     void* scratch = nullptr;     // grow-only arena for the per-diagonal statistics (avoids cudaMalloc/cudaFree per call)
     size_t scratch_bytes = 0;
@@ -292,9 +294,10 @@ extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
     {
         const int smem = 6 * SYM_R * MV_THREADS * (int)sizeof(float4);
         CK(cudaFuncSetAttribute(k_matvec_sym_tma<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(k_ic_pass_sym_tma<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k_ic_pass_sym_tma<6, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k_ic_pass_sym_tma<6, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ3 = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_ic_pass_sym_tma<6, 2>, TMA_THREADS, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_ic_pass_sym_tma<6, 2, true>, TMA_THREADS, smem));
         c->sym_grid = c->sm_count * std::min(occ3, 2);
         if (occ3 < 1) c->sym_enable = 0;
     }
@@ -307,10 +310,8 @@ static void free_map(gcx_ctx* c) {
     cudaFree(c->Out); c->Out = nullptr;
     cudaFree(c->rowpart); c->rowpart = nullptr;
     cudaFree(c->colpart); c->colpart = nullptr;
-    cudaFree(c->sym_cta_u0); c->sym_cta_u0 = nullptr;
-    cudaFree(c->sym_cta_kf); c->sym_cta_kf = nullptr;
-    cudaFree(c->sym_panel_cta); c->sym_panel_cta = nullptr;
-    cudaFree(c->sym_panel_cta_hi); c->sym_panel_cta_hi = nullptr;
+    cudaFree(c->sym_tab_ll); c->sym_tab_ll = nullptr;
+    cudaFree(c->sym_tab_i); c->sym_tab_i = nullptr;
     c->sym_state = -1;
     cudaFree(c->slab); c->slab = nullptr;
     cudaFree(c->csum32); c->csum32 = nullptr;
@@ -625,14 +626,54 @@ extern "C" int gcx_map_checksum(gcx_ctx* c, int which, uint64_t* sum) {
 // ---------------------------------------------------------------------------------------------------
 // collectives (no-ops on a single rank)
 // ---------------------------------------------------------------------------------------------------
+__global__ void k_zero_outside_f64(double* v, int nv, int lo, int hi) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x)
+        if (i < lo || i >= hi) v[i] = 0.0;
+}
+__global__ void k_zero_outside_i32(int* v, int nv, int lo, int hi) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x)
+        if (i < lo || i >= hi) v[i] = 0;
+}
+
+static int allreduce_f64(gcx_ctx* c, double* vec, size_t count) {
+    if (c->world == 1) return 0;
+    NK(g_nccl.AllReduce(vec, vec, count, ncclFloat64, ncclSum, c->comm, c->stream));
+    return 0;
+}
+
+// Every rank wrote its own rows [row0, row0+nloc) of an n-vector; afterwards every rank holds all of it.
+// Equal row blocks: one in-place NCCL allgather.  Custom (unequal) blocks: zero the foreign entries and allreduce
+// (x + 0 + ... + 0 is exact, so the result is the same bits on every rank).
 static int allgather_f64(gcx_ctx* c, double* vec) {
     if (c->world == 1) return 0;
+    if (c->exchange_allreduce) {
+        k_zero_outside_f64<<<64, 256, 0, c->stream>>>(vec, (int)c->nv, (int)c->row0, (int)(c->row0 + c->nloc));
+        CK(cudaGetLastError());
+        return allreduce_f64(c, vec, (size_t)c->n);
+    }
     NK(g_nccl.AllGather(vec + c->rank * c->rpr, vec, (size_t)c->rpr, ncclFloat64, c->comm, c->stream));
     return 0;
 }
 static int allgather_i32(gcx_ctx* c, int32_t* vec) {
     if (c->world == 1) return 0;
+    if (c->exchange_allreduce) {
+        k_zero_outside_i32<<<64, 256, 0, c->stream>>>(vec, (int)c->nv, (int)c->row0, (int)(c->row0 + c->nloc));
+        CK(cudaGetLastError());
+        NK(g_nccl.AllReduce(vec, vec, (size_t)c->n, ncclInt32, ncclSum, c->comm, c->stream));
+        return 0;
+    }
     NK(g_nccl.AllGather(vec + c->rank * c->rpr, vec, (size_t)c->rpr, ncclInt32, c->comm, c->stream));
+    return 0;
+}
+
+extern "C" int gcx_set_option(gcx_ctx* c, const char* key, double value) {
+    if (!c || !key) return fail("gcx_set_option: null argument");
+    const std::string k(key);
+    if (k == "sym") c->sym_enable = (int)value;
+    else if (k == "assume_symmetric") { c->assume_symmetric = (int)value; c->sym_state = -1; }
+    else if (k == "exchange_allreduce") c->exchange_allreduce = (int)value;
+    else if (k == "matvec_variant") c->mv_variant = (int)value;
+    else return fail("gcx_set_option: unknown key '%s'", key);
     return 0;
 }
 
@@ -698,56 +739,67 @@ extern "C" int gcx_set_mask(gcx_ctx* c, const uint8_t* keep) {
 // ---------------------------------------------------------------------------------------------------
 // symmetric (upper-triangle) passes
 // ---------------------------------------------------------------------------------------------------
-static int64_t sym_bytes_per_pass(gcx_ctx* c) {
-    const int n = (int)c->n, n4 = (int)(c->ld / 4), nch = (n4 + MV_THREADS - 1) / MV_THREADS;
-    int64_t bytes = 0;
-    for (int k = 0; k < nch; ++k) {
-        const int64_t rows = (k < nch - 1) ? (int64_t)(k + 1) * 1024 : ((int64_t)(n + SYM_R - 1) / SYM_R) * SYM_R;
-        const int64_t width = std::min<int64_t>(1024, c->ld - (int64_t)k * 1024);
-        bytes += rows * width * 4;
-    }
-    return bytes;
-}
+static int64_t sym_bytes_per_pass(gcx_ctx* c) { return c->sym_bytes; }
 
-// decides (and caches) whether the resident map can use the upper-triangle passes
+// decides (and caches) whether the resident map can use the upper-triangle passes, and tabulates the geometry
 static int sym_ready(gcx_ctx* c, bool* ok) {
     *ok = false;
-    if (!c->sym_enable || c->world != 1 || c->row0 != 0 || c->nloc != c->n || c->n < 2048) return 0;
+    if (!c->sym_enable || c->n < 2048) return 0;
+    if (c->world > 1 && !(c->assume_symmetric && c->exchange_allreduce && c->row0 % 1024 == 0)) return 0;
+    if (c->world == 1 && (c->row0 != 0 || c->nloc != c->n)) return 0;
     if (c->sym_state < 0) {
-        CK(cudaMemsetAsync(c->csum_dev, 0, sizeof(unsigned long long), c->stream));
-        k_count_asym<<<c->sm_count * 8, 256, 0, c->stream>>>(c->A, c->ld, (int)c->n, c->csum_dev);
-        CK(cudaGetLastError());
-        c->launches += 1;
-        unsigned long long bad = 0;
-        CKR(read_small(c, c->csum_dev, sizeof bad, &bad));
-        c->sym_state = bad == 0 ? 1 : 0;
+        if (c->world > 1 || c->assume_symmetric) {
+            c->sym_state = 1;             // a rank cannot see the mirrored block: the caller vouches (gcx_set_option "assume_symmetric")
+        } else {
+            CK(cudaMemsetAsync(c->csum_dev, 0, sizeof(unsigned long long), c->stream));
+            k_count_asym<<<c->sm_count * 8, 256, 0, c->stream>>>(c->A, c->ld, (int)c->n, c->csum_dev);
+            CK(cudaGetLastError());
+            c->launches += 1;
+            unsigned long long bad = 0;
+            CKR(read_small(c, c->csum_dev, sizeof bad, &bad));
+            c->sym_state = bad == 0 ? 1 : 0;
+        }
     }
     if (c->sym_state != 1) return 0;
     if (!c->rowpart) {
-        // every CTA's share of the panel-major unit list, computed once per map (the kernels do no 64-bit divisions)
-        const int n4 = (int)(c->ld / 4), nch = (n4 + MV_THREADS - 1) / MV_THREADS, G = c->sym_grid;
-        const long long U = sym_total_units((int)c->n, nch);
+        // every panel's and every CTA's share of the panel-major unit list (the kernels do no 64-bit divisions)
+        const int n = (int)c->n, n4 = (int)(c->ld / 4), nch = (n4 + MV_THREADS - 1) / MV_THREADS, G = c->sym_grid;
+        const long long r0 = c->row0, r1 = c->row0 + c->nloc;
+        std::vector<long long> pu((size_t)nch + 1, 0);
+        int64_t bytes = 0;
+        for (int k = 0; k < nch; ++k) {
+            const long long rows_end = std::min<long long>(r1, (k < nch - 1) ? (long long)(k + 1) * 1024 : (long long)n);
+            const long long nb = rows_end > r0 ? (rows_end - r0 + SYM_R - 1) / SYM_R : 0;
+            pu[k + 1] = pu[k] + nb;
+            bytes += nb * SYM_R * std::min<int64_t>(1024, c->ld - (int64_t)k * 1024) * 4;
+        }
+        const long long U = pu[nch];
+        if (U < G) return 0;          // tiny share: keep the dense pass
+        auto panel_of = [&](long long u) { return (int)(std::upper_bound(pu.begin(), pu.end(), u) - pu.begin()) - 1; };
         std::vector<long long> u0((size_t)G + 1);
-        std::vector<int> kf((size_t)G, 0), pc((size_t)nch, G), ph((size_t)nch, -1);
-        if (U < G) return 0;          // tiny maps: not every CTA would get a unit (n >= 2048 guarantees U >= 262k/...); keep the dense pass
+        std::vector<int> kf((size_t)G, 0), kl((size_t)G, 0), pc((size_t)nch, G), ph((size_t)nch, -1);
         for (int g = 0; g <= G; ++g) u0[g] = (long long)g * U / G;
         int slots = 1;
         for (int g = 0; g < G; ++g) {
             if (u0[g + 1] <= u0[g]) continue;
-            kf[g] = sym_panel_of(u0[g], nch);
-            const int kl = sym_panel_of(u0[g + 1] - 1, nch);
-            slots = std::max(slots, kl - kf[g] + 1);
-            for (int k = kf[g]; k <= kl; ++k) { pc[k] = std::min(pc[k], g); ph[k] = std::max(ph[k], g); }
+            kf[g] = panel_of(u0[g]);
+            kl[g] = panel_of(u0[g + 1] - 1);
+            slots = std::max(slots, kl[g] - kf[g] + 1);
+            for (int k = kf[g]; k <= kl[g]; ++k) { pc[k] = std::min(pc[k], g); ph[k] = std::max(ph[k], g); }
         }
         c->sym_slots = slots;
-        CK(cudaMalloc(&c->sym_cta_u0, sizeof(long long) * ((size_t)G + 1)));
-        CK(cudaMalloc(&c->sym_cta_kf, sizeof(int) * (size_t)G));
-        CK(cudaMalloc(&c->sym_panel_cta, sizeof(int) * (size_t)nch));
-        CK(cudaMalloc(&c->sym_panel_cta_hi, sizeof(int) * (size_t)nch));
-        CK(cudaMemcpy(c->sym_panel_cta_hi, ph.data(), sizeof(int) * (size_t)nch, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->sym_cta_u0, u0.data(), sizeof(long long) * ((size_t)G + 1), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->sym_cta_kf, kf.data(), sizeof(int) * (size_t)G, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->sym_panel_cta, pc.data(), sizeof(int) * (size_t)nch, cudaMemcpyHostToDevice));
+        c->sym_nch = nch;
+        c->sym_bytes = bytes;
+        std::vector<long long> tll(pu);
+        tll.insert(tll.end(), u0.begin(), u0.end());
+        std::vector<int> ti(kf);
+        ti.insert(ti.end(), kl.begin(), kl.end());
+        ti.insert(ti.end(), pc.begin(), pc.end());
+        ti.insert(ti.end(), ph.begin(), ph.end());
+        CK(cudaMalloc(&c->sym_tab_ll, sizeof(long long) * tll.size()));
+        CK(cudaMalloc(&c->sym_tab_i, sizeof(int) * ti.size()));
+        CK(cudaMemcpy(c->sym_tab_ll, tll.data(), sizeof(long long) * tll.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->sym_tab_i, ti.data(), sizeof(int) * ti.size(), cudaMemcpyHostToDevice));
         const size_t rp_bytes = sizeof(double) * (size_t)nch * SYM_NG * c->ld;
         const size_t cp_bytes = sizeof(double) * (size_t)G * slots * SYM_NG * 1024;
         CK(cudaMalloc(&c->rowpart, rp_bytes));
@@ -760,18 +812,33 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
     return 0;
 }
 
-static SymTab sym_tab(gcx_ctx* c) { return SymTab{c->sym_cta_u0, c->sym_cta_kf, c->sym_panel_cta, c->sym_panel_cta_hi, c->sym_slots}; }
+static SymTab sym_tab(gcx_ctx* c) {
+    const int nch = c->sym_nch, G = c->sym_grid;
+    SymTab T;
+    T.panel_u0 = c->sym_tab_ll;
+    T.cta_u0 = c->sym_tab_ll + nch + 1;
+    T.cta_kf = c->sym_tab_i;
+    T.cta_kl = c->sym_tab_i + G;
+    T.panel_cta = c->sym_tab_i + 2 * G;
+    T.panel_cta_hi = c->sym_tab_i + 2 * G + nch;
+    T.nslots = c->sym_slots;
+    T.row0 = (int)c->row0;
+    T.nloc = (int)c->nloc;
+    return T;
+}
 
+// q = A z through the upper-triangle pass; sharded: every rank folds its partial t, an allreduce adds them
 static int matvec_sym(gcx_ctx* c, const double* z, double* q, const int* done) {
     const size_t smem = (size_t)6 * SYM_R * MV_THREADS * sizeof(float4);
     const int n = (int)c->n, n4 = (int)(c->ld / 4);
     {
         ProfScope ps(c, 0);
-        k_matvec_sym_tma<6, 2><<<c->sym_grid, TMA_THREADS, smem, c->stream>>>(c->A, c->ld, n, n4, z, c->rowpart, c->colpart, sym_tab(c), done);
-        k_sym_fold<<<(n * 8 + 255) / 256, 256, 0, c->stream>>>(n, n4, c->sym_grid, c->rowpart, c->colpart, sym_tab(c), q, done);
+        k_matvec_sym_tma<6, 2><<<c->sym_grid, TMA_THREADS, smem, c->stream>>>(c->A, c->ld, n4, z, c->rowpart, c->colpart, sym_tab(c), done);
+        k_sym_fold<<<(n * 8 + 255) / 256, 256, 0, c->stream>>>(n, n4, c->rowpart, c->colpart, sym_tab(c), q, done);
     }
     c->launches += 1;
     CK(cudaGetLastError());
+    if (c->world > 1) CKR(allreduce_f64(c, q, (size_t)c->n));
     return 0;
 }
 
@@ -851,7 +918,8 @@ extern "C" int gcx_bench_matvec(gcx_ctx* c, int variant, int iters, double* ms_t
 // host's convergence check, so the GPU never waits for the host; launches after convergence exit at once.
 // ---------------------------------------------------------------------------------------------------
 static int chunk_len(gcx_ctx* c) {
-    const double est_ms = 4.0 * (double)c->nloc * (double)c->ld / 5.0e9;   // ~5 TB/s
+    // must be the same on every rank (each chunk carries collectives): derived from global quantities only
+    const double est_ms = 4.0 * (double)c->n * (double)c->ld / (double)c->world / 5.0e9;   // ~5 TB/s per rank
     int ch = (int)(0.25 / std::max(est_ms, 1e-4)) + 1;
     return std::max(2, std::min(ch, 16));
 }
@@ -949,10 +1017,21 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         SymTab tab = sym_tab(c);
         void* args[] = {(void*)&c->A, (void*)&c->ld, (void*)&n, (void*)&n4, (void*)&c->keep, (void*)&c->vq, (void*)&c->vz, (void*)&c->vB,
                         (void*)&c->rowpart, (void*)&c->colpart, (void*)&tab, (void*)&c->ticket, (void*)&c->ic_state, (void*)&c->part};
+        const size_t smem = 6 * SYM_R * MV_THREADS * sizeof(float4);
         {
             ProfScope ps(c, 0);
-            CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_sym_tma<6, 2>, dim3(c->sym_grid), dim3(TMA_THREADS), args,
-                                           6 * SYM_R * MV_THREADS * sizeof(float4), c->stream));
+            if (c->world == 1) {
+                CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_sym_tma<6, 2, true>, dim3(c->sym_grid), dim3(TMA_THREADS), args, smem, c->stream));
+            } else {
+                // sharded: the fold runs as its own kernel so that the ranks' partial t can be added before the next launch
+                CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_sym_tma<6, 2, false>, dim3(c->sym_grid), dim3(TMA_THREADS), args, smem, c->stream));
+                k_sym_fold<<<(n * 8 + 255) / 256, 256, 0, c->stream>>>(n, n4, c->rowpart, c->colpart, tab, c->vq, &c->ic_state->done);
+            }
+        }
+        if (c->world > 1) {
+            CK(cudaGetLastError());
+            c->launches += 1;
+            CKR(allreduce_f64(c, c->vq, (size_t)c->n));
         }
         return 0;
     };
@@ -986,7 +1065,7 @@ extern "C" int gcx_kr_run(gcx_ctx* c, double tol, double delta, double Delta, do
     c->last_sym = sym;
     auto step = [&]() -> int {
         CKR(matvec(c, sym ? 100 : c->mv_variant, c->vz, c->vq, &c->kr_state->done));
-        CKR(allgather_f64(c, c->vq));
+        if (!sym) CKR(allgather_f64(c, c->vq));      // the symmetric pass already left the complete vector (allreduce)
         {
             ProfScope ps(c, 6);
             k_kr_step<<<EP_CL, EP_THREADS, 0, c->stream>>>(c->kr_state, n, c->keep, c->vq, c->kr);

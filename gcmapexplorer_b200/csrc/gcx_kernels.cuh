@@ -524,38 +524,31 @@ constexpr int SYM_R = 4;
 constexpr int SYM_BPP = 1024 / SYM_R;        // bands per 1024 rows
 constexpr int SYM_NG = 2;                    // consumer groups per CTA (4 warps each, 8 columns per thread)
 
+// Geometry of one rank's share of the upper triangle, tabulated on the host once per map.  The rank owns the global
+// rows [row0, row0 + nloc) (row0 a multiple of 1024 when sharded).  Panel k holds the local bands whose global rows lie
+// in [row0, min(row0 + nloc, 1024 (k+1))); panel_u0 is the running count of those bands (units) over the panels.
 struct SymTab {
+    const long long* panel_u0; // [nch + 1] first unit of every panel (units of panels left of row0's panel: none)
     const long long* cta_u0;   // [G + 1] first unit of every CTA's share
-    const int* cta_kf;         // [G] panel of that unit
-    const int* panel_cta;      // [nch] first CTA whose (non-empty) share intersects the panel
-    const int* panel_cta_hi;   // [nch] last such CTA; every CTA in between has a non-empty share inside the panel
+    const int* cta_kf;         // [G] panel of a share's first unit
+    const int* cta_kl;         // [G] panel of a share's last unit
+    const int* panel_cta;      // [nch] first CTA whose (non-empty) share intersects the panel (G if none)
+    const int* panel_cta_hi;   // [nch] last such CTA (-1 if none); every CTA in between has units in the panel
     int nslots;                // panels a share may touch (sizes colpart)
+    int row0, nloc;            // this rank's global row block
 };
 
-__host__ __device__ __forceinline__ long long sym_panel_begin(int k) { return (long long)(SYM_BPP / 2) * k * (k + 1); }
-__host__ __device__ __forceinline__ long long sym_total_units(int n, int nch) {
-    return sym_panel_begin(nch - 1) + (n + SYM_R - 1) / SYM_R;
-}
-__host__ __device__ __forceinline__ int sym_panel_of(long long u, int nch) {
-    int k = (int)((sqrt(1.0 + (double)u / (SYM_BPP / 8)) - 1.0) * 0.5);
-    if (k > nch - 1) k = nch - 1;
-    if (k < 0) k = 0;
-    while (k > 0 && sym_panel_begin(k) > u) --k;
-    while (k < nch - 1 && sym_panel_begin(k + 1) <= u) ++k;
-    return k;
-}
-
 template <int NG, int STAGES, bool ZNC>
-__device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, long long ld, int n, int n4, const double* z,
+__device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, long long ld, int n4, const double* z,
                                                 double* rowpart, double* colpart, SymTab T, float4* tiles, uint64_t* full_bar,
                                                 uint64_t* empty_bar, double* gred) {
     constexpr int R = SYM_R;
     constexpr int WPG = (MV_THREADS / 32) / NG;      // warps per group
     constexpr int TG = MV_THREADS / NG;              // threads per group
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
-    const long long U = sym_total_units(n, nch), c = blockIdx.x;
+    const long long c = blockIdx.x;
     const long long u0 = T.cta_u0[c], u1 = T.cta_u0[c + 1];
+    const int nloc = T.nloc, row0 = T.row0;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
@@ -574,13 +567,13 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
             int stage = 0;
             unsigned int phase = 0;
             int k = kfirst;
-            long long pbeg = sym_panel_begin(k);
-            long long pend = (k < nch - 1) ? sym_panel_begin(k + 1) : U;
+            long long pbeg = T.panel_u0[k];
+            long long pend = T.panel_u0[k + 1];
             for (long long u = u0; u < u1; ++u) {
-                if (u >= pend) {
+                while (u >= pend) {
                     ++k;
                     pbeg = pend;
-                    pend = (k < nch - 1) ? sym_panel_begin(k + 1) : U;
+                    pend = T.panel_u0[k + 1];
                 }
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 const int b = (int)(u - pbeg);
@@ -590,8 +583,8 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
                 mbar_expect_tx(&full_bar[stage], row_bytes * R);
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) {
-                    int r = b * R + rr;
-                    r = r < n ? r : n - 1;
+                    int r = b * R + rr;                 // local row
+                    r = r < nloc ? r : nloc - 1;
                     bulk_g2s(tiles + ((size_t)stage * R + rr) * MV_THREADS, A + (long long)r * ld + 4LL * c0, row_bytes, &full_bar[stage]);
                 }
                 if (++stage == STAGES) {
@@ -608,8 +601,8 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
     const double2* z2 = reinterpret_cast<const double2*>(z);
     const long long rp_ld = (long long)n4 * 4;
     int k = kfirst;
-    long long pbeg = sym_panel_begin(k);
-    long long pend = (k < nch - 1) ? sym_panel_begin(k + 1) : U;
+    long long pbeg = T.panel_u0[k];
+    long long pend = T.panel_u0[k + 1];
     double cacc[NG][4], zc[NG][4];
     auto load_zc = [&](int kk) {
 #pragma unroll
@@ -640,13 +633,14 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
             flush(k);
             ++k;
             pbeg = pend;
-            pend = (k < nch - 1) ? sym_panel_begin(k + 1) : U;
+            pend = T.panel_u0[k + 1];
             load_zc(k);
         }
         const int it = (int)(u - u0);
         const int stage = it % STAGES;
         const unsigned int phase = (unsigned int)(it / STAGES) & 1u;
-        const int i0 = (int)(u - pbeg) * R;
+        const int l0 = (int)(u - pbeg) * R;          // local row of the band
+        const int i0 = row0 + l0;                    // global row (row0 is a multiple of 4)
         // z of the band's rows (broadcast loads); rows past n read the zero padding of z
         double2 zr01, zr23;
         if (ZNC) { zr01 = __ldg(z2 + (i0 >> 1)); zr23 = __ldg(z2 + (i0 >> 1) + 1); }
@@ -713,13 +707,12 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
                 double ssum = 0.0;
 #pragma unroll
                 for (int w = 0; w < WPG; ++w) ssum += gred[((par * NG + g) * WPG + w) * R + lane];
-                const int i = i0 + lane;
-                if (i < n) rowpart[((long long)k * NG + g) * rp_ld + i] = ssum;
+                if (l0 + lane < nloc) rowpart[((long long)k * NG + g) * rp_ld + i0 + lane] = ssum;
             }
         }
     }
     // every group flushes every panel the CTA's share touches (groups that saw no unit of a panel flush zeros)
-    const int klast = sym_panel_of(u1 - 1, nch);
+    const int klast = T.cta_kl[c];
     while (true) {
         flush(k);
         if (k >= klast) break;
@@ -729,34 +722,32 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
 
 template <int STAGES, int OCC>
 __global__ void __launch_bounds__(TMA_THREADS, OCC)
-k_matvec_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, const double* __restrict__ z, double* rowpart,
+k_matvec_sym_tma(const float* __restrict__ A, long long ld, int n4, const double* __restrict__ z, double* rowpart,
                  double* colpart, SymTab T, const int* __restrict__ done) {
     if (done != nullptr && *done) return;
     extern __shared__ __align__(128) unsigned char tma_smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ double gred[2 * (MV_THREADS / 32) * SYM_R];
-    matvec_sym_core<SYM_NG, STAGES, true>(A, ld, n, n4, z, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred);
+    matvec_sym_core<SYM_NG, STAGES, true>(A, ld, n4, z, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred);
 }
 
-// t_i, computed by 8 cooperating lanes: lane j sums the row partials of (group, warp-in-group) pair j over the panels
-// k >= i/1024 (a unit of a panel belongs to exactly one group, the other group's slot for that band holds a stale or
-// zero value -- so every (panel, band) is written by ONE group; both slots are zero-initialised and only the owner's
-// is ever written, hence summing both is exact), lane 0 also adds the column partials, then a fixed 3-step shuffle
-// tree joins them.  Must be called by all 8 lanes of an aligned group; every lane returns t_i.
-__device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n, int n4, int G, const double* rowpart, const double* colpart,
-                                                  SymTab T) {
+// This rank's contribution to t_i, computed by 8 cooperating lanes: lane j sums the row partials of consumer group
+// j % NG over the panels ki + j / NG, + 8/NG, ... (only for the rank's own rows; a (panel, band) is written by ONE
+// group, the other group's entry keeps its initial zero, so adding both is exact) and every 8th of the CTAs that walked
+// panel ki for the column partials; a fixed 3-step shuffle tree joins them.  Must be called by all 8 lanes of an aligned
+// group; every lane returns the sum.  On one rank this is t_i; sharded, the ranks' sums are added by an allreduce.
+__device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n4, const double* rowpart, const double* colpart, SymTab T) {
     const int j = threadIdx.x & 7;
     const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
     const long long rp_ld = (long long)n4 * 4;
     double s = 0.0;
     if (valid) {
         const int ki = i >> 10;
-        // lane j: consumer group j % NG, panels ki + j / NG, + 8/NG, ...  (a (panel, band) is written by ONE group; the
-        // other group's entry keeps its initial zero, so adding both is exact)
+        if (i >= T.row0 && i < T.row0 + T.nloc) {
 #pragma unroll 4
-        for (int k = ki + j / SYM_NG; k < nch; k += 8 / SYM_NG) s += __ldcg(rowpart + ((long long)k * SYM_NG + (j % SYM_NG)) * rp_ld + i);
-        // column partials: the CTAs [panel_cta[ki], panel_cta_hi[ki]] walked panel ki; lane j takes every 8th of them
+            for (int k = ki + j / SYM_NG; k < nch; k += 8 / SYM_NG) s += __ldcg(rowpart + ((long long)k * SYM_NG + (j % SYM_NG)) * rp_ld + i);
+        }
         const int clo = T.panel_cta[ki], chi = T.panel_cta_hi[ki];
 #pragma unroll 2
         for (int c = clo + j; c <= chi; c += 8) {
@@ -772,11 +763,10 @@ __device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n, int 
 }
 
 __global__ void __launch_bounds__(256)
-k_sym_fold(int n, int n4, int G, const double* rowpart, const double* colpart, SymTab T, double* __restrict__ t,
-           const int* __restrict__ done) {
+k_sym_fold(int n, int n4, const double* rowpart, const double* colpart, SymTab T, double* __restrict__ t, const int* __restrict__ done) {
     if (done != nullptr && *done) return;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const double ti = sym_fold_group8(i, i < n, n, n4, G, rowpart, colpart, T);
+    const double ti = sym_fold_group8(i, i < n, n4, rowpart, colpart, T);
     if (i < n && (threadIdx.x & 7) == 0) t[i] = ti;
 }
 
@@ -1678,7 +1668,7 @@ k_ic_pass_tma(const float* __restrict__ A, long long ld, int nloc, int n4, int n
 
 // Fused IC pass on the upper triangle: P1 folds t_i from the partials of the previous launch's symmetric
 // matvec on the fly, P2/P3 as in k_ic_pass, then the symmetric TMA main loop with z = v.
-template <int STAGES, int OCC>
+template <int STAGES, int OCC, bool FOLD>
 __global__ void __launch_bounds__(TMA_THREADS, OCC)
 k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, const uint8_t* __restrict__ keep, double* t, double* v,
                   double* B, double* rowpart, double* colpart, SymTab T, unsigned int* ticket, IcState* st, double* part) {
@@ -1700,14 +1690,25 @@ k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, cons
         const double cc_prev = st->cc, tol = st->tol;
         const int max_iter = st->max_iter;
         double s = 0.0, c = 0.0;
-        // t_i is folded by groups of 8 lanes (TMA_THREADS = 288 is a multiple of 8); lane 0 of a group owns bin i
-        for (int base = 0; base < n; base += nth / 8) {
-            const int i = base + (gth >> 3);
-            const double ti = sym_fold_group8(i, i < n, n, n4, G, rowpart, colpart, T);
-            if (i < n && (tid & 7) == 0) {
-                t[i] = ti;
+        if (FOLD) {
+            // one rank: t_i is folded here by groups of 8 lanes (TMA_THREADS = 288 is a multiple of 8); lane 0 owns bin i
+            for (int base = 0; base < n; base += nth / 8) {
+                const int i = base + (gth >> 3);
+                const double ti = sym_fold_group8(i, i < n, n4, rowpart, colpart, T);
+                if (i < n && (tid & 7) == 0) {
+                    t[i] = ti;
+                    if (keep[i]) {
+                        const double p = v[i] * ti;
+                        s += p;
+                        c += (p != 0.0) ? 1.0 : 0.0;
+                    }
+                }
+            }
+        } else {
+            // sharded: k_sym_fold + an allreduce between the launches left the complete t
+            for (int i = gth; i < n; i += nth) {
                 if (keep[i]) {
-                    const double p = v[i] * ti;
+                    const double p = v[i] * t[i];
                     s += p;
                     c += (p != 0.0) ? 1.0 : 0.0;
                 }
@@ -1758,7 +1759,7 @@ k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, cons
         if (done) return;
     }
     // the previous launch's partials have been consumed by every CTA (grid barriers above, or m == 0)
-    matvec_sym_core<SYM_NG, STAGES, false>(A, ld, n, n4, v, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred);
+    matvec_sym_core<SYM_NG, STAGES, false>(A, ld, n4, v, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred);
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(ticket, 1u) == (unsigned int)(G - 1)) {       // last CTA to issue its work: safe to bump the counter

@@ -61,8 +61,9 @@ class PinnedArray:
 
 
 class DeviceMap:
-    def __init__(self, n, row0=0, nloc=None, device=None, dist=None):
-        """dist: None or (rank, world, id128 bytes) for row-block sharding over NCCL."""
+    def __init__(self, n, row0=0, nloc=None, device=None, dist=None, options=None):
+        """dist: None or (rank, world, id128 bytes) for row-block sharding over NCCL.
+        options: dict for gcx_set_option, applied before the map is created."""
         self._ctx = C.c_void_p()
         self.n = int(n)
         self.row0 = int(row0)
@@ -74,10 +75,15 @@ class DeviceMap:
                 rank, world, id128 = dist
                 buf = C.create_string_buffer(bytes(id128), 128)
                 check(lib().gcx_dist_init(self._ctx, int(rank), int(world), buf))
+            for key, val in (options or {}).items():
+                self.set_option(key, val)
             check(lib().gcx_map_create(self._ctx, self.n, self.row0, self.nloc))
         except Exception:
             self.close()
             raise
+
+    def set_option(self, key, value):
+        check(lib().gcx_set_option(self._ctx, str(key).encode(), float(value)))
 
     # ---- lifetime -------------------------------------------------------------------------------
     def close(self):

@@ -19,6 +19,19 @@ def row_partition(n, world, rank):
     return row0, max(0, min(rpr, int(n) - row0))
 
 
+def row_partition_equal_area(n, world, rank, align=1024):
+    """(row0, nloc) so that every rank owns the same share of the UPPER TRIANGLE: row i has n-i entries right of the
+    diagonal, so the cut after a fraction f of the area is at n (1 - sqrt(1 - f)).  Cuts are rounded to `align` rows
+    (the 1024-column panels of the symmetric pass).  Used with the options exchange_allreduce=1, assume_symmetric=1."""
+    def cut(r):
+        if r >= world:
+            return int(n)
+        x = n * (1.0 - (1.0 - r / world) ** 0.5)
+        return min(int(n), int(round(x / align)) * align)
+    row0, row1 = cut(rank), cut(rank + 1)
+    return row0, max(0, row1 - row0)
+
+
 def padded_length(n, world):
     return rows_per_rank(n, world) * int(world)
 
@@ -49,13 +62,22 @@ def broadcast_unique_id(rank, device=None):
     return bytes(t.cpu().tolist())
 
 
-def sharded_device_map(n, device=None):
-    """DeviceMap for this rank's row block, wired to the other ranks (torch.distributed must be initialised)."""
+def sharded_device_map(n, device=None, partition="rows", symmetric=False):
+    """DeviceMap for this rank's row block, wired to the other ranks (torch.distributed must be initialised).
+
+    partition="rows": equal ceil(n/world) row blocks, n-vectors exchanged by allgather, dense passes.
+    partition="equal_area" (+ symmetric=True, the caller vouching that the map is symmetric): row blocks holding equal
+    shares of the upper triangle, n-vectors exchanged by allreduce, IC/KR passes read the upper triangle only."""
     import torch.distributed as tdist
     from .device import DeviceMap
     rank, world = tdist.get_rank(), tdist.get_world_size()
-    row0, nloc = row_partition(n, world, rank)
+    options = {}
+    if partition == "equal_area" and world > 1:
+        row0, nloc = row_partition_equal_area(n, world, rank)
+        options = {"exchange_allreduce": 1, "assume_symmetric": 1 if symmetric else 0}
+    else:
+        row0, nloc = row_partition(n, world, rank)
     if nloc == 0:
         raise ValueError("more ranks than row blocks")
     dist = (rank, world, broadcast_unique_id(rank)) if world > 1 else None
-    return DeviceMap(n, row0, nloc, device=device, dist=dist)
+    return DeviceMap(n, row0, nloc, device=device, dist=dist, options=options)

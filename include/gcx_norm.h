@@ -106,6 +106,14 @@ int gcx_diag_apply(gcx_ctx* ctx, const double* avg, int subtract, int in_place, 
  * nccl_unique_id: the 128-byte ncclUniqueId from gcx_dist_unique_id on rank 0, broadcast by the host
  * (torch.distributed / any store).  After init, ic/kr/row_stats/diag_stats exchange their n-vectors with
  * one NCCL allgather per matrix pass on the context's stream. */
+/* options (all optional):
+ *   "sym"                0/1  use the upper-triangle pass when possible (default 1; env GCX_SYM)
+ *   "assume_symmetric"   0/1  skip the exact symmetry test; REQUIRED for the upper-triangle pass on a sharded map, where a rank
+ *                             cannot see the mirrored block (the caller vouches that the map is symmetric)
+ *   "exchange_allreduce" 0/1  the row blocks are not the equal ceil(n/world) blocks: exchange n-vectors by zero-fill +
+ *                             allreduce instead of allgather (set it on every rank, before gcx_map_create)
+ *   "matvec_variant"     kernel variant for sweeps */
+int gcx_set_option(gcx_ctx* ctx, const char* key, double value);
 int gcx_dist_unique_id(void* id128);
 int gcx_dist_init(gcx_ctx* ctx, int rank, int world, const void* id128);
 

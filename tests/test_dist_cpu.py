@@ -27,6 +27,21 @@ def test_row_partition_covers_everything(n, world):
     assert seen == n and gd.padded_length(n, world) >= n
 
 
+@pytest.mark.parametrize("n,world", [(24926, 2), (49852, 4), (70501, 8), (249251, 8), (3000, 2)])
+def test_equal_area_partition(n, world):
+    """Cuts are panel aligned, cover [0, n) and give every rank (nearly) the same share of the upper triangle."""
+    cuts = [gd.row_partition_equal_area(n, world, r) for r in range(world)]
+    assert cuts[0][0] == 0 and sum(c[1] for c in cuts) == n
+    area = []
+    for r, (row0, nloc) in enumerate(cuts):
+        assert row0 % 1024 == 0 and (r == world - 1 or (row0 + nloc) % 1024 == 0)
+        assert r == 0 or row0 == cuts[r - 1][0] + cuts[r - 1][1]
+        i = np.arange(row0, row0 + nloc, dtype=np.float64)
+        area.append(float((n - i).sum()))
+    if n >= 20000:
+        assert max(area) / (sum(area) / world) < 1.0 + 2.5 * 1024.0 * world / n     # panel rounding only
+
+
 def _sharded_ic(rank, world, port, n, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     tdist.init_process_group("gloo", rank=rank, world_size=world)

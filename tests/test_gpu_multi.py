@@ -15,13 +15,13 @@ def _ngpu():
     return _lib.device_count()
 
 
-@pytest.mark.parametrize("n", [6001, 997])
-def test_sharded_matches_single_gpu(n):
+@pytest.mark.parametrize("n,partition", [(6001, "rows"), (997, "rows"), (9000, "equal_area"), (12345, "equal_area")])
+def test_sharded_matches_single_gpu(n, partition):
     g = _ngpu()
     if g < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if g < 4 else 4
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29600 + n % 97), os.path.join(ROOT, "tools", "multi_gpu_check.py"), str(n)]
+           "--master-port", str(29600 + n % 97), os.path.join(ROOT, "tools", "multi_gpu_check.py"), str(n), partition]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]

@@ -13,28 +13,38 @@ from gcmapexplorer_b200 import device as gx      # noqa: E402
 from gcmapexplorer_b200 import dist as gd        # noqa: E402
 
 
+def mark(msg):
+    if os.environ.get("GCX_TRACE"):
+        print(f"[rank {os.environ.get('RANK')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 6001
+    partition = sys.argv[2] if len(sys.argv) > 2 else "rows"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dm = gd.sharded_device_map(n, device=local)
+    dm = gd.sharded_device_map(n, device=local, partition=partition, symmetric=True)
     dm.synth(seed=5, scale=200.0, alpha=1.0, empty_frac=0.01)
-    rs, zc = dm.row_stats()
+    mark('created+synth'); rs, zc = dm.row_stats()
     keep = rs != 0
     res = {}
+    mark('row_stats')
     dm.set_mask(np.ones(n, dtype=bool))
     ic = dm.ic(1e-4, 500)
+    mark(f'ic done sym={ic["symmetric"]} passes={ic["passes"]}')
     mn_ic, mx_ic = dm.apply_sym(None, masked_mode=1, in_place=False)
     cs_ic = dm.checksum(1)
     dm.set_mask(keep)
-    kr = dm.kr(1e-12, 0.1, 3.0)
+    mark('apply ic'); kr = dm.kr(1e-12, 0.1, 3.0)
+    mark('kr done')
     mn_kr, mx_kr = dm.apply_sym(None, masked_mode=0, in_place=False)
     cs_kr = dm.checksum(1)
     mn_vc, mx_vc, csum = dm.vc(False, in_place=False)
     cs_vc = dm.checksum(1)
-    avg_mean = dm.diag_stats("mean")
+    mark('vc done'); avg_mean = dm.diag_stats("mean")
     avg_med = dm.diag_stats("median")
+    mark('diag done')
     # all ranks hold identical vectors / counters
     def same_everywhere(arr):
         t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).copy()).cuda()
@@ -67,7 +77,7 @@ def main():
             c_vc = one.checksum(1)
             a_mean = one.diag_stats("mean")
             a_med = one.diag_stats("median")
-        res.update(
+        res.update(partition=partition, sharded_symmetric_pass=bool(ic["symmetric"]), single_symmetric_pass=bool(ic1["symmetric"]),
             rowstats_equal=bool(np.array_equal(rs, rs1) and np.array_equal(zc, zc1)),
             ic_passes=(ic["passes"], ic1["passes"]), ic_bias_rel=float(np.max(np.abs(ic["bias"] / ic1["bias"] - 1))),
             kr_counters=((kr["outer"], kr["MVP"]), (kr1["outer"], kr1["MVP"])),
