@@ -176,6 +176,11 @@ def run_b200(args):
 
     ones = np.ones(n, dtype=bool)
     info = {}
+    # the out-of-place result buffer doubles the footprint; with the equal-area partition the last rank holds ~35 % of the
+    # rows, so at chr1 @ 1 kb (88 GB there) it does not fit -> such runs time mask + solver only and say so
+    free_b = dm.info()["hbm_free"]
+    fits = min_over_ranks_flag(tdist, free_b > 4.0 * nloc * (n + 32) * 1.02 + (2 << 30))
+    solver_only = not fits
 
     def step():
         rs, zc = dm.row_stats(force=True)                 # K1: mask pass
@@ -183,14 +188,16 @@ def run_b200(args):
         if kr_mode:
             dm.set_mask(keep)
             r = dm.kr(1e-12, 0.1, 3.0)
-            dm.apply_sym(None, masked_mode=0, in_place=False)
+            if not solver_only:
+                dm.apply_sym(None, masked_mode=0, in_place=False)
             info.update(matvecs=r["MVP"] + 1, outer=r["outer"], converge_ms=r["ms"], passes=r["MVP"], pass_bytes=r["pass_bytes"], symmetric=r["symmetric"])
         else:
             dm.set_mask(ones)                             # IC without filter runs on the whole map (normalizer.py:592)
             r = dm.ic(IC_TOL, IC_ITER)                    # K2 x passes + vector epilogues
-            dm.apply_sym(None, masked_mode=1, in_place=False)   # K4
-            dm.set_mask(keep)
-            dm.vc(False, in_place=False)                  # K5 (row sums reused from the mask pass)
+            if not solver_only:
+                dm.apply_sym(None, masked_mode=1, in_place=False)   # K4
+                dm.set_mask(keep)
+                dm.vc(False, in_place=False)              # K5 (row sums reused from the mask pass)
             info.update(matvecs=r["matvecs"], passes=r["passes"], converge_ms=r["ms"], l1=r["l1"], pass_bytes=r["pass_bytes"], symmetric=r["symmetric"])
 
     clocks = ClockSampler(local)
@@ -220,8 +227,9 @@ def run_b200(args):
     # bytes the step actually has to move: mask 4n^2 + matvecs x (bytes of one pass over the resident layout:
     # 4n^2 dense, ~2n(n+1024) when the upper-triangle pass is used) + apply 8n^2 (+ VC apply 8n^2)
     pass_bytes_all = sum_over_ranks(float(info["pass_bytes"]))
-    bytes_step = 4.0 * n * n + mv * pass_bytes_all + (8.0 if kr_mode else 16.0) * n * n
-    dense_equiv = (4.0 * (1 + mv) + (8.0 if kr_mode else 16.0)) * n * n
+    ew = 0.0 if solver_only else (8.0 if kr_mode else 16.0)
+    bytes_step = 4.0 * n * n + mv * pass_bytes_all + ew * n * n
+    dense_equiv = (4.0 * (1 + mv) + ew) * n * n
     value = bytes_step / (ms_per_step * 1e-3) / 1e9
 
     # roofline of the dominant kernel: mean duration over the *effective* launches (launches after the
@@ -237,7 +245,7 @@ def run_b200(args):
 
     # ---- e2e: the same pipeline through the C ABI with HOST (pinned) buffers ------------------------------
     e2e = None
-    if not args.no_e2e and nloc * n * 8 < 0.4 * psutil_avail():
+    if not args.no_e2e and not solver_only and nloc * n * 8 < 0.4 * psutil_avail():
         hin = gx.PinnedArray((nloc, n))
         hout = gx.PinnedArray((nloc, n))
         dm.download(0, out=hin.array)
@@ -294,7 +302,8 @@ def run_b200(args):
             "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 accumulate / f32 storage", "data": "synthetic (device-generated Poisson power-law map, 1% empty bins)",
-            "config": {"workload": wl, "n": n, "rows_this_rank": nloc, "map_bytes_per_gpu_mean": int(4 * rpr * n), "partition": (args.partition if world > 1 else "single"), "l2": "inputs larger than L2 (no flush needed)",
+            "config": {"workload": wl, "n": n, "rows_this_rank": nloc, "map_bytes_per_gpu_mean": int(4 * rpr * n), "partition": (args.partition if world > 1 else "single"),
+                       "step": "mask + solver only (out-of-place result buffer does not fit on the largest rank)" if solver_only else "mask + solver + apply (+ VC)", "l2": "inputs larger than L2 (no flush needed)",
                        "tol": IC_TOL if not kr_mode else 1e-12, "parallelism": ("row-block x%d (%s), one NCCL %s of the n-vector per pass" % (world, args.partition, "allreduce" if info["symmetric"] else "allgather")) if world > 1 else "single GPU"},
             "time_to_converge_s": round(float(np.median(conv_ms)) * 1e-3, 5), "passes": info["passes"], "matvecs": mv,
             "hbm_bytes_per_step": bytes_step, "dense_equivalent_bytes_per_step": dense_equiv,
@@ -360,6 +369,15 @@ def run_mcfs_wg(args):
     print(json.dumps(line))
     for dm in maps:
         dm.close()
+
+
+def min_over_ranks_flag(tdist, flag):
+    if tdist is None:
+        return bool(flag)
+    import torch
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
+    tdist.all_reduce(t, op=tdist.ReduceOp.MIN)
+    return bool(t.item())
 
 
 def psutil_avail():
