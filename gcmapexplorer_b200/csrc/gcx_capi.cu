@@ -101,7 +101,7 @@ struct gcx_ctx {
     float* Out = nullptr;
     // vectors (float64, nv each) carved from one slab
     double* slab = nullptr;
-    double *vz = nullptr, *vq = nullptr, *vB = nullptr, *vBd = nullptr, *vscale = nullptr, *vrowsum = nullptr, *vavg = nullptr;
+    double *vz = nullptr, *vq = nullptr, *vB = nullptr, *vscale = nullptr, *vrowsum = nullptr, *vavg = nullptr;
     KrVecs kr{};
     float* csum32 = nullptr;
     int32_t* zero_count = nullptr;
@@ -391,7 +391,7 @@ extern "C" int gcx_map_create(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc)
     CK(cudaMemsetAsync(c->slab, 0, sizeof(double) * (size_t)c->nv * NVEC, c->stream));
     double* p = c->slab;
     auto take = [&]() { double* r = p; p += c->nv; return r; };
-    c->vz = take(); c->vq = take(); c->vB = take(); c->vBd = take(); c->vscale = take(); c->vrowsum = take(); c->vavg = take();
+    c->vz = take(); c->vq = take(); c->vB = take(); c->vscale = take(); c->vrowsum = take(); c->vavg = take();
     c->kr.x = take(); c->kr.v = take(); c->kr.rk = take(); c->kr.y = take(); c->kr.Z = take(); c->kr.p = take(); c->kr.w = take();
     c->kr.z = c->vz;
     CK(cudaMalloc(&c->csum32, sizeof(float) * (size_t)c->nv));

@@ -164,13 +164,6 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 
 // Even split of U work units over G CTAs: CTA c owns [c*U/G, (c+1)*U/G).
 __device__ __forceinline__ long long unit_begin(long long c, long long U, long long G) { return c * U / G; }
-__device__ __forceinline__ long long unit_owner(long long u, long long U, long long G) {
-    long long c = ((u + 1) * G - 1) / U;
-    while (c + 1 < G && unit_begin(c + 1, U, G) <= u) ++c;
-    while (c > 0 && unit_begin(c, U, G) > u) --c;
-    return c;
-}
-
 // ---------------------------------------------------------------------------------------------------
 // K2/K3: q[row0 + r] = sum_j A[r][j] * z[j]   (float32 map, float64 vector, float64 accumulation)
 // Replaces np.sum(matrix, axis=0) of lib/normalizeCore.pyx:42 (symmetric map: column sums = row sums
