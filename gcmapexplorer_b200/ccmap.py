@@ -159,6 +159,55 @@ class CCMAP:
         return other
 
 
+# ---- coarsening (lib/ccmap.py:655-842) ------------------------------------------------------------------
+def getOutputShapeFor2DMapDownsampling(inputShape, level=2):
+    """Shape of the map after coarsening by `level` (lib/ccmap.py:712-735)."""
+    return (int(np.ceil(float(inputShape[0] - 1) / level)) + 1, int(np.ceil(float(inputShape[1] - 1) / level)) + 1)
+
+
+def downSample2DMap(inMatrix, outMatrix=None, level=2, method='sum'):
+    """Coarsen a square matrix by `level` on the GPU (lib/ccmap.py:737-842): 'sum', 'mean' or 'max' over level x level blocks,
+    row/column 0 left at zero, NumPy's arithmetic reproduced bit for bit.  Fills `outMatrix` when given, else returns the result
+    (the reference returns after the first band in that case -- an obvious slip at :839-840 that is not reproduced)."""
+    from .device import DeviceMap
+    with DeviceMap.from_host(inMatrix) as dm:
+        out, _, _ = dm.downsample(int(level), method)
+    if outMatrix is None:
+        return out
+    outMatrix[:] = out
+    return None
+
+
+def downSampleCCMap(cmap, level=2, method='sum', workDir=None):
+    """Coarsened copy of a CCMAP (lib/ccmap.py:655-710): new temporary map with binsize * level, bNoData OR-ed over each
+    group of fine bins (bin 0 never flagged), minvalue / maxvalue of the result."""
+    from .device import DeviceMap
+    level = int(level)
+    cmap.make_readable()
+    with DeviceMap.from_host(cmap.matrix) as dm:
+        out, mn, mx = dm.downsample(level, method)
+    res = CCMAP(dtype=cmap.dtype)
+    res.shape = out.shape
+    res.gen_matrix_file(workDir=workDir)
+    res.make_writable()
+    res.matrix[:] = out
+    res.matrix.flush()
+    if cmap.bNoData is not None:
+        b = np.zeros(out.shape[0], dtype=bool)
+        pad = int((out.shape[0] - 1) * level - (cmap.shape[0] - 1))
+        x = np.asarray(cmap.bNoData[1:], dtype=np.float64)
+        if pad != 0:
+            x = np.hstack((x, np.zeros(pad)))
+        b[1:] = x.reshape(-1, level).sum(axis=1)
+        res.bNoData = b
+    res.minvalue = mn
+    res.maxvalue = mx
+    res.binsize = cmap.binsize * level
+    res.xlabel = cmap.xlabel
+    res.ylabel = cmap.ylabel
+    return res
+
+
 def is_ccmap(obj):
     return isinstance(obj, CCMAP) or all(hasattr(obj, a) for a in ("path2matrix", "shape", "make_readable", "bNoData", "state"))
 

@@ -1262,6 +1262,32 @@ extern "C" int gcx_diag_apply(gcx_ctx* c, const double* avg, int subtract, int i
 }
 
 // ---------------------------------------------------------------------------------------------------
+// coarsening
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gcx_downsample(gcx_ctx* c, int level, int method, float* host_out, int64_t out_n, float* minv, float* maxv) {
+    CKR(need_map(c));
+    if (c->world != 1) return fail("gcx_downsample: single-rank maps only");
+    if (level < 1 || level > 128) return fail("gcx_downsample: level must be in [1, 128]");
+    if (method < 0 || method > 2) return fail("gcx_downsample: method must be 0 (sum), 1 (mean) or 2 (max)");
+    const int n = (int)c->n;
+    const int64_t on = (n - 1 + level - 1) / level + 1;         // lib/ccmap.py:731-734
+    if (out_n != on) return fail("gcx_downsample: output must be %lld x %lld", (long long)on, (long long)on);
+    const bool padded = ((on - 1) * level - (n - 1)) != 0;      // :786-788: padding promotes the arithmetic to float64
+    CKR(ensure_scratch(c, sizeof(float) * (size_t)on * on));
+    float* dout = (float*)c->scratch;
+    CKR(mm_begin(c));
+    const int grid = (int)std::min<int64_t>((on * on + 255) / 256, (int64_t)c->sm_count * 16);
+    {
+        ProfScope ps(c, 7);
+        if (padded) k_downsample<double><<<grid, 256, 0, c->stream>>>(c->A, c->ld, n, level, method, (int)on, dout, c->mm);
+        else k_downsample<float><<<grid, 256, 0, c->stream>>>(c->A, c->ld, n, level, method, (int)on, dout, c->mm);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host_out, dout, sizeof(float) * (size_t)on * on, cudaMemcpyDeviceToHost, c->stream));
+    return mm_end(c, minv, maxv);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // measurement
 // ---------------------------------------------------------------------------------------------------
 extern "C" int gcx_profile(gcx_ctx* c, int enable) {

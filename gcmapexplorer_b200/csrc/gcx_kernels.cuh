@@ -1217,6 +1217,66 @@ __global__ void k_diag_median_final(int n, DiagSel S, double* __restrict__ avg) 
     avg[d] = ((S.cnt[d] & 1u) == 0u) ? (lo + hi) / 2.0 : lo;             // np.median semantics
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Coarsening: downSample2DMap, lib/ccmap.py:737-842.  One thread per output element.
+// Output row/column 0 stay zero; output (c, 1+g) reduces input rows 1+(c-1)*level.. and columns 1+g*level..
+// The reduction order is NumPy's, so results are bit-identical: over the rows of the block sequentially, then over
+// the `level` column results with NumPy's pairwise_sum (sequential below 8 terms; 8 interleaved accumulators, a
+// fixed combine tree and a sequential tail up to 128 terms).  When the column count needs padding the reference
+// hstacks float64 zeros, which promotes that whole case to float64 arithmetic (T = double); otherwise T = float.
+// method: 0 sum, 1 mean, 2 max.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_downsample(const float* __restrict__ A, long long ld, int n, int level, int method, int on, float* __restrict__ out, MinMax* mm) {
+    float mn = GCX_PINF, mx = GCX_NINF;
+    const long long total = (long long)on * on;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx / on), gq = (int)(idx - (long long)c * on);
+        float res = 0.f;
+        if (c > 0 && gq > 0) {
+            const int i0 = 1 + (c - 1) * level, j0 = 1 + (gq - 1) * level;
+            const int rows = min(level, n - i0);
+            T r8[8];
+            T acc = (T)0;
+            const int nfull = level - (level % 8);
+            for (int j = 0; j < level; ++j) {
+                // column j of the block, reduced over its rows (missing columns are the zero padding)
+                T cv = (T)0;
+                const int col = j0 + j;
+                if (col < n) {
+                    if (method == 2) {
+                        cv = (T)A[(long long)i0 * ld + col];
+                        for (int r = 1; r < rows; ++r) cv = max(cv, (T)A[(long long)(i0 + r) * ld + col]);
+                    } else {
+                        for (int r = 0; r < rows; ++r) cv = cv + (T)A[(long long)(i0 + r) * ld + col];
+                        if (method == 1) cv = cv / (T)rows;
+                    }
+                }
+                // feed NumPy's reduction over the `level` column results
+                if (method == 2) {
+                    acc = (j == 0) ? cv : max(acc, cv);
+                } else if (level < 8) {
+                    acc = acc + cv;
+                } else if (j < 8) {
+                    r8[j] = cv;
+                } else if (j < nfull) {
+                    r8[j & 7] = r8[j & 7] + cv;
+                } else {
+                    if (j == nfull) acc = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+                    acc = acc + cv;
+                }
+            }
+            if (method != 2 && level >= 8 && nfull == level) acc = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
+            if (method == 1) acc = acc / (T)level;
+            res = (float)acc;
+        }
+        out[idx] = res;
+        mm_update(res, mn, mx);
+    }
+    mm_commit(mn, mx, mm);
+}
+
 // vmin/vmax clamp + scale, in place (lib/normalizer.py:567-569, 832-834)
 __global__ void __launch_bounds__(MV_THREADS)
 k_clamp_scale(float* __restrict__ A, long long total4, int has_vmin, float vmin, int has_vmax, float vmax, int has_scale,

@@ -230,6 +230,15 @@ class DeviceMap:
         check(lib().gcx_diag_apply(self._ctx, ap, int(bool(subtract)), int(bool(in_place)), C.byref(mn), C.byref(mx)))
         return mn.value, mx.value
 
+    def downsample(self, level=2, method="sum"):
+        """(coarse float32 matrix, min non-zero, max): downSample2DMap of lib/ccmap.py:737-842, bit-identical."""
+        code = {"sum": 0, "mean": 1, "max": 2}.get(method, 0)        # the reference treats unknown methods as 'sum'
+        on = (self.n - 1 + int(level) - 1) // int(level) + 1
+        out = np.empty((on, on), dtype=np.float32)
+        mn, mx = C.c_float(0), C.c_float(0)
+        check(lib().gcx_downsample(self._ctx, int(level), code, out.ctypes.data_as(_lib._c_f32p), on, C.byref(mn), C.byref(mx)))
+        return out, mn.value, mx.value
+
     # ---- measurement ----------------------------------------------------------------------------
     def profile(self, enable=True):
         check(lib().gcx_profile(self._ctx, int(bool(enable))))

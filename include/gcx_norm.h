@@ -102,6 +102,12 @@ int gcx_vc_run(gcx_ctx* ctx, int sqroot, int in_place, float* minv, float* maxv,
 int gcx_diag_stats(gcx_ctx* ctx, int median, double* avg);
 int gcx_diag_apply(gcx_ctx* ctx, const double* avg, int subtract, int in_place, float* minv, float* maxv);
 
+/* ---- coarsening ---------------------------------------------------------
+ * Replaces ccmap.downSample2DMap (lib/ccmap.py:737-842) on the resident map: out is (ceil((n-1)/level)+1)^2 floats on the
+ * host; method 0 sum, 1 mean, 2 max; NumPy's reduction order and float32/float64 promotion are reproduced, so the result is
+ * bit-identical.  minv/maxv: min non-zero / max of the output. */
+int gcx_downsample(gcx_ctx* ctx, int level, int method, float* host_out, int64_t out_n, float* minv, float* maxv);
+
 /* ---- multi-GPU (row-block sharding; one context per rank) ------------------------------------
  * nccl_unique_id: the 128-byte ncclUniqueId from gcx_dist_unique_id on rank 0, broadcast by the host
  * (torch.distributed / any store).  After init, ic/kr/row_stats/diag_stats exchange their n-vectors with

@@ -398,3 +398,44 @@ def synth_map(n, seed=0, scale=200.0, alpha=1.0, empty_frac=0.01):
     A[empty, :] = 0.0
     A[:, empty] = 0.0
     return np.ascontiguousarray(A, dtype=np.float32)
+
+
+# --------------------------------------------------------------------------------------------------
+# coarsening  lib/ccmap.py:655-842
+# --------------------------------------------------------------------------------------------------
+def downsample_shape(shape, level=2):
+    """lib/ccmap.py:712-735."""
+    return (int(np.ceil(float(shape[0] - 1) / level)) + 1, int(np.ceil(float(shape[1] - 1) / level)) + 1)
+
+
+def downsample_2d(M, level=2, method="sum"):
+    """lib/ccmap.py:737-842 (downSample2DMap with an output matrix given): output row/column 0 stay zero; output
+    (c, 1+g) reduces input rows 1+(c-1)*level ... and columns 1+g*level ...; when the column count needs padding the
+    reference hstacks float64 zeros (:789-797), which silently promotes that case to float64 arithmetic."""
+    n0, n1 = M.shape
+    oshape = downsample_shape(M.shape, level)
+    out = np.zeros(oshape, dtype=M.dtype)
+    pad_inner = int((oshape[1] - 1) * level - (n1 - 1))
+    red = {"mean": np.mean, "max": np.max}.get(method, np.sum)
+    count, i = 1, 1
+    while i < n0:
+        blk = M[i:i + level, 1:]
+        if pad_inner != 0:
+            blk = np.hstack((blk, np.zeros((blk.shape[0], pad_inner))))       # float64 zeros -> float64 block
+            group = level
+        else:
+            group = level if i + level < n0 else n0 - i                        # :818-826 ("remain")
+        r = red(red(blk, axis=0).reshape(-1, group), axis=1)
+        out[count, 1:] = r
+        i += level
+        count += 1
+    return out
+
+
+def downsample_nodata(bNoData, out_n, level):
+    """lib/ccmap.py:694-702: a coarse bin has no data if any of its fine bins has none; bin 0 is never flagged."""
+    b = np.zeros(out_n, dtype=bool)
+    pad = int((out_n - 1) * level - (bNoData.shape[0] - 1))
+    x = np.hstack((bNoData[1:], np.zeros(pad))) if pad != 0 else bNoData[1:]
+    b[1:] = x.reshape(-1, level).sum(axis=1)
+    return b

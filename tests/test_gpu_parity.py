@@ -486,3 +486,34 @@ def test_symmetric_pass_vs_oracle_and_asymmetric_fallback(gx):
     A2[5, 1900] += 1.0                       # break the symmetry in one entry
     r2 = _ic_device(gx, A2, 1e-4, 500, np.ones(n, dtype=bool))
     assert not r2["symmetric"]               # dense pass: row sums of the stored matrix, like every other dense run
+
+
+# --------------------------------------------------------------------------------------------------
+# coarsening
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("DS"))
+def test_downsample_golden_bit_exact(gx, name):
+    """ccmap.downSampleCCMap vs the real reference's output: matrix bit-exact, bNoData, binsize, min/max."""
+    from gcmapexplorer_b200 import ccmap as cmp
+    g = load_golden(name)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(g["input"], 1000, xlabel="chrS", ylabel="chrS")
+    if g["bNoData_in"].size:
+        c.bNoData = g["bNoData_in"]
+    out = cmp.downSampleCCMap(c, **g["kwargs"])
+    assert out.shape == g["matrix"].shape == cmp.getOutputShapeFor2DMapDownsampling(g["input"].shape, g["kwargs"]["level"])
+    assert np.array_equal(np.array(out.matrix), g["matrix"])
+    if g["bNoData_in"].size:
+        assert np.array_equal(out.bNoData, g["bNoData"])
+    assert out.binsize == int(g["binsize"])
+    assert np.float32(out.minvalue) == np.float32(g["minvalue"]) and np.float32(out.maxvalue) == np.float32(g["maxvalue"])
+
+
+@pytest.mark.parametrize("n,level,method", [(1000, 2, "sum"), (1001, 4, "mean"), (2049, 8, "sum"), (1500, 13, "mean"), (3001, 100, "sum"), (777, 5, "max")])
+def test_downsample_vs_oracle(gx, n, level, method):
+    from gcmapexplorer_b200 import ccmap as cmp
+    A = onp.normalize_vc(onp.synth_map(n, seed=n))["matrix"]        # non-integer values: rounding order matters
+    assert np.array_equal(cmp.downSample2DMap(A, level=level, method=method), onp.downsample_2d(A, level, method))
+    out = np.zeros(onp.downsample_shape(A.shape, level), dtype=np.float32)
+    assert cmp.downSample2DMap(A, outMatrix=out, level=level, method=method) is None
+    assert np.array_equal(out, onp.downsample_2d(A, level, method))

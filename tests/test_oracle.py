@@ -137,3 +137,12 @@ def test_oracle_vs_live_reference_cores(n, seed):
     o2 = np.zeros_like(A); core.normalizeByAvgContactBySubtraction(A, avg, Out=o2)
     assert np.array_equal(o1, onp.mcfs_divide(A, avg))
     assert np.array_equal(o2, onp.mcfs_subtract(A, avg))
+
+
+@pytest.mark.parametrize("name", golden_names("DS"))
+def test_downsample_golden(name):
+    g = load_golden(name)
+    out = onp.downsample_2d(g["input"], g["kwargs"]["level"], g["kwargs"]["method"])
+    assert np.array_equal(out, g["matrix"])
+    if g["bNoData_in"].size:
+        assert np.array_equal(onp.downsample_nodata(g["bNoData_in"], out.shape[0], g["kwargs"]["level"]), g["bNoData"])
