@@ -13,4 +13,8 @@ with gx.DeviceMap(n) as dm:
     dm.apply_sym(np.ones(n), masked_mode=0, in_place=False)
     dm.vc(False, in_place=False)
     dm.diag_apply(np.ones(n), subtract=False, in_place=False)
+    dm.set_mask(np.ones(n, dtype=bool))
+    r = dm.ic(1e-4, 6)
+    print("ic sym", r["symmetric"], r["passes"])
+    print("sym matvec us", dm.bench_matvec(4, 100) * 1e3)
     print("ok")
