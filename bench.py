@@ -134,11 +134,17 @@ def run_b200(args):
     from gcmapexplorer_b200 import dist as gd
     rpr = (n + world - 1) // world
     options = {}
-    if world > 1 and args.partition == "equal_area":
+    if world > 1 and args.partition == "balanced":
+        # near-equal row blocks (cuts on 1024 rows); each unordered pair of bins is read once, the off-diagonal blocks dealt out
+        # to the ranks in a circulant pattern.  The synthetic map is symmetric by construction, which a rank cannot verify
+        # locally -> assume_symmetric.
+        row0, nloc = gd.row_partition_aligned(n, world, rank)
+        options = {"exchange_allreduce": 1, "assume_symmetric": 1}
+    elif world > 1 and args.partition == "equal_area":
         # equal shares of the upper triangle per rank (panel-aligned cuts): the IC/KR passes read the upper triangle only.
         # The synthetic map is symmetric by construction, which a rank cannot verify locally -> assume_symmetric.
         row0, nloc = gd.row_partition_equal_area(n, world, rank)
-        options = {"exchange_allreduce": 1, "assume_symmetric": 1}
+        options = {"exchange_allreduce": 1, "assume_symmetric": 1, "sym_blocks": 0}
     else:
         row0, nloc = gd.row_partition(n, world, rank)
     if world > 1:
@@ -542,8 +548,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--partition", default="equal_area", choices=["equal_area", "rows"],
-                    help="N>1: equal_area = equal upper-triangle shares per rank + symmetric passes; rows = equal row blocks + dense passes")
+    ap.add_argument("--partition", default="balanced", choices=["balanced", "equal_area", "rows"],
+                    help="N>1: balanced = near-equal row blocks + symmetric passes with circulant block assignment; equal_area = equal "
+                         "upper-triangle shares per rank; rows = equal row blocks + dense passes")
     ap.add_argument("--kr", action="store_true", help="run KR instead of IC + VC on the selected workload")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -119,6 +119,8 @@ struct gcx_ctx {
     int* sym_tab_i = nullptr;             // cta_kf [G] | cta_kl [G] | panel_cta [nch] | panel_cta_hi [nch]
     int sym_nch = 0;
     int64_t sym_bytes = 0;
+    int sym_blocks = 1;                   // sharded: circulant assignment of off-diagonal blocks (needs the aligned row partition)
+    int sym_kfold_lo = -1;
     int assume_symmetric = 0;             // sharded runs cannot test symmetry locally: the caller vouches for it
     int exchange_allreduce = 0;           // custom (unequal) row partition: vectors are exchanged by zero-fill + allreduce
     int sym_slots = 0, sym_grid = 0;
@@ -672,6 +674,7 @@ extern "C" int gcx_set_option(gcx_ctx* c, const char* key, double value) {
     if (k == "sym") c->sym_enable = (int)value;
     else if (k == "assume_symmetric") { c->assume_symmetric = (int)value; c->sym_state = -1; }
     else if (k == "exchange_allreduce") c->exchange_allreduce = (int)value;
+    else if (k == "sym_blocks") c->sym_blocks = (int)value;
     else if (k == "matvec_variant") c->mv_variant = (int)value;
     else return fail("gcx_set_option: unknown key '%s'", key);
     return 0;
@@ -741,6 +744,21 @@ extern "C" int gcx_set_mask(gcx_ctx* c, const uint8_t* keep) {
 // ---------------------------------------------------------------------------------------------------
 static int64_t sym_bytes_per_pass(gcx_ctx* c) { return c->sym_bytes; }
 
+// The aligned row partition: cuts at r*n/world rounded to 1024 rows (the panel width of the symmetric pass).
+static int64_t aligned_cut(int64_t n, int world, int r) {
+    if (r <= 0) return 0;
+    if (r >= world) return n;
+    const int64_t x = (2 * (int64_t)r * n / world + 1024) / 2048 * 1024;
+    return std::min(n, x);
+}
+
+extern "C" int gcx_partition_rows(int64_t n, int world, int rank, int64_t* row0, int64_t* nloc) {
+    if (world < 1 || rank < 0 || rank >= world || n < 1) return fail("gcx_partition_rows: bad arguments");
+    *row0 = aligned_cut(n, world, rank);
+    *nloc = aligned_cut(n, world, rank + 1) - *row0;
+    return 0;
+}
+
 // decides (and caches) whether the resident map can use the upper-triangle passes, and tabulates the geometry
 static int sym_ready(gcx_ctx* c, bool* ok) {
     *ok = false;
@@ -766,13 +784,52 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         const int n = (int)c->n, n4 = (int)(c->ld / 4), nch = (n4 + MV_THREADS - 1) / MV_THREADS, G = c->sym_grid;
         const long long r0 = c->row0, r1 = c->row0 + c->nloc;
         std::vector<long long> pu((size_t)nch + 1, 0);
+        std::vector<int> pfull((size_t)nch, 0);
+        const int W = c->world, me = c->rank;
+        // sharded + aligned partition: off-diagonal blocks are dealt out in a circulant pattern -- rank r takes the blocks
+        // (r, r+1) ... (r, r+floor((W-1)/2)) from its own rows (the mirrored blocks belong to nobody else), and for even W the
+        // antipodal pair {r, r+W/2} is split: the lower rank walks the first half of its rows, the upper rank the remaining
+        // columns of the mirrored block.  Every unordered pair of bins is then visited exactly once, W/2 blocks per rank.
+        bool blocks = W > 1 && c->sym_blocks;
+        if (blocks) {
+            blocks = (r0 == aligned_cut(n, W, me) && r1 == aligned_cut(n, W, me + 1));
+            for (int r = 0; r < W && blocks; ++r) blocks = aligned_cut(n, W, r + 1) - aligned_cut(n, W, r) >= 2048;
+        }
+        auto half_cut = [&](int r) {           // panel-aligned middle of rank r's rows
+            const int64_t a = aligned_cut(n, W, r), b = aligned_cut(n, W, r + 1);
+            return a + ((b - a) / 2 + 512) / 1024 * 1024;
+        };
+        const long long all_bands = (c->nloc + SYM_R - 1) / SYM_R;
         int64_t bytes = 0;
+        int kfold_lo = -1;
         for (int k = 0; k < nch; ++k) {
-            const long long rows_end = std::min<long long>(r1, (k < nch - 1) ? (long long)(k + 1) * 1024 : (long long)n);
-            const long long nb = rows_end > r0 ? (rows_end - r0 + SYM_R - 1) / SYM_R : 0;
+            long long nb = 0;
+            int full = 0;
+            const long long col0 = (long long)k * 1024;
+            int s_blk = 0;
+            if (blocks) {
+                while (s_blk + 1 < W && aligned_cut(n, W, s_blk + 1) <= col0) ++s_blk;
+            }
+            if (!blocks || s_blk == me) {
+                // own diagonal region (or the whole upper triangle of the rank's rows when blocks are off)
+                const long long rows_end = std::min<long long>(r1, (k < nch - 1) ? (long long)(k + 1) * 1024 : (long long)n);
+                nb = rows_end > r0 ? (rows_end - r0 + SYM_R - 1) / SYM_R : 0;
+                if (blocks && col0 >= r1) nb = 0;
+            } else {
+                const int d = ((s_blk - me) % W + W) % W;
+                if (2 * d < W) { nb = all_bands; full = 1; }
+                else if (2 * d == W) {
+                    full = 1;
+                    if (me < s_blk) nb = (half_cut(me) - r0) / SYM_R;                 // lower rank: first half of its rows
+                    else nb = (col0 >= half_cut(s_blk)) ? all_bands : 0;              // upper rank: columns of the partner's second half
+                }
+            }
+            if (nb > 0 && kfold_lo < 0) kfold_lo = k;
+            pfull[k] = full;
             pu[k + 1] = pu[k] + nb;
             bytes += nb * SYM_R * std::min<int64_t>(1024, c->ld - (int64_t)k * 1024) * 4;
         }
+        c->sym_kfold_lo = blocks ? kfold_lo : -1;
         const long long U = pu[nch];
         if (U < G) return 0;          // tiny share: keep the dense pass
         auto panel_of = [&](long long u) { return (int)(std::upper_bound(pu.begin(), pu.end(), u) - pu.begin()) - 1; };
@@ -796,6 +853,7 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         ti.insert(ti.end(), kl.begin(), kl.end());
         ti.insert(ti.end(), pc.begin(), pc.end());
         ti.insert(ti.end(), ph.begin(), ph.end());
+        ti.insert(ti.end(), pfull.begin(), pfull.end());
         CK(cudaMalloc(&c->sym_tab_ll, sizeof(long long) * tll.size()));
         CK(cudaMalloc(&c->sym_tab_i, sizeof(int) * ti.size()));
         CK(cudaMemcpy(c->sym_tab_ll, tll.data(), sizeof(long long) * tll.size(), cudaMemcpyHostToDevice));
@@ -821,6 +879,8 @@ static SymTab sym_tab(gcx_ctx* c) {
     T.cta_kl = c->sym_tab_i + G;
     T.panel_cta = c->sym_tab_i + 2 * G;
     T.panel_cta_hi = c->sym_tab_i + 2 * G + nch;
+    T.panel_full = c->sym_tab_i + 2 * G + 2 * nch;
+    T.kfold_lo = c->sym_kfold_lo;
     T.nslots = c->sym_slots;
     T.row0 = (int)c->row0;
     T.nloc = (int)c->nloc;

@@ -527,6 +527,9 @@ struct SymTab {
     const int* cta_kl;         // [G] panel of a share's last unit
     const int* panel_cta;      // [nch] first CTA whose (non-empty) share intersects the panel (G if none)
     const int* panel_cta_hi;   // [nch] last such CTA (-1 if none); every CTA in between has units in the panel
+    const int* panel_full;     // [nch] 1: the panel is an off-diagonal block assigned to this rank (every element counts for
+                               //      the row AND the column part); 0: the rank's own diagonal region (j >= i / j > i rules)
+    int kfold_lo;              // first panel with units on this rank (row-partial fold starts here)
     int nslots;                // panels a share may touch (sizes colpart)
     int row0, nloc;            // this rank's global row block
 };
@@ -597,7 +600,9 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
     long long pbeg = T.panel_u0[k];
     long long pend = T.panel_u0[k + 1];
     double cacc[NG][4], zc[NG][4];
+    int pfull = T.panel_full[k];
     auto load_zc = [&](int kk) {
+        pfull = T.panel_full[kk];
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
             const int c4 = kk * MV_THREADS + q * TG + tig;
@@ -647,7 +652,8 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
             const int c4 = k * MV_THREADS + cl;
             // j0 and i0 are multiples of 4: a thread's 4x4 block is entirely above the diagonal (delta > 0), entirely
             // below it (delta < 0: nothing to do) or the diagonal block itself (delta == 0, one thread per unit)
-            const int delta = 4 * c4 - i0;
+            // (an off-diagonal block assigned to this rank -- pfull -- counts every element for both parts)
+            const int delta = pfull ? 4 : 4 * c4 - i0;
             if (c4 < n4 && delta >= 0) {
                 float4 a[R];
 #pragma unroll
@@ -738,8 +744,10 @@ __device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n4, con
     if (valid) {
         const int ki = i >> 10;
         if (i >= T.row0 && i < T.row0 + T.nloc) {
+            // entries of panels (or bands) this rank never walks keep their initial zero, so the loop may cover them
+            const int kstart = T.kfold_lo < 0 ? ki : T.kfold_lo;
 #pragma unroll 4
-            for (int k = ki + j / SYM_NG; k < nch; k += 8 / SYM_NG) s += __ldcg(rowpart + ((long long)k * SYM_NG + (j % SYM_NG)) * rp_ld + i);
+            for (int k = kstart + j / SYM_NG; k < nch; k += 8 / SYM_NG) s += __ldcg(rowpart + ((long long)k * SYM_NG + (j % SYM_NG)) * rp_ld + i);
         }
         const int clo = T.panel_cta[ki], chi = T.panel_cta_hi[ki];
 #pragma unroll 2

@@ -19,6 +19,17 @@ def row_partition(n, world, rank):
     return row0, max(0, min(rpr, int(n) - row0))
 
 
+def row_partition_aligned(n, world, rank):
+    """(row0, nloc) of the library's aligned partition: near-equal row blocks with cuts on multiples of 1024 rows
+    (gcx_partition_rows).  With symmetric=True a sharded map then runs the upper-triangle pass with the off-diagonal
+    blocks dealt out in a circulant pattern -- rows, PCIe traffic and symmetric work all balanced."""
+    import ctypes as C
+    from ._lib import check, lib
+    r0, nl = C.c_int64(0), C.c_int64(0)
+    check(lib().gcx_partition_rows(int(n), int(world), int(rank), C.byref(r0), C.byref(nl)))
+    return r0.value, nl.value
+
+
 def row_partition_equal_area(n, world, rank, align=1024):
     """(row0, nloc) so that every rank owns the same share of the UPPER TRIANGLE: row i has n-i entries right of the
     diagonal, so the cut after a fraction f of the area is at n (1 - sqrt(1 - f)).  Cuts are rounded to `align` rows
@@ -66,15 +77,20 @@ def sharded_device_map(n, device=None, partition="rows", symmetric=False):
     """DeviceMap for this rank's row block, wired to the other ranks (torch.distributed must be initialised).
 
     partition="rows": equal ceil(n/world) row blocks, n-vectors exchanged by allgather, dense passes.
+    partition="balanced" (+ symmetric=True): near-equal row blocks cut on multiples of 1024 rows; IC/KR passes read each
+    unordered pair of bins once, the off-diagonal blocks dealt out to the ranks in a circulant pattern; allreduce exchange.
     partition="equal_area" (+ symmetric=True, the caller vouching that the map is symmetric): row blocks holding equal
     shares of the upper triangle, n-vectors exchanged by allreduce, IC/KR passes read the upper triangle only."""
     import torch.distributed as tdist
     from .device import DeviceMap
     rank, world = tdist.get_rank(), tdist.get_world_size()
     options = {}
-    if partition == "equal_area" and world > 1:
-        row0, nloc = row_partition_equal_area(n, world, rank)
+    if partition == "balanced" and world > 1:
+        row0, nloc = row_partition_aligned(n, world, rank)
         options = {"exchange_allreduce": 1, "assume_symmetric": 1 if symmetric else 0}
+    elif partition == "equal_area" and world > 1:
+        row0, nloc = row_partition_equal_area(n, world, rank)
+        options = {"exchange_allreduce": 1, "assume_symmetric": 1 if symmetric else 0, "sym_blocks": 0}
     else:
         row0, nloc = row_partition(n, world, rank)
     if nloc == 0:

@@ -120,6 +120,10 @@ int gcx_downsample(gcx_ctx* ctx, int level, int method, float* host_out, int64_t
  *                             allreduce instead of allgather (set it on every rank, before gcx_map_create)
  *   "matvec_variant"     kernel variant for sweeps */
 int gcx_set_option(gcx_ctx* ctx, const char* key, double value);
+/* The aligned row partition (cuts at rank*n/world rounded to 1024 rows).  With it, "assume_symmetric" and
+ * "exchange_allreduce", a sharded map runs the upper-triangle pass with the off-diagonal blocks dealt out in a circulant
+ * pattern: rows, PCIe traffic and the symmetric work are all balanced across ranks.  Needs no GPU. */
+int gcx_partition_rows(int64_t n, int world, int rank, int64_t* row0, int64_t* nloc);
 int gcx_dist_unique_id(void* id128);
 int gcx_dist_init(gcx_ctx* ctx, int rank, int world, const void* id128);
 

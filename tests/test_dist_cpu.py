@@ -95,3 +95,76 @@ def test_sharded_ic_world2_gloo_matches_oracle():
     assert m0 == m1 == passes
     assert np.array_equal(B0, B1)                       # ranks hold bitwise identical state
     np.testing.assert_allclose(B0, Bo, rtol=1e-10)
+
+
+# --------------------------------------------------------------------------------------------------
+# circulant block assignment of the sharded upper-triangle pass (mirror of sym_ready() in csrc/gcx_capi.cu)
+# --------------------------------------------------------------------------------------------------
+def _aligned_cut(n, W, r):
+    if r <= 0:
+        return 0
+    if r >= W:
+        return n
+    return min(n, (2 * r * n // W + 1024) // 2048 * 1024)
+
+
+def _panel_table(n, W, me):
+    """(row0, nloc, [(bands, full)] per 1024-column panel) for rank `me` -- same rules as the C++ table builder."""
+    ld = (n + 31) // 32 * 32
+    nch = (ld // 4 + 255) // 256
+    r0, r1 = _aligned_cut(n, W, me), _aligned_cut(n, W, me + 1)
+    nloc = r1 - r0
+
+    def half_cut(r):
+        a, b = _aligned_cut(n, W, r), _aligned_cut(n, W, r + 1)
+        return a + ((b - a) // 2 + 512) // 1024 * 1024
+    all_bands = (nloc + 3) // 4
+    out = []
+    for k in range(nch):
+        col0, nb, full, s = k * 1024, 0, 0, 0
+        while W > 1 and s + 1 < W and _aligned_cut(n, W, s + 1) <= col0:
+            s += 1
+        if W == 1 or s == me:
+            rows_end = min(r1, (k + 1) * 1024 if k < nch - 1 else n)
+            nb = (rows_end - r0 + 3) // 4 if rows_end > r0 else 0
+            if W > 1 and col0 >= r1:
+                nb = 0
+        else:
+            d = (s - me) % W
+            if 2 * d < W:
+                nb, full = all_bands, 1
+            elif 2 * d == W:
+                full = 1
+                nb = (half_cut(me) - r0) // 4 if me < s else (all_bands if col0 >= half_cut(s) else 0)
+        out.append((nb, full))
+    return r0, nloc, out
+
+
+@pytest.mark.parametrize("n,W", [(9000, 1), (9000, 2), (12345, 2), (13000, 3), (17000, 4), (21000, 5), (30000, 8)])
+def test_circulant_blocks_cover_every_pair_once(n, W):
+    """Every ordered pair (i, j) -- i.e. every term A_ij z_j of t_i -- is produced by exactly one rank, and the aligned
+    partition matches the library's gcx_partition_rows."""
+    C = np.zeros((n, n), dtype=np.int8)
+    work = []
+    for me in range(W):
+        r0, nloc, tab = _panel_table(n, W, me)
+        assert (r0, nloc) == gd.row_partition_aligned(n, W, me)
+        w = 0
+        for k, (nb, full) in enumerate(tab):
+            if nb == 0:
+                continue
+            rows = np.arange(r0, min(r0 + nb * 4, r0 + nloc))
+            cols = np.arange(k * 1024, min((k + 1) * 1024, n))
+            w += len(rows) * len(cols)
+            I, J = np.meshgrid(rows, cols, indexing="ij")
+            if full:
+                C[I, J] += 1
+                C[J, I] += 1
+            else:
+                m = J >= I
+                C[I[m], J[m]] += 1
+                m = J > I
+                C[J[m], I[m]] += 1
+        work.append(w)
+    assert (C == 1).all()
+    assert max(work) / (sum(work) / W) < 1.15

@@ -15,7 +15,7 @@ def _ngpu():
     return _lib.device_count()
 
 
-@pytest.mark.parametrize("n,partition", [(6001, "rows"), (997, "rows"), (9000, "equal_area"), (12345, "equal_area")])
+@pytest.mark.parametrize("n,partition", [(6001, "rows"), (9000, "equal_area"), (9000, "balanced"), (12345, "balanced")])
 def test_sharded_matches_single_gpu(n, partition):
     g = _ngpu()
     if g < 2:
