@@ -64,6 +64,7 @@ _PROTOS = {
     "gcx_timer_start": (C.c_int, [_ctx]),
     "gcx_timer_stop": (C.c_int, [_ctx, _c_f64p]),
     "gcx_map_invalidate": (C.c_int, [_ctx]),
+    "gcx_debug_sym_cycles": (C.c_int, [_ctx, _c_i64p, C.c_int, C.POINTER(C.c_int)]),
     "gcx_pass_bytes": (C.c_int, [_ctx, _c_i64p, C.POINTER(C.c_int)]),
     "gcx_last_run_ms": (C.c_int, [_ctx, _c_f64p]),
     "gcx_launch_count": (C.c_int, [_ctx, _c_i64p]),

@@ -119,6 +119,7 @@ struct gcx_ctx {
     int* sym_tab_i = nullptr;             // cta_kf [G] | cta_kl [G] | panel_cta [nch] | panel_cta_hi [nch]
     int sym_nch = 0;
     int64_t sym_bytes = 0;
+    long long* sym_dbg = nullptr;          // per-CTA main-loop cycles (GCX_SYM_DEBUG=1)
     int sym_blocks = 1;                   // sharded: circulant assignment of off-diagonal blocks (needs the aligned row partition)
     int sym_kfold_lo = -1;
     int assume_symmetric = 0;             // sharded runs cannot test symmetry locally: the caller vouches for it
@@ -314,6 +315,7 @@ static void free_map(gcx_ctx* c) {
     cudaFree(c->colpart); c->colpart = nullptr;
     cudaFree(c->sym_tab_ll); c->sym_tab_ll = nullptr;
     cudaFree(c->sym_tab_i); c->sym_tab_i = nullptr;
+    cudaFree(c->sym_dbg); c->sym_dbg = nullptr;
     c->sym_state = -1;
     cudaFree(c->slab); c->slab = nullptr;
     cudaFree(c->csum32); c->csum32 = nullptr;
@@ -862,6 +864,10 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         const size_t cp_bytes = sizeof(double) * (size_t)G * slots * SYM_NG * 1024;
         CK(cudaMalloc(&c->rowpart, rp_bytes));
         CK(cudaMalloc(&c->colpart, cp_bytes));
+        if (getenv("GCX_SYM_DEBUG") && !c->sym_dbg) {
+            CK(cudaMalloc(&c->sym_dbg, sizeof(long long) * (size_t)G));
+            CK(cudaMemset(c->sym_dbg, 0, sizeof(long long) * (size_t)G));
+        }
         // rowpart must start from zero: a (panel, band) is written by one consumer group only, the fold adds both
         CK(cudaMemsetAsync(c->rowpart, 0, rp_bytes, c->stream));
         CK(cudaMemsetAsync(c->colpart, 0, cp_bytes, c->stream));
@@ -881,6 +887,7 @@ static SymTab sym_tab(gcx_ctx* c) {
     T.panel_cta_hi = c->sym_tab_i + 2 * G + nch;
     T.panel_full = c->sym_tab_i + 2 * G + 2 * nch;
     T.kfold_lo = c->sym_kfold_lo;
+    T.dbg_cycles = c->sym_dbg;
     T.nslots = c->sym_slots;
     T.row0 = (int)c->row0;
     T.nloc = (int)c->nloc;
@@ -1387,6 +1394,17 @@ extern "C" int gcx_timer_stop(gcx_ctx* c, double* ms) {
 
 extern "C" int gcx_map_invalidate(gcx_ctx* c) {
     c->have_rowsum = false;
+    return 0;
+}
+
+extern "C" int gcx_debug_sym_cycles(gcx_ctx* c, int64_t* cycles, int capacity, int* count) {
+    CKR(need_map(c));
+    if (!c->sym_dbg) return fail("per-CTA cycle recording is off (set GCX_SYM_DEBUG=1 before the first symmetric pass)");
+    const int G = c->sym_grid;
+    if (capacity < G) return fail("capacity < grid (%d)", G);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(cycles, c->sym_dbg, sizeof(long long) * (size_t)G, cudaMemcpyDeviceToHost));
+    *count = G;
     return 0;
 }
 

@@ -530,6 +530,7 @@ struct SymTab {
     const int* panel_full;     // [nch] 1: the panel is an off-diagonal block assigned to this rank (every element counts for
                                //      the row AND the column part); 0: the rank's own diagonal region (j >= i / j > i rules)
     int kfold_lo;              // first panel with units on this rank (row-partial fold starts here)
+    long long* dbg_cycles;     // optional [G]: cycles every CTA spent in the main loop (GCX_SYM_DEBUG=1), else nullptr
     int nslots;                // panels a share may touch (sizes colpart)
     int row0, nloc;            // this rank's global row block
 };
@@ -556,6 +557,7 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
     __syncthreads();
     if (u0 >= u1) return;
     const int kfirst = T.cta_kf[c];
+    const long long t_start = (T.dbg_cycles != nullptr && tid == 0) ? clock64() : 0;
 
     if (warp == MV_THREADS / 32) {
         // ---------------- producer ----------------
@@ -717,6 +719,7 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
         if (k >= klast) break;
         ++k;
     }
+    if (T.dbg_cycles != nullptr && tid == 0) T.dbg_cycles[c] = clock64() - t_start;
 }
 
 template <int STAGES, int OCC>

@@ -142,6 +142,8 @@ int gcx_map_invalidate(gcx_ctx* ctx);
 /* HBM bytes one matrix pass of the last ic/kr run read: 4*nloc*n for the dense pass, ~2*n*(n+1024) when the
  * upper-triangle pass was used (single rank, exactly symmetric map, n >= 2048; GCX_SYM=0 disables it) */
 int gcx_pass_bytes(gcx_ctx* ctx, int64_t* bytes, int* symmetric);
+/* diagnostics: cycles every CTA of the last upper-triangle pass spent in its main loop (needs GCX_SYM_DEBUG=1) */
+int gcx_debug_sym_cycles(gcx_ctx* ctx, int64_t* cycles, int capacity, int* count);
 /* device time (ms, CUDA events) of the last ic/kr run: matrix resident -> final vector */
 int gcx_last_run_ms(gcx_ctx* ctx, double* ms);
 /* total kernel launches issued by this context since creation */
