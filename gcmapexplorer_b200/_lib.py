@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgcxnorm.so")
+LIB_PATH = os.environ.get("GCX_LIB") or os.path.join(_HERE, "libgcxnorm.so")
 NCLASS = 8
 KERNEL_CLASSES = ("matvec", "apply_sym", "vc_apply", "row_stats", "diag_reduce", "diag_apply", "vector_step", "other")
 

@@ -295,13 +295,13 @@ extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
     if (sy) c->sym_enable = atoi(sy);
     if (c->ic_fused != 2) c->sym_enable = c->sym_enable && (c->ic_fused != 1);   // the fused LDG pass has no symmetric twin
     {
-        const int smem = 6 * SYM_R * MV_THREADS * (int)sizeof(float4);
-        CK(cudaFuncSetAttribute(k_matvec_sym_tma<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(k_ic_pass_sym_tma<6, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(k_ic_pass_sym_tma<6, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int smem = SYM_STAGES * SYM_R * MV_THREADS * (int)sizeof(float4);
+        CK(cudaFuncSetAttribute(k_matvec_sym_tma<SYM_STAGES, SYM_OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k_ic_pass_sym_tma<SYM_STAGES, SYM_OCC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k_ic_pass_sym_tma<SYM_STAGES, SYM_OCC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ3 = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_ic_pass_sym_tma<6, 2, true>, TMA_THREADS, smem));
-        c->sym_grid = c->sm_count * std::min(occ3, 2);
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_ic_pass_sym_tma<SYM_STAGES, SYM_OCC, true>, SYM_THREADS, smem));
+        c->sym_grid = c->sm_count * std::min(occ3, SYM_OCC);
         if (occ3 < 1) c->sym_enable = 0;
     }
     *out = c;
@@ -896,11 +896,11 @@ static SymTab sym_tab(gcx_ctx* c) {
 
 // q = A z through the upper-triangle pass; sharded: every rank folds its partial t, an allreduce adds them
 static int matvec_sym(gcx_ctx* c, const double* z, double* q, const int* done) {
-    const size_t smem = (size_t)6 * SYM_R * MV_THREADS * sizeof(float4);
+    const size_t smem = (size_t)SYM_STAGES * SYM_R * MV_THREADS * sizeof(float4);
     const int n = (int)c->n, n4 = (int)(c->ld / 4);
     {
         ProfScope ps(c, 0);
-        k_matvec_sym_tma<6, 2><<<c->sym_grid, TMA_THREADS, smem, c->stream>>>(c->A, c->ld, n4, z, c->rowpart, c->colpart, sym_tab(c), done);
+        k_matvec_sym_tma<SYM_STAGES, SYM_OCC><<<c->sym_grid, SYM_THREADS, smem, c->stream>>>(c->A, c->ld, n4, z, c->rowpart, c->colpart, sym_tab(c), done);
         k_sym_fold<<<(n * 8 + 255) / 256, 256, 0, c->stream>>>(n, n4, c->rowpart, c->colpart, sym_tab(c), q, done);
     }
     c->launches += 1;
@@ -1084,14 +1084,14 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         SymTab tab = sym_tab(c);
         void* args[] = {(void*)&c->A, (void*)&c->ld, (void*)&n, (void*)&n4, (void*)&c->keep, (void*)&c->vq, (void*)&c->vz, (void*)&c->vB,
                         (void*)&c->rowpart, (void*)&c->colpart, (void*)&tab, (void*)&c->ticket, (void*)&c->ic_state, (void*)&c->part};
-        const size_t smem = 6 * SYM_R * MV_THREADS * sizeof(float4);
+        const size_t smem = SYM_STAGES * SYM_R * MV_THREADS * sizeof(float4);
         {
             ProfScope ps(c, 0);
             if (c->world == 1) {
-                CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_sym_tma<6, 2, true>, dim3(c->sym_grid), dim3(TMA_THREADS), args, smem, c->stream));
+                CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_sym_tma<SYM_STAGES, SYM_OCC, true>, dim3(c->sym_grid), dim3(SYM_THREADS), args, smem, c->stream));
             } else {
                 // sharded: the fold runs as its own kernel so that the ranks' partial t can be added before the next launch
-                CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_sym_tma<6, 2, false>, dim3(c->sym_grid), dim3(TMA_THREADS), args, smem, c->stream));
+                CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_sym_tma<SYM_STAGES, SYM_OCC, false>, dim3(c->sym_grid), dim3(SYM_THREADS), args, smem, c->stream));
                 k_sym_fold<<<(n * 8 + 255) / 256, 256, 0, c->stream>>>(n, n4, c->rowpart, c->colpart, tab, c->vq, &c->ic_state->done);
             }
         }

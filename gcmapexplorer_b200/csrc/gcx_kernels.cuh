@@ -515,7 +515,15 @@ k_matvec_tma(const float* __restrict__ A, long long ld, int nloc, int n4, const 
 // ---------------------------------------------------------------------------------------------------
 constexpr int SYM_R = 4;
 constexpr int SYM_BPP = 1024 / SYM_R;        // bands per 1024 rows
-constexpr int SYM_NG = 2;                    // consumer groups per CTA (4 warps each, 8 columns per thread)
+#ifndef GCX_SYM_CFG
+#define GCX_SYM_CFG 0
+#endif
+#if GCX_SYM_CFG == 1                         // one CTA per SM: 16 consumer warps in 4 groups, 12 stages (192 KB)
+constexpr int SYM_CW = 16, SYM_NG = 4, SYM_STAGES = 12, SYM_OCC = 1;
+#else                                        // two CTAs per SM: 8 consumer warps in 2 groups, 6 stages (96 KB) each
+constexpr int SYM_CW = 8, SYM_NG = 2, SYM_STAGES = 6, SYM_OCC = 2;
+#endif
+constexpr int SYM_THREADS = (SYM_CW + 1) * 32;   // consumer warps + 1 producer warp
 
 // Geometry of one rank's share of the upper triangle, tabulated on the host once per map.  The rank owns the global
 // rows [row0, row0 + nloc) (row0 a multiple of 1024 when sharded).  Panel k holds the local bands whose global rows lie
@@ -540,8 +548,9 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
                                                 double* rowpart, double* colpart, SymTab T, float4* tiles, uint64_t* full_bar,
                                                 uint64_t* empty_bar, double* gred) {
     constexpr int R = SYM_R;
-    constexpr int WPG = (MV_THREADS / 32) / NG;      // warps per group
-    constexpr int TG = MV_THREADS / NG;              // threads per group
+    constexpr int WPG = SYM_CW / NG;                 // warps per group
+    constexpr int TG = WPG * 32;                     // threads per group
+    constexpr int NQ = MV_THREADS / TG;              // float4 columns of the 1024-column panel per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long c = blockIdx.x;
     const long long u0 = T.cta_u0[c], u1 = T.cta_u0[c + 1];
@@ -559,7 +568,7 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
     const int kfirst = T.cta_kf[c];
     const long long t_start = (T.dbg_cycles != nullptr && tid == 0) ? clock64() : 0;
 
-    if (warp == MV_THREADS / 32) {
+    if (warp == SYM_CW) {
         // ---------------- producer ----------------
         if (lane == 0) {
             int stage = 0;
@@ -601,12 +610,12 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
     int k = kfirst;
     long long pbeg = T.panel_u0[k];
     long long pend = T.panel_u0[k + 1];
-    double cacc[NG][4], zc[NG][4];
+    double cacc[NQ][4], zc[NQ][4];
     int pfull = T.panel_full[k];
     auto load_zc = [&](int kk) {
         pfull = T.panel_full[kk];
 #pragma unroll
-        for (int q = 0; q < NG; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             const int c4 = kk * MV_THREADS + q * TG + tig;
             double2 za = make_double2(0.0, 0.0), zb = za;
             if (c4 < n4) {
@@ -618,7 +627,7 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
     };
     auto flush = [&](int kk) {
 #pragma unroll
-        for (int q = 0; q < NG; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             double2* dst = reinterpret_cast<double2*>(colpart + (((size_t)c * T.nslots + (kk - kfirst)) * NG + g) * 1024) + 2 * (q * TG + tig);
             dst[0] = make_double2(cacc[q][0], cacc[q][1]);
             dst[1] = make_double2(cacc[q][2], cacc[q][3]);
@@ -626,7 +635,7 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
         }
     };
 #pragma unroll
-    for (int q = 0; q < NG; ++q) cacc[q][0] = cacc[q][1] = cacc[q][2] = cacc[q][3] = 0.0;
+    for (int q = 0; q < NQ; ++q) cacc[q][0] = cacc[q][1] = cacc[q][2] = cacc[q][3] = 0.0;
     load_zc(k);
     for (long long u = u0 + g; u < u1; u += NG) {
         while (u >= pend) {
@@ -649,7 +658,7 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
         mbar_wait(&full_bar[stage], phase);
         double rp[R] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int q = 0; q < NG; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             const int cl = q * TG + tig;                    // float4 column inside the panel
             const int c4 = k * MV_THREADS + cl;
             // j0 and i0 are multiples of 4: a thread's 4x4 block is entirely above the diagonal (delta > 0), entirely
@@ -723,14 +732,14 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
 }
 
 template <int STAGES, int OCC>
-__global__ void __launch_bounds__(TMA_THREADS, OCC)
+__global__ void __launch_bounds__(SYM_THREADS, OCC)
 k_matvec_sym_tma(const float* __restrict__ A, long long ld, int n4, const double* __restrict__ z, double* rowpart,
                  double* colpart, SymTab T, const int* __restrict__ done) {
     if (done != nullptr && *done) return;
     extern __shared__ __align__(128) unsigned char tma_smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
-    __shared__ double gred[2 * (MV_THREADS / 32) * SYM_R];
+    __shared__ double gred[2 * SYM_CW * SYM_R];
     matvec_sym_core<SYM_NG, STAGES, true>(A, ld, n4, z, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred);
 }
 
@@ -1733,7 +1742,7 @@ k_ic_pass_tma(const float* __restrict__ A, long long ld, int nloc, int n4, int n
 // Fused IC pass on the upper triangle: P1 folds t_i from the partials of the previous launch's symmetric
 // matvec on the fly, P2/P3 as in k_ic_pass, then the symmetric TMA main loop with z = v.
 template <int STAGES, int OCC, bool FOLD>
-__global__ void __launch_bounds__(TMA_THREADS, OCC)
+__global__ void __launch_bounds__(SYM_THREADS, OCC)
 k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, const uint8_t* __restrict__ keep, double* t, double* v,
                   double* B, double* rowpart, double* colpart, SymTab T, unsigned int* ticket, IcState* st, double* part) {
     namespace cg = cooperative_groups;
@@ -1743,11 +1752,11 @@ k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, cons
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ double sm[32];
-    __shared__ double gred[2 * (MV_THREADS / 32) * SYM_R];
+    __shared__ double gred[2 * SYM_CW * SYM_R];
     const int tid = threadIdx.x;
     const int G = gridDim.x, bid = blockIdx.x;
     const int m = st->matvecs;
-    const int gth = bid * TMA_THREADS + tid, nth = G * TMA_THREADS;
+    const int gth = bid * SYM_THREADS + tid, nth = G * SYM_THREADS;
 
     if (m > 0) {
         const int mm = m - 1;
@@ -1755,7 +1764,7 @@ k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, cons
         const int max_iter = st->max_iter;
         double s = 0.0, c = 0.0;
         if (FOLD) {
-            // one rank: t_i is folded here by groups of 8 lanes (TMA_THREADS = 288 is a multiple of 8); lane 0 owns bin i
+            // one rank: t_i is folded here by groups of 8 lanes (SYM_THREADS = 288 is a multiple of 8); lane 0 owns bin i
             for (int base = 0; base < n; base += nth / 8) {
                 const int i = base + (gth >> 3);
                 const double ti = sym_fold_group8(i, i < n, n4, rowpart, colpart, T);
@@ -1786,7 +1795,7 @@ k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, cons
         }
         grid.sync();
         double a0 = 0.0, a1 = 0.0;
-        for (int b = tid; b < G; b += TMA_THREADS) {
+        for (int b = tid; b < G; b += SYM_THREADS) {
             a0 += __ldcg(part + b);
             a1 += __ldcg(part + G + b);
         }
@@ -1813,7 +1822,7 @@ k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, cons
         if (tid == 0) part[2 * G + bid] = l1;
         grid.sync();
         double a2 = 0.0;
-        for (int b = tid; b < G; b += TMA_THREADS) a2 += __ldcg(part + 2 * G + b);
+        for (int b = tid; b < G; b += SYM_THREADS) a2 += __ldcg(part + 2 * G + b);
         const double L1 = block_reduce<RED_SUM>(a2, sm);
         const bool done = (mm >= 2) && (L1 < tol || (mm - 1) > max_iter);       // :55-57
         if (bid == 0 && tid == 0) {
