@@ -386,6 +386,54 @@ def min_over_ranks_flag(tdist, flag):
     return bool(t.item())
 
 
+def run_chr21(args):
+    """BASELINE configs[0]: chr21 @ 100 kb (n = 482) -- the one size where the reference runs as-is to convergence on the CPU.
+    Three-way report: the reference's compiled IC core (fp32 in place), the fp64 restatement, and this library, same map."""
+    from gcmapexplorer_b200 import device as gx
+    from oracle import oracle_np as onp
+    n = args.n or 482
+    A = onp.synth_map(n, seed=21100, scale=2000.0)
+    kind, ic, vc, mask = _load_reference()
+    t0 = time.perf_counter()
+    M = A.copy()
+    ic(M, IC_TOL, IC_ITER)
+    t_ref = time.perf_counter() - t0
+    passes_ref = None
+    try:
+        from oracle import ref_loader as rl
+        rl.ic_pass_counter(reset=True)
+        M2 = A.copy()
+        ic(M2, IC_TOL, IC_ITER)
+        passes_ref = rl.ic_pass_counter()
+    except Exception:
+        pass
+    M64, B64, passes64, _ = onp.ic_fp64(A, IC_TOL, IC_ITER)
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.set_mask(np.ones(n, dtype=bool))
+        for _ in range(args.warmup):
+            r = dm.ic(IC_TOL, IC_ITER)
+        ts = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            dm.upload(A)
+            dm.set_mask(np.ones(n, dtype=bool))
+            r = dm.ic(IC_TOL, IC_ITER)
+            dm.apply_sym(None, masked_mode=1, in_place=True)
+            out = dm.download(0)
+            ts.append(time.perf_counter() - t0)
+    nz = M64 != 0
+    line = {"metric": "IC time-to-converge, chr21 @ 100 kb (s, whole call incl. upload/download)", "value": round(float(np.median(ts)), 6), "unit": "s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(float(np.median(ts)) * 1e3, 3), "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 accumulate / f32 storage", "data": "synthetic (host-generated, n=%d)" % n,
+            "config": {"workload": "synthetic chr21 @ 100 kb (n=%d), IC" % n},
+            "passes": {"gpu": r["passes"], "fp64_restatement": passes64, "reference_as_is": passes_ref}, "device_ms": r["ms"],
+            "cpu_baseline": {"value": round(t_ref, 4), "unit": "s", "cores": 1, "kind": kind, "sample": "full run of the reference's IC core, as-is"},
+            "agreement": {"gpu_vs_fp64_max_rel": float(np.max(np.abs(out[nz] - M64[nz].astype(np.float32)) / M64[nz])),
+                          "gpu_vs_reference_max_rel": float(np.max(np.abs(out[nz] - M[nz]) / M64[nz])),
+                          "reference_vs_fp64_max_rel": float(np.max(np.abs(M[nz] - M64[nz]) / M64[nz]))}}
+    print(json.dumps(line))
+
+
 def psutil_avail():
     try:
         import psutil
@@ -540,7 +588,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "chr1_10kb", "chr1_5kb_kr", "chr1_1kb", "wg_25kb_mcfs"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "chr1_10kb", "chr1_5kb_kr", "chr1_1kb", "wg_25kb_mcfs", "chr21_100kb"])
     ap.add_argument("--mcfs-stats", default="median", choices=["median", "mean"])
     ap.add_argument("--n", type=int, default=0, help="override the number of bins (quick checks)")
     ap.add_argument("--seed", type=int, default=110)
@@ -557,6 +605,8 @@ def main():
         run_reference(args)
     elif args.workload == "wg_25kb_mcfs":
         run_mcfs_wg(args)
+    elif args.workload == "chr21_100kb":
+        run_chr21(args)
     else:
         run_b200(args)
 

@@ -85,10 +85,14 @@ def get_nonzeros_index(matrix, threshold_percentile=None, threshold_data_occup=N
 
 
 def remove_zeros(matrix, threshold_percentile=None, threshold_data_occup=None, workDir=None):
-    """Drop-in for ccmapHelpers.remove_zeros: (MemoryMappedArray float64 of the kept block, bNoData)."""
-    bData = get_nonzeros_index(matrix, threshold_percentile=threshold_percentile, threshold_data_occup=threshold_data_occup)
-    kept = np.nonzero(bData)[0]
-    A = MemoryMappedArray((kept.size, kept.size), workDir=workDir, dtype="float64")
-    for ci, i in enumerate(kept):
-        A.arr[ci] = matrix[i][kept]
+    """Drop-in for ccmapHelpers.remove_zeros: (MemoryMappedArray float64 of the kept block, bNoData).  Mask and
+    compaction both run on the device from one upload (the reference's element loop, :286-299, is O(n^2) interpreter steps)."""
+    with DeviceMap.from_host(matrix) as dm:
+        bData = device_mask(dm, threshold_percentile, threshold_data_occup)
+        nk = int(bData.sum())
+        A = MemoryMappedArray((nk, nk), workDir=workDir, dtype="float64")
+        if isinstance(A.arr, np.ndarray) and A.arr.flags.c_contiguous:
+            dm.compact_f64(bData, out=A.arr)
+        else:
+            A.arr[:] = dm.compact_f64(bData)
     return A, ~bData

@@ -1329,6 +1329,32 @@ extern "C" int gcx_diag_apply(gcx_ctx* c, const double* avg, int subtract, int i
 }
 
 // ---------------------------------------------------------------------------------------------------
+// compaction (inner-seam remove_zeros)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gcx_compact_f64(gcx_ctx* c, const int32_t* kept, int64_t nk, double* host_out) {
+    CKR(need_map(c));
+    if (c->world != 1) return fail("gcx_compact_f64: single-rank maps only");
+    if (nk < 1 || nk > c->n) return fail("gcx_compact_f64: bad kept count");
+    const size_t b_idx = align256(sizeof(int) * (size_t)nk);
+    const int64_t rows_per = std::max<int64_t>(1, std::min<int64_t>(nk, (int64_t)(256ll << 20) / (8 * nk)));   // <= 256 MB per slab
+    CKR(ensure_scratch(c, b_idx + sizeof(double) * (size_t)rows_per * nk));
+    int* didx = (int*)c->scratch;
+    double* dout = (double*)((char*)c->scratch + b_idx);
+    CK(cudaMemcpyAsync(didx, kept, sizeof(int) * (size_t)nk, cudaMemcpyHostToDevice, c->stream));
+    for (int64_t r0 = 0; r0 < nk; r0 += rows_per) {
+        const int rows = (int)std::min<int64_t>(rows_per, nk - r0);
+        {
+            ProfScope ps(c, 7);
+            k_compact_f64<<<std::min(rows, c->sm_count * 8), 256, 0, c->stream>>>(c->A, c->ld, didx + r0, rows, didx, (int)nk, dout);
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(host_out + r0 * nk, dout, sizeof(double) * (size_t)rows * nk, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // coarsening
 // ---------------------------------------------------------------------------------------------------
 extern "C" int gcx_downsample(gcx_ctx* c, int level, int method, float* host_out, int64_t out_n, float* minv, float* maxv) {

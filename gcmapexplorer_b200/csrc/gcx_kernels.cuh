@@ -1297,6 +1297,18 @@ k_downsample(const float* __restrict__ A, long long ld, int n, int level, int me
     mm_commit(mn, mx, mm);
 }
 
+// K0 compaction: out[ci][cj] = (double) A[kept[ci]][kept[cj]]  -- ccmapHelpers.remove_zeros (lib/ccmapHelpers.pyx:286-299),
+// which builds a float64 matrix of the kept rows/columns.  The normalizers here never compact (masked bins are zeroed vector
+// entries); this serves callers of the inner seam.
+__global__ void __launch_bounds__(256)
+k_compact_f64(const float* __restrict__ A, long long ld, const int* __restrict__ kept_rows, int nrows, const int* __restrict__ kept_cols,
+              int nk, double* __restrict__ out) {
+    for (int ci = blockIdx.x; ci < nrows; ci += gridDim.x) {
+        const float* row = A + (long long)kept_rows[ci] * ld;
+        for (int cj = threadIdx.x; cj < nk; cj += blockDim.x) out[(long long)ci * nk + cj] = (double)row[kept_cols[cj]];
+    }
+}
+
 // vmin/vmax clamp + scale, in place (lib/normalizer.py:567-569, 832-834)
 __global__ void __launch_bounds__(MV_THREADS)
 k_clamp_scale(float* __restrict__ A, long long total4, int has_vmin, float vmin, int has_vmax, float vmax, int has_scale,

@@ -230,6 +230,17 @@ class DeviceMap:
         check(lib().gcx_diag_apply(self._ctx, ap, int(bool(subtract)), int(bool(in_place)), C.byref(mn), C.byref(mx)))
         return mn.value, mx.value
 
+    def compact_f64(self, keep, out=None):
+        """float64 [nk, nk] copy of the kept rows/columns (remove_zeros, lib/ccmapHelpers.pyx:286-299)."""
+        kept = np.ascontiguousarray(np.nonzero(np.asarray(keep, dtype=bool))[0].astype(np.int32))
+        nk = int(kept.size)
+        if out is None:
+            out = np.empty((nk, nk), dtype=np.float64)
+        if out.shape != (nk, nk) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 [nk, nk] array")
+        check(lib().gcx_compact_f64(self._ctx, kept.ctypes.data_as(_lib._c_i32p), nk, out.ctypes.data_as(_lib._c_f64p)))
+        return out
+
     def downsample(self, level=2, method="sum"):
         """(coarse float32 matrix, min non-zero, max): downSample2DMap of lib/ccmap.py:737-842, bit-identical."""
         code = {"sum": 0, "mean": 1, "max": 2}.get(method, 0)        # the reference treats unknown methods as 'sum'

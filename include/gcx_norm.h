@@ -102,6 +102,11 @@ int gcx_vc_run(gcx_ctx* ctx, int sqroot, int in_place, float* minv, float* maxv,
 int gcx_diag_stats(gcx_ctx* ctx, int median, double* avg);
 int gcx_diag_apply(gcx_ctx* ctx, const double* avg, int subtract, int in_place, float* minv, float* maxv);
 
+/* ---- compaction ---------------------------------------------------------------------------------
+ * Replaces the element loop of ccmapHelpers.remove_zeros (lib/ccmapHelpers.pyx:286-299): host_out[ci][cj] =
+ * (double) A[kept[ci]][kept[cj]], nk x nk float64.  Only for callers of the inner seam -- the normalizers never compact. */
+int gcx_compact_f64(gcx_ctx* ctx, const int32_t* kept, int64_t nk, double* host_out);
+
 /* ---- coarsening ---------------------------------------------------------
  * Replaces ccmap.downSample2DMap (lib/ccmap.py:737-842) on the resident map: out is (ceil((n-1)/level)+1)^2 floats on the
  * host; method 0 sum, 1 mean, 2 max; NumPy's reduction order and float32/float64 promotion are reproduced, so the result is

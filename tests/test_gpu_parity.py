@@ -202,6 +202,13 @@ def test_inner_seam_functions(gx):
     assert rel_err(O, exp) < MAT_RTOL
     with pytest.raises(ValueError):
         krn.KnightRuizNorm(sub, memory="TAPE")
+    # remove_zeros: device mask + device compaction into a float64 memmap (lib/ccmapHelpers.pyx:241-301)
+    from gcmapexplorer_b200 import ccmapHelpers as cmh
+    for kw in (dict(), dict(threshold_percentile=95)):
+        Z, bNo = cmh.remove_zeros(A, **kw)
+        k2 = onp.get_nonzeros_index(A, kw.get("threshold_percentile"), None)
+        assert np.array_equal(bNo, ~k2) and Z.arr.dtype == np.float64
+        assert np.array_equal(np.asarray(Z.arr), A[k2][:, k2].astype(np.float64))
 
 
 @pytest.mark.skipif(not rl.have_cores(), reason="oracle/_ref not built")
@@ -273,6 +280,17 @@ def test_device_synth_properties_and_full_size_invariants(gx):
         dm.swap()
         rs_kr, _ = dm.row_stats()
         assert np.max(np.abs(rs_kr[keep] - 1.0)) < 1e-5 and np.all(rs_kr[~keep] == 0)   # fp32 storage
+        # MCFS invariants on the KR-balanced (non-integer) map: after o/e scaling every diagonal's statistic is 1
+        for stats in ("mean", "median"):
+            avg = dm.diag_stats(stats)
+            dm.diag_apply(None, subtract=False, in_place=False)
+            dm.swap()
+            after = dm.diag_stats(stats)
+            dm.swap()
+            has = avg != 0
+            assert has.sum() > n // 2
+            assert np.max(np.abs(after[has] - 1.0)) < (1e-6 if stats == "mean" else 2e-7)
+            assert np.all(after[~has] == 0)
 
 
 # --------------------------------------------------------------------------------------------------
