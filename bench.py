@@ -97,6 +97,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def recorded_traffic(kernel, n):
+    """DRAM bytes per launch of `kernel` at size n from this round's ncu --set full capture (profiles/r01_traffic.json), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f).get("%s@%d" % (kernel, n), {}).get("bytes")
+    except Exception:
+        return None
+
+
 def step_bytes(n, nloc_total, matvecs):
     """Algorithmic HBM bytes of one step: mask 4, IC 4/matvec, apply 8, VC apply 8 -- times rows x n."""
     return (4.0 * (1 + matvecs) + 16.0) * nloc_total * n
@@ -245,7 +254,7 @@ def run_b200(args):
     achieved = mv_bytes / (mv_ms * 1e-3) / 1e9
     kname = ("k_matvec_sym_tma+k_sym_fold" if kr_mode else "k_ic_pass_sym_tma") if info["symmetric"] else ("k_matvec_tma" if kr_mode else "k_ic_pass_tma")
     roofline = {"kernel": kname, "layout": "dense fp32, upper triangle read (symmetric pass)" if info["symmetric"] else "dense fp32, all rows read", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "bytes_per_launch": mv_bytes, "us_per_launch": round(mv_ms * 1e3, 2),
+                "frac": round(achieved / peak, 4), "traffic": recorded_traffic(kname, n) if world == 1 else None, "bytes_per_launch": mv_bytes, "us_per_launch": round(mv_ms * 1e3, 2),
                 "launches_timed": args.steps * mv,
                 "other_kernels_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if k != "matvec" and v["launches"]}}
 

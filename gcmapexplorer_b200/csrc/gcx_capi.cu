@@ -837,7 +837,21 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         auto panel_of = [&](long long u) { return (int)(std::upper_bound(pu.begin(), pu.end(), u) - pu.begin()) - 1; };
         std::vector<long long> u0((size_t)G + 1);
         std::vector<int> kf((size_t)G, 0), kl((size_t)G, 0), pc((size_t)nch, G), ph((size_t)nch, -1);
-        for (int g = 0; g <= G; ++g) u0[g] = (long long)g * U / G;
+        // static split of the unit list over the CTAs.  The second CTA of every SM (index >= SM count) measurably gets a
+        // smaller share of the SM's bandwidth (tools/sym_cta_cycles.py), so it is given `skew` percent fewer units.
+        {
+            double skew = 0.0;
+            if (const char* e = getenv("GCX_SYM_SKEW")) skew = atof(e) / 100.0;
+            const int first = std::min(G, c->sm_count);
+            const double wa = 1.0 + skew, wb = 1.0 - skew;
+            const double W = wa * first + wb * (G - first);
+            double acc = 0.0;
+            u0[0] = 0;
+            for (int g = 0; g < G; ++g) {
+                acc += (g < first ? wa : wb);
+                u0[g + 1] = (g + 1 == G) ? U : (long long)((double)U * acc / W);
+            }
+        }
         int slots = 1;
         for (int g = 0; g < G; ++g) {
             if (u0[g + 1] <= u0[g]) continue;
