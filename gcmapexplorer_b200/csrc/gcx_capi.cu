@@ -467,6 +467,8 @@ extern "C" int gcx_map_upload(gcx_ctx* c, const float* host, int64_t host_ld) {
     CKR(need_map(c));
     CKR(fence_copy(c));
     c->sym_state = -1;
+    c->have_rowsum = false;      // everything derived from the previous contents is stale
+    c->have_scale = false;
     if (host_ld < c->n) return fail("host_ld < n");
     const size_t width = sizeof(float) * (size_t)c->n;
     if (is_pinned(host)) {

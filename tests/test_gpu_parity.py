@@ -437,6 +437,21 @@ def test_error_conventions(gx, caplog):
         nz.normalizeGCMapByIC("in.gcmap", "out.gcmap")
 
 
+def test_reupload_invalidates_cached_row_statistics(gx):
+    A = onp.synth_map(200, seed=1)
+    B = onp.synth_map(200, seed=2)
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.set_mask(onp.get_nonzeros_index(A))
+        dm.vc(False, False)
+        dm.upload(B)                                   # same context, new map
+        keepB = onp.get_nonzeros_index(B)
+        dm.set_mask(keepB)
+        dm.vc(False, False)
+        assert np.array_equal(dm.download(1), onp.vc(B, bNoData=~keepB, out=B.copy())[0])
+        with pytest.raises(gx.GcxError):
+            dm.apply_sym(None, 0, False)               # no solver has run on the new map
+
+
 def test_non_float32_and_non_contiguous_inputs(gx):
     A = onp.synth_map(90, seed=2)
     with gx.DeviceMap.from_host(A.astype(np.float64)) as dm:         # converted on the host
