@@ -1222,7 +1222,7 @@ extern "C" int gcx_apply_sym_scale(gcx_ctx* c, const double* s, int masked_mode,
     CKR(mm_begin(c));
     {
         ProfScope ps(c, 1);
-        EW_DISPATCH(k_apply_sym, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->row0, c->vscale, c->keep, masked_mode, c->mm)
+            EW_DISPATCH(k_apply_sym, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->row0, c->vscale, c->keep, masked_mode, c->mm)
     }
     CK(cudaGetLastError());
     if (in_place) { c->have_rowsum = false; c->sym_state = -1; }
