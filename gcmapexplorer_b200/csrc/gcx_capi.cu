@@ -450,7 +450,8 @@ static bool is_pinned(const void* p) {
 
 static void par_copy_rows(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, int64_t rows) {
     unsigned hw = std::thread::hardware_concurrency();
-    int T = (int)std::min<int64_t>(std::max(1u, std::min(hw, 8u)), rows);
+    static const unsigned cap = [] { const char* e = getenv("GCX_COPY_THREADS"); return e ? (unsigned)std::max(1, atoi(e)) : 16u; }();
+    int T = (int)std::min<int64_t>(std::max(1u, std::min(hw, cap)), rows);
     if ((size_t)rows * width < (4u << 20)) T = 1;
     auto work = [=](int t) {
         const int64_t a = rows * t / T, b = rows * (t + 1) / T;
