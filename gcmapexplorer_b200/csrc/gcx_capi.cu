@@ -120,6 +120,9 @@ struct gcx_ctx {
     int sym_nch = 0;
     int64_t sym_bytes = 0;
     long long* sym_dbg = nullptr;          // per-CTA main-loop cycles (GCX_SYM_DEBUG=1)
+    double* colpart_dyn = nullptr;         // [ndyn][SYM_NG][1024] column partials of the dynamic chunks
+    unsigned int* sym_dyn_counter = nullptr;
+    int sym_ndyn = 0;
     int sym_blocks = 1;                   // sharded: circulant assignment of off-diagonal blocks (needs the aligned row partition)
     int sym_kfold_lo = -1;
     int assume_symmetric = 0;             // sharded runs cannot test symmetry locally: the caller vouches for it
@@ -316,6 +319,9 @@ static void free_map(gcx_ctx* c) {
     cudaFree(c->sym_tab_ll); c->sym_tab_ll = nullptr;
     cudaFree(c->sym_tab_i); c->sym_tab_i = nullptr;
     cudaFree(c->sym_dbg); c->sym_dbg = nullptr;
+    cudaFree(c->colpart_dyn); c->colpart_dyn = nullptr;
+    cudaFree(c->sym_dyn_counter); c->sym_dyn_counter = nullptr;
+    c->sym_ndyn = 0;
     c->sym_state = -1;
     cudaFree(c->slab); c->slab = nullptr;
     cudaFree(c->csum32); c->csum32 = nullptr;
@@ -807,6 +813,7 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         const long long all_bands = (c->nloc + SYM_R - 1) / SYM_R;
         int64_t bytes = 0;
         int kfold_lo = -1;
+        std::vector<long long> nbk((size_t)nch, 0);
         for (int k = 0; k < nch; ++k) {
             long long nb = 0;
             int full = 0;
@@ -831,10 +838,45 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
             }
             if (nb > 0 && kfold_lo < 0) kfold_lo = k;
             pfull[k] = full;
-            pu[k + 1] = pu[k] + nb;
+            nbk[k] = nb;
             bytes += nb * SYM_R * std::min<int64_t>(1024, c->ld - (int64_t)k * 1024) * 4;
         }
         c->sym_kfold_lo = blocks ? kfold_lo : -1;
+        // dynamic pool: the largest full-width panels, ~GCX_SYM_DYN percent of the units, cut into chunks of DYN_CHUNK bands
+        int DYN_CHUNK = 32;
+        if (const char* e = getenv("GCX_SYM_DYN_CHUNK")) DYN_CHUNK = std::max(4, atoi(e));
+        double dyn_frac = 0.10;
+        if (const char* e = getenv("GCX_SYM_DYN")) dyn_frac = atof(e) / 100.0;
+        long long Uall = 0;
+        for (int k = 0; k < nch; ++k) Uall += nbk[k];
+        std::vector<char> in_pool((size_t)nch, 0);
+        {
+            std::vector<int> order;
+            for (int k = 0; k < nch; ++k)
+                if (nbk[k] > 0 && std::min<int64_t>(1024, c->ld - (int64_t)k * 1024) == 1024) order.push_back(k);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nbk[a] != nbk[b] ? nbk[a] > nbk[b] : a > b; });
+            long long pooled = 0;
+            for (int k : order) {
+                if ((double)pooled >= dyn_frac * (double)Uall) break;
+                if (Uall - pooled - nbk[k] < 4LL * G) break;             // keep a meaningful static share
+                in_pool[k] = 1;
+                pooled += nbk[k];
+            }
+        }
+        std::vector<int> dk, db0, dcnt, pdyn0((size_t)nch + 1, 0);
+        for (int k = 0; k < nch; ++k) {
+            pdyn0[k] = (int)dk.size();
+            if (in_pool[k]) {
+                for (long long b = 0; b < nbk[k]; b += DYN_CHUNK) {
+                    dk.push_back(k);
+                    db0.push_back((int)b);
+                    dcnt.push_back((int)std::min<long long>((long long)DYN_CHUNK, nbk[k] - b));
+                }
+            }
+            pu[k + 1] = pu[k] + (in_pool[k] ? 0 : nbk[k]);
+        }
+        pdyn0[nch] = (int)dk.size();
+        const int ndyn = (int)dk.size();
         const long long U = pu[nch];
         if (U < G) return 0;          // tiny share: keep the dense pass
         auto panel_of = [&](long long u) { return (int)(std::upper_bound(pu.begin(), pu.end(), u) - pu.begin()) - 1; };
@@ -873,6 +915,11 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         ti.insert(ti.end(), pc.begin(), pc.end());
         ti.insert(ti.end(), ph.begin(), ph.end());
         ti.insert(ti.end(), pfull.begin(), pfull.end());
+        ti.insert(ti.end(), dk.begin(), dk.end());
+        ti.insert(ti.end(), db0.begin(), db0.end());
+        ti.insert(ti.end(), dcnt.begin(), dcnt.end());
+        ti.insert(ti.end(), pdyn0.begin(), pdyn0.end());
+        c->sym_ndyn = ndyn;
         CK(cudaMalloc(&c->sym_tab_ll, sizeof(long long) * tll.size()));
         CK(cudaMalloc(&c->sym_tab_i, sizeof(int) * ti.size()));
         CK(cudaMemcpy(c->sym_tab_ll, tll.data(), sizeof(long long) * tll.size(), cudaMemcpyHostToDevice));
@@ -881,6 +928,12 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         const size_t cp_bytes = sizeof(double) * (size_t)G * slots * SYM_NG * 1024;
         CK(cudaMalloc(&c->rowpart, rp_bytes));
         CK(cudaMalloc(&c->colpart, cp_bytes));
+        CK(cudaMalloc(&c->sym_dyn_counter, sizeof(unsigned int)));
+        CK(cudaMemsetAsync(c->sym_dyn_counter, 0, sizeof(unsigned int), c->stream));
+        if (ndyn > 0) {
+            CK(cudaMalloc(&c->colpart_dyn, sizeof(double) * (size_t)ndyn * SYM_NG * 1024));
+            CK(cudaMemsetAsync(c->colpart_dyn, 0, sizeof(double) * (size_t)ndyn * SYM_NG * 1024, c->stream));
+        }
         if (getenv("GCX_SYM_DEBUG") && !c->sym_dbg) {
             CK(cudaMalloc(&c->sym_dbg, sizeof(long long) * (size_t)G));
             CK(cudaMemset(c->sym_dbg, 0, sizeof(long long) * (size_t)G));
@@ -905,6 +958,13 @@ static SymTab sym_tab(gcx_ctx* c) {
     T.panel_full = c->sym_tab_i + 2 * G + 2 * nch;
     T.kfold_lo = c->sym_kfold_lo;
     T.dbg_cycles = c->sym_dbg;
+    T.ndyn = c->sym_ndyn;
+    T.dyn_k = c->sym_tab_i + 2 * G + 3 * nch;
+    T.dyn_b0 = T.dyn_k + c->sym_ndyn;
+    T.dyn_cnt = T.dyn_b0 + c->sym_ndyn;
+    T.panel_dyn0 = T.dyn_cnt + c->sym_ndyn;
+    T.colpart_dyn = c->colpart_dyn;
+    T.dyn_counter = c->sym_dyn_counter;
     T.nslots = c->sym_slots;
     T.row0 = (int)c->row0;
     T.nloc = (int)c->nloc;
@@ -915,6 +975,7 @@ static SymTab sym_tab(gcx_ctx* c) {
 static int matvec_sym(gcx_ctx* c, const double* z, double* q, const int* done) {
     const size_t smem = (size_t)SYM_STAGES * SYM_R * MV_THREADS * sizeof(float4);
     const int n = (int)c->n, n4 = (int)(c->ld / 4);
+    if (c->sym_ndyn > 0) CK(cudaMemsetAsync(c->sym_dyn_counter, 0, sizeof(unsigned int), c->stream));
     {
         ProfScope ps(c, 0);
         k_matvec_sym_tma<SYM_STAGES, SYM_OCC><<<c->sym_grid, SYM_THREADS, smem, c->stream>>>(c->A, c->ld, n4, z, c->rowpart, c->colpart, sym_tab(c), done);
@@ -1102,6 +1163,7 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         void* args[] = {(void*)&c->A, (void*)&c->ld, (void*)&n, (void*)&n4, (void*)&c->keep, (void*)&c->vq, (void*)&c->vz, (void*)&c->vB,
                         (void*)&c->rowpart, (void*)&c->colpart, (void*)&tab, (void*)&c->ticket, (void*)&c->ic_state, (void*)&c->part};
         const size_t smem = SYM_STAGES * SYM_R * MV_THREADS * sizeof(float4);
+        if (c->sym_ndyn > 0) CK(cudaMemsetAsync(c->sym_dyn_counter, 0, sizeof(unsigned int), c->stream));
         {
             ProfScope ps(c, 0);
             if (c->world == 1) {

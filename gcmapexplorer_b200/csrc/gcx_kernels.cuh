@@ -539,22 +539,34 @@ struct SymTab {
                                //      the row AND the column part); 0: the rank's own diagonal region (j >= i / j > i rules)
     int kfold_lo;              // first panel with units on this rank (row-partial fold starts here)
     long long* dbg_cycles;     // optional [G]: cycles every CTA spent in the main loop (GCX_SYM_DEBUG=1), else nullptr
+    // dynamic pool: the units of a few large panels are not part of any CTA's static share; they are cut into chunks of
+    // consecutive bands of one panel and handed to whichever CTA finishes its static share first (atomic counter).  A chunk
+    // is always walked by one CTA in a fixed order and leaves its own column partial, so results do not depend on who ran it.
+    int ndyn;                  // number of chunks
+    const int* dyn_k;          // [ndyn] panel of the chunk
+    const int* dyn_b0;         // [ndyn] first local band
+    const int* dyn_cnt;        // [ndyn] number of bands
+    const int* panel_dyn0;     // [nch + 1] first chunk of every panel
+    double* colpart_dyn;       // [ndyn][NG][1024]
+    unsigned int* dyn_counter; // zeroed by the host before every launch
     int nslots;                // panels a share may touch (sizes colpart)
     int row0, nloc;            // this rank's global row block
 };
 
 template <int NG, int STAGES, bool ZNC>
-__device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, long long ld, int n4, const double* z,
-                                                double* rowpart, double* colpart, SymTab T, float4* tiles, uint64_t* full_bar,
-                                                uint64_t* empty_bar, double* gred) {
+__device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, long long ld, int n4, const double* z, double* rowpart,
+                                                 double* colslots, const SymTab& T, float4* tiles, uint64_t* full_bar, uint64_t* empty_bar,
+                                                 double* gred, long long u0, long long u1, int kfirst, int klast, bool single_panel) {
+    // Walks the units [u0, u1).  Static share: unit numbers of the panel-major list (panel_u0 maps them to (panel, band)),
+    // panels kfirst..klast, column partials to colslots[(panel - kfirst)][group].  Dynamic chunk (single_panel): the units are the
+    // bands u0..u1-1 of panel kfirst.  Every thread of the CTA must call this; it starts and ends with a CTA-wide barrier.
     constexpr int R = SYM_R;
     constexpr int WPG = SYM_CW / NG;                 // warps per group
     constexpr int TG = WPG * 32;                     // threads per group
     constexpr int NQ = MV_THREADS / TG;              // float4 columns of the 1024-column panel per thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long c = blockIdx.x;
-    const long long u0 = T.cta_u0[c], u1 = T.cta_u0[c + 1];
     const int nloc = T.nloc, row0 = T.row0;
+    const long long NOEND = 0x7fffffffffffffffLL;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
@@ -564,18 +576,15 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (u0 >= u1) return;
-    const int kfirst = T.cta_kf[c];
-    const long long t_start = (T.dbg_cycles != nullptr && tid == 0) ? clock64() : 0;
-
+    if (u0 < u1) {
     if (warp == SYM_CW) {
         // ---------------- producer ----------------
         if (lane == 0) {
             int stage = 0;
             unsigned int phase = 0;
             int k = kfirst;
-            long long pbeg = T.panel_u0[k];
-            long long pend = T.panel_u0[k + 1];
+            long long pbeg = single_panel ? 0 : T.panel_u0[k];
+            long long pend = single_panel ? NOEND : T.panel_u0[k + 1];
             for (long long u = u0; u < u1; ++u) {
                 while (u >= pend) {
                     ++k;
@@ -600,16 +609,14 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
                 }
             }
         }
-        return;
-    }
-
+    } else {
     // ---------------- consumers: group g takes units u0+g, u0+g+NG, ... ----------------
     const int g = warp / WPG, wig = warp % WPG, tig = tid - g * TG;
     const double2* z2 = reinterpret_cast<const double2*>(z);
     const long long rp_ld = (long long)n4 * 4;
     int k = kfirst;
-    long long pbeg = T.panel_u0[k];
-    long long pend = T.panel_u0[k + 1];
+    long long pbeg = single_panel ? 0 : T.panel_u0[k];
+    long long pend = single_panel ? NOEND : T.panel_u0[k + 1];
     double cacc[NQ][4], zc[NQ][4];
     int pfull = T.panel_full[k];
     auto load_zc = [&](int kk) {
@@ -628,7 +635,7 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
     auto flush = [&](int kk) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            double2* dst = reinterpret_cast<double2*>(colpart + (((size_t)c * T.nslots + (kk - kfirst)) * NG + g) * 1024) + 2 * (q * TG + tig);
+            double2* dst = reinterpret_cast<double2*>(colslots + ((size_t)(kk - kfirst) * NG + g) * 1024) + 2 * (q * TG + tig);
             dst[0] = make_double2(cacc[q][0], cacc[q][1]);
             dst[1] = make_double2(cacc[q][2], cacc[q][3]);
             cacc[q][0] = cacc[q][1] = cacc[q][2] = cacc[q][3] = 0.0;
@@ -722,13 +729,37 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
         }
     }
     // every group flushes every panel the CTA's share touches (groups that saw no unit of a panel flush zeros)
-    const int klast = T.cta_kl[c];
     while (true) {
         flush(k);
         if (k >= klast) break;
         ++k;
     }
-    if (T.dbg_cycles != nullptr && tid == 0) T.dbg_cycles[c] = clock64() - t_start;
+    }   // consumers
+    }   // u0 < u1
+    __syncthreads();
+}
+
+// One CTA's whole job in a symmetric pass: its static share, then chunks of the dynamic pool until the pool is empty.
+template <int NG, int STAGES, bool ZNC>
+__device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, long long ld, int n4, const double* z, double* rowpart,
+                                                double* colpart, const SymTab& T, float4* tiles, uint64_t* full_bar, uint64_t* empty_bar,
+                                                double* gred) {
+    __shared__ int s_chunk;
+    const long long c = blockIdx.x;
+    const long long t_start = (T.dbg_cycles != nullptr && threadIdx.x == 0) ? clock64() : 0;
+    matvec_sym_range<NG, STAGES, ZNC>(A, ld, n4, z, rowpart, colpart + (size_t)c * T.nslots * NG * 1024, T, tiles, full_bar, empty_bar, gred,
+                                      T.cta_u0[c], T.cta_u0[c + 1], T.cta_kf[c], T.cta_kl[c], false);
+    while (T.ndyn > 0) {
+        if (threadIdx.x == 0) s_chunk = (int)atomicAdd(T.dyn_counter, 1u);
+        __syncthreads();
+        const int ch = s_chunk;
+        if (ch >= T.ndyn) break;
+        const int k = T.dyn_k[ch], b0 = T.dyn_b0[ch], cnt = T.dyn_cnt[ch];
+        // (the range function's leading barrier also protects s_chunk against the next fetch)
+        matvec_sym_range<NG, STAGES, ZNC>(A, ld, n4, z, rowpart, T.colpart_dyn + (size_t)ch * NG * 1024, T, tiles, full_bar, empty_bar, gred,
+                                          b0, b0 + cnt, k, k, true);
+    }
+    if (T.dbg_cycles != nullptr && threadIdx.x == 0) T.dbg_cycles[c] = clock64() - t_start;
 }
 
 template <int STAGES, int OCC>
@@ -767,6 +798,16 @@ __device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n4, con
             const double* cp = colpart + ((size_t)c * T.nslots + (ki - T.cta_kf[c])) * SYM_NG * 1024 + (i & 1023);
 #pragma unroll
             for (int gg = 0; gg < SYM_NG; ++gg) s += __ldcg(cp + gg * 1024);
+        }
+        if (T.ndyn > 0) {
+            // column partials of the dynamic chunks of panel ki, in chunk order
+            const int d0 = T.panel_dyn0[ki], d1 = T.panel_dyn0[ki + 1];
+#pragma unroll 2
+            for (int ch = d0 + j; ch < d1; ch += 8) {
+                const double* cp = T.colpart_dyn + (size_t)ch * SYM_NG * 1024 + (i & 1023);
+#pragma unroll
+                for (int gg = 0; gg < SYM_NG; ++gg) s += __ldcg(cp + gg * 1024);
+            }
         }
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
