@@ -1337,7 +1337,7 @@ static int diag_mean(gcx_ctx* c) {
         k_diag_mean_partial<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, psum, pcnt);
     }
     CK(cudaGetLastError());
-    k_diag_mean_reduce<<<(n + 255) / 256, 256, 0, c->stream>>>(nbands, n, (int)c->row0, psum, pcnt, sumcnt, sumcnt + c->nv);
+    k_diag_mean_reduce<<<(n + 63) / 64, 64 * DIAG_RED_SL, 0, c->stream>>>(nbands, n, (int)c->row0, psum, pcnt, sumcnt, sumcnt + c->nv);
     CK(cudaGetLastError());
     c->launches += 1;
     if (c->world > 1) NK(g_nccl.AllReduce(sumcnt, sumcnt, 2 * (size_t)c->nv, ncclFloat64, ncclSum, c->comm, c->stream));

@@ -1105,6 +1105,7 @@ k_diag_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld,
 // floats (coalesced, descending).  Algorithmic bytes: 2 * n^2 per traversal (half the map).
 // ---------------------------------------------------------------------------------------------------
 constexpr int DIAG_RB = 64;
+constexpr int DIAG_BATCH = 16;     // loads in flight per thread in the histogram traversal
 
 // mean: per-(band, diagonal) partial sum/count, then a fixed-order reduction over bands (deterministic)
 __global__ void __launch_bounds__(MV_THREADS)
@@ -1130,18 +1131,34 @@ k_diag_mean_partial(const float* __restrict__ A, long long ld, int nloc, int n, 
     pcnt[(long long)band * n + d] = c;
 }
 
-__global__ void k_diag_mean_reduce(int nbands, int n, int row0, const double* __restrict__ psum, const int* __restrict__ pcnt,
-                                   double* __restrict__ sum, double* __restrict__ cnt) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n) return;
+// 64 diagonals x 4 band slices per CTA; slice s adds bands b0+s, b0+s+4, ... in order, the four slice sums are
+// combined in slice order -> the same result on every launch and for every grid shape
+constexpr int DIAG_RED_SL = 4;
+__global__ void __launch_bounds__(64 * DIAG_RED_SL)
+k_diag_mean_reduce(int nbands, int n, int row0, const double* __restrict__ psum, const int* __restrict__ pcnt,
+                   double* __restrict__ sum, double* __restrict__ cnt) {
+    __shared__ double ss[DIAG_RED_SL][64];
+    __shared__ double sc[DIAG_RED_SL][64];
+    const int dl = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    const int d = blockIdx.x * 64 + dl;
     double s = 0.0, c = 0.0;
-    const int b0 = max(0, d - row0) / DIAG_RB;
-    for (int b = b0; b < nbands; ++b) {
-        s += psum[(long long)b * n + d];
-        c += (double)pcnt[(long long)b * n + d];
+    if (d < n) {
+        const int b0 = max(0, d - row0) / DIAG_RB;
+#pragma unroll 8
+        for (int b = b0 + sl; b < nbands; b += DIAG_RED_SL) {
+            s += psum[(long long)b * n + d];
+            c += (double)pcnt[(long long)b * n + d];
+        }
     }
-    sum[d] = s;
-    cnt[d] = c;
+    ss[sl][dl] = s;
+    sc[sl][dl] = c;
+    __syncthreads();
+    if (sl == 0 && d < n) {
+#pragma unroll
+        for (int k = 1; k < DIAG_RED_SL; ++k) { s += ss[k][dl]; c += sc[k][dl]; }
+        sum[d] = s;
+        cnt[d] = c;
+    }
 }
 
 __global__ void k_diag_mean_final(int n, const double* __restrict__ sum, const double* __restrict__ cnt, double* __restrict__ avg) {
@@ -1173,9 +1190,9 @@ k_diag_hist(const float* __restrict__ A, long long ld, int nloc, int n, int row0
     const int rs = max(r0, d - row0);
     int run_bin = -1;
     unsigned int run = 0;
-#pragma unroll 8
-    for (int r = rs; r < r1; ++r) {
-        const float v = __ldg(A + (long long)r * ld + (row0 + r - d));
+    // the loads of a batch are issued before any atomic (an atomic inside the loop keeps the compiler from hoisting them)
+    const long long off = (long long)row0 - d;
+    auto take = [&](float v) {
         if (v != 0.f) {
             const unsigned int key = f2ord(v);
             if (pass == 0 || (key >> sh_hi) == pre) {
@@ -1189,7 +1206,16 @@ k_diag_hist(const float* __restrict__ A, long long ld, int nloc, int n, int row0
                 }
             }
         }
+    };
+    int r = rs;
+    for (; r + DIAG_BATCH <= r1; r += DIAG_BATCH) {
+        float v[DIAG_BATCH];
+#pragma unroll
+        for (int k = 0; k < DIAG_BATCH; ++k) v[k] = __ldg(A + ((long long)(r + k) * (ld + 1) + off));
+#pragma unroll
+        for (int k = 0; k < DIAG_BATCH; ++k) take(v[k]);
     }
+    for (; r < r1; ++r) take(__ldg(A + ((long long)r * (ld + 1) + off)));
     if (run) atomicAdd(h + run_bin, run);
 }
 
