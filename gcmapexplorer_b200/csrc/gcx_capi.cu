@@ -241,20 +241,14 @@ extern "C" int gcx_device_count(int* count) {
     return 0;
 }
 
-extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
-    int cnt = 0;
-    CK(cudaGetDeviceCount(&cnt));
-    if (cnt <= 0) return fail("no CUDA device visible: libgcxnorm has no CPU fallback");
-    if (device < 0 || device >= cnt) return fail("device %d out of range (%d visible)", device, cnt);
-    gcx_ctx* c = new gcx_ctx();
+extern "C" int gcx_ctx_destroy(gcx_ctx* c);
+
+static int ctx_init(gcx_ctx* c, int device) {
     c->device = device;
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        delete c;
-        return fail("device %d is sm_%d%d; libgcxnorm is built for sm_100a (B200) only", device, prop.major, prop.minor);
-    }
+    if (prop.major < 10) return fail("device %d is sm_%d%d; libgcxnorm is built for sm_100a (B200) only", device, prop.major, prop.minor);
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -307,13 +301,27 @@ extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
         c->sym_grid = c->sm_count * std::min(occ3, SYM_OCC);
         if (occ3 < 1) c->sym_enable = 0;
     }
+    return 0;
+}
+
+extern "C" int gcx_ctx_create(int device, gcx_ctx** out) {
+    if (!out) return fail("gcx_ctx_create: null output pointer");
+    *out = nullptr;
+    int cnt = 0;
+    CK(cudaGetDeviceCount(&cnt));
+    if (cnt <= 0) return fail("no CUDA device visible: libgcxnorm has no CPU fallback");
+    if (device < 0 || device >= cnt) return fail("device %d out of range (%d visible)", device, cnt);
+    gcx_ctx* c = new gcx_ctx();
+    if (ctx_init(c, device)) {
+        gcx_ctx_destroy(c);       // releases whatever was created; the error text stays
+        return 1;
+    }
     *out = c;
     return 0;
 }
 
-static void free_map(gcx_ctx* c) {
-    cudaFree(c->A); c->A = nullptr;
-    cudaFree(c->Out); c->Out = nullptr;
+// tables and partial buffers of the upper-triangle pass (rebuilt by sym_ready on the next run)
+static void free_sym(gcx_ctx* c) {
     cudaFree(c->rowpart); c->rowpart = nullptr;
     cudaFree(c->colpart); c->colpart = nullptr;
     cudaFree(c->sym_tab_ll); c->sym_tab_ll = nullptr;
@@ -322,6 +330,12 @@ static void free_map(gcx_ctx* c) {
     cudaFree(c->colpart_dyn); c->colpart_dyn = nullptr;
     cudaFree(c->sym_dyn_counter); c->sym_dyn_counter = nullptr;
     c->sym_ndyn = 0;
+}
+
+static void free_map(gcx_ctx* c) {
+    cudaFree(c->A); c->A = nullptr;
+    cudaFree(c->Out); c->Out = nullptr;
+    free_sym(c);
     c->sym_state = -1;
     cudaFree(c->slab); c->slab = nullptr;
     cudaFree(c->csum32); c->csum32 = nullptr;
@@ -333,23 +347,25 @@ static void free_map(gcx_ctx* c) {
 extern "C" int gcx_ctx_destroy(gcx_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     free_map(c);
     for (auto& p : c->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->mm); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws); cudaFree(c->part); cudaFree(c->scratch);
-    cudaFreeHost(c->h_state);
+    if (c->h_state) cudaFreeHost(c->h_state);
     for (int i = 0; i < 2; ++i) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
         if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
     }
-    cudaEventDestroy(c->run_a); cudaEventDestroy(c->run_b);
-    cudaEventDestroy(c->tm_a); cudaEventDestroy(c->tm_b);
-    cudaStreamSynchronize(c->copy_stream);
-    cudaEventDestroy(c->ev_ready); cudaEventDestroy(c->ev_copied);
-    cudaStreamDestroy(c->copy_stream);
-    cudaStreamDestroy(c->stream);
+    for (cudaEvent_t e : {c->run_a, c->run_b, c->tm_a, c->tm_b})
+        if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    for (cudaEvent_t e : {c->ev_ready, c->ev_copied})
+        if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();           // a half-built context may have produced sticky-free errors above
     delete c;
     return 0;
 }
@@ -384,7 +400,19 @@ extern "C" int gcx_host_free(void* ptr) {
 // ---------------------------------------------------------------------------------------------------
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+static int map_alloc(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc);
+
 extern "C" int gcx_map_create(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc) {
+    if (!c) return fail("gcx_map_create: null context");
+    const int rc = map_alloc(c, n, row0, nloc);
+    if (rc) {
+        free_map(c);              // never leave a half-allocated map behind (need_map keys on c->A)
+        cudaGetLastError();       // e.g. an out-of-memory error must not surface again at the next launch check
+    }
+    return rc;
+}
+
+static int map_alloc(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc) {
     CKR(set_dev(c));
     if (n <= 0 || nloc <= 0 || row0 < 0 || row0 + nloc > n) return fail("bad map geometry n=%lld row0=%lld nloc=%lld", (long long)n, (long long)row0, (long long)nloc);
     if (n > 0x7ffffff0LL) return fail("n too large");
@@ -685,7 +713,14 @@ extern "C" int gcx_set_option(gcx_ctx* c, const char* key, double value) {
     if (k == "sym") c->sym_enable = (int)value;
     else if (k == "assume_symmetric") { c->assume_symmetric = (int)value; c->sym_state = -1; }
     else if (k == "exchange_allreduce") c->exchange_allreduce = (int)value;
-    else if (k == "sym_blocks") c->sym_blocks = (int)value;
+    else if (k == "sym_blocks") {
+        if (c->sym_blocks != (int)value && c->stream) {       // the unit tables depend on it: rebuild on the next run
+            cudaSetDevice(c->device);
+            cudaStreamSynchronize(c->stream);
+            free_sym(c);
+        }
+        c->sym_blocks = (int)value;
+    }
     else if (k == "matvec_variant") c->mv_variant = (int)value;
     else return fail("gcx_set_option: unknown key '%s'", key);
     return 0;
@@ -702,6 +737,8 @@ extern "C" int gcx_dist_unique_id(void* id128) {
 extern "C" int gcx_dist_init(gcx_ctx* c, int rank, int world, const void* id128) {
     CKR(set_dev(c));
     if (c->A) return fail("gcx_dist_init must precede gcx_map_create");
+    if (c->comm) return fail("gcx_dist_init: this context already has a communicator");
+    if (!id128 && world > 1) return fail("gcx_dist_init: null unique id");
     if (world < 1 || rank < 0 || rank >= world) return fail("bad rank/world");
     c->rank = rank; c->world = world;
     if (world == 1) return 0;
@@ -739,6 +776,7 @@ extern "C" int gcx_row_stats(gcx_ctx* c, double* rowsum, int32_t* zero_count) {
 
 extern "C" int gcx_set_mask(gcx_ctx* c, const uint8_t* keep) {
     CKR(need_map(c));
+    if (!keep) return fail("gcx_set_mask: null mask");
     CK(cudaMemsetAsync(c->keep, 0, (size_t)c->nv, c->stream));
     CK(cudaMemcpyAsync(c->keep, keep, (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -791,6 +829,7 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
     }
     if (c->sym_state != 1) return 0;
     if (!c->rowpart) {
+        free_sym(c);          // nothing stale survives an earlier, failed build
         // every panel's and every CTA's share of the panel-major unit list (the kernels do no 64-bit divisions)
         const int n = (int)c->n, n4 = (int)(c->ld / 4), nch = (n4 + MV_THREADS - 1) / MV_THREADS, G = c->sym_grid;
         const long long r0 = c->row0, r1 = c->row0 + c->nloc;
@@ -1037,6 +1076,7 @@ static int matvec(gcx_ctx* c, int variant, const double* z, double* q, const int
 
 extern "C" int gcx_bench_matvec(gcx_ctx* c, int variant, int iters, double* ms_total) {
     CKR(need_map(c));
+    if (!ms_total || iters < 1) return fail("gcx_bench_matvec: bad arguments");
     if (variant < 0) variant = c->mv_variant;
     if (variant == 100) {
         bool ok = false;

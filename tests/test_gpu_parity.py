@@ -452,6 +452,25 @@ def test_reupload_invalidates_cached_row_statistics(gx):
             dm.apply_sym(None, 0, False)               # no solver has run on the new map
 
 
+def test_failed_map_allocation_leaves_the_context_usable(gx):
+    """A map that cannot fit (n = 600,000 -> 1.4 TB) fails with a message, frees everything, and the same context
+    then serves a normal map; misuse of the mask entry point is an error, not a crash."""
+    import ctypes as C
+    from gcmapexplorer_b200 import _lib
+    A = onp.synth_map(150, seed=4)
+    with gx.DeviceMap(150) as dm:
+        rc = _lib.lib().gcx_map_create(dm._ctx, 600000, 0, 600000)
+        assert rc != 0 and b"cudaMalloc" in _lib.lib().gcx_last_error()
+        with pytest.raises(gx.GcxError):
+            dm.row_stats()                                            # no resident map any more
+        _lib.check(_lib.lib().gcx_map_create(dm._ctx, 150, 0, 150))
+        dm.upload(A)
+        assert _lib.lib().gcx_set_mask(dm._ctx, None) != 0
+        keep = onp.get_nonzeros_index(A)
+        dm.set_mask(keep)
+        assert dm.ic(1e-4, 500)["passes"] == onp.ic_fp64(A[np.ix_(keep, keep)].astype(np.float64), 1e-4, 500)[2]
+
+
 def test_non_float32_and_non_contiguous_inputs(gx):
     A = onp.synth_map(90, seed=2)
     with gx.DeviceMap.from_host(A.astype(np.float64)) as dm:         # converted on the host
