@@ -56,6 +56,8 @@ _PROTOS = {
     "gcx_diag_apply": (C.c_int, [_ctx, _c_f64p, C.c_int, C.c_int, _c_f32p, _c_f32p]),
     "gcx_compact_f64": (C.c_int, [_ctx, _c_i32p, C.c_int64, _c_f64p]),
     "gcx_downsample": (C.c_int, [_ctx, C.c_int, C.c_int, _c_f32p, C.c_int64, _c_f32p, _c_f32p]),
+    "gcx_transition_run": (C.c_int, [_ctx, C.c_int, _c_f32p, _c_f32p]),
+    "gcx_stationary_run": (C.c_int, [_ctx, C.c_double, C.c_int, _c_f64p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "gcx_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_double]),
     "gcx_partition_rows": (C.c_int, [C.c_int64, C.c_int, C.c_int, _c_i64p, _c_i64p]),
     "gcx_dist_unique_id": (C.c_int, [C.c_void_p]),

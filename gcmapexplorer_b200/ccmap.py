@@ -208,6 +208,25 @@ def downSampleCCMap(cmap, level=2, method='sum', workDir=None):
     return res
 
 
+def downSample1D(array, level=2, masked_equal=0.0, func='max'):
+    """Coarsen a 1-D track the way the maps are coarsened (lib/ccmap.py:845-870): element 0 is kept apart, the
+    rest is zero-padded to a multiple of `level` and reduced in groups ('sum', 'mean' over the entries different
+    from `masked_equal`, anything else: max).  O(n) host work."""
+    level = int(level)
+    groups = int(np.ceil(float(array.shape[0] - 1) / level))
+    pad = int(groups * level - (array.shape[0] - 1))
+    out = np.zeros(groups + 1, dtype=array.dtype)
+    body = np.hstack((array[1:], np.zeros(pad))) if pad != 0 else array[1:]
+    body = body.reshape(-1, level)
+    if func == 'sum':
+        out[1:] = body.sum(axis=1)
+    elif func == 'mean':
+        out[1:] = np.ma.filled(np.ma.mean(np.ma.masked_equal(body, masked_equal), axis=1))[:]
+    else:
+        out[1:] = body.max(axis=1)
+    return out
+
+
 def is_ccmap(obj):
     return isinstance(obj, CCMAP) or all(hasattr(obj, a) for a in ("path2matrix", "shape", "make_readable", "bNoData", "state"))
 

@@ -137,6 +137,7 @@ struct gcx_ctx {
     // states
     IcState* ic_state = nullptr;
     KrState* kr_state = nullptr;
+    SdState* sd_state = nullptr;
     MinMax* mm = nullptr;
     unsigned long long* csum_dev = nullptr;
     void* h_state = nullptr;   // pinned, 4 KB
@@ -256,6 +257,7 @@ static int ctx_init(gcx_ctx* c, int device) {
     CK(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
     CK(cudaMalloc(&c->ic_state, sizeof(IcState)));
     CK(cudaMalloc(&c->kr_state, sizeof(KrState)));
+    CK(cudaMalloc(&c->sd_state, sizeof(SdState)));
     CK(cudaMalloc(&c->mm, sizeof(MinMax)));
     CK(cudaMalloc(&c->csum_dev, sizeof(unsigned long long)));
     CK(cudaMalloc(&c->ticket, sizeof(unsigned int)));
@@ -352,7 +354,7 @@ extern "C" int gcx_ctx_destroy(gcx_ctx* c) {
     free_map(c);
     for (auto& p : c->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
-    cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->mm); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws); cudaFree(c->part); cudaFree(c->scratch);
+    cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->sd_state); cudaFree(c->mm); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws); cudaFree(c->part); cudaFree(c->scratch);
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int i = 0; i < 2; ++i) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
@@ -1497,6 +1499,105 @@ extern "C" int gcx_downsample(gcx_ctx* c, int level, int method, float* host_out
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(host_out, dout, sizeof(float) * (size_t)on * on, cudaMemcpyDeviceToHost, c->stream));
     return mm_end(c, minv, maxv);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// transition probabilities + stationary distribution
+// ---------------------------------------------------------------------------------------------------
+#define EW_DISPATCH_B(KERNEL, FLAG, ...)                                                                            \
+    switch (ew_variant()) {                                                                                        \
+        case 1: KERNEL<8, 2, FLAG><<<c->sm_count * 2, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;              \
+        case 2: KERNEL<8, 3, FLAG><<<c->sm_count * 3, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;              \
+        case 3: KERNEL<4, 4, FLAG><<<c->sm_count * 4, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;              \
+        case 4: KERNEL<4, 6, FLAG><<<c->sm_count * 6, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;              \
+        case 5: KERNEL<2, 8, FLAG><<<c->sm_count * 8, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;              \
+        default: KERNEL<4, 3, FLAG><<<c->sm_count * 3, MV_THREADS, 0, c->stream>>>(__VA_ARGS__); break;             \
+    }
+
+extern "C" int gcx_transition_run(gcx_ctx* c, int in_place, float* minv, float* maxv) {
+    CKR(need_map(c));
+    CKR(fence_copy(c));
+    if (!c->have_mask) return fail("gcx_transition_run: call gcx_set_mask first");
+    CKR(run_row_stats(c));
+    // sumr = A[m].sum() is float32 in the reference (lib/statDist.py:83)
+    k_f64_to_f32<<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>((int)c->nv, c->vrowsum, c->csum32);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    float* out = c->A;
+    if (!in_place) { CKR(ensure_out(c)); out = c->Out; }
+    CKR(mm_begin(c));
+    {
+        ProfScope ps(c, 2);
+        EW_DISPATCH_B(k_tp_pass, false, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->csum32, c->keep, 0.f, c->mm)
+    }
+    CK(cudaGetLastError());
+    float fill = 0.f, qmax = 0.f;
+    CKR(mm_end(c, &fill, &qmax));
+    if (fill != fill) return fail("gcx_transition_run: no non-zero entry in the kept rows");
+    CKR(mm_begin(c));
+    {
+        ProfScope ps(c, 2);
+        EW_DISPATCH_B(k_tp_pass, true, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->csum32, c->keep, fill, c->mm)
+    }
+    CK(cudaGetLastError());
+    if (in_place) { c->have_rowsum = false; c->sym_state = -1; }
+    return mm_end(c, minv, maxv);
+}
+
+extern "C" int gcx_stationary_run(gcx_ctx* c, double tol, int max_iter, double* x, int* iterations, double* last_delta) {
+    CKR(need_map(c));
+    if (!c->have_mask) return fail("gcx_stationary_run: call gcx_set_mask first");
+    if (max_iter < 1) return fail("gcx_stationary_run: max_iter must be positive");
+    const int n = (int)c->n, n4 = (int)(c->ld / 4), nloc = (int)c->nloc;
+    // m0: smallest non-zero entry of the kept block (:466-469)
+    CKR(mm_begin(c));
+    {
+        ProfScope ps(c, 3);
+        EW_DISPATCH(k_block_min, c->A, c->ld, nloc, n4, n, (int)c->row0, c->keep, c->mm)
+    }
+    CK(cudaGetLastError());
+    float m0 = 0.f, mx = 0.f;
+    CKR(mm_end(c, &m0, &mx));
+    if (m0 != m0) return fail("gcx_stationary_run: the kept block has no non-zero entry");
+    // row chunks: ~6 CTAs per SM over (column chunks x row chunks), chunk length a multiple of the unroll depth
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    int nrc = std::max(1, (c->sm_count * 6 + nch - 1) / nch);
+    int rpc = (nloc + nrc - 1) / nrc;
+    rpc = std::max(MVT_UNR, (rpc + MVT_UNR - 1) / MVT_UNR * MVT_UNR);
+    nrc = (nloc + rpc - 1) / rpc;
+    CKR(ensure_scratch(c, sizeof(double) * (size_t)nrc * c->ld));
+    double* part = (double*)c->scratch;
+    double* xv = c->kr.x;
+    double* yv = c->vq;
+    k_sd_init<<<EP_CL, EP_THREADS, 0, c->stream>>>(c->sd_state, (int)c->nv, n, c->keep, xv, tol, max_iter);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    c->last_sym = false;
+    c->have_scale = false;           // the KR vector slab is reused
+    auto step = [&]() -> int {
+        {
+            ProfScope ps(c, 0);
+            k_matvec_t<<<dim3(nch, nrc), MV_THREADS, 0, c->stream>>>(c->A, c->ld, nloc, n4, (int)c->row0, rpc, xv, m0, part, &c->sd_state->done);
+        }
+        CK(cudaGetLastError());
+        k_sd_fold<<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>(c->sd_state, (int)c->nv, n, nrc, c->ld, c->keep, part, yv);
+        CK(cudaGetLastError());
+        c->launches += 1;
+        CKR(allreduce_f64(c, yv, (size_t)c->n));
+        {
+            ProfScope ps(c, 6);
+            k_sd_step<<<EP_CL, EP_THREADS, 0, c->stream>>>(c->sd_state, n, c->keep, yv, xv);
+        }
+        CK(cudaGetLastError());
+        return 0;
+    };
+    SdState fin;
+    CKR(iterate<SdState>(c, c->sd_state, max_iter + 4, step, &fin));
+    if (x) CK(cudaMemcpyAsync(x, xv, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (iterations) *iterations = fin.iters;
+    if (last_delta) *last_delta = fin.delta;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -2120,4 +2120,206 @@ k_kr_step(KrState* st, int n, const uint8_t* __restrict__ keep, const double* __
     if (tid == 0) *st = s;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// N3: transition probability matrix, lib/statDist.py:50-99.
+//   kept row i: q_ij = fl32(A_ij / s_i), s_i the row sum (:83-84); minvalue = smallest non-zero q over the kept rows,
+//   ALL columns (:86-87); output = q_ij where i and j are kept and q_ij != 0, minvalue everywhere else (:89-95).
+// WRITE = false: the minimum pass (reads 4 nloc n bytes); WRITE = true: the output pass (reads + writes, 8 nloc n).
+// Pad columns (j >= n) stay zero, like everywhere else.
+// ---------------------------------------------------------------------------------------------------
+template <int R, int OCC, bool WRITE>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
+k_tp_pass(const float* __restrict__ A, float* __restrict__ Out, long long ld, int nloc, int n4, int n, int row0,
+          const float* __restrict__ rsum, const uint8_t* __restrict__ keep, float fill, MinMax* mm) {
+    const int tid = threadIdx.x;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
+    const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
+    float mn = GCX_PINF, mx = GCX_NINF;
+    const uchar4* __restrict__ k4 = reinterpret_cast<const uchar4*>(keep);
+    for (long long u = u0; u < u1; ++u) {
+        const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
+        const int c4 = k * MV_THREADS + tid;
+        if (c4 >= n4) continue;
+        float4 a[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r < nloc) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(A + (long long)r * ld) + c4);
+        }
+        const uchar4 kc = __ldg(k4 + c4);
+        const unsigned char kcol[4] = {kc.x, kc.y, kc.z, kc.w};
+        const int j0 = 4 * c4;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r >= nloc) break;
+            const int i = row0 + r;
+            const bool ki = __ldg(keep + i) != 0;
+            const float si = __ldg(rsum + i);
+            const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float q = 0.f;
+                if (ki && in[e] != 0.f) q = __fdiv_rn(in[e], si);
+                if (WRITE) {
+                    q = (kcol[e] && q != 0.f) ? q : fill;
+                    if (j0 + e >= n) q = 0.f;
+                }
+                o[e] = q;
+                if (j0 + e < n) mm_update(q, mn, mx);
+            }
+            if (WRITE) st_stream_f4(reinterpret_cast<float4*>(Out + (long long)r * ld) + c4, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+    mm_commit(mn, mx, mm);
+}
+
+// smallest non-zero entry of the kept block (lib/statDist.py:466-469 replaces the zeros of that block with it)
+template <int R, int OCC>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
+k_block_min(const float* __restrict__ A, long long ld, int nloc, int n4, int n, int row0, const uint8_t* __restrict__ keep, MinMax* mm) {
+    const int tid = threadIdx.x;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
+    const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
+    float mn = GCX_PINF, mx = GCX_NINF;
+    const uchar4* __restrict__ k4 = reinterpret_cast<const uchar4*>(keep);
+    for (long long u = u0; u < u1; ++u) {
+        const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
+        const int c4 = k * MV_THREADS + tid;
+        if (c4 >= n4) continue;
+        float4 a[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r < nloc) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(A + (long long)r * ld) + c4);
+        }
+        const uchar4 kc = __ldg(k4 + c4);
+        const unsigned char kcol[4] = {kc.x, kc.y, kc.z, kc.w};
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r >= nloc) break;
+            if (!__ldg(keep + row0 + r)) continue;
+            const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (kcol[e]) mm_update(in[e], mn, mx);          // keep is zero beyond n: pad columns never count
+        }
+    }
+    mm_commit(mn, mx, mm);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// N3: stationary distribution, lib/statDist.py:436-498.  The reference takes the first eigenvector of a dense LAPACK
+// eigendecomposition of the transposed kept block (O(n^3)); here the same vector -- the dominant left eigenvector of
+// a positive matrix -- comes from the power iteration  x <- x P' / |x P'|_1 ,  P'_ij = P_ij or m0 where P_ij = 0.
+// One matrix read (4 nloc n bytes) per iteration: the transposed product below.
+//
+// k_matvec_t: CTA (k, c) = 1024 columns x one chunk of `rpc` rows; every thread keeps 4 column sums in registers
+// (fp64) over the chunk's rows and writes them to part[c][.]; k_sd_fold adds the chunks in order.  No-data rows have
+// x_i = 0 and drop out; no-data columns are ignored by the fold.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MVT_UNR = 8;
+
+__global__ void __launch_bounds__(MV_THREADS)
+k_matvec_t(const float* __restrict__ A, long long ld, int nloc, int n4, int row0, int rpc, const double* __restrict__ x, float m0,
+           double* __restrict__ part, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int c4 = blockIdx.x * MV_THREADS + threadIdx.x;
+    if (c4 >= n4) return;
+    const int r0 = blockIdx.y * rpc, r1 = min(r0 + rpc, nloc);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const float4* __restrict__ base = reinterpret_cast<const float4*>(A) + c4;
+    const long long ld4 = ld / 4;
+    auto take = [&](const float4& a, double xv) {
+        acc[0] = fma(xv, (double)(a.x == 0.f ? m0 : a.x), acc[0]);
+        acc[1] = fma(xv, (double)(a.y == 0.f ? m0 : a.y), acc[1]);
+        acc[2] = fma(xv, (double)(a.z == 0.f ? m0 : a.z), acc[2]);
+        acc[3] = fma(xv, (double)(a.w == 0.f ? m0 : a.w), acc[3]);
+    };
+    int r = r0;
+    for (; r + MVT_UNR <= r1; r += MVT_UNR) {
+        float4 a[MVT_UNR];
+        double xv[MVT_UNR];
+#pragma unroll
+        for (int u = 0; u < MVT_UNR; ++u) {
+            a[u] = ld_stream_f4(base + (long long)(r + u) * ld4);
+            xv[u] = __ldg(x + row0 + r + u);
+        }
+#pragma unroll
+        for (int u = 0; u < MVT_UNR; ++u) take(a[u], xv[u]);
+    }
+    for (; r < r1; ++r) take(ld_stream_f4(base + (long long)r * ld4), __ldg(x + row0 + r));
+    double2* dst = reinterpret_cast<double2*>(part + (long long)blockIdx.y * ld + 4 * (long long)c4);
+    dst[0] = make_double2(acc[0], acc[1]);
+    dst[1] = make_double2(acc[2], acc[3]);
+}
+
+struct SdState {
+    double tol, delta, prev, sum;
+    int iters, max_iter, done, matvecs, kept, pad;
+};
+
+__global__ void __cluster_dims__(EP_CL, 1, 1) __launch_bounds__(EP_THREADS)
+k_sd_init(SdState* st, int nv, int n, const uint8_t* __restrict__ keep, double* x, double tol, int max_iter) {
+    __shared__ double sm[32];
+    __shared__ double slots[8];
+    Team T(slots, sm);
+    double cnt = 0.0;
+    for (int i = T.gtid; i < n; i += T.nthreads) cnt += keep[i] ? 1.0 : 0.0;
+    const double K = T.reduce1<RED_SUM>(cnt);
+    for (int i = T.gtid; i < nv; i += T.nthreads) x[i] = (i < n && keep[i]) ? 1.0 / K : 0.0;
+    if (T.gtid == 0) {
+        st->tol = tol; st->delta = 0.0; st->prev = __longlong_as_double(0x7ff0000000000000LL); st->sum = 0.0;
+        st->iters = 0; st->max_iter = max_iter; st->done = 0; st->matvecs = 0; st->kept = (int)K; st->pad = 0;
+    }
+    T.finish();
+}
+
+__global__ void __launch_bounds__(256)
+k_sd_fold(const SdState* __restrict__ st, int nv, int n, int nrc, long long ld, const uint8_t* __restrict__ keep,
+          const double* __restrict__ part, double* __restrict__ y) {
+    if (st->done) return;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nv; j += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        if (j < n && keep[j])
+            for (int c = 0; c < nrc; ++c) s += part[(long long)c * ld + j];
+        y[j] = s;
+    }
+}
+
+// x <- y / sum(y); L1 change; stop below tol, at the iteration cap, or when the change stalls at the rounding floor
+__global__ void __cluster_dims__(EP_CL, 1, 1) __launch_bounds__(EP_THREADS)
+k_sd_step(SdState* st, int n, const uint8_t* __restrict__ keep, const double* __restrict__ y, double* x) {
+    __shared__ double sm[32];
+    __shared__ double slots[8];
+    if (st->done) return;
+    Team T(slots, sm);
+    const SdState s = *st;
+    double acc = 0.0;
+    for (int i = T.gtid; i < n; i += T.nthreads)
+        if (keep[i]) acc += y[i];
+    const double S = T.reduce1<RED_SUM>(acc);
+    double d = 0.0;
+    for (int i = T.gtid; i < n; i += T.nthreads) {
+        if (keep[i]) {
+            const double yn = y[i] / S;
+            d += fabs(yn - x[i]);
+            x[i] = yn;
+        }
+    }
+    const double delta = T.reduce1<RED_SUM>(d);
+    if (T.gtid == 0) {
+        const int it = s.iters + 1;
+        st->sum = S; st->delta = delta; st->prev = delta; st->iters = it; st->matvecs = s.matvecs + 1;
+        st->done = (delta < s.tol || it >= s.max_iter || (delta >= s.prev && delta < 1e-11)) ? 1 : 0;
+    }
+    T.finish();
+}
+
 }  // namespace gcx

@@ -197,6 +197,22 @@ class DeviceMap:
         pb, sym = self.pass_bytes()
         return dict(x=x, outer=outer.value, MVP=mvp.value, rout=rout.value, ms=self.last_run_ms(), pass_bytes=pb, symmetric=sym)
 
+    def transition(self, in_place=False):
+        """Transition probability matrix of the resident map under the resident mask (lib/statDist.py:50-99);
+        result in the output map (download(1)) or in place.  Returns (min non-zero, max)."""
+        mn, mx = C.c_float(0), C.c_float(0)
+        check(lib().gcx_transition_run(self._ctx, int(bool(in_place)), C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
+    def stationary(self, tol=1e-13, max_iter=100000):
+        """Dominant left eigenvector of the kept block of the resident (transition) matrix by power iteration
+        (replaces the dense eigendecomposition of lib/statDist.py:480-484).  x sums to 1 over the kept bins."""
+        x = np.empty(self.n, dtype=np.float64)
+        iters, delta = C.c_int(0), C.c_double(0)
+        check(lib().gcx_stationary_run(self._ctx, float(tol), int(max_iter), x.ctypes.data_as(_lib._c_f64p),
+                                       C.byref(iters), C.byref(delta)))
+        return dict(x=x, iterations=iters.value, delta=delta.value, ms=self.last_run_ms(), pass_bytes=self.pass_bytes()[0])
+
     # ---- elementwise passes ---------------------------------------------------------------------
     def apply_sym(self, s=None, masked_mode=0, in_place=False):
         mn, mx = C.c_float(0), C.c_float(0)

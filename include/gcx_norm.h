@@ -113,6 +113,18 @@ int gcx_compact_f64(gcx_ctx* ctx, const int32_t* kept, int64_t nk, double* host_
  * bit-identical.  minv/maxv: min non-zero / max of the output. */
 int gcx_downsample(gcx_ctx* ctx, int level, int method, float* host_out, int64_t out_n, float* minv, float* maxv);
 
+/* ---- transition probabilities and stationary distribution -----------------
+ * gcx_transition_run replaces statDist.calculateTransitionProbabilityMatrix (lib/statDist.py:50-99) on the resident map
+ * with the resident mask: kept rows divided by their row sum in float32, every no-data row/column entry and every zero
+ * set to the smallest non-zero quotient.  Result in the output map (or in place).  minv/maxv: min non-zero / max.
+ * gcx_stationary_run replaces statDist.stationaryDistributionByEigenDecomp (lib/statDist.py:436-498) up to its scatter
+ * step: dominant left eigenvector of the kept block of the resident (transition) matrix, zeros of that block counted as
+ * its smallest non-zero entry (:466-469), by power iteration in float64 instead of a dense eigendecomposition.
+ * x: n doubles, sum 1 over the kept bins, 0 on no-data bins (the host applies the min-fill of :486-496).
+ * Stops when the L1 change of x drops below tol, stalls at the rounding floor, or after max_iter products. */
+int gcx_transition_run(gcx_ctx* ctx, int in_place, float* minv, float* maxv);
+int gcx_stationary_run(gcx_ctx* ctx, double tol, int max_iter, double* x, int* iterations, double* last_delta);
+
 /* ---- multi-GPU (row-block sharding; one context per rank) ------------------------------------
  * nccl_unique_id: the 128-byte ncclUniqueId from gcx_dist_unique_id on rank 0, broadcast by the host
  * (torch.distributed / any store).  After init, ic/kr/row_stats/diag_stats exchange their n-vectors with

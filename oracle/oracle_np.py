@@ -439,3 +439,91 @@ def downsample_nodata(bNoData, out_n, level):
     x = np.hstack((bNoData[1:], np.zeros(pad))) if pad != 0 else bNoData[1:]
     b[1:] = x.reshape(-1, level).sum(axis=1)
     return b
+
+
+# --------------------------------------------------------------------------------------------------
+# transition probability matrix + stationary distribution  lib/statDist.py
+# --------------------------------------------------------------------------------------------------
+def transition_matrix(A, bNoData, out=None):
+    """lib/statDist.py:50-99 (calculateTransitionProbabilityMatrix).  Kept rows are divided by their own sum in the
+    matrix dtype (:83-84); `minvalue` is the smallest non-zero quotient (:86-87); every entry of a no-data row or
+    column, and every zero of a kept row, becomes `minvalue` (:89-95).  Returns (Out, minvalue)."""
+    A = np.asarray(A)
+    bNoData = np.asarray(bNoData, dtype=bool)
+    Out = np.zeros(A.shape, dtype=A.dtype) if out is None else out
+    for m in np.nonzero(~bNoData)[0]:
+        sumr = A[m].sum()
+        Out[m] = (A[m] / sumr)[:]
+    minvalue = np.ma.masked_equal(Out, 0.0, copy=False).min()
+    Out[bNoData, :] = minvalue
+    Out[:, bNoData] = minvalue
+    Out[Out == 0] = minvalue
+    return Out, minvalue
+
+
+def stationary_eig(prob_matrix, bNoData):
+    """lib/statDist.py:436-498 (stationaryDistributionByEigenDecomp): the kept block in float64, zeros replaced by
+    the smallest non-zero entry (:466-469), first eigenvector LAPACK returns for the transposed block (:480-481),
+    scaled to sum 1, no-data bins set to the smallest component (:486-494), scaled to sum 1 again (:496)."""
+    from scipy import linalg as sp_linalg
+    bNoData = np.asarray(bNoData, dtype=bool)
+    n = prob_matrix.shape[0]
+    A = np.array((prob_matrix[~bNoData, :])[:, ~bNoData], dtype=np.float64)
+    A[A == 0] = np.ma.masked_equal(A, 0.0, copy=False).min()
+    _, eigvector = sp_linalg.eig(A.T)
+    distrib = eigvector[:, 0]
+    distrib = np.real(distrib / distrib.sum())
+    full = np.zeros(n)
+    full[bNoData] = np.amin(distrib)
+    full[~bNoData] = distrib
+    return full / full.sum()
+
+
+def stationary_power(prob_matrix, bNoData, tol=1e-13, max_iter=100000):
+    """The stationary distribution as the GPU computes it: power iteration x <- x P' / |x P'|_1 on
+    the kept block in float64 (zeros replaced like :466-469), stopped when the L1 change drops below `tol` or stalls at
+    the rounding floor.  NOT the reference's algorithm (that is `stationary_eig`); used to check iteration counts and
+    at sizes where a dense eigendecomposition takes minutes.  Returns (vector like stationary_eig, iterations)."""
+    bNoData = np.asarray(bNoData, dtype=bool)
+    n = prob_matrix.shape[0]
+    A = np.array((prob_matrix[~bNoData, :])[:, ~bNoData], dtype=np.float64)
+    A[A == 0] = np.ma.masked_equal(A, 0.0, copy=False).min()
+    nk = A.shape[0]
+    x = np.full(nk, 1.0 / nk)
+    prev = np.inf
+    it = 0
+    while it < max_iter:
+        y = x @ A
+        y /= y.sum()
+        delta = np.abs(y - x).sum()
+        x = y
+        it += 1
+        if delta < tol or (delta >= prev and delta < 1e-11):
+            break
+        prev = delta
+    full = np.zeros(n)
+    full[bNoData] = np.amin(x)
+    full[~bNoData] = x
+    return full / full.sum(), it
+
+
+def detect_outliers_1d(points, thresh=3.5):
+    """lib/util.py:100-138: modified z-score on the median absolute deviation."""
+    p = points[:, None] if points.ndim == 1 else points
+    median = np.median(p, axis=0)
+    diff = np.sqrt(np.sum((p - median) ** 2, axis=-1))
+    mad = np.median(diff)
+    return 0.6745 * diff / mad > thresh
+
+
+def stationary_postprocess(sdist, thresh=8):
+    """lib/statDist.py:320-333: components equal to the minimum (the no-data fill) are masked, outliers of the rest
+    are zeroed (lib/util.py:140-174), everything masked becomes 0, and the vector is scaled to sum 1."""
+    minvalue = np.amin(sdist)
+    mx = np.ma.masked_equal(sdist, minvalue)
+    pts = mx.compressed().copy()
+    pts[detect_outliers_1d(pts, thresh=thresh)] = 0.0
+    result = np.zeros(mx.shape, dtype=mx.dtype)
+    result[~np.ma.getmaskarray(mx)] = pts
+    out = np.ma.masked_values(result, 0.0).filled(0.0)
+    return out / np.sum(out)

@@ -569,3 +569,126 @@ def test_downsample_vs_oracle(gx, n, level, method):
     out = np.zeros(onp.downsample_shape(A.shape, level), dtype=np.float32)
     assert cmp.downSample2DMap(A, outMatrix=out, level=level, method=method) is None
     assert np.array_equal(out, onp.downsample_2d(A, level, method))
+
+
+# ---- transition probabilities + stationary distribution (lib/statDist.py) ----
+SD_RTOL = 1e-9          # stationary vectors vs the reference's eigendecomposition
+
+
+def _sd_rel(a, b):
+    return float(np.max(np.abs(a - b) / b))
+
+
+@pytest.mark.parametrize("name", golden_names("SD"))
+def test_transition_matrix_golden(gx, name):
+    from gcmapexplorer_b200 import ccmap as cmp, statDist as sdm
+    g = load_golden(name)
+    exact = name != "sd_s97ic"           # count data: float32 row sums are exact in any order -> bit-identical output
+    P = sdm.calculateTransitionProbabilityMatrix(g["input"], bNoData=g["bNoData"])
+    assert P.dtype == np.float32
+    assert np.array_equal(P, g["matrix"]) if exact else rel_err(P, g["matrix"]) < MAT_RTOL
+    out = np.zeros_like(g["input"])
+    assert sdm.calculateTransitionProbabilityMatrix(g["input"], Out=out, bNoData=g["bNoData"]) is None
+    assert np.array_equal(out, P)
+    # the public entry point on a CCMAP, thresholds included
+    c = cmp.CCMAP()
+    c.gen_from_matrix(g["input"], 100000, xlabel="chrS", ylabel="chrS")
+    c.make_unreadable()
+    tp = sdm.transitionProbabilityMatrixForCCMap(c, **g["kwargs"])
+    assert tp.matrix is None and c.matrix is not None                  # output unreadable, input readable (:129, :155)
+    tp.make_readable()
+    assert np.array_equal(tp.bNoData, g["bNoData"])
+    assert np.array_equal(tp.matrix, g["matrix"]) if exact else rel_err(tp.matrix, g["matrix"]) < MAT_RTOL
+    tol = 0 if exact else MAT_RTOL
+    assert abs(tp.minvalue - g["minvalue"]) <= tol * g["minvalue"] and abs(tp.maxvalue - g["maxvalue"]) <= tol * g["maxvalue"]
+
+
+@pytest.mark.parametrize("name", golden_names("SD"))
+def test_stationary_distribution_golden(gx, name):
+    from gcmapexplorer_b200 import ccmap as cmp, statDist as sdm
+    g = load_golden(name)
+    core = sdm.stationaryDistributionByEigenDecomp(g["matrix"], g["bNoData"])
+    assert core.dtype == np.float64 and abs(core.sum() - 1.0) < 1e-12
+    assert _sd_rel(core, g["sdist_core"]) < SD_RTOL
+    _, iters = onp.stationary_power(g["matrix"], g["bNoData"])
+    assert abs(sdm.last_run_info["iterations"] - iters) <= 2
+    c = cmp.CCMAP()
+    c.gen_from_matrix(g["matrix"], 100000, xlabel="chrS", ylabel="chrS")
+    c.bNoData = g["bNoData"]
+    c.make_unreadable()
+    final = sdm.statDistrByEigenDecompForCCMap(c)
+    assert c.matrix is None                                              # :318
+    assert np.array_equal(final == 0, g["sdist"] == 0)
+    nz = g["sdist"] != 0
+    assert _sd_rel(final[nz], g["sdist"][nz]) < SD_RTOL
+
+
+@pytest.mark.parametrize("n,seed", [(1031, 3), (2500, 4)])
+def test_stationary_vs_power_oracle_and_zero_fill(gx, n, seed):
+    """Larger maps against the float64 restatement of the same iteration; the second run feeds the raw count map,
+    whose kept block contains zeros (lib/statDist.py:466-469 replaces them with the smallest non-zero entry)."""
+    A = onp.synth_map(n, seed=seed, scale=40.0, alpha=1.2, empty_frac=0.02)
+    b = ~onp.get_nonzeros_index(A)
+    P, _ = onp.transition_matrix(A, b)
+    for M in (P, A):
+        exp, iters = onp.stationary_power(M, b)
+        with gx.DeviceMap.from_host(M) as dm:
+            dm.set_mask(~b)
+            r = dm.stationary()
+        got = r["x"]
+        assert abs(r["iterations"] - iters) <= 2 and r["delta"] < 1e-11
+        assert np.all(got[b] == 0) and abs(got.sum() - 1.0) < 1e-12
+        ref = exp[~b] / exp[~b].sum()
+        assert _sd_rel(got[~b], ref) < 1e-10
+    if n <= 1100:
+        assert _sd_rel(onp.stationary_eig(P, b), onp.stationary_power(P, b)[0]) < SD_RTOL
+
+
+def test_transition_in_place_and_large_against_oracle(gx):
+    A = onp.synth_map(2049, seed=9, scale=25.0, alpha=1.3, empty_frac=0.02)
+    keep = onp.get_nonzeros_index(A, threshold_data_occup=0.02)          # drops 11 bins that do hold data
+    exp, mv = onp.transition_matrix(A, ~keep)
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.set_mask(keep)
+        mn, mx = dm.transition(in_place=False)
+        assert np.array_equal(dm.download(1), exp) and mn == float(mv) and mx == float(exp.max())
+        assert np.array_equal(dm.download(0), A)                          # input untouched
+        dm.transition(in_place=True)
+        assert np.array_equal(dm.download(0), exp)
+
+
+def test_statdist_hdf5_handle_and_errors(gx):
+    from gcmapexplorer_b200 import ccmap as cmp, statDist as sdm, util
+    g = load_golden("sd_s400")
+
+    class Handle:
+        def __init__(self):
+            self.calls, self.opened, self.closed = [], 0, 0
+
+        def open(self):
+            self.opened += 1
+
+        def close(self):
+            self.closed += 1
+
+        def addDataByArray(self, chrom, resolution, key, arr, compression="lzf"):
+            self.calls.append((chrom, resolution, key, np.array(arr), compression))
+
+    c = cmp.CCMAP()
+    c.gen_from_matrix(g["matrix"], 100000, xlabel="chrS", ylabel="chrS")
+    c.bNoData = g["bNoData"]
+    h = Handle()
+    assert sdm.statDistrByEigenDecompForCCMap(c, hdf5Handle=h) is None and not h.calls       # no chrom: skipped (:305-307)
+    assert sdm.statDistrByEigenDecompForCCMap(c, chrom="chrS", hdf5Handle=h, compression="gzip") is None
+    assert h.opened == 1 and h.closed == 1
+    res = [r for (_, r, k, _, _) in h.calls if k == "sum"]
+    assert res == ["100kb", "200kb"]                                     # 400 bins -> 201 coarse bins (< 250: stop, :355-356)
+    full = h.calls[0][3]
+    assert np.max(np.abs(full[g["sdist"] != 0] - g["sdist"][g["sdist"] != 0]) / g["sdist"][g["sdist"] != 0]) < SD_RTOL
+    by = {(r, k): a for (_, r, k, a, _) in h.calls}
+    assert np.array_equal(by[("200kb", "maximum")], cmp.downSample1D(full, level=2, func="max"))
+    assert all(cmpr == "gzip" for (*_, cmpr) in h.calls) and util.resolutionToBinsize("200kb") == 200000
+    with pytest.raises(TypeError):
+        sdm.calculateTransitionProbabilityMatrix(g["input"])             # bNoData=None fails in the reference too (:90)
+    with pytest.raises(NotImplementedError):
+        sdm.statDistrByEigenDecompForGCMap("in.gcmap", "out.h5", "100kb")

@@ -146,3 +146,30 @@ def test_downsample_golden(name):
     assert np.array_equal(out, g["matrix"])
     if g["bNoData_in"].size:
         assert np.array_equal(onp.downsample_nodata(g["bNoData_in"], out.shape[0], g["kwargs"]["level"]), g["bNoData"])
+
+
+# ---- transition probabilities + stationary distribution (lib/statDist.py) ----
+@pytest.mark.parametrize("name", golden_names("SD"))
+def test_statdist_golden(name):
+    g = load_golden(name)
+    b = g["bNoData"]
+    P, mv = onp.transition_matrix(g["input"], b)
+    assert np.array_equal(P, g["matrix"])                                  # float32 divisions: bit-exact
+    assert float(mv) == g["minvalue"] and float(P.max()) == g["maxvalue"]
+    core = onp.stationary_eig(g["matrix"], b)
+    assert np.max(np.abs(core - g["sdist_core"]) / g["sdist_core"]) < 1e-10       # LAPACK build differences only
+    power, iters = onp.stationary_power(g["matrix"], b)
+    assert np.max(np.abs(power - g["sdist_core"]) / g["sdist_core"]) < 1e-9 and iters < 1000
+    final = onp.stationary_postprocess(g["sdist_core"])
+    np.testing.assert_allclose(final, g["sdist"], rtol=1e-13, atol=0)
+    assert np.array_equal(final == 0, g["sdist"] == 0)
+
+
+def test_stationary_replaces_zeros_of_the_kept_block():
+    """lib/statDist.py:466-469: a raw count map (zeros inside the kept block) still gives a positive vector."""
+    A = onp.synth_map(131, seed=131, scale=30.0, alpha=1.3, empty_frac=0.03)
+    b = ~onp.get_nonzeros_index(A)
+    assert (A[~b][:, ~b] == 0).any()
+    e = onp.stationary_eig(A, b)
+    p, _ = onp.stationary_power(A, b)
+    assert (e > 0).all() and abs(e.sum() - 1) < 1e-12 and np.max(np.abs(p - e) / e) < 1e-9

@@ -45,6 +45,12 @@ def main():
     mark('vc done'); avg_mean = dm.diag_stats("mean")
     avg_med = dm.diag_stats("median")
     mark('diag done')
+    mn_tp, mx_tp = dm.transition(in_place=False)                 # lib/statDist.py: transition matrix, then its stationary vector
+    cs_tp = dm.checksum(1)
+    dm.swap()
+    sd = dm.stationary()
+    dm.swap()
+    mark('statdist done')
     # all ranks hold identical vectors / counters
     def same_everywhere(arr):
         t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).copy()).cuda()
@@ -53,10 +59,11 @@ def main():
         ok = torch.tensor([int(torch.equal(t, ref))], device="cuda")
         tdist.all_reduce(ok, op=tdist.ReduceOp.MIN)
         return bool(ok.item())
-    res["ranks_identical"] = all(same_everywhere(a) for a in (ic["bias"], kr["x"], rs, zc, csum, avg_mean, avg_med))
+    res["ranks_identical"] = all(same_everywhere(a) for a in (ic["bias"], kr["x"], rs, zc, csum, avg_mean, avg_med, sd["x"]))
     # checksums of the sharded outputs add up
-    cs = torch.tensor([cs_ic & 0x7fffffffffffffff, cs_kr & 0x7fffffffffffffff, cs_vc & 0x7fffffffffffffff], dtype=torch.int64, device="cuda")
-    hi = torch.tensor([cs_ic >> 63, cs_kr >> 63, cs_vc >> 63], dtype=torch.int64, device="cuda")
+    cs = torch.tensor([cs_ic & 0x7fffffffffffffff, cs_kr & 0x7fffffffffffffff, cs_vc & 0x7fffffffffffffff, cs_tp & 0x7fffffffffffffff],
+                      dtype=torch.int64, device="cuda")
+    hi = torch.tensor([cs_ic >> 63, cs_kr >> 63, cs_vc >> 63, cs_tp >> 63], dtype=torch.int64, device="cuda")
     tdist.all_reduce(cs)
     tdist.all_reduce(hi)
     tot = [((int(c) + (int(h) << 63)) & 0xffffffffffffffff) for c, h in zip(cs.tolist(), hi.tolist())]
@@ -77,6 +84,10 @@ def main():
             c_vc = one.checksum(1)
             a_mean = one.diag_stats("mean")
             a_med = one.diag_stats("median")
+            m4 = one.transition(in_place=False)
+            c_tp = one.checksum(1)
+            one.swap()
+            sd1 = one.stationary()
         res.update(partition=partition, sharded_symmetric_pass=bool(ic["symmetric"]), single_symmetric_pass=bool(ic1["symmetric"]),
             rowstats_equal=bool(np.array_equal(rs, rs1) and np.array_equal(zc, zc1)),
             ic_passes=(ic["passes"], ic1["passes"]), ic_bias_rel=float(np.max(np.abs(ic["bias"] / ic1["bias"] - 1))),
@@ -85,12 +96,16 @@ def main():
             minmax_ic=((mn_ic, mx_ic), m1), minmax_kr=((mn_kr, mx_kr), m2), minmax_vc=((mn_vc, mx_vc), m3[:2]),
             checksum_vc_equal=bool(tot[2] == c_vc), checksum_ic_equal=bool(tot[0] == c_ic), checksum_kr_equal=bool(tot[1] == c_kr),
             median_equal=bool(np.array_equal(avg_med, a_med)), mean_rel=float(np.max(np.abs(avg_mean - a_mean) / np.maximum(np.abs(a_mean), 1e-300))),
-            ic_ms=(ic["ms"], ic1["ms"]), kr_ms=(kr["ms"], kr1["ms"]))
+            checksum_tp_equal=bool(tot[3] == c_tp), minmax_tp=((mn_tp, mx_tp), m4),
+            sd_iterations=(sd["iterations"], sd1["iterations"]), sd_rel=float(np.max(np.abs(sd["x"][keep] / sd1["x"][keep] - 1))),
+            ic_ms=(ic["ms"], ic1["ms"]), kr_ms=(kr["ms"], kr1["ms"]), sd_ms=(sd["ms"], sd1["ms"]))
         ok = (res["ranks_identical"] and res["rowstats_equal"] and res["ic_passes"][0] == res["ic_passes"][1]
               and res["ic_bias_rel"] < 1e-12 and res["kr_counters"][0] == res["kr_counters"][1] and res["kr_x_rel"] < 1e-11
               and res["checksum_vc_equal"] and res["median_equal"] and res["mean_rel"] < 1e-13
               and np.float32(mn_vc) == np.float32(m3[0]) and np.float32(mx_vc) == np.float32(m3[1])
-              and abs(mn_ic / m1[0] - 1) < 1e-6 and abs(mx_kr / m2[1] - 1) < 1e-6)
+              and abs(mn_ic / m1[0] - 1) < 1e-6 and abs(mx_kr / m2[1] - 1) < 1e-6
+              and res["checksum_tp_equal"] and (mn_tp, mx_tp) == tuple(m4) and abs(sd["iterations"] - sd1["iterations"]) <= 1
+              and res["sd_rel"] < 1e-11)
         res["ok"] = bool(ok)
         print(json.dumps(res, default=str))
     flag = torch.tensor([int(ok)], device="cuda")
