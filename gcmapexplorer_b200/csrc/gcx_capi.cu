@@ -133,6 +133,7 @@ struct gcx_ctx {
     double* part = nullptr;      // per-CTA partials of the fused IC pass (3 x grid)
     int ic_fused = 1;            // 1: one cooperative launch per IC pass (k_ic_pass); 0: k_matvec + k_ic_epilogue
     int ic_grid = 0, ic_grid_tma = 0;
+    int sd_variant = 1;   // stationary distribution: 1 = TMA-bulk transposed product, 0 = LDG (GCX_SD_VARIANT / option "sd_variant")
     int mv_variant = 7;   // TMA-bulk, R=4 rows per band, 6 stages, 2 CTAs/SM: best of profiles/r01_matvec_variants.txt
     // states
     IcState* ic_state = nullptr;
@@ -290,6 +291,7 @@ static int ctx_init(gcx_ctx* c, int device) {
     CK(cudaEventCreate(&c->tm_b));
     const char* v = getenv("GCX_MATVEC_VARIANT");
     if (v) c->mv_variant = atoi(v);
+    if (const char* sv = getenv("GCX_SD_VARIANT")) c->sd_variant = atoi(sv);
     const char* sy = getenv("GCX_SYM");
     if (sy) c->sym_enable = atoi(sy);
     if (c->ic_fused != 2) c->sym_enable = c->sym_enable && (c->ic_fused != 1);   // the fused LDG pass has no symmetric twin
@@ -724,6 +726,7 @@ extern "C" int gcx_set_option(gcx_ctx* c, const char* key, double value) {
         c->sym_blocks = (int)value;
     }
     else if (k == "matvec_variant") c->mv_variant = (int)value;
+    else if (k == "sd_variant") c->sd_variant = (int)value;
     else return fail("gcx_set_option: unknown key '%s'", key);
     return 0;
 }
@@ -1559,16 +1562,59 @@ extern "C" int gcx_stationary_run(gcx_ctx* c, double tol, int max_iter, double* 
     float m0 = 0.f, mx = 0.f;
     CKR(mm_end(c, &m0, &mx));
     if (m0 != m0) return fail("gcx_stationary_run: the kept block has no non-zero entry");
-    // row chunks: ~6 CTAs per SM over (column chunks x row chunks), chunk length a multiple of the unroll depth
     const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    double* xv = c->kr.x;
+    double* yv = c->vq;
+    constexpr int TKG = 4, TSTAGES = 6, TOCC = 2;                 // 16 KB per stage, 96 KB per CTA, 2 CTAs per SM (like the dense TMA product)
+    const size_t smem = (size_t)TSTAGES * TKG * MV_THREADS * sizeof(float4);
+    static int mvt_occ = -1;
+    if (mvt_occ < 0) {
+        CK(cudaFuncSetAttribute(k_matvec_t_tma<TKG, TSTAGES, TOCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_matvec_t_tma<TKG, TSTAGES, TOCC>, TMA_THREADS, smem));
+        mvt_occ = std::min(occ, TOCC);
+    }
+    const bool use_tma = c->sd_variant == 1 && mvt_occ >= 1;
+    // LDG variant: (column chunks x row chunks) grid, ~6 CTAs per SM, chunk length a multiple of the unroll depth
     int nrc = std::max(1, (c->sm_count * 6 + nch - 1) / nch);
     int rpc = (nloc + nrc - 1) / nrc;
     rpc = std::max(MVT_UNR, (rpc + MVT_UNR - 1) / MVT_UNR * MVT_UNR);
     nrc = (nloc + rpc - 1) / rpc;
-    CKR(ensure_scratch(c, sizeof(double) * (size_t)nrc * c->ld));
+    // TMA variant: persistent grid over the strip-major unit list; tabulate every CTA's first strip and every strip's CTA range
+    const int G = c->sm_count * std::max(1, mvt_occ);
+    MvtTab tab{};
+    size_t part_bytes = sizeof(double) * (size_t)nrc * c->ld, tab_bytes = 0;
+    std::vector<int> ht;
+    const int nst = (nch + TKG - 1) / TKG;
+    if (use_tma) {
+        const long long U = (long long)nst * nloc;
+        std::vector<int> gf((size_t)G, 0), lo((size_t)nst, G), hi((size_t)nst, -1);
+        int slots = 1;
+        for (int g = 0; g < G; ++g) {
+            const long long u0 = (long long)g * U / G, u1 = (long long)(g + 1) * U / G;
+            if (u1 <= u0) continue;
+            const int s0 = (int)(u0 / nloc), s1 = (int)((u1 - 1) / nloc);
+            gf[g] = s0;
+            slots = std::max(slots, s1 - s0 + 1);
+            for (int k = s0; k <= s1; ++k) { lo[k] = std::min(lo[k], g); hi[k] = std::max(hi[k], g); }
+        }
+        ht = gf;
+        ht.insert(ht.end(), lo.begin(), lo.end());
+        ht.insert(ht.end(), hi.begin(), hi.end());
+        tab.slots = slots;
+        part_bytes = sizeof(double) * (size_t)G * slots * TKG * 1024;
+        tab_bytes = align256(sizeof(int) * ht.size());
+    }
+    CKR(ensure_scratch(c, align256(part_bytes) + tab_bytes));
     double* part = (double*)c->scratch;
-    double* xv = c->kr.x;
-    double* yv = c->vq;
+    if (use_tma) {
+        int* dt = (int*)((char*)c->scratch + align256(part_bytes));
+        CK(cudaMemcpyAsync(dt, ht.data(), sizeof(int) * ht.size(), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));          // ht is a local
+        tab.cta_gf = dt;
+        tab.strip_lo = dt + G;
+        tab.strip_hi = dt + G + nst;
+    }
     k_sd_init<<<EP_CL, EP_THREADS, 0, c->stream>>>(c->sd_state, (int)c->nv, n, c->keep, xv, tol, max_iter);
     CK(cudaGetLastError());
     c->launches += 1;
@@ -1577,10 +1623,17 @@ extern "C" int gcx_stationary_run(gcx_ctx* c, double tol, int max_iter, double* 
     auto step = [&]() -> int {
         {
             ProfScope ps(c, 0);
-            k_matvec_t<<<dim3(nch, nrc), MV_THREADS, 0, c->stream>>>(c->A, c->ld, nloc, n4, (int)c->row0, rpc, xv, m0, part, &c->sd_state->done);
+            if (use_tma)
+                k_matvec_t_tma<TKG, TSTAGES, TOCC><<<G, TMA_THREADS, smem, c->stream>>>(c->A, c->ld, nloc, n4, (int)c->row0, xv, m0, part, tab,
+                                                                                      &c->sd_state->done);
+            else
+                k_matvec_t<<<dim3(nch, nrc), MV_THREADS, 0, c->stream>>>(c->A, c->ld, nloc, n4, (int)c->row0, rpc, xv, m0, part, &c->sd_state->done);
         }
         CK(cudaGetLastError());
-        k_sd_fold<<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>(c->sd_state, (int)c->nv, n, nrc, c->ld, c->keep, part, yv);
+        if (use_tma)
+            k_sd_fold_t<TKG><<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>(c->sd_state, (int)c->nv, n, c->keep, part, tab, yv);
+        else
+            k_sd_fold<<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>(c->sd_state, (int)c->nv, n, nrc, c->ld, c->keep, part, yv);
         CK(cudaGetLastError());
         c->launches += 1;
         CKR(allreduce_f64(c, yv, (size_t)c->n));

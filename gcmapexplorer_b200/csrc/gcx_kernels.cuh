@@ -2159,19 +2159,45 @@ k_tp_pass(const float* __restrict__ A, float* __restrict__ Out, long long ld, in
             const bool ki = __ldg(keep + i) != 0;
             const float si = __ldg(rsum + i);
             const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
-            float o[4];
+            if constexpr (!WRITE) {
+                // minimum pass: for a positive row sum the float32 quotient is a non-decreasing function of a positive entry,
+                // so the smallest non-zero quotient of the thread's four entries comes from their smallest positive one: one
+                // division per row segment.  Negative entries, a non-positive row sum or an underflowing quotient take the
+                // exact per-entry path.  (Pad columns are zero and never count.)
+                if (!ki) continue;
+                float rmin = GCX_PINF;
+                bool odd = !(si > 0.f);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float q = 0.f;
-                if (ki && in[e] != 0.f) q = __fdiv_rn(in[e], si);
-                if (WRITE) {
+                for (int e = 0; e < 4; ++e) {
+                    rmin = fminf(rmin, in[e] > 0.f ? in[e] : GCX_PINF);
+                    odd |= in[e] < 0.f;
+                }
+                if (!odd && rmin != GCX_PINF) {
+                    const float q = __fdiv_rn(rmin, si);
+                    if (q != 0.f) mn = fminf(mn, q);
+                    else odd = true;
+                }
+                if (odd) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (in[e] == 0.f) continue;
+                        const float q = __fdiv_rn(in[e], si);
+                        if (q != 0.f) mn = fminf(mn, q);
+                    }
+                }
+            } else {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float q = 0.f;
+                    if (ki && in[e] != 0.f) q = __fdiv_rn(in[e], si);
                     q = (kcol[e] && q != 0.f) ? q : fill;
                     if (j0 + e >= n) q = 0.f;
+                    o[e] = q;
+                    if (j0 + e < n) mm_update(q, mn, mx);
                 }
-                o[e] = q;
-                if (j0 + e < n) mm_update(q, mn, mx);
+                st_stream_f4(reinterpret_cast<float4*>(Out + (long long)r * ld) + c4, make_float4(o[0], o[1], o[2], o[3]));
             }
-            if (WRITE) st_stream_f4(reinterpret_cast<float4*>(Out + (long long)r * ld) + c4, make_float4(o[0], o[1], o[2], o[3]));
         }
     }
     mm_commit(mn, mx, mm);
@@ -2320,6 +2346,130 @@ k_sd_step(SdState* st, int n, const uint8_t* __restrict__ keep, const double* __
         st->done = (delta < s.tol || it >= s.max_iter || (delta >= s.prev && delta < 1e-11)) ? 1 : 0;
     }
     T.finish();
+}
+
+// TMA-bulk variant of the transposed product (the default): persistent grid, units = (strip g of KG column chunks,
+// row r) in g-major order split evenly over the CTAs, so a CTA walks down the rows of one KG x 4 KB wide column strip (two
+// strips at most when its share crosses a strip boundary -> `slots` partial rows per CTA).  One producer lane keeps
+// STAGES row segments (one contiguous KG x 4 KB copy each) in flight behind mbarriers; the 8 consumer warps add
+// x_i * P'_ij into 4 KG register column sums per thread -- no cross-thread reduction at all.
+// part: [grid][slots][KG * 1024] doubles; k_sd_fold_t adds the CTAs of a strip in CTA order.
+struct MvtTab {
+    const int* cta_gf;      // [G] first strip of every CTA
+    const int* strip_lo;    // [nstrips] first / last CTA holding units of the strip
+    const int* strip_hi;
+    int slots;
+};
+
+template <int KG, int STAGES, int OCC>
+__global__ void __launch_bounds__(TMA_THREADS, OCC)
+k_matvec_t_tma(const float* __restrict__ A, long long ld, int nloc, int n4, int row0, const double* __restrict__ x, float m0,
+               double* __restrict__ part, MvtTab T, const int* __restrict__ done) {
+    if (done != nullptr && *done) return;
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    float4* tiles = reinterpret_cast<float4*>(tma_smem);
+    constexpr int SW4 = KG * MV_THREADS;                  // float4 columns per strip
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nst = (n4 + SW4 - 1) / SW4;
+    const long long U = (long long)nst * nloc, G = gridDim.x, c = blockIdx.x;
+    const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], MV_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (u1 <= u0) return;
+    int g = (int)(u0 / nloc), r = (int)(u0 - (long long)g * nloc);      // the only 64-bit divisions of the kernel
+    const int gfirst = g;
+    if (warp == MV_THREADS / 32) {
+        if (lane == 0) {
+            int stage = 0;
+            unsigned int phase = 0;
+            for (long long u = u0; u < u1; ++u) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                const int c0 = g * SW4;
+                const unsigned int bytes = (unsigned int)min(SW4, n4 - c0) * 16u;
+                mbar_expect_tx(&full_bar[stage], bytes);
+                bulk_g2s(tiles + (size_t)stage * SW4, A + (long long)r * ld + 4LL * c0, bytes, &full_bar[stage]);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+                if (++r == nloc) {
+                    r = 0;
+                    ++g;
+                }
+            }
+        }
+        return;
+    }
+    double acc[KG][4];
+#pragma unroll
+    for (int kk = 0; kk < KG; ++kk) acc[kk][0] = acc[kk][1] = acc[kk][2] = acc[kk][3] = 0.0;
+    auto flush = [&](int gg) {
+        double* base = part + ((long long)c * T.slots + (gg - gfirst)) * (4LL * SW4);
+#pragma unroll
+        for (int kk = 0; kk < KG; ++kk) {
+            double2* dst = reinterpret_cast<double2*>(base + 4 * (kk * MV_THREADS + tid));
+            dst[0] = make_double2(acc[kk][0], acc[kk][1]);
+            dst[1] = make_double2(acc[kk][2], acc[kk][3]);
+            acc[kk][0] = acc[kk][1] = acc[kk][2] = acc[kk][3] = 0.0;
+        }
+    };
+    int stage = 0;
+    unsigned int phase = 0;
+    for (long long u = u0; u < u1; ++u) {
+        const double xv = __ldg(x + row0 + r);
+        const int c0 = g * SW4;
+        mbar_wait(&full_bar[stage], phase);
+        if (xv != 0.0) {                                       // no-data rows contribute nothing
+#pragma unroll
+            for (int kk = 0; kk < KG; ++kk) {
+                if (c0 + kk * MV_THREADS + tid < n4) {
+                    const float4 a = tiles[(size_t)stage * SW4 + kk * MV_THREADS + tid];
+                    acc[kk][0] = fma(xv, (double)(a.x == 0.f ? m0 : a.x), acc[kk][0]);
+                    acc[kk][1] = fma(xv, (double)(a.y == 0.f ? m0 : a.y), acc[kk][1]);
+                    acc[kk][2] = fma(xv, (double)(a.z == 0.f ? m0 : a.z), acc[kk][2]);
+                    acc[kk][3] = fma(xv, (double)(a.w == 0.f ? m0 : a.w), acc[kk][3]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+        }
+        if (++r == nloc) {
+            flush(g);
+            r = 0;
+            ++g;
+        }
+    }
+    if (r != 0) flush(g);
+}
+
+template <int KG>
+__global__ void __launch_bounds__(256)
+k_sd_fold_t(const SdState* __restrict__ st, int nv, int n, const uint8_t* __restrict__ keep, const double* __restrict__ part, MvtTab T,
+            double* __restrict__ y) {
+    if (st->done) return;
+    constexpr int SW = KG * 1024;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nv; j += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        if (j < n && keep[j]) {
+            const int g = j / SW, o = j - g * SW;
+            const int lo = T.strip_lo[g], hi = T.strip_hi[g];
+            for (int cta = lo; cta <= hi; ++cta) s += part[((long long)cta * T.slots + (g - T.cta_gf[cta])) * SW + o];
+        }
+        y[j] = s;
+    }
 }
 
 }  // namespace gcx

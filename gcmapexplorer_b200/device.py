@@ -164,6 +164,10 @@ class DeviceMap:
         return dict(sm_count=sm.value, hbm_total=tot.value, hbm_free=free.value)
 
     # ---- mask -----------------------------------------------------------------------------------
+    def invalidate(self):
+        """Drop the cached row statistics (benchmark steps that must re-read the map)."""
+        check(lib().gcx_map_invalidate(self._ctx))
+
     def row_stats(self, force=False):
         """(rowsum float64[n], raw zero_count int32[n]).  Cached on the device until the map changes;
         force=True re-reads the map (benchmark steps)."""

@@ -135,7 +135,9 @@ int gcx_stationary_run(gcx_ctx* ctx, double tol, int max_iter, double* x, int* i
  *                             cannot see the mirrored block (the caller vouches that the map is symmetric)
  *   "exchange_allreduce" 0/1  the row blocks are not the equal ceil(n/world) blocks: exchange n-vectors by zero-fill +
  *                             allreduce instead of allgather (set it on every rank, before gcx_map_create)
- *   "matvec_variant"     kernel variant for sweeps */
+ *   "sym_blocks"         0/1  sharded upper-triangle pass: deal the off-diagonal blocks out in the circulant pattern (default 1)
+ *   "matvec_variant"     kernel variant for sweeps
+ *   "sd_variant"         stationary distribution: 1 TMA-bulk transposed product (default), 0 per-thread loads */
 int gcx_set_option(gcx_ctx* ctx, const char* key, double value);
 /* The aligned row partition (cuts at rank*n/world rounded to 1024 rows).  With it, "assume_symmetric" and
  * "exchange_allreduce", a sharded map runs the upper-triangle pass with the off-diagonal blocks dealt out in a circulant

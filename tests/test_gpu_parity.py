@@ -632,14 +632,16 @@ def test_stationary_vs_power_oracle_and_zero_fill(gx, n, seed):
     P, _ = onp.transition_matrix(A, b)
     for M in (P, A):
         exp, iters = onp.stationary_power(M, b)
-        with gx.DeviceMap.from_host(M) as dm:
-            dm.set_mask(~b)
-            r = dm.stationary()
-        got = r["x"]
-        assert abs(r["iterations"] - iters) <= 2 and r["delta"] < 1e-11
-        assert np.all(got[b] == 0) and abs(got.sum() - 1.0) < 1e-12
-        ref = exp[~b] / exp[~b].sum()
-        assert _sd_rel(got[~b], ref) < 1e-10
+        for variant in (1, 0):                   # TMA-bulk transposed product (default) and the per-thread-load one
+            with gx.DeviceMap.from_host(M) as dm:
+                dm.set_option("sd_variant", variant)
+                dm.set_mask(~b)
+                r = dm.stationary()
+            got = r["x"]
+            assert abs(r["iterations"] - iters) <= 2 and r["delta"] < 1e-11
+            assert np.all(got[b] == 0) and abs(got.sum() - 1.0) < 1e-12
+            ref = exp[~b] / exp[~b].sum()
+            assert _sd_rel(got[~b], ref) < 1e-10
     if n <= 1100:
         assert _sd_rel(onp.stationary_eig(P, b), onp.stationary_power(P, b)[0]) < SD_RTOL
 
@@ -655,6 +657,24 @@ def test_transition_in_place_and_large_against_oracle(gx):
         assert np.array_equal(dm.download(0), A)                          # input untouched
         dm.transition(in_place=True)
         assert np.array_equal(dm.download(0), exp)
+
+
+def test_transition_with_negative_entries_takes_the_exact_path(gx):
+    """Signed integer-valued map (exact float32 row sums), one row with a negative sum: the per-entry division path of the
+    minimum pass must give the reference's fill value bit for bit."""
+    rng = np.random.default_rng(12)
+    A = rng.integers(-3, 10, size=(300, 300)).astype(np.float32)
+    A = np.triu(A) + np.triu(A, 1).T
+    A[np.arange(300), np.arange(300)] = 50.0
+    A[7, 7] = -4000.0
+    b = np.zeros(300, dtype=bool)
+    b[[3, 150]] = True
+    exp, mv = onp.transition_matrix(A, b)
+    assert mv < 0
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.set_mask(~b)
+        mn, mx = dm.transition(in_place=False)
+        assert np.array_equal(dm.download(1), exp) and mn == float(mv)
 
 
 def test_statdist_hdf5_handle_and_errors(gx):
