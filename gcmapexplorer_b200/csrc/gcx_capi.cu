@@ -81,6 +81,40 @@ static int nccl_load() {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------------
+// cuBLAS through dlopen (row N4 only: three plain float64 GEMMs per correlation matrix)
+// ---------------------------------------------------------------------------------------------------
+typedef struct cublasContext* cublasHandle_t;
+enum { CUBLAS_OP_N_ = 0, CUBLAS_OP_T_ = 1 };
+struct CublasApi {
+    void* h = nullptr;
+    int (*Create)(cublasHandle_t*) = nullptr;
+    int (*Destroy)(cublasHandle_t) = nullptr;
+    int (*SetStream)(cublasHandle_t, cudaStream_t) = nullptr;
+    int (*Dgemm)(cublasHandle_t, int, int, int, int, int, const double*, const double*, int, const double*, int, const double*, double*, int) = nullptr;
+};
+static CublasApi g_cublas;
+static int cublas_load() {
+    if (g_cublas.h) return 0;
+    const char* names[] = {"libcublas.so.12", "libcublas.so"};
+    for (const char* nm : names) {
+        g_cublas.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_cublas.h) break;
+    }
+    if (!g_cublas.h) return fail("cannot dlopen libcublas.so.12: %s", dlerror());
+    *(void**)(&g_cublas.Create) = dlsym(g_cublas.h, "cublasCreate_v2");
+    *(void**)(&g_cublas.Destroy) = dlsym(g_cublas.h, "cublasDestroy_v2");
+    *(void**)(&g_cublas.SetStream) = dlsym(g_cublas.h, "cublasSetStream_v2");
+    *(void**)(&g_cublas.Dgemm) = dlsym(g_cublas.h, "cublasDgemm_v2");
+    if (!g_cublas.Create || !g_cublas.Destroy || !g_cublas.SetStream || !g_cublas.Dgemm) return fail("libcublas: missing symbol");
+    return 0;
+}
+#define BK(call)                                                                                  \
+    do {                                                                                          \
+        int e__ = (call);                                                                         \
+        if (e__ != 0) return fail("%s failed at %s:%d: cuBLAS status %d", #call, __FILE__, __LINE__, e__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
 struct EvPair {
@@ -150,6 +184,7 @@ struct gcx_ctx {
     int rank = 0, world = 1;
     int64_t rpr = 0;   // rows per rank (allgather count)
     ncclComm_t comm = nullptr;
+    cublasHandle_t blas = nullptr;          // created on the first correlation run
     // measurement
     bool profile = false;
     std::vector<EvPair> evs;
@@ -353,6 +388,7 @@ extern "C" int gcx_ctx_destroy(gcx_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->blas && g_cublas.Destroy) g_cublas.Destroy(c->blas);
     free_map(c);
     for (auto& p : c->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -1650,6 +1686,126 @@ extern "C" int gcx_stationary_run(gcx_ctx* c, double tol, int max_iter, double* 
     CK(cudaStreamSynchronize(c->stream));
     if (iterations) *iterations = fin.iters;
     if (last_delta) *last_delta = fin.delta;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// correlation matrix
+// ---------------------------------------------------------------------------------------------------
+static int blas_ready(gcx_ctx* c) {
+    CKR(cublas_load());
+    if (!c->blas) {
+        BK(g_cublas.Create(&c->blas));
+        BK(g_cublas.SetStream(c->blas, c->stream));
+    }
+    return 0;
+}
+
+// row-major P = L R^T for row-major m x m factors (column-major view: P^T = R_cm^T L_cm)
+static int gemm_nt(gcx_ctx* c, int m, const double* L, const double* R, double* P) {
+    const double one = 1.0, zero = 0.0;
+    ProfScope ps(c, 7);
+    BK(g_cublas.Dgemm(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, m, m, m, &one, R, m, L, m, &zero, P, m));
+    return 0;
+}
+
+struct CorrBufs {
+    double *X0, *I, *N, *Sx, *Sxy, *var;
+    int* kept;
+};
+
+static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
+    const size_t mm = align256(sizeof(double) * (size_t)m * m), bv = align256(sizeof(double) * (size_t)m), bi = align256(sizeof(int) * (size_t)m);
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (5 * mm + bv + bi > free_b + c->scratch_bytes)
+        return fail("correlation of %lld bins needs %.1f GB of float64 workspace, %.1f GB are free", (long long)m, (5 * mm + bv + bi) / 1e9,
+                    (free_b + c->scratch_bytes) / 1e9);
+    CKR(ensure_scratch(c, 5 * mm + bv + bi));
+    char* p = (char*)c->scratch;
+    B->X0 = (double*)p; p += mm;
+    B->I = (double*)p; p += mm;
+    B->N = (double*)p; p += mm;
+    B->Sx = (double*)p; p += mm;
+    B->Sxy = (double*)p; p += mm;
+    B->var = (double*)p; p += bv;
+    B->kept = (int*)p;
+    return 0;
+}
+
+// the three products and the row variances, from X0 / I
+static int corr_core(gcx_ctx* c, int m, const CorrBufs& B) {
+    CKR(blas_ready(c));
+    CKR(gemm_nt(c, m, B.I, B.I, B.N));
+    CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
+    CKR(gemm_nt(c, m, B.X0, B.X0, B.Sxy));
+    k_corr_selfvar<<<(m + 127) / 128, 128, 0, c->stream>>>(B.X0, B.I, m, B.var);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    return 0;
+}
+
+extern "C" int gcx_corr_run(gcx_ctx* c, int has_mask, double maskvalue, int logspace, int has_vmin, float vmin, int has_vmax, float vmax) {
+    CKR(need_map(c));
+    CKR(fence_copy(c));
+    if (c->world != 1) return fail("gcx_corr_run: single-rank maps only");
+    if (!c->have_mask) return fail("gcx_corr_run: call gcx_set_mask first");
+    const int n = (int)c->n;
+    std::vector<uint8_t> keep((size_t)n);
+    CK(cudaMemcpyAsync(keep.data(), c->keep, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<int> kept;
+    for (int i = 0; i < n; ++i)
+        if (keep[i]) kept.push_back(i);
+    const int m = (int)kept.size();
+    if (m < 1) return fail("gcx_corr_run: no bin with data");
+    CorrBufs B{};
+    CKR(corr_bufs(c, m, &B));
+    CK(cudaMemcpyAsync(B.kept, kept.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));          // `kept` is a local
+    CorrPrep P{};
+    P.has_mask = has_mask; P.logspace = logspace; P.has_vmin = has_vmin; P.has_vmax = has_vmax;
+    P.maskf = (float)maskvalue;                      // the wrapper rounds the mask value to float32 (lib/_corrMatrixCore.pyx:88)
+    P.mask = (double)P.maskf;
+    P.vmin = vmin; P.vmax = vmax;
+    {
+        ProfScope ps(c, 7);
+        k_corr_prep<<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(c->A, c->ld, B.kept, m, P, B.X0, B.I);
+    }
+    CK(cudaGetLastError());
+    CKR(corr_core(c, m, B));
+    CKR(ensure_out(c));
+    CK(cudaMemsetAsync(c->Out, 0, sizeof(float) * (size_t)c->nloc * c->ld, c->stream));
+    {
+        ProfScope ps(c, 7);
+        k_corr_finish<true><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(B.N, B.Sx, B.Sxy, B.var, m, B.kept, c->Out, c->ld, nullptr, 0);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gcx_corr_matrix_f64(gcx_ctx* c, const double* in, int64_t m64, int has_mask, double maskvalue, int covariance, double* out) {
+    if (!c) return fail("gcx_corr_matrix_f64: null context");
+    CKR(set_dev(c));
+    if (!in || !out || m64 < 1 || m64 > 0x7fffffff) return fail("gcx_corr_matrix_f64: bad arguments");
+    const int m = (int)m64;
+    CorrBufs B{};
+    CKR(corr_bufs(c, m, &B));
+    const size_t bytes = sizeof(double) * (size_t)m * m;
+    CK(cudaMemcpyAsync(B.X0, in, bytes, cudaMemcpyHostToDevice, c->stream));
+    const float maskf = (float)maskvalue;            // lib/_corrMatrixCore.pyx:88
+    k_corr_prep_f64<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, B.I, (long long)m * m, has_mask, (double)maskf);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    CKR(corr_core(c, m, B));
+    // the result overwrites the indicator buffer (no longer needed once the products are done)
+    CK(cudaMemsetAsync(B.I, 0, bytes, c->stream));
+    k_corr_finish<false><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(B.N, B.Sx, B.Sxy, B.var, m, nullptr, nullptr, 0, B.I, covariance);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    CK(cudaMemcpyAsync(out, B.I, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -2472,4 +2472,141 @@ k_sd_fold_t(const SdState* __restrict__ st, int nv, int n, const uint8_t* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// N4: pairwise-masked Pearson correlation of the rows of X = (kept block)^T, lib/corrMatrixCoreSRC.c.
+// For a pair (i, j) the reference sums over the entries where BOTH rows differ from the mask value (:146-152, :181-186):
+//   cov_ij = sum (x - xbar)(y - ybar) / N,  xbar = sum x / N  over those N entries, 0 unless N > 3 (:171);
+//   corr_ij = cov_ij / sqrt(var_i var_j),   var_i = cov(x_i, x_i) with x_i's OWN mask only (:115-116) -- so |corr| can exceed 1.
+// With X0 = x where unmasked else 0 and I = the 0/1 indicator, the pair sums are three GEMM-shaped products,
+//   N = I I^T,  Sx = X0 I^T (sum of x_i over the common entries; sum of y is its transpose),  Sxy = X0 X0^T,
+// and cov_ij = (Sxy_ij - Sx_ij Sx_ji / N_ij) / N_ij.  The products run as float64 library GEMMs (cuBLAS DGEMM: plain GEMMs,
+// no fusion to gain); everything around them is below.  var_i repeats the reference's sequential two-pass arithmetic
+// (no FMA contraction), so the `var == 0` tests of :121 decide exactly as the reference does.
+// ---------------------------------------------------------------------------------------------------
+struct CorrPrep {
+    int has_mask, logspace, has_vmin, has_vmax;
+    double mask;
+    float vmin, vmax, maskf;
+};
+
+__device__ __forceinline__ void corr_value(float a, const CorrPrep& P, double& x0, double& ind) {
+    if (P.has_vmin && a <= P.vmin) a = P.maskf;                   // lib/corrMatrix.py:96-99 (on the float32 map)
+    if (P.has_vmax && a >= P.vmax) a = P.maskf;
+    double v = (double)a;                                          // :109
+    if (P.logspace) {                                              // :111-113
+        v = log10(v);
+        if (isinf(v)) v = 0.0;
+    }
+    const bool on = !P.has_mask || v != P.mask;
+    ind = on ? 1.0 : 0.0;
+    x0 = on ? v : 0.0;
+}
+
+// X[i][k] = f(A[kept[k]][kept[i]]) -- compaction + transpose (:108-109) through a 32 x 32 shared tile; writes X0 and I
+__global__ void __launch_bounds__(256)
+k_corr_prep(const float* __restrict__ A, long long ld, const int* __restrict__ kept, int m, CorrPrep P, double* __restrict__ X0,
+            double* __restrict__ I) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    // read: rows kept[k0 + r], columns kept[i0 + tx] (consecutive kept columns are close in memory)
+    const int ci = i0 + tx < m ? kept[i0 + tx] : -1;
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r;
+        tile[r][tx] = (k < m && ci >= 0) ? A[(long long)kept[k] * ld + ci] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, k = k0 + tx;
+        if (i < m && k < m) {
+            double x0, ind;
+            corr_value(tile[tx][r], P, x0, ind);
+            X0[(long long)i * m + k] = x0;
+            I[(long long)i * m + k] = ind;
+        }
+    }
+}
+
+// host float64 input (inner seam, lib/_corrMatrixCore.pyx:49): split into X0 and I in place (X holds the raw rows)
+__global__ void __launch_bounds__(256)
+k_corr_prep_f64(double* __restrict__ X, double* __restrict__ I, long long total, int has_mask, double mask) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const double v = X[t];
+        const bool on = !has_mask || v != mask;
+        I[t] = on ? 1.0 : 0.0;
+        X[t] = on ? v : 0.0;
+    }
+}
+
+// var_i = cov(x_i, x_i) in the reference's own order and operations (:140-192): sequential sum, mean, sequential sum of squared
+// deviations, no fused multiply-add.  One thread per row.
+__global__ void __launch_bounds__(128)
+k_corr_selfvar(const double* __restrict__ X0, const double* __restrict__ I, int m, double* __restrict__ var) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double* x = X0 + (long long)i * m;
+    const double* w = I + (long long)i * m;
+    double xsum = 0.0, cnt = 0.0;
+    for (int k = 0; k < m; ++k) {
+        if (w[k] != 0.0) {
+            xsum = __dadd_rn(xsum, x[k]);
+            cnt += 1.0;
+        }
+    }
+    double v = 0.0;
+    if (cnt > 3.0) {
+        const double mean = xsum / cnt;
+        double dev = 0.0;
+        for (int k = 0; k < m; ++k) {
+            if (w[k] != 0.0) {
+                const double d = __dsub_rn(x[k], mean);
+                dev = __dadd_rn(dev, __dmul_rn(d, d));
+            }
+        }
+        v = dev / cnt;
+    }
+    var[i] = v;
+}
+
+// tile (ti, tj), tj <= ti: corr for the pairs j < i, written to (i, j) and mirrored to (j, i) like :36-37; the diagonal stays 0.
+// OUT32: scatter into the full float32 map at the kept indices; else dense float64 m x m.
+template <bool OUT32>
+__global__ void __launch_bounds__(256)
+k_corr_finish(const double* __restrict__ N, const double* __restrict__ Sx, const double* __restrict__ Sxy, const double* __restrict__ var,
+              int m, const int* __restrict__ kept, float* __restrict__ out32, long long ld, double* __restrict__ out64, int cov_mode) {
+    const int ti = blockIdx.x, tj = blockIdx.y;
+    if (tj > ti) return;
+    __shared__ double sT[32][33];                                    // Sx tile (tj, ti): holds Sx[j][i]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int j = tj * 32 + r, i = ti * 32 + tx;
+        sT[r][tx] = (i < m && j < m) ? Sx[(long long)j * m + i] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = ti * 32 + r, j = tj * 32 + tx;
+        if (i >= m || j >= m || j > i || (j == i && !cov_mode)) continue;
+        const long long o = (long long)i * m + j;
+        const double cnt = N[o];
+        double cov = 0.0;
+        if (cnt > 3.0) cov = (Sxy[o] - Sx[o] * sT[tx][r] / cnt) / cnt;
+        const double vi = var[i], vj = var[j];
+        double c;
+        if (cov_mode) {
+            c = (i == j) ? vi : cov;                                               // _covarianceMatrix, :83-92 (j <= i)
+        } else {
+            c = (vi == 0.0 || vj == 0.0) ? 0.0 : cov / sqrt(vi * vj);              // :121-128
+            if (c != c) c = 0.0;                                                   // lib/corrMatrix.py:120
+        }
+        if (OUT32) {
+            const int gi = kept[i], gj = kept[j];
+            out32[(long long)gi * ld + gj] = (float)c;
+            out32[(long long)gj * ld + gi] = (float)c;
+        } else {
+            out64[o] = c;
+            out64[(long long)j * m + i] = c;
+        }
+    }
+}
+
 }  // namespace gcx

@@ -217,6 +217,26 @@ class DeviceMap:
                                        C.byref(iters), C.byref(delta)))
         return dict(x=x, iterations=iters.value, delta=delta.value, ms=self.last_run_ms(), pass_bytes=self.pass_bytes()[0])
 
+    def corr(self, maskvalue=0.0, logspace=False, vmin=None, vmax=None):
+        """Pairwise-masked Pearson correlation of the kept block's columns (lib/corrMatrix.py:92-135 +
+        lib/corrMatrixCoreSRC.c) into the output map (download(1)); no-data rows/columns and the diagonal are 0."""
+        check(lib().gcx_corr_run(self._ctx, int(maskvalue is not None), float(0.0 if maskvalue is None else maskvalue), int(bool(logspace)),
+                                 int(vmin is not None), float(np.float32(0.0 if vmin is None else vmin)),
+                                 int(vmax is not None), float(np.float32(0.0 if vmax is None else vmax))))
+
+    def corr_f64(self, in_array, maskvalue=None, covariance=False, out=None):
+        """Correlation (or covariance) matrix of the rows of a square float64 array, float64 result
+        (lib/_corrMatrixCore.pyx:49-146).  Needs no resident map."""
+        a = np.ascontiguousarray(in_array, dtype=np.float64)
+        if a.ndim != 2 or a.shape[0] != a.shape[1]:
+            raise ValueError("in_array must be square")
+        res = out if (out is not None and out.dtype == np.float64 and out.flags.c_contiguous and out.shape == a.shape) else np.empty_like(a)
+        check(lib().gcx_corr_matrix_f64(self._ctx, a.ctypes.data_as(_lib._c_f64p), a.shape[0], int(maskvalue is not None),
+                                        float(0.0 if maskvalue is None else maskvalue), int(bool(covariance)), res.ctypes.data_as(_lib._c_f64p)))
+        if out is not None and res is not out:
+            out[:] = res
+        return res
+
     # ---- elementwise passes ---------------------------------------------------------------------
     def apply_sym(self, s=None, masked_mode=0, in_place=False):
         mn, mx = C.c_float(0), C.c_float(0)

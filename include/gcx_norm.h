@@ -125,6 +125,18 @@ int gcx_downsample(gcx_ctx* ctx, int level, int method, float* host_out, int64_t
 int gcx_transition_run(gcx_ctx* ctx, int in_place, float* minv, float* maxv);
 int gcx_stationary_run(gcx_ctx* ctx, double tol, int max_iter, double* x, int* iterations, double* last_delta);
 
+/* ---- correlation matrix ---------------------------------------------------
+ * gcx_corr_run replaces the numeric part of corrMatrix.calculateCorrMatrixForCCMap (lib/corrMatrix.py:92-135) on the resident
+ * map with the resident mask: entries <= vmin / >= vmax become the mask value, the kept block is transposed and promoted to
+ * float64, optionally log10'd (infinities -> 0), and the pairwise-masked Pearson correlation of its rows
+ * (lib/corrMatrixCoreSRC.c:8-58, 102-192; mask value rounded to float32 like lib/_corrMatrixCore.pyx:88) is scattered into the
+ * output map (no-data rows/columns and the diagonal 0, NaN -> 0).  The pair sums are three float64 GEMMs (cuBLAS, dlopen'ed).
+ * gcx_corr_matrix_f64 replaces _corrMatrixCore.calculateCorrMatrix (lib/_corrMatrixCore.pyx:49-98): in/out m x m float64 on
+ * the host, rows of `in` are the variables; has_mask = 0 is maskvalue=None; covariance != 0 gives calculateCovMatrix instead
+ * (lib/_corrMatrixCore.pyx:100-146, diagonal included).  Works on a context without a resident map. */
+int gcx_corr_run(gcx_ctx* ctx, int has_mask, double maskvalue, int logspace, int has_vmin, float vmin, int has_vmax, float vmax);
+int gcx_corr_matrix_f64(gcx_ctx* ctx, const double* in, int64_t m, int has_mask, double maskvalue, int covariance, double* out);
+
 /* ---- multi-GPU (row-block sharding; one context per rank) ------------------------------------
  * nccl_unique_id: the 128-byte ncclUniqueId from gcx_dist_unique_id on rank 0, broadcast by the host
  * (torch.distributed / any store).  After init, ic/kr/row_stats/diag_stats exchange their n-vectors with

@@ -527,3 +527,56 @@ def stationary_postprocess(sdist, thresh=8):
     result[~np.ma.getmaskarray(mx)] = pts
     out = np.ma.masked_values(result, 0.0).filled(0.0)
     return out / np.sum(out)
+
+
+# --------------------------------------------------------------------------------------------------
+# correlation matrix  lib/corrMatrixCoreSRC.c, lib/_corrMatrixCore.pyx, lib/corrMatrix.py
+# --------------------------------------------------------------------------------------------------
+def _pair_cov(x, y, mask):
+    """lib/corrMatrixCoreSRC.c:132-192: covariance over the entries where both vectors differ from the mask value
+    (all entries when mask is None); 0 unless more than 3 entries are left (:171)."""
+    both = np.ones(x.shape, dtype=bool) if mask is None else (x != mask) & (y != mask)
+    cnt = int(both.sum())
+    if cnt <= 3:
+        return 0.0
+    xs, ys = x[both], y[both]
+    return float(np.sum((xs - xs.sum() / cnt) * (ys - ys.sum() / cnt)) / cnt)
+
+
+def corr_matrix(in_array, maskvalue=None, covariance=False):
+    """lib/_corrMatrixCore.pyx:49-146 around lib/corrMatrixCoreSRC.c:8-100: correlation (pairs j < i, diagonal left 0) or
+    covariance (pairs j <= i) between the rows of a square float64 array; the mask value is rounded to float32 (:88).
+    A row's variance uses its own mask only (:115-116), the covariance the pair's common mask."""
+    X = np.asarray(in_array, dtype=np.float64)
+    m = X.shape[0]
+    mask = None if maskvalue is None else float(np.float32(maskvalue))
+    out = np.zeros((m, m))
+    var = np.array([_pair_cov(X[i], X[i], mask) for i in range(m)])
+    for i in range(m):
+        for j in range(i + 1 if covariance else i):
+            c = _pair_cov(X[i], X[j], mask)
+            if not covariance:
+                c = 0.0 if (var[i] == 0 or var[j] == 0) else c / np.sqrt(var[i] * var[j])
+            out[i, j] = out[j, i] = c
+    return out
+
+
+def corr_for_map(A, bNoData, logspace=False, maskvalue=0.0, vmin=None, vmax=None):
+    """lib/corrMatrix.py:92-135: threshold to the mask value, kept block transposed in float64, optional log10 with
+    infinities set to 0, correlation of the rows, NaN -> 0, scattered into a zero float32 map of the input's shape."""
+    M = np.array(A, dtype=np.float32, copy=True)
+    if vmin is not None:
+        M[M <= vmin] = maskvalue
+    if vmax is not None:
+        M[M >= vmax] = maskvalue
+    keep = ~np.asarray(bNoData, dtype=bool)
+    X = (M[keep, :])[:, keep].T.astype(np.float64, order='C')
+    if logspace:
+        with np.errstate(divide='ignore', invalid='ignore'):
+            X = np.log10(X)
+        X[np.isinf(X)] = 0
+    C = corr_matrix(X, maskvalue=maskvalue)
+    C[np.isnan(C)] = 0
+    out = np.zeros(M.shape, dtype=np.float32)
+    out[np.ix_(keep, keep)] = C
+    return out

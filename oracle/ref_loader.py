@@ -160,3 +160,74 @@ def load_full():
     nz = importlib.import_module("gcMapExplorer.lib.normalizer")
     _loaded["full"] = nz
     return nz
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's C correlation core (lib/corrMatrixCoreSRC.c), compiled as it lies into
+# oracle/_ref/gcMapExplorer/lib/libcorrMatrixCore.so.  Its Cython wrapper does not build against NumPy 2.x, so the
+# stand-in below does what lib/_corrMatrixCore.pyx:49-98 does around the C call: zero-initialised float64 output,
+# mask value rounded to float32 (:88) and passed by pointer, NULL for maskvalue=None.
+# --------------------------------------------------------------------------------------------------
+def have_corr():
+    return os.path.isfile(os.path.join(REF_SO_DIR, "libcorrMatrixCore.so"))
+
+
+class _CorrCore:
+    def __init__(self):
+        import ctypes as C
+        self.C = C
+        self.lib = C.CDLL(os.path.join(REF_SO_DIR, "libcorrMatrixCore.so"))
+        dp = C.POINTER(C.c_double)
+        for name in ("_correlationMatrix", "_covarianceMatrix"):
+            f = getattr(self.lib, name)
+            f.restype = C.c_int
+            f.argtypes = [dp, dp, C.c_int, dp]
+
+    def _run(self, fn, in_array, out, maskvalue):
+        C = self.C
+        a = _np.ascontiguousarray(in_array, dtype=_np.float64)
+        size = a.shape[0]
+        ret = out is None
+        if out is None:
+            out = _np.zeros((size, size), dtype=_np.float64)
+        dp = C.POINTER(C.c_double)
+        mask = None if maskvalue is None else C.byref(C.c_double(float(_np.float32(maskvalue))))
+        # the C code reports progress on stdout (lib/corrMatrixCoreSRC.c:38-42); keep it off the test log
+        fd = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        try:
+            sys.stdout.flush()
+            os.dup2(devnull, 1)
+            fn(a.ctypes.data_as(dp), out.ctypes.data_as(dp), size, mask)
+        finally:
+            os.dup2(fd, 1)
+            os.close(fd)
+            os.close(devnull)
+        return out if ret else None
+
+    def calculateCorrMatrix(self, in_array, out=None, maskvalue=None):
+        return self._run(self.lib._correlationMatrix, in_array, out, maskvalue)
+
+    def calculateCovMatrix(self, in_array, out=None, maskvalue=None):
+        return self._run(self.lib._covarianceMatrix, in_array, out, maskvalue)
+
+
+def load_corr():
+    """The reference's compiled C correlation core behind the wrapper's calling convention."""
+    if "corr" not in _loaded:
+        if not have_corr():
+            raise ImportError("oracle/_ref/libcorrMatrixCore.so is not built: run `make -C oracle ref` where /root/reference exists")
+        _loaded["corr"] = _CorrCore()
+    return _loaded["corr"]
+
+
+def load_corr_module():
+    """The reference's lib/corrMatrix.py (container only), with the stand-in above registered as its `_corrMatrixCore`."""
+    if "corr_module" in _loaded:
+        return _loaded["corr_module"]
+    load_full()
+    core = load_corr()
+    _stub_module("gcMapExplorer.lib._corrMatrixCore", calculateCorrMatrix=core.calculateCorrMatrix, calculateCovMatrix=core.calculateCovMatrix,
+                 calculateCorrelation=None, calculateCovariance=None, _calculateCorrMatrixOLDSLOW=None)
+    _loaded["corr_module"] = importlib.import_module("gcMapExplorer.lib.corrMatrix")
+    return _loaded["corr_module"]

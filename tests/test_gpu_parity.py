@@ -712,3 +712,73 @@ def test_statdist_hdf5_handle_and_errors(gx):
         sdm.calculateTransitionProbabilityMatrix(g["input"])             # bNoData=None fails in the reference too (:90)
     with pytest.raises(NotImplementedError):
         sdm.statDistrByEigenDecompForGCMap("in.gcmap", "out.h5", "100kb")
+
+
+# ---- correlation matrix (lib/corrMatrix.py, lib/corrMatrixCoreSRC.c) ----
+CORR_ATOL32 = 3e-7          # float32 maps of O(1) coefficients vs the reference's output (float64 agreement ~1e-15, then one rounding)
+CORR_ATOL64 = 1e-10
+
+
+@pytest.mark.parametrize("name", golden_names("CORR"))
+def test_corr_matrix_golden(gx, name):
+    from gcmapexplorer_b200 import ccmap as cmp, corrMatrix as cm
+    g = load_golden(name)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(g["input"], 100000, xlabel="chrS", ylabel="chrS")
+    c.bNoData = g["bNoData"]
+    c.make_unreadable()
+    out = cm.calculateCorrMatrixForCCMap(c, **g["kwargs"])
+    assert out.minvalue == -1 and out.maxvalue == 1 and np.array_equal(out.bNoData, g["bNoData"])
+    M = np.array(out.matrix)
+    assert M.dtype == np.float32 and np.abs(M.astype(np.float64) - g["matrix"]).max() < CORR_ATOL32
+    assert np.array_equal(M, M.T) and np.all(np.diag(M) == 0) and np.all(M[g["bNoData"]] == 0) and np.all(M[:, g["bNoData"]] == 0)
+    assert (M != g["matrix"]).mean() < 1e-3                               # all but a few rounding flips are bit-identical
+
+
+@pytest.mark.parametrize("name", golden_names("CORRCORE"))
+def test_corr_core_golden(gx, name):
+    from gcmapexplorer_b200 import corrMatrix as cm
+    g = load_golden(name)
+    mv = g["kwargs"]["maskvalue"]
+    corr = cm.calculateCorrMatrix(g["input"], maskvalue=mv)
+    assert corr.dtype == np.float64 and np.abs(corr - g["corr"]).max() < CORR_ATOL64
+    assert np.array_equal(corr == 0, g["corr"] == 0)                     # constant row, <= 3 common entries, diagonal: the same zeros
+    out = np.full_like(g["input"], 7.0)
+    assert cm.calculateCovMatrix(g["input"], out=out, maskvalue=mv) is None
+    assert np.abs(out - g["cov"]).max() < CORR_ATOL64 * np.abs(g["cov"]).max()
+    assert np.array_equal(np.diag(out), np.diag(g["cov"]))               # variances: the reference's own arithmetic, bit for bit
+
+
+def test_corr_vs_compiled_reference_core(gx):
+    """n = 1500 against the reference's C core compiled as it lies (oracle/_ref), raw counts and log space."""
+    if not rl.have_corr():
+        pytest.skip("oracle/_ref/libcorrMatrixCore.so not built")
+    from gcmapexplorer_b200 import corrMatrix as cm
+    A = onp.synth_map(1500, seed=15, scale=40.0, alpha=1.2, empty_frac=0.02)
+    keep = onp.get_nonzeros_index(A)
+    X = A[keep][:, keep].T.astype(np.float64, order="C")
+    ref = rl.load_corr().calculateCorrMatrix(X, maskvalue=0.0)
+    got = cm.calculateCorrMatrix(X, maskvalue=0.0)
+    assert np.abs(got - ref).max() < CORR_ATOL64
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.set_mask(keep)
+        dm.corr(0.0, logspace=True)
+        M = dm.download(1)
+    with np.errstate(divide="ignore"):
+        L = np.log10(X)
+    L[np.isinf(L)] = 0
+    refl = rl.load_corr().calculateCorrMatrix(L, maskvalue=0.0)
+    refl[np.isnan(refl)] = 0
+    assert np.abs(M[np.ix_(keep, keep)].astype(np.float64) - refl).max() < CORR_ATOL32 and np.all(M[~keep] == 0)
+
+
+def test_corr_errors(gx):
+    from gcmapexplorer_b200 import ccmap as cmp, corrMatrix as cm
+    A = onp.synth_map(60, seed=2)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(A, 100000)
+    assert cm.calculateCorrMatrixForCCMap(c) is None                    # no bNoData: warning + None, like the reference (:145-151)
+    with pytest.raises(ValueError):
+        cm.calculateCorrMatrix(np.zeros((4, 5)))
+    with pytest.raises(NotImplementedError):
+        cm.calculateCorrMatrixForGCMaps("in.gcmap", "out.gcmap")

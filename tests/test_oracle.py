@@ -173,3 +173,23 @@ def test_stationary_replaces_zeros_of_the_kept_block():
     e = onp.stationary_eig(A, b)
     p, _ = onp.stationary_power(A, b)
     assert (e > 0).all() and abs(e.sum() - 1) < 1e-12 and np.max(np.abs(p - e) / e) < 1e-9
+
+
+# ---- correlation matrix (lib/corrMatrix.py, lib/corrMatrixCoreSRC.c) ----
+@pytest.mark.parametrize("name", golden_names("CORR"))
+def test_corr_golden(name):
+    g = load_golden(name)
+    exp = onp.corr_for_map(g["input"], g["bNoData"], **g["kwargs"])
+    assert exp.dtype == np.float32 and np.abs(exp.astype(np.float64) - g["matrix"]).max() < 2e-7       # float32 rounding of ~1e-16 differences
+    assert g["minvalue"] == -1 and g["maxvalue"] == 1
+    assert np.all(g["matrix"][g["bNoData"]] == 0) and np.all(np.diag(g["matrix"]) == 0)
+
+
+@pytest.mark.parametrize("name", golden_names("CORRCORE"))
+def test_corr_core_golden(name):
+    g = load_golden(name)
+    mv = g["kwargs"]["maskvalue"]
+    assert np.abs(onp.corr_matrix(g["input"], mv) - g["corr"]).max() < 1e-12
+    cov = onp.corr_matrix(g["input"], mv, covariance=True)
+    assert np.abs(cov - g["cov"]).max() < 1e-12 * np.abs(g["cov"]).max()
+    assert np.all(g["corr"][7] == 0) and np.all(np.diag(g["corr"]) == 0)       # constant row / untouched diagonal
