@@ -537,6 +537,66 @@ def cpu_statdist_sample(n, budget_s):
                       "extrapolated -- a 24,926^2 float64 eigendecomposition does not finish in a bench run" % (m, t_tp, t_eig)}
 
 
+def run_corr(args):
+    """SURVEY.md 8f row N4 at chr1 @ 10 kb: pairwise-masked Pearson correlation matrix of the synthetic map (lib/corrMatrix.py:92-135,
+    lib/corrMatrixCoreSRC.c).  The pair sums are three float64 GEMMs (cuBLAS); the bound is the fp64 tensor rate, not HBM."""
+    from gcmapexplorer_b200 import device as gx
+    n = args.n or 24926
+    dm = gx.DeviceMap(n)
+    dm.synth(seed=args.seed, scale=200.0, alpha=1.0, empty_frac=0.01)
+    rs, zc = dm.row_stats()
+    keep = rs != 0
+    m = int(keep.sum())
+    dm.set_mask(keep)
+    for _ in range(max(1, args.warmup)):
+        dm.corr(0.0)
+    clocks = ClockSampler(0)
+    clocks.start()
+    ts = []
+    l0 = dm.launch_count()
+    for _ in range(args.steps):
+        dm.timer_start()
+        dm.corr(0.0)
+        ts.append(dm.timer_stop())
+    launches = dm.launch_count() - l0
+    ck = clocks.stop()
+    t = float(np.median(ts)) * 1e-3
+    flops = 3 * 2.0 * m ** 3
+    FP64_NOMINAL_TFLOPS = 40.0            # B200 data sheet (dense fp64); MEASURED_PEAKS.json carries no fp64 figure
+    line = {"metric": "correlation matrix time (s), chr1 @ 10 kb", "value": round(t, 4), "unit": "s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(1, args.warmup), "ms_per_step": round(t * 1e3, 2), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (device-generated)",
+            "config": {"workload": "synthetic chr1 @ 10 kb (n=%d, %d bins with data): correlation matrix" % (n, m), "n": n, "kept": m},
+            "roofline": {"bound": "tensor", "kernel": "cublasDgemm x3 (N = I I^T, Sx = X0 I^T, Sxy = X0 X0^T)", "achieved": round(flops / t / 1e12, 2),
+                         "peak": FP64_NOMINAL_TFLOPS, "peak_source": "nominal (no measured fp64 peak on file)", "unit": "TFLOP/s",
+                         "frac": round(flops / t / 1e12 / FP64_NOMINAL_TFLOPS, 4), "traffic": None,
+                         "note": "achieved = 6 m^3 flops over the WHOLE call (prep, three GEMMs, variances, scatter), a lower bound for the GEMMs"},
+            "gpu_launches": int(launches), "clocks": ck}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_corr_sample(n, m)
+    print(json.dumps(line))
+
+
+def cpu_corr_sample(n, m):
+    """The reference's C core (OpenMP, all host threads), compiled as it lies into oracle/_ref, on an 1200-bin map; scaled by (m/1200)^3."""
+    from oracle import oracle_np as onp
+    from oracle import ref_loader as rl
+    ms = 1200
+    A = onp.synth_map(ms, seed=5, scale=200.0)
+    keep = onp.get_nonzeros_index(A)
+    X = A[keep][:, keep].T.astype(np.float64, order="C")
+    if rl.have_corr():
+        kind, fn = "reference", (lambda: rl.load_corr().calculateCorrMatrix(X, maskvalue=0.0))
+    else:
+        kind, fn = "port", (lambda: onp.corr_matrix(X[:300, :300], maskvalue=0.0))
+    t0 = time.perf_counter()
+    fn()
+    dt = time.perf_counter() - t0
+    mk = X.shape[0] if kind == "reference" else 300
+    return {"value": round(dt * (m / mk) ** 3, 1), "unit": "s", "cores": os.cpu_count(), "kind": kind,
+            "sample": "%d bins: %.2f s, scaled by (m/%d)^3 -- extrapolated" % (mk, dt, mk)}
+
+
 def psutil_avail():
     try:
         import psutil
@@ -691,7 +751,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "chr1_10kb", "chr1_5kb_kr", "chr1_1kb", "wg_25kb_mcfs", "chr21_100kb", "chr1_10kb_statdist"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "chr1_10kb", "chr1_5kb_kr", "chr1_1kb", "wg_25kb_mcfs", "chr21_100kb", "chr1_10kb_statdist", "chr1_10kb_corr"])
     ap.add_argument("--mcfs-stats", default="median", choices=["median", "mean"])
     ap.add_argument("--mcfs-threads", type=int, default=6, help="host threads driving the 24 independent maps of wg_25kb_mcfs")
     ap.add_argument("--n", type=int, default=0, help="override the number of bins (quick checks)")
@@ -713,6 +773,8 @@ def main():
         run_chr21(args)
     elif args.workload == "chr1_10kb_statdist":
         run_statdist(args)
+    elif args.workload == "chr1_10kb_corr":
+        run_corr(args)
     else:
         run_b200(args)
 
