@@ -561,16 +561,20 @@ def run_corr(args):
     launches = dm.launch_count() - l0
     ck = clocks.stop()
     t = float(np.median(ts)) * 1e-3
-    flops = 3 * 2.0 * m ** 3
+    variant = int(os.environ.get("GCX_CORR_VARIANT", "1"))
+    # float64 flops: Sx = X0 I^T (2 m^3) + Sxy as a SYRK (m^3); the counts run on the bf16 tensor cores (2 m^3 more, not counted here).
+    # GCX_CORR_VARIANT=0: three float64 GEMMs (6 m^3).
+    flops = (3.0 if variant == 1 else 6.0) * m ** 3
     FP64_NOMINAL_TFLOPS = 40.0            # B200 data sheet (dense fp64); MEASURED_PEAKS.json carries no fp64 figure
     line = {"metric": "correlation matrix time (s), chr1 @ 10 kb", "value": round(t, 4), "unit": "s", "n_gpus": 1, "steps": args.steps,
             "warmup": max(1, args.warmup), "ms_per_step": round(t * 1e3, 2), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (device-generated)",
             "config": {"workload": "synthetic chr1 @ 10 kb (n=%d, %d bins with data): correlation matrix" % (n, m), "n": n, "kept": m},
-            "roofline": {"bound": "tensor", "kernel": "cublasDgemm x3 (N = I I^T, Sx = X0 I^T, Sxy = X0 X0^T)", "achieved": round(flops / t / 1e12, 2),
+            "roofline": {"bound": "tensor", "kernel": ("cublasGemmEx bf16 (N = I I^T) + cublasDgemm (Sx = X0 I^T) + cublasDsyrk (Sxy = X0 X0^T)" if variant == 1
+                                                    else "cublasDgemm x3 (N = I I^T, Sx = X0 I^T, Sxy = X0 X0^T)"), "achieved": round(flops / t / 1e12, 2),
                          "peak": FP64_NOMINAL_TFLOPS, "peak_source": "nominal (no measured fp64 peak on file)", "unit": "TFLOP/s",
                          "frac": round(flops / t / 1e12 / FP64_NOMINAL_TFLOPS, 4), "traffic": None,
-                         "note": "achieved = 6 m^3 flops over the WHOLE call (prep, three GEMMs, variances, scatter), a lower bound for the GEMMs"},
+                         "note": "achieved = float64 flops of the products over the WHOLE call (prep, products, variances, scatter): a lower bound for the GEMMs"},
             "gpu_launches": int(launches), "clocks": ck}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_corr_sample(n, m)

@@ -91,6 +91,9 @@ struct CublasApi {
     int (*Destroy)(cublasHandle_t) = nullptr;
     int (*SetStream)(cublasHandle_t, cudaStream_t) = nullptr;
     int (*Dgemm)(cublasHandle_t, int, int, int, int, int, const double*, const double*, int, const double*, int, const double*, double*, int) = nullptr;
+    int (*Dsyrk)(cublasHandle_t, int, int, int, int, const double*, const double*, int, const double*, double*, int) = nullptr;
+    int (*GemmEx)(cublasHandle_t, int, int, int, int, int, const void*, const void*, int, int, const void*, int, int, const void*, void*, int, int,
+                  int, int) = nullptr;
 };
 static CublasApi g_cublas;
 static int cublas_load() {
@@ -105,7 +108,10 @@ static int cublas_load() {
     *(void**)(&g_cublas.Destroy) = dlsym(g_cublas.h, "cublasDestroy_v2");
     *(void**)(&g_cublas.SetStream) = dlsym(g_cublas.h, "cublasSetStream_v2");
     *(void**)(&g_cublas.Dgemm) = dlsym(g_cublas.h, "cublasDgemm_v2");
-    if (!g_cublas.Create || !g_cublas.Destroy || !g_cublas.SetStream || !g_cublas.Dgemm) return fail("libcublas: missing symbol");
+    *(void**)(&g_cublas.Dsyrk) = dlsym(g_cublas.h, "cublasDsyrk_v2");
+    *(void**)(&g_cublas.GemmEx) = dlsym(g_cublas.h, "cublasGemmEx");
+    if (!g_cublas.Create || !g_cublas.Destroy || !g_cublas.SetStream || !g_cublas.Dgemm || !g_cublas.Dsyrk || !g_cublas.GemmEx)
+        return fail("libcublas: missing symbol");
     return 0;
 }
 #define BK(call)                                                                                  \
@@ -167,6 +173,7 @@ struct gcx_ctx {
     double* part = nullptr;      // per-CTA partials of the fused IC pass (3 x grid)
     int ic_fused = 1;            // 1: one cooperative launch per IC pass (k_ic_pass); 0: k_matvec + k_ic_epilogue
     int ic_grid = 0, ic_grid_tma = 0;
+    int corr_variant = 1;   // correlation: 1 = bf16 tensor-core counts + DSYRK + DGEMM, 0 = three DGEMMs (GCX_CORR_VARIANT / option "corr_variant")
     int sd_variant = 1;   // stationary distribution: 1 = TMA-bulk transposed product, 0 = LDG (GCX_SD_VARIANT / option "sd_variant")
     int mv_variant = 7;   // TMA-bulk, R=4 rows per band, 6 stages, 2 CTAs/SM: best of profiles/r01_matvec_variants.txt
     // states
@@ -327,6 +334,7 @@ static int ctx_init(gcx_ctx* c, int device) {
     const char* v = getenv("GCX_MATVEC_VARIANT");
     if (v) c->mv_variant = atoi(v);
     if (const char* sv = getenv("GCX_SD_VARIANT")) c->sd_variant = atoi(sv);
+    if (const char* cv = getenv("GCX_CORR_VARIANT")) c->corr_variant = atoi(cv);
     const char* sy = getenv("GCX_SYM");
     if (sy) c->sym_enable = atoi(sy);
     if (c->ic_fused != 2) c->sym_enable = c->sym_enable && (c->ic_fused != 1);   // the fused LDG pass has no symmetric twin
@@ -763,6 +771,7 @@ extern "C" int gcx_set_option(gcx_ctx* c, const char* key, double value) {
     }
     else if (k == "matvec_variant") c->mv_variant = (int)value;
     else if (k == "sd_variant") c->sd_variant = (int)value;
+    else if (k == "corr_variant") c->corr_variant = (int)value;
     else return fail("gcx_set_option: unknown key '%s'", key);
     return 0;
 }
@@ -1711,34 +1720,54 @@ static int gemm_nt(gcx_ctx* c, int m, const double* L, const double* R, double* 
 
 struct CorrBufs {
     double *X0, *I, *N, *Sx, *Sxy, *var;
+    float* Nf;               // counts from the bf16 tensor-core product (corr_variant 1)
+    unsigned short* Ib;      // bf16 copy of the indicator
     int* kept;
 };
 
 static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
     const size_t mm = align256(sizeof(double) * (size_t)m * m), bv = align256(sizeof(double) * (size_t)m), bi = align256(sizeof(int) * (size_t)m);
+    const size_t need = 5 * mm + mm / 4 + bv + bi;           // N (8 B) doubles as Nf (4 B) in variant 1; + the 2-byte indicator
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    if (5 * mm + bv + bi > free_b + c->scratch_bytes)
-        return fail("correlation of %lld bins needs %.1f GB of float64 workspace, %.1f GB are free", (long long)m, (5 * mm + bv + bi) / 1e9,
-                    (free_b + c->scratch_bytes) / 1e9);
-    CKR(ensure_scratch(c, 5 * mm + bv + bi));
+    if (need > free_b + c->scratch_bytes)
+        return fail("correlation of %lld bins needs %.1f GB of workspace, %.1f GB are free", (long long)m, need / 1e9, (free_b + c->scratch_bytes) / 1e9);
+    CKR(ensure_scratch(c, need));
     char* p = (char*)c->scratch;
     B->X0 = (double*)p; p += mm;
     B->I = (double*)p; p += mm;
-    B->N = (double*)p; p += mm;
+    B->N = (double*)p; B->Nf = (float*)p; p += mm;
     B->Sx = (double*)p; p += mm;
     B->Sxy = (double*)p; p += mm;
+    B->Ib = (unsigned short*)p; p += mm / 4;
     B->var = (double*)p; p += bv;
     B->kept = (int*)p;
     return 0;
 }
 
-// the three products and the row variances, from X0 / I
-static int corr_core(gcx_ctx* c, int m, const CorrBufs& B) {
+// the three products and the row variances, from X0 / I.  corr_variant 1 (default): counts on the bf16 tensor cores + SYRK for
+// the symmetric sum; 0: three float64 GEMMs.  Returns which count buffer the epilogue must read.
+static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, bool* counts_f32) {
     CKR(blas_ready(c));
-    CKR(gemm_nt(c, m, B.I, B.I, B.N));
-    CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
-    CKR(gemm_nt(c, m, B.X0, B.X0, B.Sxy));
+    *counts_f32 = c->corr_variant == 1;
+    if (c->corr_variant == 1) {
+        const float one = 1.f, zero = 0.f;
+        const double done = 1.0, dzero = 0.0;
+        {
+            ProfScope ps(c, 7);      // row-major N = I I^T: column-major (I_cm)^T I_cm, bf16 x bf16 -> float32
+            BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, m, m, m, &one, B.Ib, 14 /* CUDA_R_16BF */, m, B.Ib, 14, m, &zero, B.Nf,
+                               0 /* CUDA_R_32F */, m, 68 /* CUBLAS_COMPUTE_32F */, -1 /* CUBLAS_GEMM_DEFAULT */));
+        }
+        CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
+        {
+            ProfScope ps(c, 7);      // row-major lower triangle of X0 X0^T = column-major upper triangle of (X_cm)^T X_cm
+            BK(g_cublas.Dsyrk(c->blas, 1 /* CUBLAS_FILL_MODE_UPPER */, CUBLAS_OP_T_, m, m, &done, B.X0, m, &dzero, B.Sxy, m));
+        }
+    } else {
+        CKR(gemm_nt(c, m, B.I, B.I, B.N));
+        CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
+        CKR(gemm_nt(c, m, B.X0, B.X0, B.Sxy));
+    }
     k_corr_selfvar<<<(m + 127) / 128, 128, 0, c->stream>>>(B.X0, B.I, m, B.var);
     CK(cudaGetLastError());
     c->launches += 1;
@@ -1770,15 +1799,16 @@ extern "C" int gcx_corr_run(gcx_ctx* c, int has_mask, double maskvalue, int logs
     P.vmin = vmin; P.vmax = vmax;
     {
         ProfScope ps(c, 7);
-        k_corr_prep<<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(c->A, c->ld, B.kept, m, P, B.X0, B.I);
+        k_corr_prep<<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(c->A, c->ld, B.kept, m, P, B.X0, B.I, B.Ib);
     }
     CK(cudaGetLastError());
-    CKR(corr_core(c, m, B));
+    bool nf = false;
+    CKR(corr_core(c, m, B, &nf));
     CKR(ensure_out(c));
     CK(cudaMemsetAsync(c->Out, 0, sizeof(float) * (size_t)c->nloc * c->ld, c->stream));
     {
         ProfScope ps(c, 7);
-        k_corr_finish<true><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(B.N, B.Sx, B.Sxy, B.var, m, B.kept, c->Out, c->ld, nullptr, 0);
+        k_corr_finish<true><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(nf ? nullptr : B.N, nf ? B.Nf : nullptr, B.Sx, B.Sxy, B.var, m, B.kept, c->Out, c->ld, nullptr, 0);
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
@@ -1795,13 +1825,14 @@ extern "C" int gcx_corr_matrix_f64(gcx_ctx* c, const double* in, int64_t m64, in
     const size_t bytes = sizeof(double) * (size_t)m * m;
     CK(cudaMemcpyAsync(B.X0, in, bytes, cudaMemcpyHostToDevice, c->stream));
     const float maskf = (float)maskvalue;            // lib/_corrMatrixCore.pyx:88
-    k_corr_prep_f64<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, B.I, (long long)m * m, has_mask, (double)maskf);
+    k_corr_prep_f64<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, B.I, B.Ib, (long long)m * m, has_mask, (double)maskf);
     CK(cudaGetLastError());
     c->launches += 1;
-    CKR(corr_core(c, m, B));
+    bool nf = false;
+    CKR(corr_core(c, m, B, &nf));
     // the result overwrites the indicator buffer (no longer needed once the products are done)
     CK(cudaMemsetAsync(B.I, 0, bytes, c->stream));
-    k_corr_finish<false><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(B.N, B.Sx, B.Sxy, B.var, m, nullptr, nullptr, 0, B.I, covariance);
+    k_corr_finish<false><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(nf ? nullptr : B.N, nf ? B.Nf : nullptr, B.Sx, B.Sxy, B.var, m, nullptr, nullptr, 0, B.I, covariance);
     CK(cudaGetLastError());
     c->launches += 1;
     CK(cudaMemcpyAsync(out, B.I, bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -2479,8 +2479,10 @@ k_sd_fold_t(const SdState* __restrict__ st, int nv, int n, const uint8_t* __rest
 //   corr_ij = cov_ij / sqrt(var_i var_j),   var_i = cov(x_i, x_i) with x_i's OWN mask only (:115-116) -- so |corr| can exceed 1.
 // With X0 = x where unmasked else 0 and I = the 0/1 indicator, the pair sums are three GEMM-shaped products,
 //   N = I I^T,  Sx = X0 I^T (sum of x_i over the common entries; sum of y is its transpose),  Sxy = X0 X0^T,
-// and cov_ij = (Sxy_ij - Sx_ij Sx_ji / N_ij) / N_ij.  The products run as float64 library GEMMs (cuBLAS DGEMM: plain GEMMs,
-// no fusion to gain); everything around them is below.  var_i repeats the reference's sequential two-pass arithmetic
+// and cov_ij = (Sxy_ij - Sx_ij Sx_ji / N_ij) / N_ij.  The products are plain library GEMMs (cuBLAS, nothing to fuse): the counts N
+// from the bf16 copy of I with float32 accumulation on the tensor cores (0/1 inputs, integer sums below 2^24: exact), Sx as a
+// float64 GEMM, the symmetric Sxy as a float64 SYRK (half the work; only the triangle the epilogue reads).  Everything around
+// them is below.  var_i repeats the reference's sequential two-pass arithmetic
 // (no FMA contraction), so the `var == 0` tests of :121 decide exactly as the reference does.
 // ---------------------------------------------------------------------------------------------------
 struct CorrPrep {
@@ -2505,7 +2507,7 @@ __device__ __forceinline__ void corr_value(float a, const CorrPrep& P, double& x
 // X[i][k] = f(A[kept[k]][kept[i]]) -- compaction + transpose (:108-109) through a 32 x 32 shared tile; writes X0 and I
 __global__ void __launch_bounds__(256)
 k_corr_prep(const float* __restrict__ A, long long ld, const int* __restrict__ kept, int m, CorrPrep P, double* __restrict__ X0,
-            double* __restrict__ I) {
+            double* __restrict__ I, unsigned short* __restrict__ Ib) {
     __shared__ float tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
     const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
@@ -2523,17 +2525,19 @@ k_corr_prep(const float* __restrict__ A, long long ld, const int* __restrict__ k
             corr_value(tile[tx][r], P, x0, ind);
             X0[(long long)i * m + k] = x0;
             I[(long long)i * m + k] = ind;
+            Ib[(long long)i * m + k] = ind != 0.0 ? (unsigned short)0x3F80 : (unsigned short)0;      // bf16 1.0 / 0.0
         }
     }
 }
 
 // host float64 input (inner seam, lib/_corrMatrixCore.pyx:49): split into X0 and I in place (X holds the raw rows)
 __global__ void __launch_bounds__(256)
-k_corr_prep_f64(double* __restrict__ X, double* __restrict__ I, long long total, int has_mask, double mask) {
+k_corr_prep_f64(double* __restrict__ X, double* __restrict__ I, unsigned short* __restrict__ Ib, long long total, int has_mask, double mask) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const double v = X[t];
         const bool on = !has_mask || v != mask;
         I[t] = on ? 1.0 : 0.0;
+        Ib[t] = on ? (unsigned short)0x3F80 : (unsigned short)0;
         X[t] = on ? v : 0.0;
     }
 }
@@ -2572,7 +2576,8 @@ k_corr_selfvar(const double* __restrict__ X0, const double* __restrict__ I, int 
 // OUT32: scatter into the full float32 map at the kept indices; else dense float64 m x m.
 template <bool OUT32>
 __global__ void __launch_bounds__(256)
-k_corr_finish(const double* __restrict__ N, const double* __restrict__ Sx, const double* __restrict__ Sxy, const double* __restrict__ var,
+k_corr_finish(const double* __restrict__ N, const float* __restrict__ Nf, const double* __restrict__ Sx, const double* __restrict__ Sxy,
+              const double* __restrict__ var,
               int m, const int* __restrict__ kept, float* __restrict__ out32, long long ld, double* __restrict__ out64, int cov_mode) {
     const int ti = blockIdx.x, tj = blockIdx.y;
     if (tj > ti) return;
@@ -2587,7 +2592,7 @@ k_corr_finish(const double* __restrict__ N, const double* __restrict__ Sx, const
         const int i = ti * 32 + r, j = tj * 32 + tx;
         if (i >= m || j >= m || j > i || (j == i && !cov_mode)) continue;
         const long long o = (long long)i * m + j;
-        const double cnt = N[o];
+        const double cnt = Nf ? (double)Nf[o] : N[o];        // float counts are exact: integers below 2^24
         double cov = 0.0;
         if (cnt > 3.0) cov = (Sxy[o] - Sx[o] * sT[tx][r] / cnt) / cnt;
         const double vi = var[i], vj = var[j];

@@ -130,7 +130,8 @@ int gcx_stationary_run(gcx_ctx* ctx, double tol, int max_iter, double* x, int* i
  * map with the resident mask: entries <= vmin / >= vmax become the mask value, the kept block is transposed and promoted to
  * float64, optionally log10'd (infinities -> 0), and the pairwise-masked Pearson correlation of its rows
  * (lib/corrMatrixCoreSRC.c:8-58, 102-192; mask value rounded to float32 like lib/_corrMatrixCore.pyx:88) is scattered into the
- * output map (no-data rows/columns and the diagonal 0, NaN -> 0).  The pair sums are three float64 GEMMs (cuBLAS, dlopen'ed).
+ * output map (no-data rows/columns and the diagonal 0, NaN -> 0).  The pair sums are three library GEMMs (cuBLAS, dlopen'ed):
+ * exact counts from a bf16 indicator on the tensor cores, a float64 GEMM and a float64 SYRK.
  * gcx_corr_matrix_f64 replaces _corrMatrixCore.calculateCorrMatrix (lib/_corrMatrixCore.pyx:49-98): in/out m x m float64 on
  * the host, rows of `in` are the variables; has_mask = 0 is maskvalue=None; covariance != 0 gives calculateCovMatrix instead
  * (lib/_corrMatrixCore.pyx:100-146, diagonal included).  Works on a context without a resident map. */
@@ -149,7 +150,8 @@ int gcx_corr_matrix_f64(gcx_ctx* ctx, const double* in, int64_t m, int has_mask,
  *                             allreduce instead of allgather (set it on every rank, before gcx_map_create)
  *   "sym_blocks"         0/1  sharded upper-triangle pass: deal the off-diagonal blocks out in the circulant pattern (default 1)
  *   "matvec_variant"     kernel variant for sweeps
- *   "sd_variant"         stationary distribution: 1 TMA-bulk transposed product (default), 0 per-thread loads */
+ *   "sd_variant"         stationary distribution: 1 TMA-bulk transposed product (default), 0 per-thread loads
+ *   "corr_variant"       correlation: 1 counts on the bf16 tensor cores + DSYRK + DGEMM (default), 0 three DGEMMs */
 int gcx_set_option(gcx_ctx* ctx, const char* key, double value);
 /* The aligned row partition (cuts at rank*n/world rounded to 1024 rows).  With it, "assume_symmetric" and
  * "exchange_allreduce", a sharded map runs the upper-triangle pass with the off-diagonal blocks dealt out in a circulant

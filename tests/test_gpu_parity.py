@@ -760,16 +760,20 @@ def test_corr_vs_compiled_reference_core(gx):
     ref = rl.load_corr().calculateCorrMatrix(X, maskvalue=0.0)
     got = cm.calculateCorrMatrix(X, maskvalue=0.0)
     assert np.abs(got - ref).max() < CORR_ATOL64
-    with gx.DeviceMap.from_host(A) as dm:
-        dm.set_mask(keep)
-        dm.corr(0.0, logspace=True)
-        M = dm.download(1)
     with np.errstate(divide="ignore"):
         L = np.log10(X)
     L[np.isinf(L)] = 0
     refl = rl.load_corr().calculateCorrMatrix(L, maskvalue=0.0)
     refl[np.isnan(refl)] = 0
-    assert np.abs(M[np.ix_(keep, keep)].astype(np.float64) - refl).max() < CORR_ATOL32 and np.all(M[~keep] == 0)
+    for variant in (1, 0):        # counts on the bf16 tensor cores + DSYRK + DGEMM (default) / three DGEMMs
+        with gx.DeviceMap.from_host(A) as dm:
+            dm.set_option("corr_variant", variant)
+            dm.set_mask(keep)
+            dm.corr(0.0, logspace=True)
+            M = dm.download(1)
+            assert np.abs(M[np.ix_(keep, keep)].astype(np.float64) - refl).max() < CORR_ATOL32 and np.all(M[~keep] == 0)
+            assert np.abs(dm.corr_f64(X, 0.0) - ref).max() < CORR_ATOL64
+            assert np.array_equal(M, M.T)
 
 
 def test_corr_errors(gx):
