@@ -1721,13 +1721,17 @@ static int gemm_nt(gcx_ctx* c, int m, const double* L, const double* R, double* 
 struct CorrBufs {
     double *X0, *I, *N, *Sx, *Sxy, *var;
     float* Nf;               // counts from the bf16 tensor-core product (corr_variant 1)
-    unsigned short* Ib;      // bf16 copy of the indicator
+    unsigned short* Ib;      // bf16 copy of the indicator as an mb x mb matrix, mb = m rounded up to 64 and the pad zero, so that every
+    int mb;                  // dimension and pitch of the counts product is aligned for cuBLAS' tensor-core kernels; Nf has pitch mb too
     int* kept;
 };
 
 static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
     const size_t mm = align256(sizeof(double) * (size_t)m * m), bv = align256(sizeof(double) * (size_t)m), bi = align256(sizeof(int) * (size_t)m);
-    const size_t need = 5 * mm + mm / 4 + bv + bi;           // N (8 B) doubles as Nf (4 B) in variant 1; + the 2-byte indicator
+    const int64_t mb = round_up(m, 64);
+    const size_t bb = align256(sizeof(unsigned short) * (size_t)mb * mb);
+    const size_t nn = std::max(mm, align256(sizeof(float) * (size_t)mb * mb));      // N (float64 m x m) doubles as Nf (float32 mb x mb)
+    const size_t need = 4 * mm + nn + bb + bv + bi;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     if (need > free_b + c->scratch_bytes)
@@ -1736,10 +1740,12 @@ static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
     char* p = (char*)c->scratch;
     B->X0 = (double*)p; p += mm;
     B->I = (double*)p; p += mm;
-    B->N = (double*)p; B->Nf = (float*)p; p += mm;
+    B->N = (double*)p; B->Nf = (float*)p; p += nn;
     B->Sx = (double*)p; p += mm;
     B->Sxy = (double*)p; p += mm;
-    B->Ib = (unsigned short*)p; p += mm / 4;
+    B->Ib = (unsigned short*)p; p += bb;
+    B->mb = (int)mb;
+    CK(cudaMemsetAsync(B->Ib, 0, bb, c->stream));
     B->var = (double*)p; p += bv;
     B->kept = (int*)p;
     return 0;
@@ -1755,8 +1761,8 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, bool* counts_f32) {
         const double done = 1.0, dzero = 0.0;
         {
             ProfScope ps(c, 7);      // row-major N = I I^T: column-major (I_cm)^T I_cm, bf16 x bf16 -> float32
-            BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, m, m, m, &one, B.Ib, 14 /* CUDA_R_16BF */, m, B.Ib, 14, m, &zero, B.Nf,
-                               0 /* CUDA_R_32F */, m, 68 /* CUBLAS_COMPUTE_32F */, -1 /* CUBLAS_GEMM_DEFAULT */));
+            BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &one, B.Ib, 14 /* CUDA_R_16BF */, B.mb, B.Ib, 14, B.mb, &zero,
+                               B.Nf, 0 /* CUDA_R_32F */, B.mb, 68 /* CUBLAS_COMPUTE_32F */, -1 /* CUBLAS_GEMM_DEFAULT */));
         }
         CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
         {
@@ -1799,7 +1805,7 @@ extern "C" int gcx_corr_run(gcx_ctx* c, int has_mask, double maskvalue, int logs
     P.vmin = vmin; P.vmax = vmax;
     {
         ProfScope ps(c, 7);
-        k_corr_prep<<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(c->A, c->ld, B.kept, m, P, B.X0, B.I, B.Ib);
+        k_corr_prep<<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(c->A, c->ld, B.kept, m, P, B.X0, B.I, B.Ib, B.mb);
     }
     CK(cudaGetLastError());
     bool nf = false;
@@ -1808,7 +1814,7 @@ extern "C" int gcx_corr_run(gcx_ctx* c, int has_mask, double maskvalue, int logs
     CK(cudaMemsetAsync(c->Out, 0, sizeof(float) * (size_t)c->nloc * c->ld, c->stream));
     {
         ProfScope ps(c, 7);
-        k_corr_finish<true><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(nf ? nullptr : B.N, nf ? B.Nf : nullptr, B.Sx, B.Sxy, B.var, m, B.kept, c->Out, c->ld, nullptr, 0);
+        k_corr_finish<true><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(nf ? nullptr : B.N, nf ? B.Nf : nullptr, B.Sx, B.Sxy, B.mb, B.var, m, B.kept, c->Out, c->ld, nullptr, 0);
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
@@ -1825,14 +1831,14 @@ extern "C" int gcx_corr_matrix_f64(gcx_ctx* c, const double* in, int64_t m64, in
     const size_t bytes = sizeof(double) * (size_t)m * m;
     CK(cudaMemcpyAsync(B.X0, in, bytes, cudaMemcpyHostToDevice, c->stream));
     const float maskf = (float)maskvalue;            // lib/_corrMatrixCore.pyx:88
-    k_corr_prep_f64<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, B.I, B.Ib, (long long)m * m, has_mask, (double)maskf);
+    k_corr_prep_f64<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, B.I, B.Ib, m, B.mb, has_mask, (double)maskf);
     CK(cudaGetLastError());
     c->launches += 1;
     bool nf = false;
     CKR(corr_core(c, m, B, &nf));
     // the result overwrites the indicator buffer (no longer needed once the products are done)
     CK(cudaMemsetAsync(B.I, 0, bytes, c->stream));
-    k_corr_finish<false><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(nf ? nullptr : B.N, nf ? B.Nf : nullptr, B.Sx, B.Sxy, B.var, m, nullptr, nullptr, 0, B.I, covariance);
+    k_corr_finish<false><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(nf ? nullptr : B.N, nf ? B.Nf : nullptr, B.Sx, B.Sxy, B.mb, B.var, m, nullptr, nullptr, 0, B.I, covariance);
     CK(cudaGetLastError());
     c->launches += 1;
     CK(cudaMemcpyAsync(out, B.I, bytes, cudaMemcpyDeviceToHost, c->stream));

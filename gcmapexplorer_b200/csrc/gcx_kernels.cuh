@@ -2507,7 +2507,7 @@ __device__ __forceinline__ void corr_value(float a, const CorrPrep& P, double& x
 // X[i][k] = f(A[kept[k]][kept[i]]) -- compaction + transpose (:108-109) through a 32 x 32 shared tile; writes X0 and I
 __global__ void __launch_bounds__(256)
 k_corr_prep(const float* __restrict__ A, long long ld, const int* __restrict__ kept, int m, CorrPrep P, double* __restrict__ X0,
-            double* __restrict__ I, unsigned short* __restrict__ Ib) {
+            double* __restrict__ I, unsigned short* __restrict__ Ib, int mb) {
     __shared__ float tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
     const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
@@ -2525,19 +2525,20 @@ k_corr_prep(const float* __restrict__ A, long long ld, const int* __restrict__ k
             corr_value(tile[tx][r], P, x0, ind);
             X0[(long long)i * m + k] = x0;
             I[(long long)i * m + k] = ind;
-            Ib[(long long)i * m + k] = ind != 0.0 ? (unsigned short)0x3F80 : (unsigned short)0;      // bf16 1.0 / 0.0
+            Ib[(long long)i * mb + k] = ind != 0.0 ? (unsigned short)0x3F80 : (unsigned short)0;     // bf16 1.0 / 0.0, row pitch mb
         }
     }
 }
 
 // host float64 input (inner seam, lib/_corrMatrixCore.pyx:49): split into X0 and I in place (X holds the raw rows)
 __global__ void __launch_bounds__(256)
-k_corr_prep_f64(double* __restrict__ X, double* __restrict__ I, unsigned short* __restrict__ Ib, long long total, int has_mask, double mask) {
+k_corr_prep_f64(double* __restrict__ X, double* __restrict__ I, unsigned short* __restrict__ Ib, int m, int mb, int has_mask, double mask) {
+    const long long total = (long long)m * m;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const double v = X[t];
         const bool on = !has_mask || v != mask;
         I[t] = on ? 1.0 : 0.0;
-        Ib[t] = on ? (unsigned short)0x3F80 : (unsigned short)0;
+        Ib[(t / m) * mb + (t % m)] = on ? (unsigned short)0x3F80 : (unsigned short)0;
         X[t] = on ? v : 0.0;
     }
 }
@@ -2577,7 +2578,7 @@ k_corr_selfvar(const double* __restrict__ X0, const double* __restrict__ I, int 
 template <bool OUT32>
 __global__ void __launch_bounds__(256)
 k_corr_finish(const double* __restrict__ N, const float* __restrict__ Nf, const double* __restrict__ Sx, const double* __restrict__ Sxy,
-              const double* __restrict__ var,
+              int nf_pitch, const double* __restrict__ var,
               int m, const int* __restrict__ kept, float* __restrict__ out32, long long ld, double* __restrict__ out64, int cov_mode) {
     const int ti = blockIdx.x, tj = blockIdx.y;
     if (tj > ti) return;
@@ -2592,7 +2593,7 @@ k_corr_finish(const double* __restrict__ N, const float* __restrict__ Nf, const 
         const int i = ti * 32 + r, j = tj * 32 + tx;
         if (i >= m || j >= m || j > i || (j == i && !cov_mode)) continue;
         const long long o = (long long)i * m + j;
-        const double cnt = Nf ? (double)Nf[o] : N[o];        // float counts are exact: integers below 2^24
+        const double cnt = Nf ? (double)Nf[(long long)i * nf_pitch + j] : N[o];        // float counts are exact: integers below 2^24
         double cov = 0.0;
         if (cnt > 3.0) cov = (Sxy[o] - Sx[o] * sT[tx][r] / cnt) / cnt;
         const double vi = var[i], vj = var[j];
