@@ -67,3 +67,38 @@ def test_downsample_oracle_shape_and_mass(n, level, seed):
     assert out.shape == onp.downsample_shape(A.shape, level)
     assert not out[0].any() and not out[:, 0].any()
     assert out.sum() == A[1:, 1:].sum()
+
+
+# ---- host-side helpers of the widened rows (lib/util.py, lib/ccmap.py:845-870) -- no GPU needed ----
+def test_resolution_helpers_known_answers():
+    """The examples of the reference's docstrings (lib/util.py:176-286)."""
+    from gcmapexplorer_b200 import util
+    for binsize, text in [(1, "1b"), (10, "10b"), (10000, "10kb"), (100000, "100kb"), (125500, "125.5kb"), (1000000, "1mb"), (1634300, "1.6343mb")]:
+        assert util.binsizeToResolution(binsize) == text
+    for text, binsize in [("1b", 1), ("10b", 10), ("10kb", 10000), ("16kb", 16000), ("1.23kb", 1230), ("1.6mb", 1600000), ("1.457mb", 1457000)]:
+        assert util.resolutionToBinsize(text) == binsize
+    with pytest.raises(ValueError):
+        util.resolutionToBinsize("10 parsec")
+
+
+def test_outlier_helpers_and_downsample1d():
+    from gcmapexplorer_b200 import ccmap as cmp, util
+    x = np.array([1.0, 1.1, 0.9, 1.05, 0.95, 1.0, 25.0, 1.02])
+    assert list(np.nonzero(util.detectOutliers1D(x))[0]) == [6]
+    mx = np.ma.masked_equal(np.array([0.0, 1.0, 1.1, 0.9, 0.0, 30.0, 1.05, 0.95]), 0.0)
+    out = util.detectOutliersMasked1D(mx, thresh=3.5)
+    assert np.array_equal(np.ma.getmaskarray(out), np.array([1, 0, 0, 0, 1, 1, 0, 0], dtype=bool))      # input mask kept, outlier added
+    assert np.array_equal(out.filled(0.0), np.array([0, 1.0, 1.1, 0.9, 0, 0, 1.05, 0.95]))
+    t = np.array([9.0, 1.0, 0.0, 3.0, 5.0, 0.0, 0.0, 7.0])                 # element 0 stays apart; 7 values -> 4 groups of 2, zero-padded
+    assert np.array_equal(cmp.downSample1D(t, level=2, func="sum"), [0.0, 1.0, 8.0, 0.0, 7.0])
+    assert np.array_equal(cmp.downSample1D(t, level=2, func="max"), [0.0, 1.0, 5.0, 0.0, 7.0])
+    m = cmp.downSample1D(t, level=2, func="mean")                         # mean over the non-zero entries of a group
+    assert m[1] == 1.0 and m[2] == 4.0 and m[4] == 7.0
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(min_value=1, max_value=10 ** 9))
+def test_resolution_roundtrip(binsize):
+    from gcmapexplorer_b200 import util
+    text = util.binsizeToResolution(binsize)
+    assert abs(util.resolutionToBinsize(text) - binsize) <= max(1, binsize // 10 ** 9)
