@@ -539,11 +539,15 @@ def cpu_statdist_sample(n, budget_s):
 
 def run_corr(args):
     """SURVEY.md 8f row N4 at chr1 @ 10 kb: pairwise-masked Pearson correlation matrix of the synthetic map (lib/corrMatrix.py:92-135,
-    lib/corrMatrixCoreSRC.c).  The pair sums are three float64 GEMMs (cuBLAS); the bound is the fp64 tensor rate, not HBM."""
+    lib/corrMatrixCoreSRC.c).  The pair sums are GEMM-shaped library products (cuBLAS): on the integer-valued synthetic counts all of them
+    run exactly on the int8 / bf16 tensor cores; with --corr-float the map is scaled by 0.37 first (a normalised, non-integer map) and the
+    two value products run on the float64 pipe (DGEMM + DSYRK).  The bound is the tensor rate, not HBM."""
     from gcmapexplorer_b200 import device as gx
     n = args.n or 24926
     dm = gx.DeviceMap(n)
     dm.synth(seed=args.seed, scale=200.0, alpha=1.0, empty_frac=0.01)
+    if args.corr_float:
+        dm.scale(0.37)
     rs, zc = dm.row_stats()
     keep = rs != 0
     m = int(keep.sum())
@@ -562,19 +566,24 @@ def run_corr(args):
     ck = clocks.stop()
     t = float(np.median(ts)) * 1e-3
     variant = int(os.environ.get("GCX_CORR_VARIANT", "1"))
-    # float64 flops: Sx = X0 I^T (2 m^3) + Sxy as a SYRK (m^3); the counts run on the bf16 tensor cores (2 m^3 more, not counted here).
-    # GCX_CORR_VARIANT=0: three float64 GEMMs (6 m^3).
-    flops = (3.0 if variant == 1 else 6.0) * m ** 3
-    FP64_NOMINAL_TFLOPS = 40.0            # B200 data sheet (dense fp64); MEASURED_PEAKS.json carries no fp64 figure
+    mb = (m + 63) // 64 * 64
+    if variant != 1:
+        kind, ops, peak, unit = "cublasDgemm x3 (N = I I^T, Sx = X0 I^T, Sxy = X0 X0^T)", 6.0 * m ** 3, 40.0, "TFLOP/s"
+    elif args.corr_float:
+        kind, ops, peak, unit = "cublasGemmEx bf16 (N = I I^T) + cublasDgemm (Sx = X0 I^T) + cublasDsyrk (Sxy = X0 X0^T)", 3.0 * m ** 3, 40.0, "TFLOP/s"
+    else:
+        # values < 2^14 on this map: 2 seven-bit slices -> 2 products for Sx, 4 for Sxy, all int8 x int8 -> int32, plus the bf16 counts product
+        kind, ops, peak, unit = "cublasGemmEx int8 x6 (7-bit slices of X0: Sx, Sxy) + bf16 x1 (N = I I^T)", 7 * 2.0 * mb ** 3, 4500.0, "TOP/s"
     line = {"metric": "correlation matrix time (s), chr1 @ 10 kb", "value": round(t, 4), "unit": "s", "n_gpus": 1, "steps": args.steps,
             "warmup": max(1, args.warmup), "ms_per_step": round(t * 1e3, 2), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic (device-generated)",
-            "config": {"workload": "synthetic chr1 @ 10 kb (n=%d, %d bins with data): correlation matrix" % (n, m), "n": n, "kept": m},
-            "roofline": {"bound": "tensor", "kernel": ("cublasGemmEx bf16 (N = I I^T) + cublasDgemm (Sx = X0 I^T) + cublasDsyrk (Sxy = X0 X0^T)" if variant == 1
-                                                    else "cublasDgemm x3 (N = I I^T, Sx = X0 I^T, Sxy = X0 X0^T)"), "achieved": round(flops / t / 1e12, 2),
-                         "peak": FP64_NOMINAL_TFLOPS, "peak_source": "nominal (no measured fp64 peak on file)", "unit": "TFLOP/s",
-                         "frac": round(flops / t / 1e12 / FP64_NOMINAL_TFLOPS, 4), "traffic": None,
-                         "note": "achieved = float64 flops of the products over the WHOLE call (prep, products, variances, scatter): a lower bound for the GEMMs"},
+            "dtype": "f64 (float map)" if (args.corr_float or variant != 1) else "int8/int32 exact products, f64 epilogue (integer map)",
+            "data": "synthetic (device-generated)%s" % (", scaled by 0.37" if args.corr_float else ""),
+            "config": {"workload": "synthetic chr1 @ 10 kb (n=%d, %d bins with data): correlation matrix" % (n, m), "n": n, "kept": m,
+                       "map_values": "non-integer" if args.corr_float else "integer counts"},
+            "roofline": {"bound": "tensor", "kernel": kind, "achieved": round(ops / t / 1e12, 2), "peak": peak,
+                         "peak_source": "nominal data-sheet rate (no measured fp64 / int8 peak on file)", "unit": unit,
+                         "frac": round(ops / t / 1e12 / peak, 4), "traffic": None,
+                         "note": "achieved = operations of the products over the WHOLE call (prep, slicing, products, accumulation, variances, scatter): a lower bound for the GEMMs"},
             "gpu_launches": int(launches), "clocks": ck}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_corr_sample(n, m)
@@ -768,6 +777,7 @@ def main():
                     help="N>1: balanced = near-equal row blocks + symmetric passes with circulant block assignment; equal_area = equal "
                          "upper-triangle shares per rank; rows = equal row blocks + dense passes")
     ap.add_argument("--kr", action="store_true", help="run KR instead of IC + VC on the selected workload")
+    ap.add_argument("--corr-float", action="store_true", help="chr1_10kb_corr: scale the map by 0.37 first (non-integer values -> float64 products)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

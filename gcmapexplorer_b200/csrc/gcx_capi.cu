@@ -173,6 +173,8 @@ struct gcx_ctx {
     double* part = nullptr;      // per-CTA partials of the fused IC pass (3 x grid)
     int ic_fused = 1;            // 1: one cooperative launch per IC pass (k_ic_pass); 0: k_matvec + k_ic_epilogue
     int ic_grid = 0, ic_grid_tma = 0;
+    int corr_int_path = 1;  // variant 1: exact int8 slice products for Sx and Sxy when the map is integer-valued (option "corr_int_path")
+    int corr_last_int = 0;
     int corr_variant = 1;   // correlation: 1 = bf16 tensor-core counts + DSYRK + DGEMM, 0 = three DGEMMs (GCX_CORR_VARIANT / option "corr_variant")
     int sd_variant = 1;   // stationary distribution: 1 = TMA-bulk transposed product, 0 = LDG (GCX_SD_VARIANT / option "sd_variant")
     int mv_variant = 7;   // TMA-bulk, R=4 rows per band, 6 stages, 2 CTAs/SM: best of profiles/r01_matvec_variants.txt
@@ -772,6 +774,7 @@ extern "C" int gcx_set_option(gcx_ctx* c, const char* key, double value) {
     else if (k == "matvec_variant") c->mv_variant = (int)value;
     else if (k == "sd_variant") c->sd_variant = (int)value;
     else if (k == "corr_variant") c->corr_variant = (int)value;
+    else if (k == "corr_int_path") c->corr_int_path = (int)value;
     else return fail("gcx_set_option: unknown key '%s'", key);
     return 0;
 }
@@ -1723,6 +1726,9 @@ struct CorrBufs {
     float* Nf;               // counts from the bf16 tensor-core product (corr_variant 1)
     unsigned short* Ib;      // bf16 copy of the indicator as an mb x mb matrix, mb = m rounded up to 64 and the pad zero, so that every
     int mb;                  // dimension and pitch of the counts product is aligned for cuBLAS' tensor-core kernels; Nf has pitch mb too
+    signed char* S8;         // up to 4 seven-bit slices of an integer-valued X0 as int8 (mb x mb each, pad zero)
+    signed char* I8;         // int8 indicator (mb x mb)
+    int* T32;                // one slice product (int32, mb x mb)
     int* kept;
 };
 
@@ -1731,7 +1737,8 @@ static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
     const int64_t mb = round_up(m, 64);
     const size_t bb = align256(sizeof(unsigned short) * (size_t)mb * mb);
     const size_t nn = std::max(mm, align256(sizeof(float) * (size_t)mb * mb));      // N (float64 m x m) doubles as Nf (float32 mb x mb)
-    const size_t need = 4 * mm + nn + bb + bv + bi;
+    const size_t tt = align256(sizeof(int) * (size_t)mb * mb), b8 = align256((size_t)mb * mb);
+    const size_t need = 4 * mm + nn + bb + 5 * b8 + tt + bv + bi;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     if (need > free_b + c->scratch_bytes)
@@ -1745,7 +1752,10 @@ static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
     B->Sxy = (double*)p; p += mm;
     B->Ib = (unsigned short*)p; p += bb;
     B->mb = (int)mb;
-    CK(cudaMemsetAsync(B->Ib, 0, bb, c->stream));
+    B->S8 = (signed char*)p; p += 4 * b8;
+    B->I8 = (signed char*)p; p += b8;
+    B->T32 = (int*)p; p += tt;
+    CK(cudaMemsetAsync(B->Ib, 0, bb + 5 * b8, c->stream));    // indicator and slice pads
     B->var = (double*)p; p += bv;
     B->kept = (int*)p;
     return 0;
@@ -1764,8 +1774,58 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, bool* counts_f32) {
             BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &one, B.Ib, 14 /* CUDA_R_16BF */, B.mb, B.Ib, 14, B.mb, &zero,
                                B.Nf, 0 /* CUDA_R_32F */, B.mb, 68 /* CUBLAS_COMPUTE_32F */, -1 /* CUBLAS_GEMM_DEFAULT */));
         }
-        CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
-        {
+        // integer-valued map: Sx and Sxy from exact int8 slice products (int32 accumulation) instead of the float64 GEMM / SYRK
+        int ns = 0;
+        if (c->corr_int_path && 16129LL * m < (1LL << 31)) {
+            CK(cudaMemsetAsync(c->csum_dev, 0, sizeof(unsigned long long), c->stream));
+            k_corr_intcheck<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, (long long)m * m, (unsigned int*)c->csum_dev);
+            CK(cudaGetLastError());
+            c->launches += 1;
+            unsigned int f[2] = {1u, 0u};
+            CKR(read_small(c, c->csum_dev, sizeof f, f));
+            if (!(f[0] & 1u)) {
+                int bits = 0;
+                while (bits < 32 && (f[1] >> bits)) ++bits;
+                ns = std::max(1, (bits + 6) / 7);
+            }
+        }
+        if (ns > 0) {
+            const int ione = 1, izero = 0;
+            const size_t plane = (size_t)B.mb * B.mb;
+            k_corr_slices8<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, B.I, m, B.mb, ns, B.S8, B.I8);
+            CK(cudaGetLastError());
+            c->launches += 1;
+            auto imma = [&](const signed char* L, const signed char* R) -> int {        // row-major T32 = L R^T
+                ProfScope ps(c, 7);
+                return g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &ione, R, 3 /* CUDA_R_8I */, B.mb, L, 3, B.mb, &izero,
+                                       B.T32, 10 /* CUDA_R_32I */, B.mb, 72 /* CUBLAS_COMPUTE_32I */, -1);
+            };
+            auto accum = [&](double scale, int first, double* dst) -> int {
+                k_corr_accum32<<<c->sm_count * 8, 256, 0, c->stream>>>(B.T32, m, B.mb, scale, first, dst);
+                CK(cudaGetLastError());
+                c->launches += 1;
+                return 0;
+            };
+            const int st = imma(B.S8, B.I8);
+            if (st != 0) {
+                ns = 0;                       // this cuBLAS build has no int8 path for the shape: float64 products from now on
+                c->corr_int_path = 0;
+            } else {
+                CKR(accum(1.0, 1, B.Sx));
+                for (int t = 1; t < ns; ++t) {
+                    BK(imma(B.S8 + t * plane, B.I8));
+                    CKR(accum((double)(1ull << (7 * t)), 0, B.Sx));
+                }
+                for (int a = 0; a < ns; ++a)
+                    for (int b = 0; b < ns; ++b) {
+                        BK(imma(B.S8 + a * plane, B.S8 + b * plane));
+                        CKR(accum((double)(1ull << (7 * (a + b))), a == 0 && b == 0, B.Sxy));
+                    }
+            }
+        }
+        c->corr_last_int = ns;
+        if (ns == 0) {
+            CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
             ProfScope ps(c, 7);      // row-major lower triangle of X0 X0^T = column-major upper triangle of (X_cm)^T X_cm
             BK(g_cublas.Dsyrk(c->blas, 1 /* CUBLAS_FILL_MODE_UPPER */, CUBLAS_OP_T_, m, m, &done, B.X0, m, &dzero, B.Sxy, m));
         }

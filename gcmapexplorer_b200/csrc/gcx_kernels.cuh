@@ -2533,13 +2533,15 @@ k_corr_prep(const float* __restrict__ A, long long ld, const int* __restrict__ k
 // host float64 input (inner seam, lib/_corrMatrixCore.pyx:49): split into X0 and I in place (X holds the raw rows)
 __global__ void __launch_bounds__(256)
 k_corr_prep_f64(double* __restrict__ X, double* __restrict__ I, unsigned short* __restrict__ Ib, int m, int mb, int has_mask, double mask) {
-    const long long total = (long long)m * m;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const double v = X[t];
-        const bool on = !has_mask || v != mask;
-        I[t] = on ? 1.0 : 0.0;
-        Ib[(t / m) * mb + (t % m)] = on ? (unsigned short)0x3F80 : (unsigned short)0;
-        X[t] = on ? v : 0.0;
+    for (int i = blockIdx.x; i < m; i += gridDim.x) {
+        for (int k = threadIdx.x; k < m; k += blockDim.x) {
+            const long long t = (long long)i * m + k;
+            const double v = X[t];
+            const bool on = !has_mask || v != mask;
+            I[t] = on ? 1.0 : 0.0;
+            Ib[(long long)i * mb + k] = on ? (unsigned short)0x3F80 : (unsigned short)0;
+            X[t] = on ? v : 0.0;
+        }
     }
 }
 
@@ -2611,6 +2613,56 @@ k_corr_finish(const double* __restrict__ N, const float* __restrict__ Nf, const 
         } else {
             out64[o] = c;
             out64[(long long)j * m + i] = c;
+        }
+    }
+}
+
+// Integer-valued maps (raw counts): X0 = sum_t 128^t s_t with 7-bit slices s_t in [0, 127] stored as int8.  A product of two
+// slices (or of a slice and the 0/1 indicator) sums to at most 127^2 m < 2^31, so the int8 tensor-core GEMM with int32 accumulation is
+// EXACT, and  Sx = sum_t 128^t (S_t I^T),  Sxy = sum_{a,b} 128^(a+b) (S_a S_b^T)  replace the float64 GEMM and SYRK.
+// k_corr_intcheck: flag[0] |= 1 when an entry is not an integer in [0, 2^28); flag[1] = max entry (-> number of slices).
+__global__ void __launch_bounds__(256)
+k_corr_intcheck(const double* __restrict__ X0, long long total, unsigned int* flag) {
+    int bad = 0;
+    unsigned int mx = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const double v = X0[t];
+        const bool ok = v >= 0.0 && v < 268435456.0 && v == floor(v);
+        bad |= !ok;
+        if (ok) mx = max(mx, (unsigned int)v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1u);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(flag + 1, mx);
+}
+
+// all `ns` slices of X0 and the int8 indicator, row pitch mb (pads stay 0)
+__global__ void __launch_bounds__(256)
+k_corr_slices8(const double* __restrict__ X0, const double* __restrict__ I, int m, int mb, int ns, signed char* __restrict__ S8,
+               signed char* __restrict__ I8) {
+    const long long plane = (long long)mb * mb;
+    for (int i = blockIdx.x; i < m; i += gridDim.x) {
+        const double* x = X0 + (long long)i * m;
+        const double* w = I + (long long)i * m;
+        for (int k = threadIdx.x; k < m; k += blockDim.x) {
+            const unsigned int v = (unsigned int)x[k];
+            const long long o = (long long)i * mb + k;
+            for (int t = 0; t < ns; ++t) S8[t * plane + o] = (signed char)((v >> (7 * t)) & 127u);
+            I8[o] = w[k] != 0.0 ? 1 : 0;
+        }
+    }
+}
+
+// dst = (first ? 0 : dst) + scale * T   (T: int32, row pitch mb; dst: float64 m x m)
+__global__ void __launch_bounds__(256)
+k_corr_accum32(const int* __restrict__ T, int m, int mb, double scale, int first, double* __restrict__ dst) {
+    for (int i = blockIdx.x; i < m; i += gridDim.x) {
+        const int* src = T + (long long)i * mb;
+        double* d = dst + (long long)i * m;
+        for (int k = threadIdx.x; k < m; k += blockDim.x) {
+            const double v = scale * (double)src[k];
+            d[k] = first ? v : d[k] + v;
         }
     }
 }

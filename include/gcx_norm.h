@@ -151,7 +151,9 @@ int gcx_corr_matrix_f64(gcx_ctx* ctx, const double* in, int64_t m, int has_mask,
  *   "sym_blocks"         0/1  sharded upper-triangle pass: deal the off-diagonal blocks out in the circulant pattern (default 1)
  *   "matvec_variant"     kernel variant for sweeps
  *   "sd_variant"         stationary distribution: 1 TMA-bulk transposed product (default), 0 per-thread loads
- *   "corr_variant"       correlation: 1 counts on the bf16 tensor cores + DSYRK + DGEMM (default), 0 three DGEMMs */
+ *   "corr_variant"       correlation: 1 counts on the bf16 tensor cores + DSYRK + DGEMM (default), 0 three DGEMMs
+ *   "corr_int_path"      0/1  variant 1 on an integer-valued map (raw counts): Sx and Sxy from exact 7-bit-slice products on the
+ *                             int8 tensor cores (int32 accumulation) instead of the float64 GEMM / SYRK (default 1) */
 int gcx_set_option(gcx_ctx* ctx, const char* key, double value);
 /* The aligned row partition (cuts at rank*n/world rounded to 1024 rows).  With it, "assume_symmetric" and
  * "exchange_allreduce", a sharded map runs the upper-triangle pass with the off-diagonal blocks dealt out in a circulant

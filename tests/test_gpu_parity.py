@@ -765,15 +765,22 @@ def test_corr_vs_compiled_reference_core(gx):
     L[np.isinf(L)] = 0
     refl = rl.load_corr().calculateCorrMatrix(L, maskvalue=0.0)
     refl[np.isnan(refl)] = 0
-    for variant in (1, 0):        # counts on the bf16 tensor cores + DSYRK + DGEMM (default) / three DGEMMs
+    raw = {}
+    # (variant, integer path): counts on the bf16 tensor cores + DSYRK + exact 8-bit-slice products for Sx (the default on this
+    # integer-valued map) / the same with the float64 GEMM for Sx / three DGEMMs
+    for variant, int_path in ((1, 1), (1, 0), (0, 0)):
         with gx.DeviceMap.from_host(A) as dm:
             dm.set_option("corr_variant", variant)
+            dm.set_option("corr_int_path", int_path)
             dm.set_mask(keep)
-            dm.corr(0.0, logspace=True)
+            dm.corr(0.0, logspace=True)               # log space: never integer-valued -> float64 GEMM in every variant
             M = dm.download(1)
             assert np.abs(M[np.ix_(keep, keep)].astype(np.float64) - refl).max() < CORR_ATOL32 and np.all(M[~keep] == 0)
-            assert np.abs(dm.corr_f64(X, 0.0) - ref).max() < CORR_ATOL64
             assert np.array_equal(M, M.T)
+            raw[(variant, int_path)] = dm.corr_f64(X, 0.0)
+            assert np.abs(raw[(variant, int_path)] - ref).max() < CORR_ATOL64
+    # on integer data every product is exact whichever unit computes it: bit-identical results
+    assert np.array_equal(raw[(1, 1)], raw[(1, 0)]) and np.array_equal(raw[(1, 1)], raw[(0, 0)])
 
 
 def test_corr_errors(gx):
