@@ -793,3 +793,48 @@ def test_corr_errors(gx):
         cm.calculateCorrMatrix(np.zeros((4, 5)))
     with pytest.raises(NotImplementedError):
         cm.calculateCorrMatrixForGCMaps("in.gcmap", "out.gcmap")
+
+
+# ---- size-independent properties of the widened rows on larger, device-generated maps ----
+def test_statdist_fixed_point_property_large(gx):
+    """n = 8000: the transition matrix is positive with every kept row summing to 1 up to the fill, and the stationary vector is a
+    fixed point of x -> x P' (checked with a NumPy float64 product on the downloaded matrix)."""
+    n = 8000
+    with gx.DeviceMap(n) as dm:
+        dm.synth(seed=77, scale=60.0, alpha=1.1, empty_frac=0.01)
+        rs, _ = dm.row_stats()
+        keep = rs != 0
+        dm.set_mask(keep)
+        mn, mx = dm.transition(in_place=True)
+        P = dm.download(0)
+        r = dm.stationary()
+    assert mn > 0 and P.min() == np.float32(mn) and P.max() == np.float32(mx)
+    assert np.all(P[~keep] == np.float32(mn)) and np.all(P[:, ~keep] == np.float32(mn))
+    x = r["x"]
+    assert np.all(x[~keep] == 0) and np.all(x[keep] > 0) and abs(x.sum() - 1.0) < 1e-12
+    Pk = P[np.ix_(keep, keep)].astype(np.float64)
+    y = x[keep] @ Pk
+    y /= y.sum()
+    assert np.abs(y - x[keep]).sum() < 1e-11 and r["iterations"] < 200
+
+
+def test_corr_exact_int8_route_equals_float64_route_large(gx):
+    """n = 5000: halving the map is exact in floating point and leaves every correlation unchanged, but turns the integer counts into
+    non-integers -- so the same coefficients come once from the exact int8 slice products and once from the float64 GEMM + SYRK."""
+    n = 5000
+    out = []
+    for factor in (1.0, 0.5):
+        with gx.DeviceMap(n) as dm:
+            dm.synth(seed=78, scale=80.0, alpha=1.1, empty_frac=0.01)
+            if factor != 1.0:
+                dm.scale(factor)
+            rs, _ = dm.row_stats()
+            keep = rs != 0
+            dm.set_mask(keep)
+            dm.corr(0.0)
+            out.append(dm.download(1))
+    a, b = out
+    assert np.array_equal(a, a.T) and np.all(np.diag(a) == 0) and np.all(a[~keep] == 0)
+    assert np.abs(a.astype(np.float64) - b).max() < CORR_ATOL32 and (a != b).mean() < 1e-3
+    kept = a[np.ix_(keep, keep)]
+    assert kept.max() > 0.5 and kept.min() < 0          # a real correlation structure, not zeros
