@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -51,6 +52,7 @@ enum { ncclInt32 = 2, ncclUint32 = 3, ncclFloat32 = 7, ncclFloat64 = 8, ncclUint
 enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
 struct NcclApi {
     void* h = nullptr;
+    bool ready = false;
     int (*GetUniqueId)(ncclUniqueId*) = nullptr;
     int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
@@ -59,8 +61,10 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
+static std::mutex g_loader_mutex;          // contexts may be created from several host threads
 static int nccl_load() {
-    if (g_nccl.h) return 0;
+    std::lock_guard<std::mutex> lock(g_loader_mutex);
+    if (g_nccl.ready) return 0;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* nm : names) {
         g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
@@ -72,6 +76,7 @@ static int nccl_load() {
     if (!g_nccl.f) return fail("libnccl: missing symbol nccl" #f);
     SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllGather) SYM(AllReduce) SYM(GetErrorString)
 #undef SYM
+    g_nccl.ready = true;
     return 0;
 }
 #define NK(call)                                                                                           \
@@ -87,6 +92,7 @@ typedef struct cublasContext* cublasHandle_t;
 enum { CUBLAS_OP_N_ = 0, CUBLAS_OP_T_ = 1 };
 struct CublasApi {
     void* h = nullptr;
+    bool ready = false;
     int (*Create)(cublasHandle_t*) = nullptr;
     int (*Destroy)(cublasHandle_t) = nullptr;
     int (*SetStream)(cublasHandle_t, cudaStream_t) = nullptr;
@@ -97,7 +103,8 @@ struct CublasApi {
 };
 static CublasApi g_cublas;
 static int cublas_load() {
-    if (g_cublas.h) return 0;
+    std::lock_guard<std::mutex> lock(g_loader_mutex);
+    if (g_cublas.ready) return 0;
     const char* names[] = {"libcublas.so.12", "libcublas.so"};
     for (const char* nm : names) {
         g_cublas.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
@@ -112,6 +119,7 @@ static int cublas_load() {
     *(void**)(&g_cublas.GemmEx) = dlsym(g_cublas.h, "cublasGemmEx");
     if (!g_cublas.Create || !g_cublas.Destroy || !g_cublas.SetStream || !g_cublas.Dgemm || !g_cublas.Dsyrk || !g_cublas.GemmEx)
         return fail("libcublas: missing symbol");
+    g_cublas.ready = true;
     return 0;
 }
 #define BK(call)                                                                                  \
@@ -177,6 +185,8 @@ struct gcx_ctx {
     int corr_last_int = 0;
     int corr_variant = 1;   // correlation: 1 = bf16 tensor-core counts + DSYRK + DGEMM, 0 = three DGEMMs (GCX_CORR_VARIANT / option "corr_variant")
     int sd_variant = 1;   // stationary distribution: 1 = TMA-bulk transposed product, 0 = LDG (GCX_SD_VARIANT / option "sd_variant")
+    unsigned int mv_cfg_mask = 0;   // TMA matvec variants whose shared-memory attribute has been set on this device
+    int mvt_occ = -1;               // CTAs/SM of the transposed TMA product on this device (-1: not configured yet)
     int mv_variant = 7;   // TMA-bulk, R=4 rows per band, 6 stages, 2 CTAs/SM: best of profiles/r01_matvec_variants.txt
     // states
     IcState* ic_state = nullptr;
@@ -1085,12 +1095,11 @@ static void launch_mv(gcx_ctx* c, const double* z, double* q, const int* done) {
 }
 
 template <int R, int STAGES, int OCC>
-static int launch_mv_tma(gcx_ctx* c, const double* z, double* q, const int* done) {
+static int launch_mv_tma(gcx_ctx* c, int variant, const double* z, double* q, const int* done) {
     const size_t smem = (size_t)STAGES * R * MV_THREADS * sizeof(float4);
-    static bool configured = false;
-    if (!configured) {
+    if (!(c->mv_cfg_mask & (1u << variant))) {        // function attributes are per device: remembered per context, not per process
         CK(cudaFuncSetAttribute(k_matvec_tma<R, STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        c->mv_cfg_mask |= 1u << variant;
     }
     k_matvec_tma<R, STAGES, OCC><<<c->sm_count * OCC, TMA_THREADS, smem, c->stream>>>(c->A, c->ld, (int)c->nloc, (int)(c->ld / 4), z, q + c->row0, c->ws,
                                                                                       c->ticket, done);
@@ -1109,17 +1118,17 @@ static int matvec(gcx_ctx* c, int variant, const double* z, double* q, const int
             case 4: launch_mv<16, 1>(c, z, q, done); break;
             case 5: launch_mv<2, 8>(c, z, q, done); break;
             case 6: launch_mv<8, 4>(c, z, q, done); break;
-            case 7: CKR((launch_mv_tma<4, 6, 2>(c, z, q, done))); break;      // 96 KB/CTA, 2 CTAs/SM
-            case 8: CKR((launch_mv_tma<4, 12, 1>(c, z, q, done))); break;     // 192 KB/CTA, 1 CTA/SM
-            case 9: CKR((launch_mv_tma<8, 6, 1>(c, z, q, done))); break;      // 192 KB/CTA, 1 CTA/SM, 8-row bands
-            case 10: CKR((launch_mv_tma<4, 4, 3>(c, z, q, done))); break;     // 64 KB/CTA, 3 CTAs/SM
-            case 11: CKR((launch_mv_tma<2, 8, 3>(c, z, q, done))); break;     // 64 KB/CTA, 3 CTAs/SM, 2-row bands
-            case 12: CKR((launch_mv_tma<4, 7, 2>(c, z, q, done))); break;     // 112 KB/CTA, 2 CTAs/SM
-            case 13: CKR((launch_mv_tma<8, 3, 2>(c, z, q, done))); break;     // 96 KB/CTA, 2 CTAs/SM, 8-row bands
-            case 14: CKR((launch_mv_tma<2, 12, 2>(c, z, q, done))); break;    // 96 KB/CTA, 2 CTAs/SM, 2-row bands
-            case 15: CKR((launch_mv_tma<4, 5, 2>(c, z, q, done))); break;     // 80 KB/CTA, 2 CTAs/SM
-            case 16: CKR((launch_mv_tma<2, 14, 2>(c, z, q, done))); break;    // 112 KB/CTA, 2 CTAs/SM, 2-row bands
-            case 17: CKR((launch_mv_tma<1, 24, 2>(c, z, q, done))); break;    // 96 KB/CTA, 2 CTAs/SM, single rows
+            case 7: CKR((launch_mv_tma<4, 6, 2>(c, 7, z, q, done))); break;      // 96 KB/CTA, 2 CTAs/SM
+            case 8: CKR((launch_mv_tma<4, 12, 1>(c, 8, z, q, done))); break;     // 192 KB/CTA, 1 CTA/SM
+            case 9: CKR((launch_mv_tma<8, 6, 1>(c, 9, z, q, done))); break;      // 192 KB/CTA, 1 CTA/SM, 8-row bands
+            case 10: CKR((launch_mv_tma<4, 4, 3>(c, 10, z, q, done))); break;     // 64 KB/CTA, 3 CTAs/SM
+            case 11: CKR((launch_mv_tma<2, 8, 3>(c, 11, z, q, done))); break;     // 64 KB/CTA, 3 CTAs/SM, 2-row bands
+            case 12: CKR((launch_mv_tma<4, 7, 2>(c, 12, z, q, done))); break;     // 112 KB/CTA, 2 CTAs/SM
+            case 13: CKR((launch_mv_tma<8, 3, 2>(c, 13, z, q, done))); break;     // 96 KB/CTA, 2 CTAs/SM, 8-row bands
+            case 14: CKR((launch_mv_tma<2, 12, 2>(c, 14, z, q, done))); break;    // 96 KB/CTA, 2 CTAs/SM, 2-row bands
+            case 15: CKR((launch_mv_tma<4, 5, 2>(c, 15, z, q, done))); break;     // 80 KB/CTA, 2 CTAs/SM
+            case 16: CKR((launch_mv_tma<2, 14, 2>(c, 16, z, q, done))); break;    // 112 KB/CTA, 2 CTAs/SM, 2-row bands
+            case 17: CKR((launch_mv_tma<1, 24, 2>(c, 17, z, q, done))); break;    // 96 KB/CTA, 2 CTAs/SM, single rows
             default: return fail("unknown matvec variant %d", variant);
         }
     }
@@ -1615,7 +1624,7 @@ extern "C" int gcx_stationary_run(gcx_ctx* c, double tol, int max_iter, double* 
     double* yv = c->vq;
     constexpr int TKG = 4, TSTAGES = 6, TOCC = 2;                 // 16 KB per stage, 96 KB per CTA, 2 CTAs per SM (like the dense TMA product)
     const size_t smem = (size_t)TSTAGES * TKG * MV_THREADS * sizeof(float4);
-    static int mvt_occ = -1;
+    int& mvt_occ = c->mvt_occ;                 // per context: function attributes and occupancy belong to the device
     if (mvt_occ < 0) {
         CK(cudaFuncSetAttribute(k_matvec_t_tma<TKG, TSTAGES, TOCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
