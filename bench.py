@@ -567,16 +567,22 @@ def run_corr(args):
     t = float(np.median(ts)) * 1e-3
     variant = int(os.environ.get("GCX_CORR_VARIANT", "1"))
     mb = (m + 63) // 64 * 64
+    slices, sxy_sliced = dm.corr_last_route()
+    K = abs(slices)
     if variant != 1:
         kind, ops, peak, unit = "cublasDgemm x3 (N = I I^T, Sx = X0 I^T, Sxy = X0 X0^T)", 6.0 * m ** 3, 40.0, "TFLOP/s"
-    elif args.corr_float:
+    elif slices == 0:
         kind, ops, peak, unit = "cublasGemmEx bf16 (N = I I^T) + cublasDgemm (Sx = X0 I^T) + cublasDsyrk (Sxy = X0 X0^T)", 3.0 * m ** 3, 40.0, "TFLOP/s"
     else:
-        # values < 2^14 on this map: 2 seven-bit slices -> 2 products for Sx, 4 for Sxy, all int8 x int8 -> int32, plus the bf16 counts product
-        kind, ops, peak, unit = "cublasGemmEx int8 x6 (7-bit slices of X0: Sx, Sxy) + bf16 x1 (N = I I^T)", 7 * 2.0 * mb ** 3, 4500.0, "TOP/s"
+        # exact 7-bit slices of X0 (integer map: plain digits, all K^2 ordered pairs; float32-valued map: one exponent per row, pairs a <= b):
+        # K products for Sx and, when Sxy is sliced too, K^2 or K (K + 1) / 2 for Sxy -- all int8 x int8 -> int32 -- plus the bf16 counts product
+        nprod = K + ((K * K if slices > 0 else K * (K + 1) // 2) if sxy_sliced else 0)
+        kind = "cublasGemmEx int8 x%d (%d seven-bit slices of X0: Sx%s) + bf16 x1 (N = I I^T)%s" % (
+            nprod, K, ", Sxy" if sxy_sliced else "", "" if sxy_sliced else " + cublasDsyrk (Sxy)")
+        ops, peak, unit = (nprod + 1) * 2.0 * mb ** 3, 4500.0, "TOP/s"
     line = {"metric": "correlation matrix time (s), chr1 @ 10 kb", "value": round(t, 4), "unit": "s", "n_gpus": 1, "steps": args.steps,
             "warmup": max(1, args.warmup), "ms_per_step": round(t * 1e3, 2), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 (float map)" if (args.corr_float or variant != 1) else "int8/int32 exact products, f64 epilogue (integer map)",
+            "dtype": "f64" if (variant != 1 or slices == 0) else "int8/int32 exact slice products, f64 accumulation and epilogue",
             "data": "synthetic (device-generated)%s" % (", scaled by 0.37" if args.corr_float else ""),
             "config": {"workload": "synthetic chr1 @ 10 kb (n=%d, %d bins with data): correlation matrix" % (n, m), "n": n, "kept": m,
                        "map_values": "non-integer" if args.corr_float else "integer counts"},

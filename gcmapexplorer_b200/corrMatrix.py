@@ -4,7 +4,8 @@ pairwise-masked Pearson correlation (and covariance) matrix of a contact map on 
 The reference loops over all row pairs on the CPU (OpenMP, two passes per pair: lib/corrMatrixCoreSRC.c:8-58, 132-192).
 Here the pair sums are three GEMM-shaped products -- N = I I^T, Sx = X0 I^T, Sxy = X0 X0^T with X0 the rows with masked
 entries zeroed and I the 0/1 indicator -- and cov = (Sxy - Sx Sx^T / N) / N.  The counts run on the bf16 tensor cores (exact);
-on an integer-valued map (raw counts) the other two run as exact int8 slice products, otherwise as a float64 GEMM and SYRK.
+on an integer-valued map (raw counts) and on a float32-valued one (anything but log space) the other two run as exact int8
+slice products, otherwise as a float64 GEMM and SYRK.
 The row variances repeat the reference's sequential arithmetic, so its ``var == 0`` decisions are reproduced exactly.  Agreement with the compiled reference core: ~1e-15
 absolute on the test maps (tests assert 1e-10).
 

@@ -1735,7 +1735,8 @@ struct CorrBufs {
     float* Nf;               // counts from the bf16 tensor-core product (corr_variant 1)
     unsigned short* Ib;      // bf16 copy of the indicator as an mb x mb matrix, mb = m rounded up to 64 and the pad zero, so that every
     int mb;                  // dimension and pitch of the counts product is aligned for cuBLAS' tensor-core kernels; Nf has pitch mb too
-    signed char* S8;         // up to 4 seven-bit slices of an integer-valued X0 as int8 (mb x mb each, pad zero)
+    signed char* S8;         // up to 9 seven-bit slices of X0 as int8 (mb x mb each, pad zero)
+    int* rhi;                // per-row exponents of the sliced float32 path
     signed char* I8;         // int8 indicator (mb x mb)
     int* T32;                // one slice product (int32, mb x mb)
     int* kept;
@@ -1747,7 +1748,7 @@ static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
     const size_t bb = align256(sizeof(unsigned short) * (size_t)mb * mb);
     const size_t nn = std::max(mm, align256(sizeof(float) * (size_t)mb * mb));      // N (float64 m x m) doubles as Nf (float32 mb x mb)
     const size_t tt = align256(sizeof(int) * (size_t)mb * mb), b8 = align256((size_t)mb * mb);
-    const size_t need = 4 * mm + nn + bb + 5 * b8 + tt + bv + bi;
+    const size_t need = 4 * mm + nn + bb + 10 * b8 + tt + bv + 2 * bi;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     if (need > free_b + c->scratch_bytes)
@@ -1761,12 +1762,13 @@ static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
     B->Sxy = (double*)p; p += mm;
     B->Ib = (unsigned short*)p; p += bb;
     B->mb = (int)mb;
-    B->S8 = (signed char*)p; p += 4 * b8;
+    B->S8 = (signed char*)p; p += 9 * b8;
     B->I8 = (signed char*)p; p += b8;
     B->T32 = (int*)p; p += tt;
-    CK(cudaMemsetAsync(B->Ib, 0, bb + 5 * b8, c->stream));    // indicator and slice pads
+    CK(cudaMemsetAsync(B->Ib, 0, bb + 10 * b8, c->stream));   // indicator and slice pads
     B->var = (double*)p; p += bv;
-    B->kept = (int*)p;
+    B->kept = (int*)p; p += bi;
+    B->rhi = (int*)p;
     return 0;
 }
 
@@ -1834,11 +1836,62 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, bool* counts_f32) {
         }
         c->corr_last_int = ns;
         if (ns == 0) {
-            CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
-            ProfScope ps(c, 7);      // row-major lower triangle of X0 X0^T = column-major upper triangle of (X_cm)^T X_cm
-            BK(g_cublas.Dsyrk(c->blas, 1 /* CUBLAS_FILL_MODE_UPPER */, CUBLAS_OP_T_, m, m, &done, B.X0, m, &dzero, B.Sxy, m));
+            // non-integer map: Sx still exact on the int8 units when every entry is a float32 number whose row fits 63 bits
+            int K = 0;
+            if (c->corr_int_path && 127LL * m < (1LL << 31)) {
+                CK(cudaMemsetAsync(c->csum_dev, 0, sizeof(unsigned long long), c->stream));
+                k_corr_f32check<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, m, B.rhi, (unsigned int*)c->csum_dev);
+                CK(cudaGetLastError());
+                c->launches += 1;
+                unsigned int f[2] = {1u, 0u};
+                CKR(read_small(c, c->csum_dev, sizeof f, f));
+                if (!(f[0] & 1u) && f[1] <= 63u) K = std::max(1, ((int)f[1] + 6) / 7);
+            }
+            if (K > 0) {
+                const int ione = 1, izero = 0;
+                const size_t plane = (size_t)B.mb * B.mb;
+                k_corr_fslices8<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, B.I, m, B.mb, K, B.rhi, B.S8, B.I8);
+                CK(cudaGetLastError());
+                c->launches += 1;
+                for (int t = 0; t < K; ++t) {
+                    {
+                        ProfScope ps(c, 7);      // row-major T32 = S_t I^T
+                        BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &ione, B.I8, 3 /* CUDA_R_8I */, B.mb,
+                                           B.S8 + t * plane, 3, B.mb, &izero, B.T32, 10 /* CUDA_R_32I */, B.mb, 72 /* CUBLAS_COMPUTE_32I */, -1));
+                    }
+                    k_corr_faccum<<<c->sm_count * 8, 256, 0, c->stream>>>(B.T32, m, B.mb, B.rhi, 7 * (t + 1), t == 0, B.Sx);
+                    CK(cudaGetLastError());
+                    c->launches += 1;
+                }
+                c->corr_last_int = -K;
+            } else {
+                CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
+            }
+            if (K > 0 && K <= 6 && 16129LL * m < (1LL << 31)) {
+                // few slices: Sxy exactly from K (K + 1) / 2 int8 products (<= 21, ~10 ms each with the accumulation) instead of the SYRK
+                const int ione = 1, izero = 0;
+                const size_t plane = (size_t)B.mb * B.mb;
+                const dim3 tg((m + 31) / 32, (m + 31) / 32);
+                bool first = true;
+                for (int a = 0; a < K; ++a)
+                    for (int b = a; b < K; ++b) {
+                        {
+                            ProfScope ps(c, 7);      // row-major T32 = S_a S_b^T
+                            BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &ione, B.S8 + b * plane, 3, B.mb,
+                                               B.S8 + a * plane, 3, B.mb, &izero, B.T32, 10, B.mb, 72, -1));
+                        }
+                        k_corr_faccum_sxy<<<tg, 256, 0, c->stream>>>(B.T32, m, B.mb, B.rhi, 7 * (a + b + 2), a != b, first ? 1 : 0, B.Sxy);
+                        CK(cudaGetLastError());
+                        c->launches += 1;
+                        first = false;
+                    }
+            } else {
+                ProfScope ps(c, 7);      // row-major lower triangle of X0 X0^T = column-major upper triangle of (X_cm)^T X_cm
+                BK(g_cublas.Dsyrk(c->blas, 1 /* CUBLAS_FILL_MODE_UPPER */, CUBLAS_OP_T_, m, m, &done, B.X0, m, &dzero, B.Sxy, m));
+            }
         }
     } else {
+        c->corr_last_int = 0;
         CKR(gemm_nt(c, m, B.I, B.I, B.N));
         CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
         CKR(gemm_nt(c, m, B.X0, B.X0, B.Sxy));
@@ -1887,6 +1940,13 @@ extern "C" int gcx_corr_run(gcx_ctx* c, int has_mask, double maskvalue, int logs
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gcx_corr_last_route(gcx_ctx* c, int* slices, int* sxy_sliced) {
+    if (!c || !slices) return fail("gcx_corr_last_route: null argument");
+    *slices = c->corr_last_int;
+    if (sxy_sliced) *sxy_sliced = c->corr_last_int > 0 || (c->corr_last_int < 0 && -c->corr_last_int <= 6);
     return 0;
 }
 

@@ -2667,4 +2667,109 @@ k_corr_accum32(const int* __restrict__ T, int m, int mb, double scale, int first
     }
 }
 
+// Non-integer maps whose entries are float32 numbers (everything but log space): Sx = X0 I^T stays EXACT on the int8 tensor cores.
+// Every entry of row i is an integer multiple of 2^(lo_i) (lo = smallest exponent - 24) and below 2^(hi_i), so
+// q = |x| 2^(7K - hi_i) is an integer below 2^(7K) as soon as 7K >= hi_i - lo_i; its K seven-bit digits (sign carried along) are the
+// slices and  Sx_ij = 2^(hi_i) sum_t 2^(-7(t+1)) (S_t I^T)_ij  with exact int32 products -- K <= 9 products of ~7 ms instead of the
+// 832 ms float64 GEMM.  k_corr_f32check finds hi_i, the largest hi_i - lo_i (info[1]) and raises info[0] when an entry is not a
+// float32 number; the caller falls back to the float64 GEMM then, or when more than 63 bits would be needed.
+__global__ void __launch_bounds__(256)
+k_corr_f32check(const double* __restrict__ X0, int m, int* __restrict__ rhi, unsigned int* info) {
+    __shared__ int s_hi[8], s_lo[8], s_bad[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = blockIdx.x; i < m; i += gridDim.x) {
+        const double* x = X0 + (long long)i * m;
+        int hi = -100000, lo = 100000, bad = 0;
+        for (int k = threadIdx.x; k < m; k += blockDim.x) {
+            const double v = x[k];
+            if (v == 0.0) continue;
+            bad |= !((double)(float)v == v) || !isfinite(v);
+            int e;
+            frexp(v, &e);                       // |v| = f 2^e, f in [0.5, 1)
+            hi = max(hi, e);
+            lo = min(lo, e - 24);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        }
+        if (lane == 0) { s_hi[warp] = hi; s_lo[warp] = lo; s_bad[warp] = bad; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) { hi = max(hi, s_hi[w]); lo = min(lo, s_lo[w]); bad |= s_bad[w]; }
+            const bool empty = hi < lo;
+            rhi[i] = empty ? 0 : hi;
+            if (bad) atomicOr(info, 1u);
+            if (!empty) atomicMax(info + 1, (unsigned int)(hi - lo));
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_corr_fslices8(const double* __restrict__ X0, const double* __restrict__ I, int m, int mb, int K, const int* __restrict__ rhi,
+                signed char* __restrict__ S8, signed char* __restrict__ I8) {
+    const long long plane = (long long)mb * mb;
+    for (int i = blockIdx.x; i < m; i += gridDim.x) {
+        const double* x = X0 + (long long)i * m;
+        const double* w = I + (long long)i * m;
+        const int sh = 7 * K - rhi[i];
+        for (int k = threadIdx.x; k < m; k += blockDim.x) {
+            const double v = x[k];
+            const unsigned long long q = (unsigned long long)ldexp(fabs(v), sh);        // exact: an integer below 2^(7K)
+            const long long o = (long long)i * mb + k;
+            for (int t = 0; t < K; ++t) {
+                const int sl = (int)((q >> (7 * (K - 1 - t))) & 127ull);
+                S8[t * plane + o] = (signed char)(v < 0.0 ? -sl : sl);
+            }
+            I8[o] = w[k] != 0.0 ? 1 : 0;
+        }
+    }
+}
+
+// Sx[i][j] (+)= T[i][j] 2^(hi_i - shift)
+__global__ void __launch_bounds__(256)
+k_corr_faccum(const int* __restrict__ T, int m, int mb, const int* __restrict__ rhi, int shift, int first, double* __restrict__ Sx) {
+    for (int i = blockIdx.x; i < m; i += gridDim.x) {
+        const int* src = T + (long long)i * mb;
+        double* d = Sx + (long long)i * m;
+        const int e = rhi[i] - shift;
+        for (int k = threadIdx.x; k < m; k += blockDim.x) {
+            const double v = ldexp((double)src[k], e);
+            d[k] = first ? v : d[k] + v;
+        }
+    }
+}
+
+// Sxy the same way when few slices suffice (K <= 6: at most 21 products):  Sxy_ij = 2^(hi_i + hi_j) sum_{a,b} 2^(-7(a+b+2)) (S_a S_b^T)_ij,
+// ALL pairs (nothing truncated: exact int32 products, exact scalings, float64 roundings only in the final sum).  S_b S_a^T is the
+// transpose of S_a S_b^T, so only a <= b is multiplied and this kernel adds T + T^T on the lower triangle -- the only part the
+// epilogue reads:  Sxy[i][j] (+)= (T[i][j] + (sym ? T[j][i] : 0)) 2^(hi_i + hi_j - shift),  j <= i.
+__global__ void __launch_bounds__(256)
+k_corr_faccum_sxy(const int* __restrict__ T, int m, int mb, const int* __restrict__ rhi, int shift, int sym, int first,
+                  double* __restrict__ Sxy) {
+    const int ti = blockIdx.x, tj = blockIdx.y;
+    if (tj > ti) return;
+    __shared__ int sT[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (sym) {
+        for (int r = ty; r < 32; r += 8) {
+            const int j = tj * 32 + r, i = ti * 32 + tx;
+            sT[r][tx] = (i < m && j < m) ? T[(long long)j * mb + i] : 0;
+        }
+        __syncthreads();
+    }
+    for (int r = ty; r < 32; r += 8) {
+        const int i = ti * 32 + r, j = tj * 32 + tx;
+        if (i >= m || j >= m || j > i) continue;
+        double v = (double)T[(long long)i * mb + j];
+        if (sym) v += (double)sT[tx][r];
+        v = ldexp(v, rhi[i] + rhi[j] - shift);
+        const long long o = (long long)i * m + j;
+        Sxy[o] = first ? v : Sxy[o] + v;
+    }
+}
+
 }  // namespace gcx

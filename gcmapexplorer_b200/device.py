@@ -224,6 +224,12 @@ class DeviceMap:
                                  int(vmin is not None), float(np.float32(0.0 if vmin is None else vmin)),
                                  int(vmax is not None), float(np.float32(0.0 if vmax is None else vmax))))
 
+    def corr_last_route(self):
+        """(slices, sxy_sliced) of the last correlation run: slices > 0 integer map, < 0 float32-valued map, 0 float64 products."""
+        a, b = C.c_int(0), C.c_int(0)
+        check(lib().gcx_corr_last_route(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, bool(b.value)
+
     def corr_f64(self, in_array, maskvalue=None, covariance=False, out=None):
         """Correlation (or covariance) matrix of the rows of a square float64 array, float64 result
         (lib/_corrMatrixCore.pyx:49-146).  Needs no resident map."""

@@ -137,6 +137,10 @@ int gcx_stationary_run(gcx_ctx* ctx, double tol, int max_iter, double* x, int* i
  * (lib/_corrMatrixCore.pyx:100-146, diagonal included).  Works on a context without a resident map. */
 int gcx_corr_run(gcx_ctx* ctx, int has_mask, double maskvalue, int logspace, int has_vmin, float vmin, int has_vmax, float vmax);
 int gcx_corr_matrix_f64(gcx_ctx* ctx, const double* in, int64_t m, int has_mask, double maskvalue, int covariance, double* out);
+/* Which route the last correlation run took for the value products (measurement only; the reference has no counterpart):
+ * slices > 0: integer-valued map, that many exact 7-bit int8 slices; slices < 0: float32-valued map, -slices exact slices with one
+ * exponent per row; 0: float64 GEMM.  sxy_sliced: 1 when Sxy came from slice products too, 0 when it came from the float64 SYRK/GEMM. */
+int gcx_corr_last_route(gcx_ctx* ctx, int* slices, int* sxy_sliced);
 
 /* ---- multi-GPU (row-block sharding; one context per rank) ------------------------------------
  * nccl_unique_id: the 128-byte ncclUniqueId from gcx_dist_unique_id on rank 0, broadcast by the host

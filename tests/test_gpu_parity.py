@@ -777,10 +777,25 @@ def test_corr_vs_compiled_reference_core(gx):
             M = dm.download(1)
             assert np.abs(M[np.ix_(keep, keep)].astype(np.float64) - refl).max() < CORR_ATOL32 and np.all(M[~keep] == 0)
             assert np.array_equal(M, M.T)
+            assert dm.corr_last_route() == (0, False)            # log space: float64 products
             raw[(variant, int_path)] = dm.corr_f64(X, 0.0)
             assert np.abs(raw[(variant, int_path)] - ref).max() < CORR_ATOL64
+            slices, sxy = dm.corr_last_route()
+            assert (slices > 0 and sxy) if (variant, int_path) == (1, 1) else (slices == 0 and not sxy)
     # on integer data every product is exact whichever unit computes it: bit-identical results
     assert np.array_equal(raw[(1, 1)], raw[(1, 0)]) and np.array_equal(raw[(1, 1)], raw[(0, 0)])
+    # non-integer float32-valued data: Sx from exact int8 slice products (per-row exponents) vs the float64 GEMM
+    Xf = (X.astype(np.float32) / np.float32(3.0)).astype(np.float64)
+    reff = rl.load_corr().calculateCorrMatrix(Xf, maskvalue=0.0)
+    got = {}
+    for int_path in (1, 0):
+        with gx.DeviceMap(32) as dm:
+            dm.set_option("corr_int_path", int_path)
+            got[int_path] = dm.corr_f64(Xf, 0.0)
+            assert np.abs(got[int_path] - reff).max() < CORR_ATOL64
+            slices, sxy = dm.corr_last_route()
+            assert (slices < 0 and sxy) if int_path else slices == 0       # counts / 3 in float32: 5 slices cover every row
+    assert np.abs(got[1] - got[0]).max() < 1e-12
 
 
 def test_corr_errors(gx):
