@@ -574,9 +574,9 @@ def run_corr(args):
     elif slices == 0:
         kind, ops, peak, unit = "cublasGemmEx bf16 (N = I I^T) + cublasDgemm (Sx = X0 I^T) + cublasDsyrk (Sxy = X0 X0^T)", 3.0 * m ** 3, 40.0, "TFLOP/s"
     else:
-        # exact 7-bit slices of X0 (integer map: plain digits, all K^2 ordered pairs; float32-valued map: one exponent per row, pairs a <= b):
-        # K products for Sx and, when Sxy is sliced too, K^2 or K (K + 1) / 2 for Sxy -- all int8 x int8 -> int32 -- plus the bf16 counts product
-        nprod = K + ((K * K if slices > 0 else K * (K + 1) // 2) if sxy_sliced else 0)
+        # exact 7-bit slices of X0 (integer map: plain digits; float32-valued map: one exponent per row): K products for Sx and, when Sxy is
+        # sliced too, K (K + 1) / 2 for Sxy (pairs a <= b) -- all int8 x int8 -> int32 -- plus the bf16 counts product
+        nprod = K + (K * (K + 1) // 2 if sxy_sliced else 0)
         kind = "cublasGemmEx int8 x%d (%d seven-bit slices of X0: Sx%s) + bf16 x1 (N = I I^T)%s" % (
             nprod, K, ", Sxy" if sxy_sliced else "", "" if sxy_sliced else " + cublasDsyrk (Sxy)")
         ops, peak, unit = (nprod + 1) * 2.0 * mb ** 3, 4500.0, "TOP/s"

@@ -1827,10 +1827,17 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, bool* counts_f32) {
                     BK(imma(B.S8 + t * plane, B.I8));
                     CKR(accum((double)(1ull << (7 * t)), 0, B.Sx));
                 }
+                // S_b S_a^T is the transpose of S_a S_b^T: multiply a <= b only, add T + T^T on the lower triangle (exponents all 0)
+                CK(cudaMemsetAsync(B.rhi, 0, sizeof(int) * (size_t)m, c->stream));
+                const dim3 tg((m + 31) / 32, (m + 31) / 32);
+                bool first = true;
                 for (int a = 0; a < ns; ++a)
-                    for (int b = 0; b < ns; ++b) {
+                    for (int b = a; b < ns; ++b) {
                         BK(imma(B.S8 + a * plane, B.S8 + b * plane));
-                        CKR(accum((double)(1ull << (7 * (a + b))), a == 0 && b == 0, B.Sxy));
+                        k_corr_faccum_sxy<<<tg, 256, 0, c->stream>>>(B.T32, m, B.mb, B.rhi, -7 * (a + b), a != b, first ? 1 : 0, B.Sxy);
+                        CK(cudaGetLastError());
+                        c->launches += 1;
+                        first = false;
                     }
             }
         }
@@ -1867,8 +1874,8 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, bool* counts_f32) {
             } else {
                 CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
             }
-            if (K > 0 && K <= 6 && 16129LL * m < (1LL << 31)) {
-                // few slices: Sxy exactly from K (K + 1) / 2 int8 products (<= 21, ~10 ms each with the accumulation) instead of the SYRK
+            if (K > 0 && K <= 8 && 16129LL * m < (1LL << 31)) {
+                // Sxy exactly from K (K + 1) / 2 int8 products (<= 36, ~10 ms each with the accumulation at n = 24,926; the SYRK takes 434 ms)
                 const int ione = 1, izero = 0;
                 const size_t plane = (size_t)B.mb * B.mb;
                 const dim3 tg((m + 31) / 32, (m + 31) / 32);
@@ -1946,7 +1953,7 @@ extern "C" int gcx_corr_run(gcx_ctx* c, int has_mask, double maskvalue, int logs
 extern "C" int gcx_corr_last_route(gcx_ctx* c, int* slices, int* sxy_sliced) {
     if (!c || !slices) return fail("gcx_corr_last_route: null argument");
     *slices = c->corr_last_int;
-    if (sxy_sliced) *sxy_sliced = c->corr_last_int > 0 || (c->corr_last_int < 0 && -c->corr_last_int <= 6);
+    if (sxy_sliced) *sxy_sliced = c->corr_last_int > 0 || (c->corr_last_int < 0 && -c->corr_last_int <= 8);
     return 0;
 }
 

@@ -2743,7 +2743,7 @@ k_corr_faccum(const int* __restrict__ T, int m, int mb, const int* __restrict__ 
     }
 }
 
-// Sxy the same way when few slices suffice (K <= 6: at most 21 products):  Sxy_ij = 2^(hi_i + hi_j) sum_{a,b} 2^(-7(a+b+2)) (S_a S_b^T)_ij,
+// Sxy the same way while it beats the SYRK (K <= 8: at most 36 products):  Sxy_ij = 2^(hi_i + hi_j) sum_{a,b} 2^(-7(a+b+2)) (S_a S_b^T)_ij,
 // ALL pairs (nothing truncated: exact int32 products, exact scalings, float64 roundings only in the final sum).  S_b S_a^T is the
 // transpose of S_a S_b^T, so only a <= b is multiplied and this kernel adds T + T^T on the lower triangle -- the only part the
 // epilogue reads:  Sxy[i][j] (+)= (T[i][j] + (sym ? T[j][i] : 0)) 2^(hi_i + hi_j - shift),  j <= i.
