@@ -1774,17 +1774,26 @@ static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
 
 // the three products and the row variances, from X0 / I.  corr_variant 1 (default): counts on the bf16 tensor cores + SYRK for
 // the symmetric sum; 0: three float64 GEMMs.  Returns which count buffer the epilogue must read.
-static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, bool* counts_f32) {
+static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
     CKR(blas_ready(c));
-    *counts_f32 = c->corr_variant == 1;
+    *counts_mode = c->corr_variant == 1 ? 1 : 0;          // 0: float64 N, 1: float32 Nf (bf16 product), 2: int32 in Nf (int8 product)
     if (c->corr_variant == 1) {
         const float one = 1.f, zero = 0.f;
         const double done = 1.0, dzero = 0.0;
-        {
+        auto counts_bf16 = [&]() -> int {
             ProfScope ps(c, 7);      // row-major N = I I^T: column-major (I_cm)^T I_cm, bf16 x bf16 -> float32
             BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &one, B.Ib, 14 /* CUDA_R_16BF */, B.mb, B.Ib, 14, B.mb, &zero,
                                B.Nf, 0 /* CUDA_R_32F */, B.mb, 68 /* CUBLAS_COMPUTE_32F */, -1 /* CUBLAS_GEMM_DEFAULT */));
-        }
+            return 0;
+        };
+        auto counts_int8 = [&]() -> int {   // the sliced routes have the int8 indicator at hand: same product at twice the rate, int32 counts
+            const int i1 = 1, i0 = 0;
+            ProfScope ps(c, 7);
+            BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &i1, B.I8, 3 /* CUDA_R_8I */, B.mb, B.I8, 3, B.mb, &i0, B.Nf,
+                               10 /* CUDA_R_32I */, B.mb, 72 /* CUBLAS_COMPUTE_32I */, -1));
+            *counts_mode = 2;
+            return 0;
+        };
         // integer-valued map: Sx and Sxy from exact int8 slice products (int32 accumulation) instead of the float64 GEMM / SYRK
         int ns = 0;
         if (c->corr_int_path && 16129LL * m < (1LL << 31)) {
@@ -1823,6 +1832,7 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, bool* counts_f32) {
                 c->corr_int_path = 0;
             } else {
                 CKR(accum(1.0, 1, B.Sx));
+                CKR(counts_int8());
                 for (int t = 1; t < ns; ++t) {
                     BK(imma(B.S8 + t * plane, B.I8));
                     CKR(accum((double)(1ull << (7 * t)), 0, B.Sx));
@@ -1860,6 +1870,7 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, bool* counts_f32) {
                 k_corr_fslices8<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, B.I, m, B.mb, K, B.rhi, B.S8, B.I8);
                 CK(cudaGetLastError());
                 c->launches += 1;
+                CKR(counts_int8());
                 for (int t = 0; t < K; ++t) {
                     {
                         ProfScope ps(c, 7);      // row-major T32 = S_t I^T
@@ -1872,6 +1883,7 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, bool* counts_f32) {
                 }
                 c->corr_last_int = -K;
             } else {
+                CKR(counts_bf16());
                 CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
             }
             if (K > 0 && K <= 8 && 16129LL * m < (1LL << 31)) {
@@ -1937,13 +1949,14 @@ extern "C" int gcx_corr_run(gcx_ctx* c, int has_mask, double maskvalue, int logs
         k_corr_prep<<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(c->A, c->ld, B.kept, m, P, B.X0, B.I, B.Ib, B.mb);
     }
     CK(cudaGetLastError());
-    bool nf = false;
-    CKR(corr_core(c, m, B, &nf));
+    int cm = 0;
+    CKR(corr_core(c, m, B, &cm));
+    const bool nf = cm != 0;
     CKR(ensure_out(c));
     CK(cudaMemsetAsync(c->Out, 0, sizeof(float) * (size_t)c->nloc * c->ld, c->stream));
     {
         ProfScope ps(c, 7);
-        k_corr_finish<true><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(nf ? nullptr : B.N, nf ? B.Nf : nullptr, B.Sx, B.Sxy, B.mb, B.var, m, B.kept, c->Out, c->ld, nullptr, 0);
+        k_corr_finish<true><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(nf ? nullptr : B.N, nf ? B.Nf : nullptr, B.Sx, B.Sxy, B.mb, cm == 2, B.var, m, B.kept, c->Out, c->ld, nullptr, 0);
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
@@ -1970,11 +1983,12 @@ extern "C" int gcx_corr_matrix_f64(gcx_ctx* c, const double* in, int64_t m64, in
     k_corr_prep_f64<<<c->sm_count * 8, 256, 0, c->stream>>>(B.X0, B.I, B.Ib, m, B.mb, has_mask, (double)maskf);
     CK(cudaGetLastError());
     c->launches += 1;
-    bool nf = false;
-    CKR(corr_core(c, m, B, &nf));
+    int cm = 0;
+    CKR(corr_core(c, m, B, &cm));
+    const bool nf = cm != 0;
     // the result overwrites the indicator buffer (no longer needed once the products are done)
     CK(cudaMemsetAsync(B.I, 0, bytes, c->stream));
-    k_corr_finish<false><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(nf ? nullptr : B.N, nf ? B.Nf : nullptr, B.Sx, B.Sxy, B.mb, B.var, m, nullptr, nullptr, 0, B.I, covariance);
+    k_corr_finish<false><<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, c->stream>>>(nf ? nullptr : B.N, nf ? B.Nf : nullptr, B.Sx, B.Sxy, B.mb, cm == 2, B.var, m, nullptr, nullptr, 0, B.I, covariance);
     CK(cudaGetLastError());
     c->launches += 1;
     CK(cudaMemcpyAsync(out, B.I, bytes, cudaMemcpyDeviceToHost, c->stream));

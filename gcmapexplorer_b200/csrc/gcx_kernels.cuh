@@ -2580,7 +2580,7 @@ k_corr_selfvar(const double* __restrict__ X0, const double* __restrict__ I, int 
 template <bool OUT32>
 __global__ void __launch_bounds__(256)
 k_corr_finish(const double* __restrict__ N, const float* __restrict__ Nf, const double* __restrict__ Sx, const double* __restrict__ Sxy,
-              int nf_pitch, const double* __restrict__ var,
+              int nf_pitch, int nf_int, const double* __restrict__ var,
               int m, const int* __restrict__ kept, float* __restrict__ out32, long long ld, double* __restrict__ out64, int cov_mode) {
     const int ti = blockIdx.x, tj = blockIdx.y;
     if (tj > ti) return;
@@ -2595,7 +2595,8 @@ k_corr_finish(const double* __restrict__ N, const float* __restrict__ Nf, const 
         const int i = ti * 32 + r, j = tj * 32 + tx;
         if (i >= m || j >= m || j > i || (j == i && !cov_mode)) continue;
         const long long o = (long long)i * m + j;
-        const double cnt = Nf ? (double)Nf[(long long)i * nf_pitch + j] : N[o];        // float counts are exact: integers below 2^24
+        // float32 counts (bf16 product) are exact: integers below 2^24; the sliced routes leave int32 counts in the same buffer
+        const double cnt = !Nf ? N[o] : (nf_int ? (double)reinterpret_cast<const int*>(Nf)[(long long)i * nf_pitch + j] : (double)Nf[(long long)i * nf_pitch + j]);
         double cov = 0.0;
         if (cnt > 3.0) cov = (Sxy[o] - Sx[o] * sT[tx][r] / cnt) / cnt;
         const double vi = var[i], vj = var[j];
