@@ -59,6 +59,7 @@ case("corr_sp131", A131)
 case("corr_sp131_clamp", A131, vmin=1.0, vmax=25.0)
 case("corr_sp131_mask1", A131, maskvalue=1.0)
 case("corr_s400", A400)
+case("corr_s97_nomask", A97, maskvalue=None)            # no pairwise masking at all: plain Pearson of the kept block
 rng = np.random.default_rng(5)
 X = rng.standard_normal((60, 60))
 X[rng.random((60, 60)) < 0.3] = 0.0
