@@ -73,6 +73,7 @@ _PROTOS = {
     "gcx_debug_sym_cycles": (C.c_int, [_ctx, _c_i64p, C.c_int, C.POINTER(C.c_int)]),
     "gcx_pass_bytes": (C.c_int, [_ctx, _c_i64p, C.POINTER(C.c_int)]),
     "gcx_last_run_ms": (C.c_int, [_ctx, _c_f64p]),
+    "gcx_last_run_products": (C.c_int, [_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gcx_launch_count": (C.c_int, [_ctx, _c_i64p]),
     "gcx_bench_matvec": (C.c_int, [_ctx, C.c_int, C.c_int, _c_f64p]),
 }

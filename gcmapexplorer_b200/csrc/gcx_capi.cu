@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <mutex>
@@ -180,6 +181,16 @@ struct gcx_ctx {
     size_t scratch_bytes = 0;
     double* part = nullptr;      // per-CTA partials of the fused IC pass (3 x grid)
     int ic_fused = 1;            // 1: one cooperative launch per IC pass (k_ic_pass); 0: k_matvec + k_ic_epilogue
+    int ic_defer = 1;            // upper-triangle path: deferred-scalar pass k_ic_pass_symd (GCX_IC_DEFER=0: literal-order k_ic_pass_sym_tma)
+    double* ic_ring = nullptr;   // [3][nv] t' ring + [2][nv] u ring of the deferred-scalar pass
+    int last_matvecs_issued = 0; // products the last ic/kr run really launched (the deferred pass runs one more than passes + 1)
+    // peer exchange of the sharded symmetric pass (NVLink stores into peer-mapped buffers; cudaIpc or same-process P2P)
+    int xchg_enable = 1;         // option "peer_exchange" / GCX_PEER_EXCHANGE=0: keep the NCCL allreduce
+    bool xchg_ok = false;
+    void* xchg_buf = nullptr;    // [world][G] flags | [2][world][nv] partial vectors
+    void* xchg_peer[8] = {nullptr};
+    bool xchg_ipc[8] = {false};
+    unsigned int xchg_seq = 1;   // flag value of the next run's launch 0 (same on every rank: SPMD call sequence)
     int ic_grid = 0, ic_grid_tma = 0;
     int corr_int_path = 1;  // variant 1: exact int8 slice products for Sx and Sxy when the map is integer-valued (option "corr_int_path")
     int corr_last_int = 0;
@@ -355,8 +366,14 @@ static int ctx_init(gcx_ctx* c, int device) {
         CK(cudaFuncSetAttribute(k_matvec_sym_tma<SYM_STAGES, SYM_OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(k_ic_pass_sym_tma<SYM_STAGES, SYM_OCC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(k_ic_pass_sym_tma<SYM_STAGES, SYM_OCC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int occ3 = 0;
+        CK(cudaFuncSetAttribute(k_ic_pass_symd<SYM_STAGES, SYM_OCC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k_ic_pass_symd<SYM_STAGES, SYM_OCC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (const char* e = getenv("GCX_IC_DEFER")) c->ic_defer = atoi(e);
+        if (const char* e = getenv("GCX_PEER_EXCHANGE")) c->xchg_enable = atoi(e);
+        int occ3 = 0, occ4 = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_ic_pass_sym_tma<SYM_STAGES, SYM_OCC, true>, SYM_THREADS, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, k_ic_pass_symd<SYM_STAGES, SYM_OCC, true>, SYM_THREADS, smem));
+        if (occ4 < occ3) c->ic_defer = 0;          // both passes share one grid (tables, partial buffers)
         c->sym_grid = c->sm_count * std::min(occ3, SYM_OCC);
         if (occ3 < 1) c->sym_enable = 0;
     }
@@ -391,7 +408,19 @@ static void free_sym(gcx_ctx* c) {
     c->sym_ndyn = 0;
 }
 
+static void xchg_free(gcx_ctx* c) {
+    for (int q = 0; q < 8; ++q) {
+        if (c->xchg_peer[q] && c->xchg_ipc[q]) cudaIpcCloseMemHandle(c->xchg_peer[q]);
+        c->xchg_peer[q] = nullptr;
+        c->xchg_ipc[q] = false;
+    }
+    cudaFree(c->xchg_buf); c->xchg_buf = nullptr;
+    c->xchg_ok = false;
+}
+
 static void free_map(gcx_ctx* c) {
+    xchg_free(c);
+    cudaFree(c->ic_ring); c->ic_ring = nullptr;
     cudaFree(c->A); c->A = nullptr;
     cudaFree(c->Out); c->Out = nullptr;
     free_sym(c);
@@ -461,6 +490,7 @@ extern "C" int gcx_host_free(void* ptr) {
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 static int map_alloc(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc);
+static int xchg_setup(gcx_ctx* c);
 
 extern "C" int gcx_map_create(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc) {
     if (!c) return fail("gcx_map_create: null context");
@@ -498,7 +528,10 @@ static int map_alloc(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc) {
     CK(cudaMemsetAsync(c->zero_count, 0, sizeof(int32_t) * (size_t)c->nv, c->stream));
     CK(cudaMalloc(&c->keep, (size_t)c->nv));
     CK(cudaMemsetAsync(c->keep, 0, (size_t)c->nv, c->stream));
+    CK(cudaMalloc(&c->ic_ring, sizeof(double) * (size_t)c->nv * 5));
+    CK(cudaMemsetAsync(c->ic_ring, 0, sizeof(double) * (size_t)c->nv * 5, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->world > 1 && c->xchg_enable) CKR(xchg_setup(c));
     return 0;
 }
 
@@ -767,12 +800,101 @@ static int allgather_i32(gcx_ctx* c, int32_t* vec) {
     return 0;
 }
 
+// Peer-mapped exchange buffers of the sharded symmetric IC pass.  Collective: every rank calls it (from gcx_map_create).  Each rank
+// allocates [world][G] flags + [2][world][nv] doubles, the ranks swap {cudaIpc handle, pid, pointer, device, G, nv} with one NCCL
+// allgather, and map each other's buffer: cudaIpcOpenMemHandle across processes, plain peer access inside one process (one host
+// thread per GPU).  Any failure leaves xchg_ok = false on EVERY rank (the verdicts are allreduced) and the pass keeps its NCCL exchange.
+struct XchgBlob {
+    cudaIpcMemHandle_t handle;     // 64 bytes
+    long long pid;
+    void* ptr;
+    int device, grid;
+    long long nv;
+    int ok, pad;
+};
+static_assert(sizeof(XchgBlob) <= 128, "blob must fit its allgather slot");
+
+static size_t xchg_flag_bytes(gcx_ctx* c) { return (sizeof(unsigned int) * (size_t)c->world * c->sym_grid + 255) / 256 * 256; }
+
+static int xchg_setup(gcx_ctx* c) {
+    xchg_free(c);
+    if (c->world < 2 || c->world > XCHG_MAX_WORLD || !c->comm || c->sym_grid < 1) return 0;
+    const int W = c->world;
+    const size_t fb = xchg_flag_bytes(c), bytes = fb + sizeof(double) * 2 * (size_t)W * c->nv;
+    unsigned char* stage = nullptr;       // device staging of the W blobs
+    CK(cudaMalloc(&stage, 128 * (size_t)W));
+    XchgBlob mine;
+    memset(&mine, 0, sizeof mine);
+    bool good = cudaMalloc(&c->xchg_buf, bytes) == cudaSuccess;
+    if (good) good = cudaMemsetAsync(c->xchg_buf, 0, bytes, c->stream) == cudaSuccess;
+    if (good) good = cudaIpcGetMemHandle(&mine.handle, c->xchg_buf) == cudaSuccess;
+    cudaGetLastError();
+    mine.pid = (long long)getpid();
+    mine.ptr = c->xchg_buf;
+    mine.device = c->device;
+    mine.grid = c->sym_grid;
+    mine.nv = c->nv;
+    mine.ok = good ? 1 : 0;
+    std::vector<unsigned char> host(128 * (size_t)W, 0);
+    memcpy(host.data() + 128 * (size_t)c->rank, &mine, sizeof mine);
+    CK(cudaMemcpyAsync(stage + 128 * (size_t)c->rank, host.data() + 128 * (size_t)c->rank, 128, cudaMemcpyHostToDevice, c->stream));
+    NK(g_nccl.AllGather(stage + 128 * (size_t)c->rank, stage, 128, ncclUint8, c->comm, c->stream));
+    CK(cudaMemcpyAsync(host.data(), stage, 128 * (size_t)W, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < W && good; ++q) {
+        XchgBlob b;
+        memcpy(&b, host.data() + 128 * (size_t)q, sizeof b);
+        if (!b.ok || b.grid != c->sym_grid || b.nv != c->nv) { good = false; break; }
+        if (q == c->rank) { c->xchg_peer[q] = c->xchg_buf; continue; }
+        if (b.pid == mine.pid) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, c->device, b.device) != cudaSuccess || !can) { good = false; break; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { good = false; break; }
+            cudaGetLastError();
+            c->xchg_peer[q] = b.ptr;
+        } else {
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, b.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { good = false; break; }
+            c->xchg_peer[q] = p;
+            c->xchg_ipc[q] = true;
+        }
+    }
+    cudaGetLastError();
+    // every rank must take the same path: min over ranks of the local verdict (device int, reusing the staging buffer)
+    int verdict = good ? 1 : 0;
+    CK(cudaMemcpyAsync(stage, &verdict, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NK(g_nccl.AllReduce(stage, stage, 1, ncclInt32, ncclMin, c->comm, c->stream));
+    CK(cudaMemcpyAsync(&verdict, stage, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(stage));
+    if (!verdict) { xchg_free(c); return 0; }
+    c->xchg_ok = true;
+    return 0;
+}
+
+static IcXchg xchg_args(gcx_ctx* c) {
+    IcXchg X;
+    memset(&X, 0, sizeof X);
+    X.world = c->world; X.rank = c->rank; X.seq0 = c->xchg_seq;
+    const size_t fb = xchg_flag_bytes(c);
+    X.flags = (unsigned int*)c->xchg_buf;
+    X.recv = (const double*)((char*)c->xchg_buf + fb);
+    for (int q = 0; q < c->world && q < XCHG_MAX_WORLD; ++q) {
+        X.peer_flags[q] = (unsigned int*)c->xchg_peer[q];
+        X.peer_recv[q] = (double*)((char*)c->xchg_peer[q] + fb);
+    }
+    return X;
+}
+
 extern "C" int gcx_set_option(gcx_ctx* c, const char* key, double value) {
     if (!c || !key) return fail("gcx_set_option: null argument");
     const std::string k(key);
     if (k == "sym") c->sym_enable = (int)value;
     else if (k == "assume_symmetric") { c->assume_symmetric = (int)value; c->sym_state = -1; }
     else if (k == "exchange_allreduce") c->exchange_allreduce = (int)value;
+    else if (k == "peer_exchange") c->xchg_enable = (int)value;          // before gcx_map_create, on every rank
+    else if (k == "ic_defer") c->ic_defer = (int)value;
     else if (k == "sym_blocks") {
         if (c->sym_blocks != (int)value && c->stream) {       // the unit tables depend on it: rebuild on the next run
             cudaSetDevice(c->device);
@@ -1220,10 +1342,40 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
     CKR(need_map(c));
     if (!c->have_mask) return fail("gcx_ic_run: call gcx_set_mask first");
     const int n = (int)c->n;
+    bool sym = false;
+    CKR(sym_ready(c, &sym));
+    c->last_sym = sym;
+    // the deferred-scalar pass (default on the upper-triangle path); sharded it needs the peer-mapped exchange buffers
+    bool defer = sym && c->ic_fused && c->ic_defer && (c->world == 1 || c->xchg_ok);
+  rerun:
     k_ic_init<<<32, EP_THREADS, 0, c->stream>>>(c->ic_state, (int)c->nv, c->keep, c->vz, c->vB, tol, iteration);
     CK(cudaGetLastError());
     c->launches += 1;
     int n4 = (int)(c->ld / 4), nloc = (int)c->nloc, row0 = (int)c->row0;
+    long long nvll = c->nv;
+    double* tring = c->ic_ring;
+    double* uring = c->ic_ring + 3 * c->nv;
+    if (defer) {
+        // u_0 = the mask (k_ic_init left it in vz); the in-kernel reset of the chunk counter needs a zero to start from
+        CK(cudaMemcpyAsync(uring, c->vz, sizeof(double) * c->nv, cudaMemcpyDeviceToDevice, c->stream));
+        if (c->sym_ndyn > 0) CK(cudaMemsetAsync(c->sym_dyn_counter, 0, sizeof(unsigned int), c->stream));
+    }
+    auto step_symd = [&]() -> int {
+        SymTab tab = sym_tab(c);
+        IcXchg X;
+        memset(&X, 0, sizeof X);
+        X.world = 1;
+        if (c->world > 1) X = xchg_args(c);
+        void* args[] = {(void*)&c->A, (void*)&c->ld, (void*)&n, (void*)&n4, (void*)&nvll, (void*)&c->keep, (void*)&tring, (void*)&uring, (void*)&c->vB,
+                        (void*)&c->rowpart, (void*)&c->colpart, (void*)&tab, (void*)&c->ticket, (void*)&c->ic_state, (void*)&c->part, (void*)&X};
+        const size_t smem = SYM_STAGES * SYM_R * MV_THREADS * sizeof(float4);
+        ProfScope ps(c, 0);
+        if (c->world == 1)
+            CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_symd<SYM_STAGES, SYM_OCC, false>, dim3(c->sym_grid), dim3(SYM_THREADS), args, smem, c->stream));
+        else
+            CK(cudaLaunchCooperativeKernel((void*)k_ic_pass_symd<SYM_STAGES, SYM_OCC, true>, dim3(c->sym_grid), dim3(SYM_THREADS), args, smem, c->stream));
+        return 0;
+    };
     auto step_split = [&]() -> int {
         CKR(matvec(c, c->mv_variant, c->vz, c->vq, &c->ic_state->done));
         CKR(allgather_f64(c, c->vq));
@@ -1248,9 +1400,6 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         CKR(allgather_f64(c, c->vq));
         return 0;
     };
-    bool sym = false;
-    CKR(sym_ready(c, &sym));
-    c->last_sym = sym;
     auto step_split_sym = [&]() -> int {
         CKR(matvec_sym(c, c->vz, c->vq, &c->ic_state->done));
         {
@@ -1284,11 +1433,22 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         return 0;
     };
     auto step = [&]() -> int {
+        if (defer) return step_symd();
         if (sym) return c->ic_fused ? step_fused_sym() : step_split_sym();
         return c->ic_fused ? step_fused() : step_split();
     };
     IcState fin;
-    CKR(iterate<IcState>(c, c->ic_state, iteration + 4, step, &fin));
+    const int rc_it = iterate<IcState>(c, c->ic_state, iteration + 6, step, &fin);
+    if (defer && c->world > 1) c->xchg_seq += (unsigned int)iteration + 4096u;      // the same on every rank
+    CKR(rc_it);
+    if (defer && fin.error) return fail("gcx_ic_run: a peer rank did not deliver its partial vector within 20 s (peer exchange)");
+    if (defer && fin.irregular) {
+        // a bin's product changed between zero and non-zero from one pass to the next (cannot happen on a symmetric non-negative
+        // map): the deferred recurrence does not cover it -- rerun in the literal order of lib/normalizeCore.pyx:42-53
+        defer = false;
+        goto rerun;
+    }
+    c->last_matvecs_issued = fin.matvecs;
     k_ic_scale<<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>((int)c->nv, n, c->keep, c->vB, c->vscale);
     CK(cudaGetLastError());
     c->launches += 1;
@@ -1297,7 +1457,7 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
     CK(cudaStreamSynchronize(c->stream));
     if (passes) *passes = fin.pass;
     if (last_l1) *last_l1 = fin.l1;
-    if (matvecs) *matvecs = fin.matvecs;
+    if (matvecs) *matvecs = fin.pass + 1;          // products the recurrence needs; gcx_last_run_products gives the launched count
     return 0;
 }
 
@@ -1323,6 +1483,7 @@ extern "C" int gcx_kr_run(gcx_ctx* c, double tol, double delta, double Delta, do
     };
     KrState fin;
     CKR(iterate<KrState>(c, c->kr_state, 20000, step, &fin));
+    c->last_matvecs_issued = fin.matvecs;
     CK(cudaMemcpyAsync(c->vscale, c->kr.x, sizeof(double) * c->nv, cudaMemcpyDeviceToDevice, c->stream));
     c->have_scale = true;
     if (x) CK(cudaMemcpyAsync(x, c->kr.x, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -2054,6 +2215,13 @@ extern "C" int gcx_pass_bytes(gcx_ctx* c, int64_t* bytes, int* symmetric) {
     CKR(need_map(c));
     if (symmetric) *symmetric = c->last_sym ? 1 : 0;
     *bytes = c->last_sym ? sym_bytes_per_pass(c) : (int64_t)4 * c->nloc * c->n;
+    return 0;
+}
+
+extern "C" int gcx_last_run_products(gcx_ctx* c, int* launched, int* peer_exchange) {
+    if (!c) return fail("null context");
+    if (launched) *launched = c->last_matvecs_issued;
+    if (peer_exchange) *peer_exchange = c->xchg_ok ? 1 : 0;
     return 0;
 }
 

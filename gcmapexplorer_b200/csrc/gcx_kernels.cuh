@@ -553,7 +553,11 @@ struct SymTab {
     int row0, nloc;            // this rank's global row block
 };
 
-template <int NG, int STAGES, bool ZNC>
+// MODE: SYM_ALL = the whole walk; SYM_BEGIN = barrier set-up + the producer's first min(STAGES, u1 - u0) loads only (the tiles of A
+// do not depend on the vector, so a fused pass issues them BEFORE its vector phase and grid barrier); SYM_CONT = the rest of a walk
+// started with SYM_BEGIN.
+enum { SYM_ALL = 0, SYM_BEGIN = 1, SYM_CONT = 2 };
+template <int NG, int STAGES, bool ZNC, int MODE = SYM_ALL>
 __device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, long long ld, int n4, const double* z, double* rowpart,
                                                  double* colslots, const SymTab& T, float4* tiles, uint64_t* full_bar, uint64_t* empty_bar,
                                                  double* gred, long long u0, long long u1, int kfirst, int klast, bool single_panel) {
@@ -567,25 +571,29 @@ __device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, lo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nloc = T.nloc, row0 = T.row0;
     const long long NOEND = 0x7fffffffffffffffLL;
-    if (tid == 0) {
+    if (MODE != SYM_CONT) {
+        if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], WPG);
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], WPG);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
     }
-    __syncthreads();
+    const long long upre = (u1 - u0 < (long long)STAGES) ? u1 : u0 + STAGES;      // end of the part SYM_BEGIN issues
     if (u0 < u1) {
     if (warp == SYM_CW) {
         // ---------------- producer ----------------
         if (lane == 0) {
-            int stage = 0;
-            unsigned int phase = 0;
+            const long long ua = MODE == SYM_CONT ? upre : u0, ub = MODE == SYM_BEGIN ? upre : u1;
+            int stage = (int)((ua - u0) % STAGES);
+            unsigned int phase = (unsigned int)((ua - u0) / STAGES) & 1u;
             int k = kfirst;
             long long pbeg = single_panel ? 0 : T.panel_u0[k];
             long long pend = single_panel ? NOEND : T.panel_u0[k + 1];
-            for (long long u = u0; u < u1; ++u) {
+            for (long long u = ua; u < ub; ++u) {
                 while (u >= pend) {
                     ++k;
                     pbeg = pend;
@@ -609,7 +617,7 @@ __device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, lo
                 }
             }
         }
-    } else {
+    } else if (MODE != SYM_BEGIN) {
     // ---------------- consumers: group g takes units u0+g, u0+g+NG, ... ----------------
     const int g = warp / WPG, wig = warp % WPG, tig = tid - g * TG;
     const double2* z2 = reinterpret_cast<const double2*>(z);
@@ -736,19 +744,19 @@ __device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, lo
     }
     }   // consumers
     }   // u0 < u1
-    __syncthreads();
+    if (MODE != SYM_BEGIN) __syncthreads();
 }
 
 // One CTA's whole job in a symmetric pass: its static share, then chunks of the dynamic pool until the pool is empty.
-template <int NG, int STAGES, bool ZNC>
+template <int NG, int STAGES, bool ZNC, bool BEGUN = false>
 __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, long long ld, int n4, const double* z, double* rowpart,
                                                 double* colpart, const SymTab& T, float4* tiles, uint64_t* full_bar, uint64_t* empty_bar,
                                                 double* gred) {
     __shared__ int s_chunk;
     const long long c = blockIdx.x;
     const long long t_start = (T.dbg_cycles != nullptr && threadIdx.x == 0) ? clock64() : 0;
-    matvec_sym_range<NG, STAGES, ZNC>(A, ld, n4, z, rowpart, colpart + (size_t)c * T.nslots * NG * 1024, T, tiles, full_bar, empty_bar, gred,
-                                      T.cta_u0[c], T.cta_u0[c + 1], T.cta_kf[c], T.cta_kl[c], false);
+    matvec_sym_range<NG, STAGES, ZNC, BEGUN ? SYM_CONT : SYM_ALL>(A, ld, n4, z, rowpart, colpart + (size_t)c * T.nslots * NG * 1024, T, tiles, full_bar,
+                                                                  empty_bar, gred, T.cta_u0[c], T.cta_u0[c + 1], T.cta_kf[c], T.cta_kl[c], false);
     while (T.ndyn > 0) {
         if (threadIdx.x == 0) s_chunk = (int)atomicAdd(T.dyn_counter, 1u);
         __syncthreads();
@@ -1474,6 +1482,10 @@ k_checksum(const float* __restrict__ A, long long ld, int nloc, int n, int row0,
 struct IcState {
     double cc, S, l1, mean, tol;
     int pass, done, cnt, max_iter, matvecs;
+    // deferred-scalar pass (k_ic_pass_symd): v = alpha * u for the vector u the next product multiplies, B = beta / u on bins with
+    // data and phi on kept bins without, for the last closed pass; irregular / error make the host fall back / fail
+    int irregular, error;
+    double alpha, beta, phi;
 };
 
 __global__ void __launch_bounds__(EP_THREADS)
@@ -1485,6 +1497,7 @@ k_ic_init(IcState* st, int nv, const uint8_t* __restrict__ keep, double* v, doub
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->cc = 0; st->S = 0; st->l1 = 0; st->mean = 0; st->tol = tol;
         st->pass = 0; st->done = 0; st->cnt = 0; st->max_iter = max_iter; st->matvecs = 0;
+        st->irregular = 0; st->error = 0; st->alpha = 1.0; st->beta = 1.0; st->phi = 1.0;
     }
 }
 
@@ -1917,6 +1930,203 @@ k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, cons
         if (atomicAdd(ticket, 1u) == (unsigned int)(G - 1)) {       // last CTA to issue its work: safe to bump the counter
             *ticket = 0u;
             st->matvecs = m + 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused IC pass, deferred scalars (default on the upper-triangle path).  The bias update of lib/normalizeCore.pyx:42-53 is
+//     v_next,i = mean / (B_next,i * d_i) = kappa / t_i          with ONE global scalar kappa = mean / (f g),
+// because B_next,i = f / v_i and d_i = g v_i t_i (f = sqrt(S'/cc) :52, g = cc/S' :53, mean = g S'/C :44).  So the product of
+// launch L runs on the UNSCALED vector u = 1/t' (t' = A u of the previous launch) the moment t' is folded -- the global sums
+// (S', count, L1) are no longer between the fold and the product.  With v = alpha u:  t = alpha t',  S' = alpha^2 sum u t',
+// alpha_next = kappa / alpha, and the bias of the pass closed by product m is B_i = (f_m / alpha_m) t'_{m-1,i} = beta_m t'_{m-1,i}
+// on bins with data, Phi_m = f_1 ... f_m on kept bins whose row is empty (their v only ever multiplies zeros).  Launch L:
+//   P0  producer warp issues the first tiles of A (they do not depend on u)
+//   P1  per bin: fold t'_{L-1}; u_L = 1/t'; partial sum u_{L-1} t'_{L-1} and count; with beta/Phi of pass L-2 (known since launch
+//       L-1): B_i, partial L1 of pass L-2                                     -> ONE grid barrier (u_L complete)
+//   P2  every CTA folds the 3 x G partials in the same order: scalars of pass L-1, convergence of pass L-2 (:55-57) -> exit or
+//   P3  the symmetric product on u_L.
+// Convergence is seen one launch later than in k_ic_pass_sym_tma (one extra product per run), the vector phase shrinks from
+// fold + 2 grid barriers + 3 block reductions + 2 sweeps to fold + 1 barrier.  Rounding differs from the literal order by a few
+// ulp per pass (parity: bias 1e-9, equal pass counts -- tests/test_gpu_parity.py).  A bin whose t' changes between zero and
+// non-zero from one pass to the next (impossible on a symmetric non-negative map) sets st->irregular; the host then reruns with
+// the literal-order kernel.
+//
+// DIST: the map is row-sharded (circulant block assignment, see sym_ready); each rank folds its PARTIAL t' for all n bins and
+// stores it straight into every peer's receive buffer over NVLink (peer-mapped memory, cudaIpc or same-process P2P); per-CTA flags
+// replace a collective: CTA b of every rank owns the same bins, so CTA b only waits for the W flags of CTA b on the peers.  Every
+// rank then adds the W partials in rank order -> bitwise identical t', u, scalars on all ranks; no NCCL call, no extra launch.
+// ---------------------------------------------------------------------------------------------------
+constexpr int XCHG_MAX_WORLD = 8;
+struct IcXchg {
+    int world, rank;
+    unsigned int seq0;                          // flag value of launch 0 of this run (flags only ever grow)
+    unsigned int* flags;                        // this rank's [world][G]: last launch for which CTA b of rank q delivered
+    const double* recv;                         // this rank's [2][world][nv]: partial t' per source rank, double-buffered by launch parity
+    unsigned int* peer_flags[XCHG_MAX_WORLD];   // the same two buffers on every rank, peer-mapped
+    double* peer_recv[XCHG_MAX_WORLD];
+};
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int STAGES, int OCC, bool DIST>
+__global__ void __launch_bounds__(SYM_THREADS, OCC)
+k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long long nv, const uint8_t* __restrict__ keep, double* tring,
+               double* uring, double* B, double* rowpart, double* colpart, SymTab T, unsigned int* ticket, IcState* st, double* part,
+               IcXchg X) {
+    namespace cg = cooperative_groups;
+    if (st->done) return;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ double sm[32];
+    __shared__ double gred[2 * SYM_CW * SYM_R];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int L = st->matvecs;                        // products completed so far; the partials hold product L-1
+    const int gth = bid * SYM_THREADS + tid, nth = G * SYM_THREADS;
+    const double alpha = st->alpha, beta = st->beta, phi = st->phi, cc_prev = st->cc, tol = st->tol;
+    const int max_iter = st->max_iter;
+    float4* tiles = reinterpret_cast<float4*>(tma_smem);
+    double* ucur = uring + (long long)(L & 1) * nv;
+    const long long su0 = T.cta_u0[bid], su1 = T.cta_u0[bid + 1];
+
+    // ---- P0: barriers + the first tiles of this CTA's static share ----
+    matvec_sym_range<SYM_NG, STAGES, false, SYM_BEGIN>(A, ld, n4, ucur, rowpart, colpart + (size_t)bid * T.nslots * SYM_NG * 1024, T, tiles, full_bar,
+                                                       empty_bar, gred, su0, su1, T.cta_kf[bid], T.cta_kl[bid], false);
+    if (L > 0) {
+        const double* uprev = uring + (long long)((L + 1) & 1) * nv;
+        double* tcur = tring + (long long)((L + 2) % 3) * nv;            // t'_{L-1}
+        const double* tm2 = tring + (long long)((L + 1) % 3) * nv;       // t'_{L-2}
+        const double* tm3 = tring + (long long)(L % 3) * nv;             // t'_{L-3} = 1 / u_{L-2}
+        const int par = L & 1;
+        if (DIST) {
+            // ---- P1a: this rank's partial t' of every bin -> all ranks' receive buffers ----
+            for (int base = 0; base < n; base += nth / 8) {
+                const int i = base + (gth >> 3);
+                const double pi = sym_fold_group8(i, i < n, n4, rowpart, colpart, T);
+                if (i < n && (tid & 7) == 0) {
+                    for (int q = 0; q < X.world; ++q) X.peer_recv[q][((long long)par * X.world + X.rank) * nv + i] = pi;
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < X.world) {
+                const unsigned int want = X.seq0 + (unsigned int)L;
+                st_release_sys_u32(X.peer_flags[tid] + (long long)X.rank * G + bid, want);
+                const unsigned int* f = X.flags + (long long)tid * G + bid;
+                const unsigned long long t0 = globaltimer_ns();
+                while ((int)(ld_acquire_sys_u32(f) - want) < 0) {
+                    if (globaltimer_ns() - t0 > 20000000000ull) {       // 20 s: a peer died -- fail instead of hanging the box
+                        st->error = 1;
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- P1: fold, next vector, partial sums ----
+        double s = 0.0, c = 0.0, l1 = 0.0;
+        int irr = 0;
+        for (int base = 0; base < n; base += nth / 8) {
+            const int i = base + (gth >> 3);
+            double tp = 0.0;
+            if (!DIST) tp = sym_fold_group8(i, i < n, n4, rowpart, colpart, T);
+            if (i < n && (tid & 7) == 0) {
+                if (DIST) {
+                    for (int q = 0; q < X.world; ++q) tp += __ldcg(X.recv + ((long long)par * X.world + q) * nv + i);     // rank order
+                }
+                tcur[i] = tp;
+                double un = 0.0;
+                if (keep[i]) {
+                    const double p = uprev[i] * tp;
+                    s += p;
+                    c += (p != 0.0) ? 1.0 : 0.0;
+                    const bool ne = tp != 0.0;
+                    un = ne ? 1.0 / tp : 0.0;
+                    if (L >= 2 && ((tm2[i] != 0.0) != ne)) irr = 1;
+                    if (L >= 3) {
+                        const double w = tm3[i];
+                        const double bn = (w != 0.0) ? beta * w : phi;       // f / v (:51-52); empty kept bin: f_1 ... f_m
+                        l1 += fabs(B[i] - bn);                               // :56
+                        B[i] = bn;
+                    }
+                }
+                ucur[i] = un;
+            }
+        }
+        if (irr) st->irregular = 1;
+        // one block reduction for the three sums (fixed tree)
+        s = warp_sum(s); c = warp_sum(c); l1 = warp_sum(l1);
+        if (lane == 0) { sm[warp] = s; gred[warp] = c; gred[16 + warp] = l1; }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0, b = 0.0, d = 0.0;
+#pragma unroll
+            for (int w = 0; w < SYM_THREADS / 32; ++w) { a += sm[w]; b += gred[w]; d += gred[16 + w]; }
+            part[bid] = a;
+            part[G + bid] = b;
+            part[2 * G + bid] = d;
+        }
+        grid.sync();
+        // ---- P2: scalars of pass L-1, convergence of pass L-2 (every CTA, same order -> same bits) ----
+        if (warp == 0) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            for (int b = lane; b < G; b += 32) {
+                a0 += __ldcg(part + b);
+                a1 += __ldcg(part + G + b);
+                a2 += __ldcg(part + 2 * G + b);
+            }
+            a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+            if (lane == 0) { sm[0] = a0; sm[1] = a1; sm[2] = a2; }
+        }
+        __syncthreads();
+        const double Sp = sm[0], C = sm[1], L1 = sm[2];
+        const int mm = L - 1;                                 // the product these sums close
+        const double S = alpha * alpha * Sp;                  // v't with v = alpha u, t = alpha t'
+        const double cc = (mm == 0) ? S : cc_prev;            // contact_count, lib/normalizeCore.pyx:36
+        const double f = (mm == 0) ? 1.0 : sqrt(S / cc);      // :52
+        const double g = (mm == 0) ? 1.0 : cc / S;            // :53
+        const double mean = g * S / C;                        // :44
+        const double kappa = mean / (f * g);
+        const int mp = L - 2;                                 // the pass whose L1 is complete now
+        const bool done = (mp >= 2) && (L1 < tol || (mp - 1) > max_iter);       // :55-57
+        const bool err = (DIST && st->error) || st->irregular;      // both written before the grid barrier
+        if (bid == 0 && tid == 0) {
+            st->cc = cc; st->S = S; st->mean = mean; st->cnt = (int)C;
+            st->alpha = kappa / alpha; st->beta = f / alpha; st->phi = phi * f;
+            if (mp >= 1) { st->l1 = L1; st->pass = mp; }
+            st->done = (done || err) ? 1 : 0;
+        }
+        if (done || err) {
+            // the tiles issued in P0 must land before the CTA may exit
+            const long long npre = (su1 - su0 < (long long)STAGES) ? (su1 - su0) : (long long)STAGES;
+            if (tid < (int)npre) mbar_wait(&full_bar[tid], 0u);
+            __syncthreads();
+            return;
+        }
+    }
+    matvec_sym_core<SYM_NG, STAGES, false, true>(A, ld, n4, ucur, rowpart, colpart, T, tiles, full_bar, empty_bar, gred);
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == (unsigned int)(G - 1)) {       // last CTA: every CTA is past its chunk fetches
+            *ticket = 0u;
+            if (T.ndyn > 0) *T.dyn_counter = 0u;
+            st->matvecs = L + 1;
         }
     }
 }

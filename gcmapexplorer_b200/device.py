@@ -191,7 +191,9 @@ class DeviceMap:
         check(lib().gcx_ic_run(self._ctx, float(tol), int(iteration), bias.ctypes.data_as(_lib._c_f64p),
                                C.byref(passes), C.byref(l1), C.byref(mv)))
         pb, sym = self.pass_bytes()
-        return dict(bias=bias, passes=passes.value, l1=l1.value, matvecs=mv.value, ms=self.last_run_ms(), pass_bytes=pb, symmetric=sym)
+        launched, peer = self.last_run_products()
+        return dict(bias=bias, passes=passes.value, l1=l1.value, matvecs=mv.value, products_launched=launched, peer_exchange=peer,
+                    ms=self.last_run_ms(), pass_bytes=pb, symmetric=sym)
 
     def kr(self, tol=1e-12, delta=0.1, Delta=3.0):
         x = np.empty(self.n, dtype=np.float64)
@@ -319,6 +321,12 @@ class DeviceMap:
         b, sym = C.c_int64(0), C.c_int(0)
         check(lib().gcx_pass_bytes(self._ctx, C.byref(b), C.byref(sym)))
         return b.value, bool(sym.value)
+
+    def last_run_products(self):
+        """(products the last ic/kr run launched, whether the sharded IC pass used the NVLink peer exchange)."""
+        a, b = C.c_int(0), C.c_int(0)
+        check(lib().gcx_last_run_products(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, bool(b.value)
 
     def last_run_ms(self):
         ms = C.c_double(0)

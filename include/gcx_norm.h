@@ -153,6 +153,10 @@ int gcx_corr_last_route(gcx_ctx* ctx, int* slices, int* sxy_sliced);
  *   "exchange_allreduce" 0/1  the row blocks are not the equal ceil(n/world) blocks: exchange n-vectors by zero-fill +
  *                             allreduce instead of allgather (set it on every rank, before gcx_map_create)
  *   "sym_blocks"         0/1  sharded upper-triangle pass: deal the off-diagonal blocks out in the circulant pattern (default 1)
+ *   "peer_exchange"      0/1  sharded upper-triangle IC pass: exchange the partial vectors by NVLink stores into peer-mapped
+ *                             buffers with per-CTA flags inside the fused launch (default 1; set before gcx_map_create on every
+ *                             rank; falls back to the NCCL allreduce when peer mapping is unavailable; env GCX_PEER_EXCHANGE)
+ *   "ic_defer"           0/1  upper-triangle IC pass with deferred scalars (default 1; env GCX_IC_DEFER; 0 = literal order)
  *   "matvec_variant"     kernel variant for sweeps
  *   "sd_variant"         stationary distribution: 1 TMA-bulk transposed product (default), 0 per-thread loads
  *   "corr_variant"       correlation: 1 counts on the bf16 tensor cores + DSYRK + DGEMM (default), 0 three DGEMMs
@@ -185,6 +189,10 @@ int gcx_pass_bytes(gcx_ctx* ctx, int64_t* bytes, int* symmetric);
 int gcx_debug_sym_cycles(gcx_ctx* ctx, int64_t* cycles, int capacity, int* count);
 /* device time (ms, CUDA events) of the last ic/kr run: matrix resident -> final vector */
 int gcx_last_run_ms(gcx_ctx* ctx, double* ms);
+/* matrix-vector products the last ic/kr run really launched: the deferred-scalar IC pass sees convergence one launch late and
+ * runs passes + 2 products where the recurrence needs passes + 1 (what gcx_ic_run reports); peer_exchange: 1 when the sharded
+ * symmetric IC pass exchanges its partial vectors through peer-mapped NVLink stores instead of an NCCL allreduce */
+int gcx_last_run_products(gcx_ctx* ctx, int* launched, int* peer_exchange);
 /* total kernel launches issued by this context since creation */
 int gcx_launch_count(gcx_ctx* ctx, int64_t* launches);
 /* micro-benchmark: `iters` back-to-back matvec launches (variant: 0 = default), device ms total */

@@ -126,6 +126,54 @@ def ic_fp64(matrix, tol=1e-4, iteration=500):
     return M, B, passes, l1
 
 
+def ic_fp64_matvec(matrix, tol=1e-4, iteration=500, matvec=None):
+    """The recurrence of lib/normalizeCore.pyx:41-60 in fp64 WITHOUT rewriting the matrix, for sizes where ic_fp64's five
+    sweeps of an n x n float64 array per pass take minutes (tests/golden/gen_golden_large.py: n = 24,926).
+
+    The working matrix of pass k is M = A o (w w') (every step of :48-53 scales rows/columns by a vector or everything by a
+    scalar), so with t = A' w (the column sums of :42 are w o t):
+        dB  = w o t / mean(w o t != 0), zeros -> 1      (:42-45)
+        w1  = w / dB                                    (:48-49)
+        s   = w1' A w1                                  (np.sum(M) of :52-53)
+        B  *= dB * sqrt(s / cc)                         (:51-52)
+        w   = w1 * sqrt(cc / s)                         (:53)
+    and the next pass's column sums come from the same product t1 = A' w1 that gave s (w o (A' w) = (cc/s) w1 o t1): one product
+    per pass.  Checked against ic_fp64 (the literal in-place form) in tests/test_oracle.py: equal pass counts, bias to 1e-12.
+    matvec(w) must return A' w in float64 (default: float64 copy of `matrix`, BLAS dgemv).
+    Returns (B, passes, l1_history)."""
+    n = matrix.shape[0]
+    if matvec is None:
+        A64 = np.asarray(matrix, dtype=np.float64)
+        matvec = lambda w: A64.T.dot(w)                                # noqa: E731
+    w = np.ones(n)
+    t = matvec(w)
+    cc = float(t.sum())                                                # :36
+    colsum = w * t
+    B = np.ones(n)
+    prev_B = None
+    count = passes = 0
+    l1 = []
+    while True:
+        dB = colsum / np.mean(colsum[colsum != 0])                     # :44
+        dB[dB == 0] = 1                                                # :45
+        w1 = w / dB                                                    # :48-49
+        t1 = matvec(w1)
+        s = float(w1 @ t1)
+        B = B * dB * math.sqrt(s / cc)                                 # :51-52
+        g = cc / s                                                     # :53
+        w = w1 * math.sqrt(g)
+        colsum = g * (w1 * t1)
+        passes += 1
+        if prev_B is not None:                                         # :55-57
+            d = float(np.abs(prev_B - B).sum())
+            l1.append(d)
+            if d < tol or count > iteration:
+                break
+        count += 1
+        prev_B = B.copy()
+    return B, passes, l1
+
+
 # --------------------------------------------------------------------------------------------------
 # KR  (lib/normalizeKnightRuiz.pyx:74-288, RAM variant)
 # --------------------------------------------------------------------------------------------------

@@ -96,6 +96,7 @@ def test_ic_vs_fp64_oracle(gx, n, seed):
     M64, B, passes, l1 = onp.ic_fp64(A, 1e-4, 500)
     r = _ic_device(gx, A, 1e-4, 500, np.ones(n, dtype=bool))
     assert r["passes"] == passes and r["matvecs"] == passes + 1
+    assert r["products_launched"] == passes + (2 if r["symmetric"] else 1)
     np.testing.assert_allclose(r["bias"], B, rtol=BIAS_RTOL)
     assert rel_err(r["matrix"], M64.astype(np.float32)) < MAT_RTOL
     assert abs(r["l1"] - l1[-1]) <= 1e-6 * max(l1[-1], 1e-30) + 1e-15
@@ -538,6 +539,103 @@ def test_symmetric_pass_vs_oracle_and_asymmetric_fallback(gx):
     A2[5, 1900] += 1.0                       # break the symmetry in one entry
     r2 = _ic_device(gx, A2, 1e-4, 500, np.ones(n, dtype=bool))
     assert not r2["symmetric"]               # dense pass: row sums of the stored matrix, like every other dense run
+
+
+@pytest.mark.parametrize("n", [2100, 4099, 6145])
+def test_deferred_scalar_pass_matches_literal_order(gx, n):
+    """The default upper-triangle IC pass defers the global scalars (k_ic_pass_symd: v_next = kappa / t, one grid barrier);
+    option ic_defer=0 runs the literal order of lib/normalizeCore.pyx:42-53 (k_ic_pass_sym_tma).  Same pass count, same last
+    L1, bias equal to rounding; the deferred pass launches exactly one more product."""
+    res = {}
+    for defer in (1, 0):
+        with gx.DeviceMap(n, options={"ic_defer": defer}) as dm:
+            dm.synth(seed=91, scale=150.0, alpha=1.0, empty_frac=0.01)
+            rs, _ = dm.row_stats()
+            for mask in (np.ones(n, dtype=bool), rs != 0):       # unfiltered (empty bins kept: the Phi branch) and filtered
+                dm.set_mask(mask)
+                res[(defer, bool(mask.all()))] = dm.ic(1e-4, 500)
+            dm.set_mask(np.ones(n, dtype=bool))
+            res[(defer, "cap")] = dm.ic(1e-4, 3)                 # iteration cap: 5 passes (lib/normalizeCore.pyx:55-60)
+            res[(defer, "cap0")] = dm.ic(1e-4, 0)
+    for key in (True, False, "cap", "cap0"):
+        a, b = res[(1, key)], res[(0, key)]
+        assert a["symmetric"] and b["symmetric"]
+        assert a["passes"] == b["passes"] and a["matvecs"] == b["matvecs"] == a["passes"] + 1
+        assert a["products_launched"] == a["passes"] + 2 and b["products_launched"] == b["passes"] + 1
+        np.testing.assert_allclose(a["bias"], b["bias"], rtol=1e-12)
+        assert abs(a["l1"] - b["l1"]) <= 1e-9 * b["l1"] + 1e-18
+    assert res[(1, "cap")]["passes"] == 5 and res[(1, "cap0")]["passes"] == 2
+
+
+def test_deferred_scalar_pass_falls_back_on_irregular_bins(gx):
+    """A bin whose product is exactly zero in one pass and non-zero in the next (here: a row holding only +1 and -1, which
+    cancel under the all-ones start vector) is outside the deferred recurrence; the run must notice and give the
+    literal-order result."""
+    n = 2100
+    A = onp.synth_map(n, seed=33)
+    i, j, k = 700, 40, 1500
+    A[i, :] = 0; A[:, i] = 0
+    A[i, j] = A[j, i] = 1.0
+    A[i, k] = A[k, i] = -1.0
+    keep = np.ones(n, dtype=bool)
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.set_mask(keep)
+        a = dm.ic(1e-4, 40)
+    with gx.DeviceMap(n, options={"ic_defer": 0}) as dm:
+        dm.upload(A)
+        dm.set_mask(keep)
+        b = dm.ic(1e-4, 40)
+    assert a["symmetric"] and b["symmetric"]
+    assert a["passes"] == b["passes"] and a["products_launched"] == b["products_launched"]      # the rerun took the literal kernel
+    assert np.array_equal(a["bias"], b["bias"])
+
+
+LARGE_DIR = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "large")
+
+
+def _large(name):
+    import os
+    p = os.path.join(LARGE_DIR, name)
+    if not os.path.isfile(p):
+        pytest.skip("fixture %s not generated yet (tests/golden/gen_golden_large.py, needs a GPU box)" % name)
+    return np.load(p, allow_pickle=False)
+
+
+@pytest.mark.parametrize("sym", [1, 0])
+def test_at_size_ic_vs_fp64_oracle(gx, sym):
+    """BASELINE configs[1] at full size (n = 24,926, the map bench.py times): bias and pass count of the CUDA path -- the
+    upper-triangle deferred pass with its 296-CTA static + dynamic-pool schedule, and the dense TMA pass -- against the fp64
+    CPU oracle (oracle_np.ic_fp64_matvec = lib/normalizeCore.pyx:41-60) run on the host copy of the same device-generated map."""
+    g = _large("ic_n24926_s110.npz")
+    n = int(g["n"])
+    with gx.DeviceMap(n, options={"sym": sym}) as dm:
+        dm.synth(seed=int(g["seed"]), scale=200.0, alpha=1.0, empty_frac=0.01)
+        assert dm.checksum(0) == int(g["checksum"])                  # the same map, bit for bit
+        dm.set_mask(np.ones(n, dtype=bool))
+        r = dm.ic(float(g["tol"]), int(g["iteration"]))
+    assert r["symmetric"] == bool(sym)
+    assert r["passes"] == int(g["passes"])
+    np.testing.assert_allclose(r["bias"], g["bias"], rtol=BIAS_RTOL)
+    assert abs(r["l1"] - float(g["l1"][-1])) <= 1e-6 * float(g["l1"][-1])
+
+
+@pytest.mark.parametrize("name,sym", [("kr_n24926_s110.npz", 1), ("kr_n24926_s110.npz", 0), ("kr_n49851_s110.npz", 1), ("kr_n49851_s110.npz", 0)])
+def test_at_size_kr_vs_oracle(gx, name, sym):
+    """KR at n = 24,926 and at BASELINE configs[2] (n = 49,851): x, outer iterations and matrix-vector products against
+    oracle_np.kr (lib/normalizeKnightRuiz.pyx:106-191, 271-286) on the host copy of the same map."""
+    g = _large(name)
+    n = int(g["n"])
+    with gx.DeviceMap(n, options={"sym": sym}) as dm:
+        dm.synth(seed=int(g["seed"]), scale=200.0, alpha=1.0, empty_frac=0.01)
+        assert dm.checksum(0) == int(g["checksum"])
+        rs, _ = dm.row_stats()
+        keep = rs != 0
+        dm.set_mask(keep)
+        r = dm.kr(float(g["tol"]), 0.1, 3.0)
+    assert r["symmetric"] == bool(sym)
+    assert (r["outer"], r["MVP"]) == (int(g["outer"]), int(g["MVP"]))
+    np.testing.assert_allclose(r["x"][keep], g["x"][keep], rtol=BIAS_RTOL)
+    assert np.all(r["x"][~keep] == 0)
 
 
 # --------------------------------------------------------------------------------------------------
