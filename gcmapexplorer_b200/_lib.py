@@ -51,6 +51,7 @@ _PROTOS = {
     "gcx_ic_run": (C.c_int, [_ctx, C.c_double, C.c_int, _c_f64p, C.POINTER(C.c_int), _c_f64p, C.POINTER(C.c_int)]),
     "gcx_kr_run": (C.c_int, [_ctx, C.c_double, C.c_double, C.c_double, _c_f64p, C.POINTER(C.c_int), C.POINTER(C.c_int), _c_f64p]),
     "gcx_apply_sym_scale": (C.c_int, [_ctx, _c_f64p, C.c_int, C.c_int, _c_f32p, _c_f32p]),
+    "gcx_apply_sym_vc": (C.c_int, [_ctx, _c_u8p, C.c_int, C.c_int, _c_f32p, _c_f32p, _c_f32p, _c_f32p]),
     "gcx_vc_run": (C.c_int, [_ctx, C.c_int, C.c_int, _c_f32p, _c_f32p, _c_f32p]),
     "gcx_diag_stats": (C.c_int, [_ctx, C.c_int, _c_f64p]),
     "gcx_diag_apply": (C.c_int, [_ctx, _c_f64p, C.c_int, C.c_int, _c_f32p, _c_f32p]),
@@ -71,6 +72,7 @@ _PROTOS = {
     "gcx_timer_stop": (C.c_int, [_ctx, _c_f64p]),
     "gcx_map_invalidate": (C.c_int, [_ctx]),
     "gcx_debug_sym_cycles": (C.c_int, [_ctx, _c_i64p, C.c_int, C.POINTER(C.c_int)]),
+    "gcx_debug_sym_stamps": (C.c_int, [_ctx, _c_i64p, C.c_int, C.POINTER(C.c_int)]),
     "gcx_pass_bytes": (C.c_int, [_ctx, _c_i64p, C.POINTER(C.c_int)]),
     "gcx_last_run_ms": (C.c_int, [_ctx, _c_f64p]),
     "gcx_last_run_products": (C.c_int, [_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

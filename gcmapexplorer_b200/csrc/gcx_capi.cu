@@ -148,6 +148,9 @@ struct gcx_ctx {
     int64_t n = 0, ld = 0, row0 = 0, nloc = 0, nv = 0;
     float* A = nullptr;
     float* Out = nullptr;
+    float* Out2 = nullptr;       // second result buffer of the fused apply + VC pass
+    uint8_t* keep2 = nullptr;    // its VC mask
+    MinMax* mm2 = nullptr;
     // vectors (float64, nv each) carved from one slab
     double* slab = nullptr;
     double *vz = nullptr, *vq = nullptr, *vB = nullptr, *vscale = nullptr, *vrowsum = nullptr, *vavg = nullptr;
@@ -169,6 +172,8 @@ struct gcx_ctx {
     int sym_nch = 0;
     int64_t sym_bytes = 0;
     long long* sym_dbg = nullptr;          // per-CTA main-loop cycles (GCX_SYM_DEBUG=1)
+    long long* sym_stamps = nullptr;       // [G][16] phase timestamps of one launch of k_ic_pass_symd (GCX_SYM_DEBUG=1)
+    int sym_dbg_launch = 20;               // GCX_SYM_DEBUG_LAUNCH
     double* colpart_dyn = nullptr;         // [ndyn][SYM_NG][1024] column partials of the dynamic chunks
     unsigned int* sym_dyn_counter = nullptr;
     int sym_ndyn = 0;
@@ -325,6 +330,7 @@ static int ctx_init(gcx_ctx* c, int device) {
     CK(cudaMalloc(&c->kr_state, sizeof(KrState)));
     CK(cudaMalloc(&c->sd_state, sizeof(SdState)));
     CK(cudaMalloc(&c->mm, sizeof(MinMax)));
+    CK(cudaMalloc(&c->mm2, sizeof(MinMax)));
     CK(cudaMalloc(&c->csum_dev, sizeof(unsigned long long)));
     CK(cudaMalloc(&c->ticket, sizeof(unsigned int)));
     CK(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
@@ -403,6 +409,7 @@ static void free_sym(gcx_ctx* c) {
     cudaFree(c->sym_tab_ll); c->sym_tab_ll = nullptr;
     cudaFree(c->sym_tab_i); c->sym_tab_i = nullptr;
     cudaFree(c->sym_dbg); c->sym_dbg = nullptr;
+    cudaFree(c->sym_stamps); c->sym_stamps = nullptr;
     cudaFree(c->colpart_dyn); c->colpart_dyn = nullptr;
     cudaFree(c->sym_dyn_counter); c->sym_dyn_counter = nullptr;
     c->sym_ndyn = 0;
@@ -423,6 +430,8 @@ static void free_map(gcx_ctx* c) {
     cudaFree(c->ic_ring); c->ic_ring = nullptr;
     cudaFree(c->A); c->A = nullptr;
     cudaFree(c->Out); c->Out = nullptr;
+    cudaFree(c->Out2); c->Out2 = nullptr;
+    cudaFree(c->keep2); c->keep2 = nullptr;
     free_sym(c);
     c->sym_state = -1;
     cudaFree(c->slab); c->slab = nullptr;
@@ -441,7 +450,7 @@ extern "C" int gcx_ctx_destroy(gcx_ctx* c) {
     free_map(c);
     for (auto& p : c->evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
-    cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->sd_state); cudaFree(c->mm); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws); cudaFree(c->part); cudaFree(c->scratch);
+    cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->sd_state); cudaFree(c->mm); cudaFree(c->mm2); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws); cudaFree(c->part); cudaFree(c->scratch);
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int i = 0; i < 2; ++i) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
@@ -627,7 +636,7 @@ extern "C" int gcx_map_upload(gcx_ctx* c, const float* host, int64_t host_ld) {
 
 extern "C" int gcx_map_download(gcx_ctx* c, int which, float* host, int64_t host_ld) {
     CKR(need_map(c));
-    const float* src = which == 0 ? c->A : c->Out;
+    const float* src = which == 0 ? c->A : (which == 2 ? c->Out2 : c->Out);
     if (!src) return fail("no output map resident");
     if (host_ld < c->n) return fail("host_ld < n");
     const size_t width = sizeof(float) * (size_t)c->n;
@@ -663,7 +672,7 @@ extern "C" int gcx_map_download(gcx_ctx* c, int which, float* host, int64_t host
 
 extern "C" int gcx_map_download_async(gcx_ctx* c, int which, float* host, int64_t host_ld) {
     CKR(need_map(c));
-    const float* src = which == 0 ? c->A : c->Out;
+    const float* src = which == 0 ? c->A : (which == 2 ? c->Out2 : c->Out);
     if (!src) return fail("no output map resident");
     if (host_ld < c->n) return fail("host_ld < n");
     if (!is_pinned(host)) return fail("gcx_map_download_async needs pinned host memory (gcx_host_alloc)");
@@ -747,7 +756,7 @@ extern "C" int gcx_map_swap(gcx_ctx* c) {
 
 extern "C" int gcx_map_checksum(gcx_ctx* c, int which, uint64_t* sum) {
     CKR(need_map(c));
-    const float* src = which == 0 ? c->A : c->Out;
+    const float* src = which == 0 ? c->A : (which == 2 ? c->Out2 : c->Out);
     if (!src) return fail("no output map resident");
     CK(cudaMemsetAsync(c->csum_dev, 0, sizeof(unsigned long long), c->stream));
     k_checksum<<<grid_rows(c), MV_THREADS, 0, c->stream>>>(src, c->ld, (int)c->nloc, (int)c->n, (int)c->row0, c->csum_dev);
@@ -1161,6 +1170,9 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         if (getenv("GCX_SYM_DEBUG") && !c->sym_dbg) {
             CK(cudaMalloc(&c->sym_dbg, sizeof(long long) * (size_t)G));
             CK(cudaMemset(c->sym_dbg, 0, sizeof(long long) * (size_t)G));
+            CK(cudaMalloc(&c->sym_stamps, sizeof(long long) * 16 * (size_t)G));
+            CK(cudaMemset(c->sym_stamps, 0, sizeof(long long) * 16 * (size_t)G));
+            if (const char* e = getenv("GCX_SYM_DEBUG_LAUNCH")) c->sym_dbg_launch = atoi(e);
         }
         // rowpart must start from zero: a (panel, band) is written by one consumer group only, the fold adds both
         CK(cudaMemsetAsync(c->rowpart, 0, rp_bytes, c->stream));
@@ -1182,6 +1194,8 @@ static SymTab sym_tab(gcx_ctx* c) {
     T.panel_full = c->sym_tab_i + 2 * G + 2 * nch;
     T.kfold_lo = c->sym_kfold_lo;
     T.dbg_cycles = c->sym_dbg;
+    T.dbg_stamps = c->sym_stamps;
+    T.dbg_launch = c->sym_dbg_launch;
     T.ndyn = c->sym_ndyn;
     T.dyn_k = c->sym_tab_i + 2 * G + 3 * nch;
     T.dyn_b0 = T.dyn_k + c->sym_ndyn;
@@ -1553,6 +1567,63 @@ extern "C" int gcx_apply_sym_scale(gcx_ctx* c, const double* s, int masked_mode,
     CK(cudaGetLastError());
     if (in_place) { c->have_rowsum = false; c->sym_state = -1; }
     return mm_end(c, minv, maxv);
+}
+
+static int mm_read(gcx_ctx* c, MinMax* dev, float* minv, float* maxv) {
+    if (c->world > 1) {
+        NK(g_nccl.AllReduce(&dev->min_nz, &dev->min_nz, 1, ncclUint32, ncclMin, c->comm, c->stream));
+        NK(g_nccl.AllReduce(&dev->max_all, &dev->max_all, 1, ncclUint32, ncclMax, c->comm, c->stream));
+    }
+    MinMax r;
+    CKR(read_small(c, dev, sizeof r, &r));
+    const float nanv = __builtin_nanf("");
+    if (minv) *minv = r.min_nz == 0xffffffffu ? nanv : ord2f(r.min_nz);
+    if (maxv) *maxv = r.max_all == 0u ? nanv : ord2f(r.max_all);
+    return 0;
+}
+
+__global__ void k_f64_to_f32(int nv, const double* __restrict__ a, float* __restrict__ b);
+
+// Fused tail of a pipeline that wants BOTH normalizations of one map (bench.py's step; the batch driver): the scaled map of
+// gcx_apply_sym_scale (resident scale vector and mask) into output 1 and the vanilla-coverage map of gcx_vc_run (mask keep_vc)
+// into output 2, from ONE read of the input: 12 n^2 bytes of HBM traffic instead of 16 n^2.
+extern "C" int gcx_apply_sym_vc(gcx_ctx* c, const uint8_t* keep_vc, int masked_mode, int sqroot, float* min_s, float* max_s, float* min_v,
+                                float* max_v) {
+    CKR(need_map(c));
+    CKR(fence_copy(c));
+    if (!c->have_mask || !c->have_scale) return fail("gcx_apply_sym_vc: needs the mask and the scale vector of a finished gcx_ic_run / gcx_kr_run");
+    if (!keep_vc) return fail("gcx_apply_sym_vc: null VC mask");
+    CKR(run_row_stats(c));
+    k_f64_to_f32<<<(int)((c->nv + 255) / 256), 256, 0, c->stream>>>((int)c->nv, c->vrowsum, c->csum32);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    CKR(ensure_out(c));
+    if (!c->Out2) CK(cudaMalloc(&c->Out2, sizeof(float) * (size_t)c->nloc * c->ld));
+    if (!c->keep2) CK(cudaMalloc(&c->keep2, (size_t)c->nv));
+    CK(cudaMemsetAsync(c->keep2, 0, (size_t)c->nv, c->stream));
+    CK(cudaMemcpyAsync(c->keep2, keep_vc, (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
+    MinMax init{0xffffffffu, 0u};
+    memcpy(c->h_state, &init, sizeof init);
+    CK(cudaMemcpyAsync(c->mm, c->h_state, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->mm2, c->h_state, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    {
+        // two results per element need more registers than the single-result passes: 3 CTAs/SM without spills is the default
+        static const int v2 = [] { const char* e = getenv("GCX_EW2_VARIANT"); return e ? atoi(e) : 0; }();
+        ProfScope ps(c, 1);
+#define EW2(RR, OC) k_apply_sym_vc<RR, OC><<<c->sm_count * OC, MV_THREADS, 0, c->stream>>>(c->A, c->Out, c->Out2, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, \
+        (int)c->row0, c->vscale, c->keep, masked_mode, c->csum32, c->keep2, sqroot, c->mm, c->mm2)
+        switch (v2) {
+            case 1: EW2(4, 4); break;
+            case 2: EW2(2, 6); break;
+            case 3: EW2(8, 2); break;
+            case 4: EW2(2, 4); break;
+            default: EW2(4, 3); break;
+        }
+#undef EW2
+    }
+    CK(cudaGetLastError());
+    CKR(mm_read(c, c->mm, min_s, max_s));
+    return mm_read(c, c->mm2, min_v, max_v);
 }
 
 __global__ void k_f64_to_f32(int nv, const double* __restrict__ a, float* __restrict__ b) {
@@ -2197,6 +2268,20 @@ extern "C" int gcx_timer_stop(gcx_ctx* c, double* ms) {
 
 extern "C" int gcx_map_invalidate(gcx_ctx* c) {
     c->have_rowsum = false;
+    return 0;
+}
+
+/* diagnostics: [G][16] int64 per CTA of launch GCX_SYM_DEBUG_LAUNCH (default 20) of the deferred-scalar IC pass -- globaltimer ns at
+ * 0 entry, 1 first tiles issued, 2 vector phase done, 3 past the grid barrier, 4 product starts, 5 static share done, 6 all done;
+ * 7 = dynamic chunks taken */
+extern "C" int gcx_debug_sym_stamps(gcx_ctx* c, int64_t* stamps, int capacity, int* count) {
+    CKR(need_map(c));
+    if (!c->sym_stamps) return fail("phase stamps are off (set GCX_SYM_DEBUG=1 before the first symmetric pass)");
+    const int G = c->sym_grid;
+    if (capacity < 16 * G) return fail("capacity < 16 x grid (%d)", G);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(stamps, c->sym_stamps, sizeof(long long) * 16 * (size_t)G, cudaMemcpyDeviceToHost));
+    *count = G;
     return 0;
 }
 

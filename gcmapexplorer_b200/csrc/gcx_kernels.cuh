@@ -320,6 +320,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned in
                  : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 constexpr int TMA_CONSUMERS = MV_THREADS;          // 8 consumer warps
 constexpr int TMA_THREADS = MV_THREADS + 32;       // + 1 producer warp
 
@@ -539,6 +545,8 @@ struct SymTab {
                                //      the row AND the column part); 0: the rank's own diagonal region (j >= i / j > i rules)
     int kfold_lo;              // first panel with units on this rank (row-partial fold starts here)
     long long* dbg_cycles;     // optional [G]: cycles every CTA spent in the main loop (GCX_SYM_DEBUG=1), else nullptr
+    long long* dbg_stamps;     // optional [G][16]: globaltimer (ns) at the phases of launch dbg_launch of k_ic_pass_symd
+    int dbg_launch;
     // dynamic pool: the units of a few large panels are not part of any CTA's static share; they are cut into chunks of
     // consecutive bands of one panel and handed to whichever CTA finishes its static share first (atomic counter).  A chunk
     // is always walked by one CTA in a fixed order and leaves its own column partial, so results do not depend on who ran it.
@@ -757,6 +765,8 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
     const long long t_start = (T.dbg_cycles != nullptr && threadIdx.x == 0) ? clock64() : 0;
     matvec_sym_range<NG, STAGES, ZNC, BEGUN ? SYM_CONT : SYM_ALL>(A, ld, n4, z, rowpart, colpart + (size_t)c * T.nslots * NG * 1024, T, tiles, full_bar,
                                                                   empty_bar, gred, T.cta_u0[c], T.cta_u0[c + 1], T.cta_kf[c], T.cta_kl[c], false);
+    if (BEGUN && T.dbg_stamps != nullptr && threadIdx.x == 0 && T.dbg_stamps[c * 16 + 8] != 0) T.dbg_stamps[c * 16 + 5] = (long long)globaltimer_ns();
+    int nchunks = 0;
     while (T.ndyn > 0) {
         if (threadIdx.x == 0) s_chunk = (int)atomicAdd(T.dyn_counter, 1u);
         __syncthreads();
@@ -766,8 +776,13 @@ __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, lon
         // (the range function's leading barrier also protects s_chunk against the next fetch)
         matvec_sym_range<NG, STAGES, ZNC>(A, ld, n4, z, rowpart, T.colpart_dyn + (size_t)ch * NG * 1024, T, tiles, full_bar, empty_bar, gred,
                                           b0, b0 + cnt, k, k, true);
+        ++nchunks;
     }
     if (T.dbg_cycles != nullptr && threadIdx.x == 0) T.dbg_cycles[c] = clock64() - t_start;
+    if (BEGUN && T.dbg_stamps != nullptr && threadIdx.x == 0 && T.dbg_stamps[c * 16 + 8] != 0) {
+        T.dbg_stamps[c * 16 + 6] = (long long)globaltimer_ns();
+        T.dbg_stamps[c * 16 + 7] = nchunks;
+    }
 }
 
 template <int STAGES, int OCC>
@@ -1045,6 +1060,85 @@ k_vc_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld, i
         }
     }
     mm_commit(mn, mx, mm);
+}
+
+// K4 + K5 fused: one read of the map, two results -- the IC (or KR) scaled map of k_apply_sym into OutS and the vanilla-coverage
+// map of k_vc_apply into OutV, each with its own mask and its own min/max.  Same arithmetic per element as the two kernels
+// (bit-identical outputs); algorithmic bytes 12 * nloc * n instead of 16 * nloc * n for the pair.
+template <int R, int OCC>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
+k_apply_sym_vc(const float* __restrict__ A, float* __restrict__ OutS, float* __restrict__ OutV, long long ld, int nloc, int n4, int n, int row0,
+               const double* __restrict__ s, const uint8_t* __restrict__ keep_s, int passthrough, const float* __restrict__ csum,
+               const uint8_t* __restrict__ keep_v, int sqroot, MinMax* mm_s, MinMax* mm_v) {
+    const int tid = threadIdx.x;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
+    const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
+    float mn_s = GCX_PINF, mx_s = GCX_NINF, mn_v = GCX_PINF, mx_v = GCX_NINF;
+    const double2* __restrict__ s2 = reinterpret_cast<const double2*>(s);
+    const uchar4* __restrict__ ks4 = reinterpret_cast<const uchar4*>(keep_s);
+    const uchar4* __restrict__ kv4 = reinterpret_cast<const uchar4*>(keep_v);
+    const float4* __restrict__ c4v = reinterpret_cast<const float4*>(csum);
+    for (long long u = u0; u < u1; ++u) {
+        const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
+        const int c4 = k * MV_THREADS + tid;
+        if (c4 >= n4) continue;
+        float4 a[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r < nloc) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(A + (long long)r * ld) + c4);
+        }
+        const double2 sa = __ldg(s2 + 2 * c4), sb = __ldg(s2 + 2 * c4 + 1);
+        const uchar4 ksc = __ldg(ks4 + c4), kvc = __ldg(kv4 + c4);
+        const float4 cs = __ldg(c4v + c4);
+        const double sc[4] = {sa.x, sa.y, sb.x, sb.y};
+        const float cc[4] = {cs.x, cs.y, cs.z, cs.w};
+        const unsigned char kscol[4] = {ksc.x, ksc.y, ksc.z, ksc.w}, kvcol[4] = {kvc.x, kvc.y, kvc.z, kvc.w};
+        const int j0 = 4 * c4;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r >= nloc) break;
+            const int i = row0 + r;
+            const double si = __ldg(s + i);
+            const float ci = __ldg(csum + i);
+            const bool ksi = __ldg(keep_s + i) != 0, kvi = __ldg(keep_v + i) != 0;
+            const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
+            float os[4], ov[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + e;
+                const float x = in[e];
+                // ---- symmetric scale (k_apply_sym) ----
+                if (ksi && kscol[e]) {
+                    if (x != 0.f) {
+                        const double lo = j < i ? sc[e] : si, hi = j < i ? si : sc[e];
+                        os[e] = (float)((lo * (double)x) * hi);
+                    } else {
+                        os[e] = x;
+                    }
+                    mm_update(os[e], mn_s, mx_s);
+                } else {
+                    os[e] = passthrough ? x : 0.f;
+                }
+                // ---- vanilla coverage (k_vc_apply) ----
+                float v = x;
+                if (v != 0.f) {
+                    if (kvi) v = __fdiv_rn(v, ci);
+                    if (kvcol[e]) v = __fdiv_rn(v, cc[e]);
+                    if (sqroot) v = __fsqrt_rn(v);
+                }
+                ov[e] = v;
+                if (j < n) mm_update(v, mn_v, mx_v);
+            }
+            st_stream_f4(reinterpret_cast<float4*>(OutS + (long long)r * ld) + c4, make_float4(os[0], os[1], os[2], os[3]));
+            st_stream_f4(reinterpret_cast<float4*>(OutV + (long long)r * ld) + c4, make_float4(ov[0], ov[1], ov[2], ov[3]));
+        }
+    }
+    mm_commit(mn_s, mx_s, mm_s);
+    mm_commit(mn_v, mx_v, mm_v);
 }
 
 // K7: distance-frequency apply (lib/normalizeCore.pyx:91-170): divide or subtract by avg[|i-j|].
@@ -1976,11 +2070,6 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
 
 template <int STAGES, int OCC, bool DIST>
 __global__ void __launch_bounds__(SYM_THREADS, OCC)
@@ -2005,9 +2094,16 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
     double* ucur = uring + (long long)(L & 1) * nv;
     const long long su0 = T.cta_u0[bid], su1 = T.cta_u0[bid + 1];
 
+    long long* stamps = (T.dbg_stamps != nullptr && tid == 0) ? T.dbg_stamps + (long long)bid * 16 : nullptr;
+    if (stamps != nullptr) {
+        stamps[8] = (L == T.dbg_launch) ? 1 : 0;           // arms the two stamps taken inside matvec_sym_core
+        if (L == T.dbg_launch) stamps[0] = (long long)globaltimer_ns();
+        else stamps = nullptr;
+    }
     // ---- P0: barriers + the first tiles of this CTA's static share ----
     matvec_sym_range<SYM_NG, STAGES, false, SYM_BEGIN>(A, ld, n4, ucur, rowpart, colpart + (size_t)bid * T.nslots * SYM_NG * 1024, T, tiles, full_bar,
                                                        empty_bar, gred, su0, su1, T.cta_kf[bid], T.cta_kl[bid], false);
+    if (stamps != nullptr) stamps[1] = (long long)globaltimer_ns();
     if (L > 0) {
         const double* uprev = uring + (long long)((L + 1) & 1) * nv;
         double* tcur = tring + (long long)((L + 2) % 3) * nv;            // t'_{L-1}
@@ -2082,7 +2178,9 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
             part[G + bid] = b;
             part[2 * G + bid] = d;
         }
+        if (stamps != nullptr) stamps[2] = (long long)globaltimer_ns();
         grid.sync();
+        if (stamps != nullptr) stamps[3] = (long long)globaltimer_ns();
         // ---- P2: scalars of pass L-1, convergence of pass L-2 (every CTA, same order -> same bits) ----
         if (warp == 0) {
             double a0 = 0.0, a1 = 0.0, a2 = 0.0;
@@ -2120,6 +2218,7 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
             return;
         }
     }
+    if (stamps != nullptr) stamps[4] = (long long)globaltimer_ns();
     matvec_sym_core<SYM_NG, STAGES, false, true>(A, ld, n4, ucur, rowpart, colpart, T, tiles, full_bar, empty_bar, gred);
     if (tid == 0) {
         __threadfence();

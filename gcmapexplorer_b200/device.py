@@ -257,6 +257,17 @@ class DeviceMap:
         check(lib().gcx_apply_sym_scale(self._ctx, sp, int(masked_mode), int(bool(in_place)), C.byref(mn), C.byref(mx)))
         return mn.value, mx.value
 
+    def apply_sym_vc(self, keep_vc, masked_mode=0, sqroot=False):
+        """Fused tail: scaled map (resident scale + mask) -> output 1, vanilla-coverage map under `keep_vc` -> output 2, one read
+        of the input.  Returns ((min, max) of the scaled map, (min, max) of the VC map)."""
+        k = np.ascontiguousarray(np.asarray(keep_vc, dtype=bool).astype(np.uint8))
+        if k.shape != (self.n,):
+            raise ValueError("mask must have n entries")
+        a, b, c, d = C.c_float(0), C.c_float(0), C.c_float(0), C.c_float(0)
+        check(lib().gcx_apply_sym_vc(self._ctx, k.ctypes.data_as(_lib._c_u8p), int(masked_mode), int(bool(sqroot)),
+                                     C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return (a.value, b.value), (c.value, d.value)
+
     def vc(self, sqroot=False, in_place=False):
         mn, mx = C.c_float(0), C.c_float(0)
         csum = np.empty(self.n, dtype=np.float32)

@@ -46,7 +46,7 @@ int gcx_host_free(void* ptr);
  * n = global number of bins, [row0, row0+nloc) = the row block this context owns (single GPU: 0, n). */
 int gcx_map_create(gcx_ctx* ctx, int64_t n, int64_t row0, int64_t nloc);
 int gcx_map_upload(gcx_ctx* ctx, const float* host_rows, int64_t host_ld);          /* host_rows -> first local row */
-int gcx_map_download(gcx_ctx* ctx, int which, float* host_rows, int64_t host_ld);   /* which: 0 input, 1 output */
+int gcx_map_download(gcx_ctx* ctx, int which, float* host_rows, int64_t host_ld);   /* which: 0 input, 1 output, 2 second output */
 /* asynchronous download into PINNED host memory on the context's copy stream: returns at once, overlaps with
  * kernels enqueued afterwards (e.g. the VC result streams out while IC iterates); gcx_download_wait blocks until
  * the last async download has landed.  Kernels that later overwrite the source buffer wait for it on the device. */
@@ -94,6 +94,14 @@ int gcx_apply_sym_scale(gcx_ctx* ctx, const double* s, int masked_mode, int in_p
  * Replaces normalizeCore.performVCNormalization (lib/normalizeCore.pyx:63-89) in its fp32 arithmetic.
  * Needs gcx_row_stats + gcx_set_mask first.  csum: n floats out (may be NULL). */
 int gcx_vc_run(gcx_ctx* ctx, int sqroot, int in_place, float* minv, float* maxv, float* csum);
+
+/* ---- fused tail: symmetric scale + vanilla coverage from ONE read of the map ----------------------
+ * For callers that want both normalizations of a map (bench.py's step, the batch driver): the result of gcx_apply_sym_scale
+ * (resident scale and mask of the last gcx_ic_run / gcx_kr_run, not in place) goes to output 1 and the result of gcx_vc_run under
+ * the mask keep_vc to output 2 (gcx_map_download / gcx_map_checksum with which = 2) -- bit-identical to the two separate
+ * calls, 12 n^2 bytes of HBM traffic instead of 16 n^2.  Replaces lib/normalizeKnightRuiz.pyx:207-227 / lib/normalizeCore.pyx:48-53
+ * and lib/normalizeCore.pyx:63-89 together. */
+int gcx_apply_sym_vc(gcx_ctx* ctx, const uint8_t* keep_vc, int masked_mode, int sqroot, float* min_s, float* max_s, float* min_v, float* max_v);
 
 /* ---- distance-frequency (MCFS) ----------------------------------------------------------------
  * gcx_diag_stats replaces cmstats.getAvgContactByDistance (lib/cmstats.py:569-605) for one map:
@@ -187,6 +195,8 @@ int gcx_map_invalidate(gcx_ctx* ctx);
 int gcx_pass_bytes(gcx_ctx* ctx, int64_t* bytes, int* symmetric);
 /* diagnostics: cycles every CTA of the last upper-triangle pass spent in its main loop (needs GCX_SYM_DEBUG=1) */
 int gcx_debug_sym_cycles(gcx_ctx* ctx, int64_t* cycles, int capacity, int* count);
+/* diagnostics: per-CTA phase timestamps (ns) of one launch of the deferred-scalar IC pass, [grid][16] (needs GCX_SYM_DEBUG=1) */
+int gcx_debug_sym_stamps(gcx_ctx* ctx, int64_t* stamps, int capacity, int* count);
 /* device time (ms, CUDA events) of the last ic/kr run: matrix resident -> final vector */
 int gcx_last_run_ms(gcx_ctx* ctx, double* ms);
 /* matrix-vector products the last ic/kr run really launched: the deferred-scalar IC pass sees convergence one launch late and
