@@ -186,6 +186,8 @@ struct gcx_ctx {
     size_t scratch_bytes = 0;
     double* part = nullptr;      // per-CTA partials of the fused IC pass (3 x grid)
     int ic_fused = 1;            // 1: one cooperative launch per IC pass (k_ic_pass); 0: k_matvec + k_ic_epilogue
+    int ic_persist = 1;          // deferred-scalar pass: the whole solve in ONE cooperative launch (GCX_IC_PERSIST=0: one launch per pass)
+    int sym_l2_hint = 1;         // evict-first L2 policy on the map stream of the upper-triangle pass (GCX_SYM_L2HINT)
     int ic_defer = 1;            // upper-triangle path: deferred-scalar pass k_ic_pass_symd (GCX_IC_DEFER=0: literal-order k_ic_pass_sym_tma)
     double* ic_ring = nullptr;   // [3][nv] t' ring + [2][nv] u ring of the deferred-scalar pass
     int last_matvecs_issued = 0; // products the last ic/kr run really launched (the deferred pass runs one more than passes + 1)
@@ -375,6 +377,8 @@ static int ctx_init(gcx_ctx* c, int device) {
         CK(cudaFuncSetAttribute(k_ic_pass_symd<SYM_STAGES, SYM_OCC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CK(cudaFuncSetAttribute(k_ic_pass_symd<SYM_STAGES, SYM_OCC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (const char* e = getenv("GCX_IC_DEFER")) c->ic_defer = atoi(e);
+        if (const char* e = getenv("GCX_IC_PERSIST")) c->ic_persist = atoi(e);
+        if (const char* e = getenv("GCX_SYM_L2HINT")) c->sym_l2_hint = atoi(e);
         if (const char* e = getenv("GCX_PEER_EXCHANGE")) c->xchg_enable = atoi(e);
         int occ3 = 0, occ4 = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_ic_pass_sym_tma<SYM_STAGES, SYM_OCC, true>, SYM_THREADS, smem));
@@ -904,6 +908,7 @@ extern "C" int gcx_set_option(gcx_ctx* c, const char* key, double value) {
     else if (k == "exchange_allreduce") c->exchange_allreduce = (int)value;
     else if (k == "peer_exchange") c->xchg_enable = (int)value;          // before gcx_map_create, on every rank
     else if (k == "ic_defer") c->ic_defer = (int)value;
+    else if (k == "ic_persist") c->ic_persist = (int)value;
     else if (k == "sym_blocks") {
         if (c->sym_blocks != (int)value && c->stream) {       // the unit tables depend on it: rebuild on the next run
             cudaSetDevice(c->device);
@@ -1075,15 +1080,20 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
             bytes += nb * SYM_R * std::min<int64_t>(1024, c->ld - (int64_t)k * 1024) * 4;
         }
         c->sym_kfold_lo = blocks ? kfold_lo : -1;
-        // dynamic pool: the largest full-width panels, ~GCX_SYM_DYN percent of the units, cut into chunks of DYN_CHUNK bands
+        // dynamic pool: ~GCX_SYM_DYN percent of the units, cut into chunks of DYN_CHUNK consecutive bands of one panel.
+        // GCX_SYM_POOL=1 (default): the LAST bands of every large full-width panel -- a bin's fold then adds a handful of chunk
+        // partials whichever panel it lies in; =0: whole panels, largest first (round 1: the ~2000 bins of the pooled panels each
+        // folded ~400 chunk partials and held the whole grid at the barrier, profiles/r02_phase_stamps.md).
         int DYN_CHUNK = 32;
         if (const char* e = getenv("GCX_SYM_DYN_CHUNK")) DYN_CHUNK = std::max(4, atoi(e));
-        double dyn_frac = 0.10;
+        double dyn_frac = 0.20;
         if (const char* e = getenv("GCX_SYM_DYN")) dyn_frac = atof(e) / 100.0;
+        int pool_mode = 1;
+        if (const char* e = getenv("GCX_SYM_POOL")) pool_mode = atoi(e);
         long long Uall = 0;
         for (int k = 0; k < nch; ++k) Uall += nbk[k];
-        std::vector<char> in_pool((size_t)nch, 0);
-        {
+        std::vector<long long> pool_bands((size_t)nch, 0);       // bands at the END of panel k that belong to the pool
+        if (pool_mode == 0) {
             std::vector<int> order;
             for (int k = 0; k < nch; ++k)
                 if (nbk[k] > 0 && std::min<int64_t>(1024, c->ld - (int64_t)k * 1024) == 1024) order.push_back(k);
@@ -1092,21 +1102,29 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
             for (int k : order) {
                 if ((double)pooled >= dyn_frac * (double)Uall) break;
                 if (Uall - pooled - nbk[k] < 4LL * G) break;             // keep a meaningful static share
-                in_pool[k] = 1;
+                pool_bands[k] = nbk[k];
                 pooled += nbk[k];
+            }
+        } else {
+            long long pooled = 0;
+            for (int k = nch - 1; k >= 0; --k) {
+                if (nbk[k] < 8LL * DYN_CHUNK || std::min<int64_t>(1024, c->ld - (int64_t)k * 1024) != 1024) continue;
+                const long long pb = (long long)(dyn_frac * (double)nbk[k] / DYN_CHUNK + 0.5) * DYN_CHUNK;
+                if (pb <= 0 || Uall - pooled - pb < 4LL * G) continue;
+                pool_bands[k] = std::min(pb, nbk[k]);
+                pooled += pool_bands[k];
             }
         }
         std::vector<int> dk, db0, dcnt, pdyn0((size_t)nch + 1, 0);
         for (int k = 0; k < nch; ++k) {
             pdyn0[k] = (int)dk.size();
-            if (in_pool[k]) {
-                for (long long b = 0; b < nbk[k]; b += DYN_CHUNK) {
-                    dk.push_back(k);
-                    db0.push_back((int)b);
-                    dcnt.push_back((int)std::min<long long>((long long)DYN_CHUNK, nbk[k] - b));
-                }
+            const long long stat = nbk[k] - pool_bands[k];
+            for (long long b = stat; b < nbk[k]; b += DYN_CHUNK) {
+                dk.push_back(k);
+                db0.push_back((int)b);
+                dcnt.push_back((int)std::min<long long>((long long)DYN_CHUNK, nbk[k] - b));
             }
-            pu[k + 1] = pu[k] + (in_pool[k] ? 0 : nbk[k]);
+            pu[k + 1] = pu[k] + stat;
         }
         pdyn0[nch] = (int)dk.size();
         const int ndyn = (int)dk.size();
@@ -1196,6 +1214,7 @@ static SymTab sym_tab(gcx_ctx* c) {
     T.dbg_cycles = c->sym_dbg;
     T.dbg_stamps = c->sym_stamps;
     T.dbg_launch = c->sym_dbg_launch;
+    T.l2_hint = c->sym_l2_hint;
     T.ndyn = c->sym_ndyn;
     T.dyn_k = c->sym_tab_i + 2 * G + 3 * nch;
     T.dyn_b0 = T.dyn_k + c->sym_ndyn;
@@ -1374,6 +1393,7 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         CK(cudaMemcpyAsync(uring, c->vz, sizeof(double) * c->nv, cudaMemcpyDeviceToDevice, c->stream));
         if (c->sym_ndyn > 0) CK(cudaMemsetAsync(c->sym_dyn_counter, 0, sizeof(unsigned int), c->stream));
     }
+    int npass_launch = 1;
     auto step_symd = [&]() -> int {
         SymTab tab = sym_tab(c);
         IcXchg X;
@@ -1381,7 +1401,8 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         X.world = 1;
         if (c->world > 1) X = xchg_args(c);
         void* args[] = {(void*)&c->A, (void*)&c->ld, (void*)&n, (void*)&n4, (void*)&nvll, (void*)&c->keep, (void*)&tring, (void*)&uring, (void*)&c->vB,
-                        (void*)&c->rowpart, (void*)&c->colpart, (void*)&tab, (void*)&c->ticket, (void*)&c->ic_state, (void*)&c->part, (void*)&X};
+                        (void*)&c->rowpart, (void*)&c->colpart, (void*)&tab, (void*)&c->ticket, (void*)&c->ic_state, (void*)&c->part, (void*)&X,
+                        (void*)&npass_launch};
         const size_t smem = SYM_STAGES * SYM_R * MV_THREADS * sizeof(float4);
         ProfScope ps(c, 0);
         if (c->world == 1)
@@ -1452,7 +1473,24 @@ extern "C" int gcx_ic_run(gcx_ctx* c, double tol, int iteration, double* bias, i
         return c->ic_fused ? step_fused() : step_split();
     };
     IcState fin;
-    const int rc_it = iterate<IcState>(c, c->ic_state, iteration + 6, step, &fin);
+    int rc_it = 0;
+    if (defer && c->ic_persist) {
+        // the whole solve is one cooperative launch: passes are separated by grid barriers, convergence is decided on the device
+        npass_launch = iteration + 8;
+        rc_it = [&]() -> int {
+            CK(cudaEventRecord(c->run_a, c->stream));
+            CKR(step_symd());
+            CK(cudaEventRecord(c->run_b, c->stream));
+            CKR(read_small(c, c->ic_state, sizeof(IcState), &fin));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, c->run_a, c->run_b));
+            c->last_run_ms = ms;
+            if (!fin.done) return fail("gcx_ic_run: the persistent pass ended without a verdict");
+            return 0;
+        }();
+    } else {
+        rc_it = iterate<IcState>(c, c->ic_state, iteration + 6, step, &fin);
+    }
     if (defer && c->world > 1) c->xchg_seq += (unsigned int)iteration + 4096u;      // the same on every rank
     CKR(rc_it);
     if (defer && fin.error) return fail("gcx_ic_run: a peer rank did not deliver its partial vector within 20 s (peer exchange)");
@@ -1608,7 +1646,7 @@ extern "C" int gcx_apply_sym_vc(gcx_ctx* c, const uint8_t* keep_vc, int masked_m
     CK(cudaMemcpyAsync(c->mm2, c->h_state, sizeof init, cudaMemcpyHostToDevice, c->stream));
     {
         // two results per element need more registers than the single-result passes: 3 CTAs/SM without spills is the default
-        static const int v2 = [] { const char* e = getenv("GCX_EW2_VARIANT"); return e ? atoi(e) : 0; }();
+        static const int v2 = [] { const char* e = getenv("GCX_EW2_VARIANT"); return e ? atoi(e) : 1; }();
         ProfScope ps(c, 1);
 #define EW2(RR, OC) k_apply_sym_vc<RR, OC><<<c->sm_count * OC, MV_THREADS, 0, c->stream>>>(c->A, c->Out, c->Out2, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, \
         (int)c->row0, c->vscale, c->keep, masked_mode, c->csum32, c->keep2, sqroot, c->mm, c->mm2)
@@ -1739,6 +1777,143 @@ extern "C" int gcx_diag_apply(gcx_ctx* c, const double* avg, int subtract, int i
     CK(cudaGetLastError());
     if (in_place) { c->have_rowsum = false; c->sym_state = -1; }
     return mm_end(c, minv, maxv);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// batched distance-frequency normalization over many resident maps (one grid per stage for the whole set)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtract, float* minv, float* maxv) {
+    if (!ctxs || count < 1) return fail("gcx_mcfs_batch: no maps");
+    if (count > 120) return fail("gcx_mcfs_batch: at most 120 maps per call");
+    gcx_ctx* c0 = ctxs[0];
+    for (int m = 0; m < count; ++m) {
+        gcx_ctx* c = ctxs[m];
+        if (!c || !c->A) return fail("gcx_mcfs_batch: map %d has no resident matrix", m);
+        if (c->device != c0->device) return fail("gcx_mcfs_batch: all maps must be resident on one device");
+        if (c->world != 1 || c->row0 != 0 || c->nloc != c->n) return fail("gcx_mcfs_batch: sharded maps are not batched");
+    }
+    CKR(set_dev(c0));
+    // workspace of the whole batch in the first context's arena: table | per map { histograms, selection state | mean partials }
+    std::vector<BMap> tab((size_t)count);
+    size_t off = align256(sizeof(BMap) * (size_t)count), zero_from = off;
+    std::vector<size_t> o_hist((size_t)count), o_small((size_t)count), o_psum((size_t)count), o_pcnt((size_t)count), o_sc((size_t)count);
+    long long blk = 0, sel = 0, red = 0, fin = 0, units = 0;
+    constexpr int R = 4;
+    for (int m = 0; m < count; ++m) {
+        gcx_ctx* c = ctxs[m];
+        const int n = (int)c->n;
+        BMap& M = tab[m];
+        memset(&M, 0, sizeof M);
+        M.ld = c->ld; M.n = n;
+        M.gx = (n + MV_THREADS - 1) / MV_THREADS;
+        M.gy = (n + DIAG_RB - 1) / DIAG_RB;
+        M.blk0 = (int)blk; M.sel0 = (int)sel; M.red0 = (int)red; M.fin0 = (int)fin; M.u0 = units;
+        blk += (long long)M.gx * M.gy;
+        sel += ((long long)n * 32 + MV_THREADS - 1) / MV_THREADS;
+        red += (n + 63) / 64;
+        fin += (n + 255) / 256;
+        units += (long long)((n + R - 1) / R) * (((int)(c->ld / 4) + MV_THREADS - 1) / MV_THREADS);
+        if (median) {
+            o_hist[m] = off; off += align256(sizeof(unsigned int) * 256 * (size_t)n);
+            o_small[m] = off; off += align256(sizeof(unsigned int) * 5 * (size_t)n);
+        } else {
+            o_psum[m] = off; off += align256(sizeof(double) * (size_t)M.gy * n);
+            o_pcnt[m] = off; off += align256(sizeof(int) * (size_t)M.gy * n);
+            o_sc[m] = off; off += align256(sizeof(double) * 2 * (size_t)n);
+        }
+    }
+    if (blk > 0x7fffffffLL || sel > 0x7fffffffLL) return fail("gcx_mcfs_batch: batch too large");
+    const size_t o_mm = off;
+    off += align256(sizeof(MinMax) * (size_t)count);
+    // the batch runs on the first context's stream: it waits for whatever the other contexts have in flight ...
+    for (int m = 1; m < count; ++m) {
+        CK(cudaEventRecord(ctxs[m]->ev_ready, ctxs[m]->stream));
+        CK(cudaStreamWaitEvent(c0->stream, ctxs[m]->ev_ready, 0));
+    }
+    CKR(ensure_scratch(c0, off));
+    char* base = (char*)c0->scratch;
+    for (int m = 0; m < count; ++m) {
+        gcx_ctx* c = ctxs[m];
+        CKR(fence_copy(c));
+        CKR(ensure_out(c));
+        BMap& M = tab[m];
+        M.A = c->A; M.Out = c->Out; M.avg = c->vavg; M.mm = c->mm;
+        if (median) {
+            const size_t n = (size_t)c->n;
+            M.S.hist = (unsigned int*)(base + o_hist[m]);
+            unsigned int* small = (unsigned int*)(base + o_small[m]);
+            M.S.prefix = small; M.S.krem = small + n; M.S.cnt = small + 2 * n; M.S.need = small + 3 * n; M.S.next = small + 4 * n;
+        } else {
+            M.psum = (double*)(base + o_psum[m]);
+            M.pcnt = (int*)(base + o_pcnt[m]);
+            M.sum = (double*)(base + o_sc[m]);
+            M.cnt = M.sum + c->n;
+        }
+    }
+    cudaStream_t st = c0->stream;
+    // the table travels through the (pageable) vector: synchronous with respect to the host, ordered on the stream
+    CK(cudaMemcpyAsync(base, tab.data(), sizeof(BMap) * (size_t)count, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    const BMap* dt = (const BMap*)base;
+    if (median) CK(cudaMemsetAsync(base + zero_from, 0, o_mm - zero_from, st));
+    k_mm_init_b<<<1, 128, 0, st>>>(dt, count);
+    if (median) {
+        for (int pass = 0; pass < 4; ++pass) {
+            {
+                ProfScope ps(c0, 4);
+                k_diag_hist_b<<<(unsigned)blk, MV_THREADS, 0, st>>>(dt, count, pass);
+            }
+            k_diag_select_b<<<(unsigned)sel, MV_THREADS, 0, st>>>(dt, count, pass);
+            c0->launches += 1;
+        }
+        {
+            ProfScope ps(c0, 4);
+            k_diag_next_b<<<(unsigned)blk, MV_THREADS, 0, st>>>(dt, count);
+        }
+        k_diag_median_final_b<<<(unsigned)fin, 256, 0, st>>>(dt, count);
+        c0->launches += 1;
+    } else {
+        {
+            ProfScope ps(c0, 4);
+            k_diag_mean_partial_b<<<(unsigned)blk, MV_THREADS, 0, st>>>(dt, count);
+        }
+        k_diag_mean_reduce_b<<<(unsigned)red, 64 * DIAG_RED_SL, 0, st>>>(dt, count);
+        k_diag_mean_final_b<<<(unsigned)fin, 256, 0, st>>>(dt, count);
+        c0->launches += 2;
+    }
+    CK(cudaGetLastError());
+    {
+        ProfScope ps(c0, 5);
+        k_diag_apply_b<R, 4><<<c0->sm_count * 4, MV_THREADS, 0, st>>>(dt, count, units, subtract);
+    }
+    CK(cudaGetLastError());
+    MinMax* gathered = (MinMax*)(base + o_mm);
+    k_mm_gather_b<<<1, 128, 0, st>>>(dt, count, gathered);
+    CK(cudaGetLastError());
+    c0->launches += 2;
+    // ... and whatever the other contexts enqueue next waits for the batch
+    CK(cudaEventRecord(c0->ev_ready, st));
+    for (int m = 1; m < count; ++m) CK(cudaStreamWaitEvent(ctxs[m]->stream, c0->ev_ready, 0));
+    std::vector<MinMax> mmh((size_t)count);
+    for (int m0 = 0; m0 < count; m0 += 120) {
+        const int k = std::min(120, count - m0);
+        CKR(read_small(c0, gathered + m0, sizeof(MinMax) * (size_t)k, mmh.data() + m0));
+    }
+    const float nanv = __builtin_nanf("");
+    for (int m = 0; m < count; ++m) {
+        if (minv) minv[m] = mmh[m].min_nz == 0xffffffffu ? nanv : ord2f(mmh[m].min_nz);
+        if (maxv) maxv[m] = mmh[m].max_all == 0u ? nanv : ord2f(mmh[m].max_all);
+    }
+    return 0;
+}
+
+/* the per-diagonal statistic left resident by the last gcx_diag_stats / gcx_mcfs_batch (n doubles) */
+extern "C" int gcx_diag_avg_read(gcx_ctx* c, double* avg) {
+    CKR(need_map(c));
+    if (!avg) return fail("gcx_diag_avg_read: null output");
+    CK(cudaMemcpyAsync(avg, c->vavg, sizeof(double) * c->n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -326,6 +326,20 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
+// The map is read once per pass and never reused; an evict-first L2 policy on its bulk copies keeps the few MB of row / column
+// partials, vectors and tables that the NEXT launch's vector phase reads resident in L2 instead of being flushed to HBM by the
+// 1.3 GB stream in between.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsigned int bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
 constexpr int TMA_CONSUMERS = MV_THREADS;          // 8 consumer warps
 constexpr int TMA_THREADS = MV_THREADS + 32;       // + 1 producer warp
 
@@ -547,6 +561,7 @@ struct SymTab {
     long long* dbg_cycles;     // optional [G]: cycles every CTA spent in the main loop (GCX_SYM_DEBUG=1), else nullptr
     long long* dbg_stamps;     // optional [G][16]: globaltimer (ns) at the phases of launch dbg_launch of k_ic_pass_symd
     int dbg_launch;
+    int l2_hint;               // 1: evict-first L2 policy on the map's bulk copies (GCX_SYM_L2HINT, default 1)
     // dynamic pool: the units of a few large panels are not part of any CTA's static share; they are cut into chunks of
     // consecutive bands of one panel and handed to whichever CTA finishes its static share first (atomic counter).  A chunk
     // is always walked by one CTA in a fixed order and leaves its own column partial, so results do not depend on who ran it.
@@ -601,6 +616,7 @@ __device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, lo
             int k = kfirst;
             long long pbeg = single_panel ? 0 : T.panel_u0[k];
             long long pend = single_panel ? NOEND : T.panel_u0[k + 1];
+            const uint64_t pol = l2_policy_evict_first();
             for (long long u = ua; u < ub; ++u) {
                 while (u >= pend) {
                     ++k;
@@ -617,7 +633,8 @@ __device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, lo
                 for (int rr = 0; rr < R; ++rr) {
                     int r = b * R + rr;                 // local row
                     r = r < nloc ? r : nloc - 1;
-                    bulk_g2s(tiles + ((size_t)stage * R + rr) * MV_THREADS, A + (long long)r * ld + 4LL * c0, row_bytes, &full_bar[stage]);
+                    if (T.l2_hint) bulk_g2s_hint(tiles + ((size_t)stage * R + rr) * MV_THREADS, A + (long long)r * ld + 4LL * c0, row_bytes, &full_bar[stage], pol);
+                    else bulk_g2s(tiles + ((size_t)stage * R + rr) * MV_THREADS, A + (long long)r * ld + 4LL * c0, row_bytes, &full_bar[stage]);
                 }
                 if (++stage == STAGES) {
                     stage = 0;
@@ -823,14 +840,26 @@ __device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n4, con
             for (int gg = 0; gg < SYM_NG; ++gg) s += __ldcg(cp + gg * 1024);
         }
         if (T.ndyn > 0) {
-            // column partials of the dynamic chunks of panel ki, in chunk order
+            // column partials of the dynamic chunks of panel ki, in chunk order; two independent chains (fixed order) keep
+            // more loads in flight
             const int d0 = T.panel_dyn0[ki], d1 = T.panel_dyn0[ki + 1];
+            double s2 = 0.0;
+            int ch = d0 + j;
 #pragma unroll 2
-            for (int ch = d0 + j; ch < d1; ch += 8) {
+            for (; ch + 8 < d1; ch += 16) {
+                const double* cp = T.colpart_dyn + (size_t)ch * SYM_NG * 1024 + (i & 1023);
+#pragma unroll
+                for (int gg = 0; gg < SYM_NG; ++gg) {
+                    s += __ldcg(cp + gg * 1024);
+                    s2 += __ldcg(cp + (size_t)8 * SYM_NG * 1024 + gg * 1024);
+                }
+            }
+            if (ch < d1) {
                 const double* cp = T.colpart_dyn + (size_t)ch * SYM_NG * 1024 + (i & 1023);
 #pragma unroll
                 for (int gg = 0; gg < SYM_NG; ++gg) s += __ldcg(cp + gg * 1024);
             }
+            s += s2;
         }
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -1210,13 +1239,12 @@ constexpr int DIAG_RB = 64;
 constexpr int DIAG_BATCH = 16;     // loads in flight per thread in the histogram traversal
 
 // mean: per-(band, diagonal) partial sum/count, then a fixed-order reduction over bands (deterministic)
-__global__ void __launch_bounds__(MV_THREADS)
-k_diag_mean_partial(const float* __restrict__ A, long long ld, int nloc, int n, int row0, double* __restrict__ psum,
-                    int* __restrict__ pcnt) {
-    const int band = blockIdx.y, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
+__device__ __forceinline__ void diag_mean_partial_body(const float* __restrict__ A, long long ld, int nloc, int n, int row0, double* __restrict__ psum,
+                                                       int* __restrict__ pcnt, int bx, int by) {
+    const int band = by, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
     const int imax = row0 + r1 - 1;
-    if ((int)(blockIdx.x * MV_THREADS) > imax) return;
-    const int d = blockIdx.x * MV_THREADS + threadIdx.x;
+    if ((int)(bx * MV_THREADS) > imax) return;
+    const int d = bx * MV_THREADS + threadIdx.x;
     if (d > imax || d >= n) return;
     double s = 0.0;
     int c = 0;
@@ -1233,16 +1261,21 @@ k_diag_mean_partial(const float* __restrict__ A, long long ld, int nloc, int n, 
     pcnt[(long long)band * n + d] = c;
 }
 
+__global__ void __launch_bounds__(MV_THREADS)
+k_diag_mean_partial(const float* __restrict__ A, long long ld, int nloc, int n, int row0, double* __restrict__ psum,
+                    int* __restrict__ pcnt) {
+    diag_mean_partial_body(A, ld, nloc, n, row0, psum, pcnt, blockIdx.x, blockIdx.y);
+}
+
 // 64 diagonals x 4 band slices per CTA; slice s adds bands b0+s, b0+s+4, ... in order, the four slice sums are
 // combined in slice order -> the same result on every launch and for every grid shape
 constexpr int DIAG_RED_SL = 4;
-__global__ void __launch_bounds__(64 * DIAG_RED_SL)
-k_diag_mean_reduce(int nbands, int n, int row0, const double* __restrict__ psum, const int* __restrict__ pcnt,
-                   double* __restrict__ sum, double* __restrict__ cnt) {
+__device__ __forceinline__ void diag_mean_reduce_body(int nbands, int n, int row0, const double* __restrict__ psum, const int* __restrict__ pcnt,
+                                                      double* __restrict__ sum, double* __restrict__ cnt, int bx) {
     __shared__ double ss[DIAG_RED_SL][64];
     __shared__ double sc[DIAG_RED_SL][64];
     const int dl = threadIdx.x & 63, sl = threadIdx.x >> 6;
-    const int d = blockIdx.x * 64 + dl;
+    const int d = bx * 64 + dl;
     double s = 0.0, c = 0.0;
     if (d < n) {
         const int b0 = max(0, d - row0) / DIAG_RB;
@@ -1263,6 +1296,12 @@ k_diag_mean_reduce(int nbands, int n, int row0, const double* __restrict__ psum,
     }
 }
 
+__global__ void __launch_bounds__(64 * DIAG_RED_SL)
+k_diag_mean_reduce(int nbands, int n, int row0, const double* __restrict__ psum, const int* __restrict__ pcnt,
+                   double* __restrict__ sum, double* __restrict__ cnt) {
+    diag_mean_reduce_body(nbands, n, row0, psum, pcnt, sum, cnt, blockIdx.x);
+}
+
 __global__ void k_diag_mean_final(int n, const double* __restrict__ sum, const double* __restrict__ cnt, double* __restrict__ avg) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d < n) avg[d] = cnt[d] > 0.0 ? sum[d] / cnt[d] : 0.0;      // lib/cmstats.py:598, :602-603
@@ -1279,12 +1318,11 @@ struct DiagSel {
     unsigned int* next;     // [n] min key > vlo
 };
 
-__global__ void __launch_bounds__(MV_THREADS)
-k_diag_hist(const float* __restrict__ A, long long ld, int nloc, int n, int row0, int pass, DiagSel S) {
-    const int band = blockIdx.y, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
+__device__ __forceinline__ void diag_hist_body(const float* __restrict__ A, long long ld, int nloc, int n, int row0, int pass, const DiagSel& S, int bx, int by) {
+    const int band = by, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
     const int imax = row0 + r1 - 1;
-    if ((int)(blockIdx.x * MV_THREADS) > imax) return;
-    const int d = blockIdx.x * MV_THREADS + threadIdx.x;
+    if ((int)(bx * MV_THREADS) > imax) return;
+    const int d = bx * MV_THREADS + threadIdx.x;
     if (d > imax || d >= n) return;
     const unsigned int pre = pass ? S.prefix[d] : 0u;
     const int sh_hi = 32 - 8 * pass, sh = 24 - 8 * pass;
@@ -1321,10 +1359,14 @@ k_diag_hist(const float* __restrict__ A, long long ld, int nloc, int n, int row0
     if (run) atomicAdd(h + run_bin, run);
 }
 
-// one warp per diagonal: find the bin holding rank krem, descend into it, clear the histogram row
 __global__ void __launch_bounds__(MV_THREADS)
-k_diag_select(int n, int pass, DiagSel S) {
-    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+k_diag_hist(const float* __restrict__ A, long long ld, int nloc, int n, int row0, int pass, DiagSel S) {
+    diag_hist_body(A, ld, nloc, n, row0, pass, S, blockIdx.x, blockIdx.y);
+}
+
+// one warp per diagonal: find the bin holding rank krem, descend into it, clear the histogram row
+__device__ __forceinline__ void diag_select_body(int n, int pass, const DiagSel& S, int bx) {
+    const int d = (bx * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (d >= n) return;
     unsigned int* h = S.hist + (long long)d * 256;
     unsigned int c[8], tot = 0;
@@ -1376,11 +1418,15 @@ k_diag_select(int n, int pass, DiagSel S) {
 }
 
 __global__ void __launch_bounds__(MV_THREADS)
-k_diag_next(const float* __restrict__ A, long long ld, int nloc, int n, int row0, DiagSel S) {
-    const int band = blockIdx.y, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
+k_diag_select(int n, int pass, DiagSel S) {
+    diag_select_body(n, pass, S, blockIdx.x);
+}
+
+__device__ __forceinline__ void diag_next_body(const float* __restrict__ A, long long ld, int nloc, int n, int row0, const DiagSel& S, int bx, int by) {
+    const int band = by, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
     const int imax = row0 + r1 - 1;
-    if ((int)(blockIdx.x * MV_THREADS) > imax) return;
-    const int d = blockIdx.x * MV_THREADS + threadIdx.x;
+    if ((int)(bx * MV_THREADS) > imax) return;
+    const int d = bx * MV_THREADS + threadIdx.x;
     if (d > imax || d >= n) return;
     if (!S.need[d]) return;
     const unsigned int vlo = S.prefix[d];
@@ -1397,6 +1443,11 @@ k_diag_next(const float* __restrict__ A, long long ld, int nloc, int n, int row0
     if (best != 0xffffffffu) atomicMin(S.next + d, best);
 }
 
+__global__ void __launch_bounds__(MV_THREADS)
+k_diag_next(const float* __restrict__ A, long long ld, int nloc, int n, int row0, DiagSel S) {
+    diag_next_body(A, ld, nloc, n, row0, S, blockIdx.x, blockIdx.y);
+}
+
 __global__ void k_diag_median_final(int n, DiagSel S, double* __restrict__ avg) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n) return;
@@ -1404,6 +1455,174 @@ __global__ void k_diag_median_final(int n, DiagSel S, double* __restrict__ avg) 
     const double lo = (double)ord2f(S.prefix[d]);
     const double hi = S.need[d] ? (double)ord2f(S.next[d]) : lo;
     avg[d] = ((S.cnt[d] & 1u) == 0u) ? (lo + hi) / 2.0 : lo;             // np.median semantics
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Batched distance-frequency normalization: MANY resident maps (BASELINE configs[3]: the 24 chromosomes of a genome at 25 kb)
+// walked by ONE grid per stage instead of ~14 launches and two host synchronisations per map.  Every stage is the single-map
+// kernel body above applied to (map, local block): a flattened block list with a per-map prefix table, so small maps ride in
+// the same launch as large ones and the results are bit-identical to the per-map calls.
+// ---------------------------------------------------------------------------------------------------
+struct BMap {
+    const float* A;
+    float* Out;
+    long long ld;
+    int n, gx, gy, pad;
+    double* avg;                 // [>= n] the map's per-diagonal statistic
+    DiagSel S;                   // median: histogram / selection state of this map
+    double *psum, *sum, *cnt;    // mean: per-band partials and their reduction
+    int* pcnt;
+    MinMax* mm;
+    int blk0;                    // first block of this map in the flattened (diagonal chunk x row band) list
+    int sel0;                    // ... in the flattened one-warp-per-diagonal list
+    int red0;                    // ... in the flattened 64-diagonals-per-block list
+    int fin0;                    // ... in the flattened 256-diagonals-per-block list
+    long long u0;                // first (band, chunk) unit of the apply pass
+};
+
+template <int FIELD>
+__device__ __forceinline__ int bmap_find(const BMap* __restrict__ maps, int count, long long b) {
+    // the map whose range holds b (count <= a few dozen: linear scan by every thread, uniform per CTA)
+    int m = 0;
+    while (m + 1 < count) {
+        const BMap& nx = maps[m + 1];
+        const long long start = FIELD == 0 ? nx.blk0 : (FIELD == 1 ? nx.sel0 : (FIELD == 2 ? nx.red0 : (FIELD == 3 ? nx.fin0 : nx.u0)));
+        if (b < start) break;
+        ++m;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(MV_THREADS)
+k_diag_hist_b(const BMap* __restrict__ maps, int count, int pass) {
+    const int m = bmap_find<0>(maps, count, blockIdx.x);
+    const BMap M = maps[m];
+    const int local = (int)blockIdx.x - M.blk0;
+    diag_hist_body(M.A, M.ld, M.n, M.n, 0, pass, M.S, local % M.gx, local / M.gx);
+}
+
+__global__ void __launch_bounds__(MV_THREADS)
+k_diag_select_b(const BMap* __restrict__ maps, int count, int pass) {
+    const int m = bmap_find<1>(maps, count, blockIdx.x);
+    const BMap M = maps[m];
+    diag_select_body(M.n, pass, M.S, (int)blockIdx.x - M.sel0);
+}
+
+__global__ void __launch_bounds__(MV_THREADS)
+k_diag_next_b(const BMap* __restrict__ maps, int count) {
+    const int m = bmap_find<0>(maps, count, blockIdx.x);
+    const BMap M = maps[m];
+    const int local = (int)blockIdx.x - M.blk0;
+    diag_next_body(M.A, M.ld, M.n, M.n, 0, M.S, local % M.gx, local / M.gx);
+}
+
+__global__ void __launch_bounds__(256)
+k_diag_median_final_b(const BMap* __restrict__ maps, int count) {
+    const int m = bmap_find<3>(maps, count, blockIdx.x);
+    const BMap M = maps[m];
+    const int d = ((int)blockIdx.x - M.fin0) * 256 + threadIdx.x;
+    if (d >= M.n) return;
+    if (M.S.cnt[d] == 0u) { M.avg[d] = 0.0; return; }
+    const double lo = (double)ord2f(M.S.prefix[d]);
+    const double hi = M.S.need[d] ? (double)ord2f(M.S.next[d]) : lo;
+    M.avg[d] = ((M.S.cnt[d] & 1u) == 0u) ? (lo + hi) / 2.0 : lo;
+}
+
+__global__ void __launch_bounds__(MV_THREADS)
+k_diag_mean_partial_b(const BMap* __restrict__ maps, int count) {
+    const int m = bmap_find<0>(maps, count, blockIdx.x);
+    const BMap M = maps[m];
+    const int local = (int)blockIdx.x - M.blk0;
+    diag_mean_partial_body(M.A, M.ld, M.n, M.n, 0, M.psum, M.pcnt, local % M.gx, local / M.gx);
+}
+
+__global__ void __launch_bounds__(64 * DIAG_RED_SL)
+k_diag_mean_reduce_b(const BMap* __restrict__ maps, int count) {
+    const int m = bmap_find<2>(maps, count, blockIdx.x);
+    const BMap M = maps[m];
+    diag_mean_reduce_body(M.gy, M.n, 0, M.psum, M.pcnt, M.sum, M.cnt, (int)blockIdx.x - M.red0);
+}
+
+__global__ void __launch_bounds__(256)
+k_diag_mean_final_b(const BMap* __restrict__ maps, int count) {
+    const int m = bmap_find<3>(maps, count, blockIdx.x);
+    const BMap M = maps[m];
+    const int d = ((int)blockIdx.x - M.fin0) * 256 + threadIdx.x;
+    if (d < M.n) M.avg[d] = M.cnt[d] > 0.0 ? M.sum[d] / M.cnt[d] : 0.0;
+}
+
+__global__ void k_mm_init_b(const BMap* __restrict__ maps, int count) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < count) { maps[m].mm->min_nz = 0xffffffffu; maps[m].mm->max_all = 0u; }
+}
+__global__ void k_mm_gather_b(const BMap* __restrict__ maps, int count, MinMax* out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < count) out[m] = *maps[m].mm;
+}
+
+// the apply pass of all maps: the (band, chunk) units of every map in one list, split evenly over a persistent grid
+template <int R, int OCC>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
+k_diag_apply_b(const BMap* __restrict__ maps, int count, long long U, int subtract) {
+    const int tid = threadIdx.x;
+    const long long G = gridDim.x, c = blockIdx.x;
+    const long long ua = unit_begin(c, U, G), ub = unit_begin(c + 1, U, G);
+    if (ua >= ub) return;
+    int m = bmap_find<4>(maps, count, ua);
+    long long u = ua;
+    while (u < ub) {
+        const BMap M = maps[m];
+        const long long uend = (m + 1 < count) ? maps[m + 1].u0 : U;
+        const long long ue = uend < ub ? uend : ub;
+        const int n = M.n, n4 = (int)(M.ld / 4);
+        const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+        const double* __restrict__ avg = M.avg;
+        float mn = GCX_PINF, mx = GCX_NINF;
+        for (; u < ue; ++u) {
+            const long long lu = u - M.u0;
+            const int b = (int)(lu / nch), k = (int)(lu - (long long)b * nch);
+            const int c4 = k * MV_THREADS + tid;
+            if (c4 >= n4) continue;
+            float4 a[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                const int r = b * R + rr;
+                if (r < n) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(M.A + (long long)r * M.ld) + c4);
+            }
+            const int j0 = 4 * c4;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                const int i = b * R + rr;
+                if (i >= n) break;
+                const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = j0 + e;
+                    float v = in[e];
+                    if (j < n) {
+                        const int d = i > j ? i - j : j - i;
+                        const double av = in[e] != 0.f ? __ldg(avg + d) : 0.0;
+                        if (av != 0.0) {
+                            if (!subtract) {
+                                v = (float)((double)in[e] / av);                       // lib/normalizeCore.pyx:105-108, :114-117
+                            } else {
+                                double t = (double)in[e] - av;                         // :138
+                                if (t < 0.0) t = 1.0;                                  // :139-141
+                                if (in[e] == 0.f) t = 0.0;                             // :142-144
+                                v = (float)t;
+                            }
+                        }
+                        mm_update(v, mn, mx);
+                    }
+                    o[e] = v;
+                }
+                st_stream_f4(reinterpret_cast<float4*>(M.Out + (long long)i * M.ld) + c4, make_float4(o[0], o[1], o[2], o[3]));
+            }
+        }
+        mm_commit(mn, mx, M.mm);
+        ++m;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -2075,7 +2294,10 @@ template <int STAGES, int OCC, bool DIST>
 __global__ void __launch_bounds__(SYM_THREADS, OCC)
 k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long long nv, const uint8_t* __restrict__ keep, double* tring,
                double* uring, double* B, double* rowpart, double* colpart, SymTab T, unsigned int* ticket, IcState* st, double* part,
-               IcXchg X) {
+               IcXchg X, int npass) {
+    // npass: passes this launch may run.  1 = one cooperative launch per pass (the host enqueues them ahead of its convergence
+    // check); large = the whole solve in ONE launch: the kernel boundary between passes becomes a grid barrier, and the first
+    // tiles of the next pass are already in flight while the grid waits at it.
     namespace cg = cooperative_groups;
     if (st->done) return;
     cg::grid_group grid = cg::this_grid();
@@ -2086,24 +2308,36 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
     __shared__ double gred[2 * SYM_CW * SYM_R];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, bid = blockIdx.x;
-    const int L = st->matvecs;                        // products completed so far; the partials hold product L-1
-    const int gth = bid * SYM_THREADS + tid, nth = G * SYM_THREADS;
-    const double alpha = st->alpha, beta = st->beta, phi = st->phi, cc_prev = st->cc, tol = st->tol;
+    const int L0 = st->matvecs;                       // products completed so far; the partials hold product L0-1
+    // vector phase: a warp takes 4 consecutive bins (8 lanes each, one 32-byte sector of every partial array) and consecutive
+    // quads go to consecutive CTAs, so bins that are expensive to fold (many column partials) are spread over the whole grid
+    constexpr int WPC = SYM_THREADS / 32;
+    const double tol = st->tol;
     const int max_iter = st->max_iter;
     float4* tiles = reinterpret_cast<float4*>(tma_smem);
-    double* ucur = uring + (long long)(L & 1) * nv;
     const long long su0 = T.cta_u0[bid], su1 = T.cta_u0[bid + 1];
+  for (int it = 0; it < npass; ++it) {
+    const int L = L0 + it;
+    double* ucur = uring + (long long)(L & 1) * nv;
 
     long long* stamps = (T.dbg_stamps != nullptr && tid == 0) ? T.dbg_stamps + (long long)bid * 16 : nullptr;
     if (stamps != nullptr) {
         stamps[8] = (L == T.dbg_launch) ? 1 : 0;           // arms the two stamps taken inside matvec_sym_core
-        if (L == T.dbg_launch) stamps[0] = (long long)globaltimer_ns();
-        else stamps = nullptr;
+        if (L == T.dbg_launch) {
+            stamps[0] = (long long)globaltimer_ns();
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            stamps[9] = smid;
+            stamps[10] = T.cta_kf[bid];
+            stamps[11] = T.cta_kl[bid];
+        } else stamps = nullptr;
     }
     // ---- P0: barriers + the first tiles of this CTA's static share ----
     matvec_sym_range<SYM_NG, STAGES, false, SYM_BEGIN>(A, ld, n4, ucur, rowpart, colpart + (size_t)bid * T.nslots * SYM_NG * 1024, T, tiles, full_bar,
                                                        empty_bar, gred, su0, su1, T.cta_kf[bid], T.cta_kl[bid], false);
     if (stamps != nullptr) stamps[1] = (long long)globaltimer_ns();
+    if (it > 0) grid.sync();          // the previous pass's partials are complete (this replaces the kernel boundary)
+    const double alpha = st->alpha, beta = st->beta, phi = st->phi, cc_prev = st->cc;
     if (L > 0) {
         const double* uprev = uring + (long long)((L + 1) & 1) * nv;
         double* tcur = tring + (long long)((L + 2) % 3) * nv;            // t'_{L-1}
@@ -2112,8 +2346,8 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
         const int par = L & 1;
         if (DIST) {
             // ---- P1a: this rank's partial t' of every bin -> all ranks' receive buffers ----
-            for (int base = 0; base < n; base += nth / 8) {
-                const int i = base + (gth >> 3);
+            for (int q0 = 0; 4 * q0 < n; q0 += WPC * G) {
+                const int i = 4 * (q0 + warp * G + bid) + (lane >> 3);
                 const double pi = sym_fold_group8(i, i < n, n4, rowpart, colpart, T);
                 if (i < n && (tid & 7) == 0) {
                     for (int q = 0; q < X.world; ++q) X.peer_recv[q][((long long)par * X.world + X.rank) * nv + i] = pi;
@@ -2138,8 +2372,8 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
         // ---- P1: fold, next vector, partial sums ----
         double s = 0.0, c = 0.0, l1 = 0.0;
         int irr = 0;
-        for (int base = 0; base < n; base += nth / 8) {
-            const int i = base + (gth >> 3);
+        for (int q0 = 0; 4 * q0 < n; q0 += WPC * G) {
+            const int i = 4 * (q0 + warp * G + bid) + (lane >> 3);
             double tp = 0.0;
             if (!DIST) tp = sym_fold_group8(i, i < n, n4, rowpart, colpart, T);
             if (i < n && (tid & 7) == 0) {
@@ -2226,8 +2460,10 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
             *ticket = 0u;
             if (T.ndyn > 0) *T.dyn_counter = 0u;
             st->matvecs = L + 1;
+            __threadfence();
         }
     }
+  }
 }
 
 // s_i = keep_i ? 1/B_i : 0 -- the symmetric scale for the final apply

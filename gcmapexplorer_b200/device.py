@@ -280,6 +280,12 @@ class DeviceMap:
         check(lib().gcx_diag_stats(self._ctx, 1 if stats == "median" else 0, avg.ctypes.data_as(_lib._c_f64p)))
         return avg
 
+    def diag_avg(self):
+        """The per-diagonal statistic left resident by the last diag_stats / MapBatch.mcfs."""
+        avg = np.empty(self.n, dtype=np.float64)
+        check(lib().gcx_diag_avg_read(self._ctx, avg.ctypes.data_as(_lib._c_f64p)))
+        return avg
+
     def diag_apply(self, avg, subtract=False, in_place=False):
         mn, mx = C.c_float(0), C.c_float(0)
         ap = None
@@ -353,6 +359,25 @@ class DeviceMap:
         ms = C.c_double(0)
         check(lib().gcx_bench_matvec(self._ctx, int(variant), int(iters), C.byref(ms)))
         return ms.value / iters
+
+
+class MapBatch:
+    """Several resident maps on one device treated as one job (the chromosomes of a genome): each stage of the
+    distance-frequency normalization is one grid over all of them (gcx_mcfs_batch)."""
+
+    def __init__(self, maps):
+        self.maps = list(maps)
+        if not self.maps:
+            raise ValueError("empty batch")
+        self._arr = (C.c_void_p * len(self.maps))(*[m._ctx for m in self.maps])
+
+    def mcfs(self, stats="median", subtract=False):
+        """diag_stats + diag_apply (into output 1) for every map; returns [(min non-zero, max)] per map."""
+        k = len(self.maps)
+        mn = (C.c_float * k)()
+        mx = (C.c_float * k)()
+        check(lib().gcx_mcfs_batch(self._arr, k, 1 if stats == "median" else 0, int(bool(subtract)), mn, mx))
+        return [(mn[i], mx[i]) for i in range(k)]
 
 
 def dist_unique_id():

@@ -110,6 +110,14 @@ int gcx_apply_sym_vc(gcx_ctx* ctx, const uint8_t* keep_vc, int masked_mode, int 
 int gcx_diag_stats(gcx_ctx* ctx, int median, double* avg);
 int gcx_diag_apply(gcx_ctx* ctx, const double* avg, int subtract, int in_place, float* minv, float* maxv);
 
+/* Batched form for MANY resident maps on one device (the 24 chromosomes of a genome, BASELINE configs[3]; the loop over maps of
+ * normalizeGCMapByMCFS, lib/normalizer.py:1013-1030): gcx_diag_stats + gcx_diag_apply (not in place) for every map, each stage ONE
+ * grid over all maps instead of ~14 launches and two host synchronisations per map.  ctxs: `count` single-rank contexts with
+ * resident maps; results as per map: output map 1, the statistic resident (gcx_diag_avg_read), minv/maxv[count].  Bit-identical
+ * to the per-map calls. */
+int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtract, float* minv, float* maxv);
+int gcx_diag_avg_read(gcx_ctx* ctx, double* avg);
+
 /* ---- compaction ---------------------------------------------------------------------------------
  * Replaces the element loop of ccmapHelpers.remove_zeros (lib/ccmapHelpers.pyx:286-299): host_out[ci][cj] =
  * (double) A[kept[ci]][kept[cj]], nk x nk float64.  Only for callers of the inner seam -- the normalizers never compact. */

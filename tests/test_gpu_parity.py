@@ -501,6 +501,55 @@ def test_in_place_equals_out_of_place_and_async_download(gx):
         pin.free()
 
 
+@pytest.mark.parametrize("stats", ["median", "mean"])
+@pytest.mark.parametrize("subtract", [False, True])
+def test_mcfs_batch_matches_per_map_calls(gx, stats, subtract):
+    """gcx_mcfs_batch (one grid per stage over many maps, BASELINE configs[3]) against diag_stats + diag_apply map by map:
+    statistics, output maps (checksums) and min/max bit-identical; ragged sizes incl. tiny maps."""
+    sizes = [5, 97, 300, 257, 1111, 2500, 64, 1926]
+    maps, single = [], []
+    try:
+        for k, n in enumerate(sizes):
+            A = onp.synth_map(n, seed=100 + k, scale=40.0, alpha=1.1, empty_frac=0.02) if n > 5 else load_golden("kat5_ic")["input"]
+            maps.append(gx.DeviceMap.from_host(A))
+            single.append(gx.DeviceMap.from_host(A))
+        mm = gx.MapBatch(maps).mcfs(stats, subtract=subtract)
+        for k, (b, o) in enumerate(zip(maps, single)):
+            avg = o.diag_stats(stats)
+            mn, mx = o.diag_apply(None, subtract=subtract, in_place=False)
+            assert np.array_equal(b.diag_avg(), avg), sizes[k]
+            assert b.checksum(1) == o.checksum(1), sizes[k]
+            assert np.array_equal(b.download(1), o.download(1))
+            assert (np.float32(mm[k][0]) == np.float32(mn) or (np.isnan(mm[k][0]) and np.isnan(mn))) and np.float32(mm[k][1]) == np.float32(mx)
+        # the batch leaves every map usable on its own stream afterwards
+        again = maps[3].diag_stats(stats)
+        assert np.array_equal(again, single[3].diag_stats(stats))
+    finally:
+        for d in maps + single:
+            d.close()
+
+
+def test_fused_apply_vc_matches_separate_passes(gx):
+    """gcx_apply_sym_vc: the IC-scaled map and the VC map from one read of the input, bit-identical to gcx_apply_sym_scale + gcx_vc_run."""
+    for n, seed in ((97, 1), (1031, 2), (2100, 3)):
+        A = onp.synth_map(n, seed=seed)
+        keep = onp.get_nonzeros_index(A)
+        for solve_mask, mode in ((np.ones(n, dtype=bool), 1), (keep, 1), (keep, 0)):
+            with gx.DeviceMap.from_host(A) as dm:
+                dm.set_mask(solve_mask)
+                dm.ic(1e-4, 500)
+                (mn_s, mx_s), (mn_v, mx_v) = dm.apply_sym_vc(keep, masked_mode=mode, sqroot=False)
+                S, V = dm.download(1), dm.download(2)
+                a = dm.apply_sym(None, masked_mode=mode, in_place=False)
+                S0 = dm.download(1)
+                dm.set_mask(keep)
+                b = dm.vc(False, in_place=False)
+                V0 = dm.download(1)
+            assert np.array_equal(S, S0) and np.array_equal(V, V0)
+            assert (np.float32(mn_s), np.float32(mx_s)) == (np.float32(a[0]), np.float32(a[1]))
+            assert (np.float32(mn_v), np.float32(mx_v)) == (np.float32(b[0]), np.float32(b[1]))
+
+
 # --------------------------------------------------------------------------------------------------
 # upper-triangle (symmetric) passes
 # --------------------------------------------------------------------------------------------------

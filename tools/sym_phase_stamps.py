@@ -29,3 +29,20 @@ with gx.DeviceMap(n) as dm:
     order = np.argsort(-end)
     print("last CTAs to finish:", [(int(c), round(float(end[c]), 1), int(ch[c])) for c in order[:10]])
     print("first CTAs to finish:", [(int(c), round(float(end[c]), 1), int(ch[c])) for c in order[-6:]])
+    # who is slow?  static-share time per CTA against its SM, its position in the unit list and the panels it walks
+    dur = (st[:, 5] - st[:, 4]) / 1e3
+    smid, kf, kl = st[:, 9], st[:, 10], st[:, 11]
+    print("static share duration: min %.1f median %.1f max %.1f us" % (dur.min(), np.median(dur), dur.max()))
+    print("by CTA-index decile (panel-major position):", [round(float(dur[i].mean()), 1) for i in np.array_split(np.arange(G), 10)])
+    order = np.argsort(smid)
+    print("by SM-id decile:", [round(float(dur[i].mean()), 1) for i in np.array_split(order, 10)])
+    print("corr(duration, CTA index) %.3f  corr(duration, smid) %.3f  corr(duration, first panel) %.3f  corr(duration, panels spanned) %.3f" % (
+        np.corrcoef(dur, np.arange(G))[0, 1], np.corrcoef(dur, smid)[0, 1], np.corrcoef(dur, kf)[0, 1], np.corrcoef(dur, kl - kf)[0, 1]))
+    same_sm = {}
+    for c in range(G):
+        same_sm.setdefault(int(smid[c]), []).append(c)
+    pairs = [v for v in same_sm.values() if len(v) == 2]
+    if pairs:
+        d = np.array([[dur[a], dur[b]] for a, b in pairs])
+        print("SMs with two CTAs: %d; corr between the two CTAs of an SM %.3f; mean |difference| %.1f us" % (len(pairs), np.corrcoef(d[:, 0], d[:, 1])[0, 1], np.abs(d[:, 0] - d[:, 1]).mean()))
+    print("vector phase by CTA (us): p50 %.1f p90 %.1f max %.1f" % tuple(np.percentile((st[:, 2] - st[:, 1]) / 1e3, [50, 90, 100])))
