@@ -127,7 +127,7 @@ class DistEnv:
         self.tdist = None
         self.numa = None
         if self.world > 1:
-            self.numa = bind_to_gpu_numa(self.local)          # before any pinned allocation: host buffers land next to the GPU
+            self.numa = {"bound": False, "why": "--no-numa-bind"} if getattr(args, "no_numa_bind", False) else bind_to_gpu_numa(self.local)   # before any pinned allocation
             import torch
             import torch.distributed as tdist
             torch.cuda.set_device(self.local)
@@ -201,7 +201,24 @@ def bind_to_gpu_numa(local):
         with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
             node = int(f.read().strip())
         if node < 0:
-            return {"node": node, "bound": False}
+            # containers often hide the PCI NUMA node: fall back to the "CPU Affinity" column of `nvidia-smi topo -m`
+            topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+            cpus = set()
+            for ln in topo.splitlines():
+                f = ln.replace("\x1b[4m", "").replace("\x1b[0m", "").split("\t")
+                if f and f[0].strip() == f"GPU{local}":
+                    for tok in f[1:]:
+                        tok = tok.strip()
+                        if tok and all(ch.isdigit() or ch in "-," for ch in tok) and any(ch.isdigit() for ch in tok) and ("-" in tok or "," in tok):
+                            for part in tok.split(","):
+                                lo, _, hi = part.partition("-")
+                                cpus.update(range(int(lo), int(hi or lo) + 1))
+                            break
+            cpus &= os.sched_getaffinity(0)
+            if not cpus or cpus == os.sched_getaffinity(0):
+                return {"node": node, "bound": False, "why": "no NUMA information narrower than the process's CPU set"}
+            os.sched_setaffinity(0, cpus)
+            return {"node": "from nvidia-smi topo", "bound": True, "cpus": len(cpus)}
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             cpus = set()
             for part in f.read().strip().split(","):
@@ -383,6 +400,8 @@ def run_b200(args):
     roofline = {"kernel": kname, "layout": "dense fp32, upper triangle read (symmetric pass)" if info["symmetric"] else "dense fp32, all rows read", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": recorded_traffic(kname, n) if world == 1 else None, "bytes_per_launch": mv_bytes, "us_per_launch": round(mv_ms * 1e3, 2),
                 "launches_timed": args.steps * launched,
+                "launch_note": ("one persistent cooperative launch runs the whole solve; `us_per_launch` = its CUDA-event duration / products it ran (one pass of the "
+                                "map each), `bytes_per_launch` = the bytes of one such pass") if kname == "k_ic_pass_symd" else None,
                 "strict_upper_triangle_bytes": 2.0 * n * (n + 1) if (info["symmetric"] and world == 1) else None,
                 "other_kernels_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in prof.items() if k != "matvec" and v["launches"]}}
 
@@ -703,6 +722,55 @@ def run_mcfs_wg(args):
     print(json.dumps(line))
     for dm in maps:
         dm.close()
+
+
+def run_host_copy_floor(args):
+    """What the host <-> device path of THIS box can do, without any of this library's code: bare cudaMemcpyAsync between pinned
+    host memory and HBM on every rank at once (torch tensors are only the allocation / stream plumbing).  Three shapes per rank:
+    H2D alone, D2H alone, H2D and D2H concurrently on two streams -- each rank moves the bytes one e2e step of the default
+    workload moves (2.485 GB up, 2 x 2.485 GB down).  Written to profiles/ as the floor the e2e numbers are read against."""
+    env = DistEnv(args)
+    import torch
+    torch.cuda.set_device(env.local)
+    nbytes = 4 * N_CHR1_10KB * N_CHR1_10KB
+    h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(2 * nbytes, dtype=torch.uint8, pin_memory=True)
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    d_b = torch.empty(2 * nbytes, dtype=torch.uint8, device="cuda")
+    h_in.fill_(1)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def timed(fn, reps=3):
+        best = 1e9
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            env.barrier()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            best = min(best, env.max(time.perf_counter() - t0))
+        return best
+
+    def up():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_in, non_blocking=True)
+
+    def down():
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_b, non_blocking=True)
+
+    def both():
+        up()
+        down()
+    up(); down()
+    t_up, t_down, t_both = timed(up), timed(down), timed(both)
+    if env.rank == 0:
+        print(json.dumps({"what": "bare cudaMemcpyAsync floor, pinned host memory, all ranks at once (max over ranks, best of 3)", "n_gpus": env.world,
+                          "numa": env.numa, "bytes_up_per_gpu": nbytes, "bytes_down_per_gpu": 2 * nbytes,
+                          "h2d_alone_gbs_per_gpu": round(nbytes / t_up / 1e9, 1), "d2h_alone_gbs_per_gpu": round(2 * nbytes / t_down / 1e9, 1),
+                          "concurrent_s": round(t_both, 4), "concurrent_gbs_per_gpu": round(3 * nbytes / t_both / 1e9, 1),
+                          "e2e_step_floor_s": round(t_both, 4), "host_cores": os.cpu_count()}))
+    env.close()
 
 
 def min_over_ranks_flag(tdist, flag):
@@ -1116,7 +1184,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "chr1_10kb", "chr1_5kb_kr", "chr1_1kb", "wg_25kb_mcfs", "chr21_100kb", "chr1_10kb_statdist", "chr1_10kb_corr"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "chr1_10kb", "chr1_5kb_kr", "chr1_1kb", "wg_25kb_mcfs", "chr21_100kb", "chr1_10kb_statdist", "chr1_10kb_corr", "host_copy_floor"])
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to the NUMA node of its GPU")
     ap.add_argument("--mcfs-stats", default="median", choices=["median", "mean"])
     ap.add_argument("--mcfs-threads", type=int, default=6, help="host threads driving the 24 independent maps of wg_25kb_mcfs")
     ap.add_argument("--n", type=int, default=0, help="override the number of bins (quick checks)")
@@ -1144,6 +1213,8 @@ def main():
         run_statdist(args)
     elif args.workload == "chr1_10kb_corr":
         run_corr(args)
+    elif args.workload == "host_copy_floor":
+        run_host_copy_floor(args)
     else:
         run_b200(args)
 

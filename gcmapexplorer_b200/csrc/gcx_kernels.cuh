@@ -868,6 +868,67 @@ __device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n4, con
     return s;
 }
 
+// The same sum for the deferred-scalar pass, organised for memory-level parallelism instead of lanes per bin: LPB (2) adjacent
+// lanes share a bin, so a warp covers 32 / LPB CONSECUTIVE bins and every load instruction of the warp reads whole 32-byte sectors
+// of one partial array; a lane takes every LPB-th source of the flattened source lists (row partials (panel, group); column
+// partials (CTA, group) of the static shares; column partials (chunk, group) of the dynamic pool), loads them in batches of
+// FOLD_UN independent loads and adds them in a fixed order.  One round of the grid covers 16 x 2664 bins, so the vector phase
+// of a pass is a handful of L2 round trips instead of three latency-bound rounds.  Every lane of the group returns the sum.
+constexpr int FOLD_LPB = 2, FOLD_UN = 16;
+__device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const double* rowpart, const double* colpart, const SymTab& T) {
+    const int j = threadIdx.x & (FOLD_LPB - 1);
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const long long rp_ld = (long long)n4 * 4;
+    double s = 0.0;
+    if (valid) {
+        const int ki = i >> 10, col = i & 1023;
+        // the three source lists, flattened into one index range so that every batch of loads is full
+        int n_row = 0;
+        const double* rbase = rowpart;
+        if (i >= T.row0 && i < T.row0 + T.nloc) {
+            const int kstart = T.kfold_lo < 0 ? ki : T.kfold_lo;
+            n_row = (nch - kstart) * SYM_NG;
+            rbase = rowpart + (long long)kstart * SYM_NG * rp_ld + i;
+        }
+        const int clo = T.panel_cta[ki], chi = T.panel_cta_hi[ki];
+        const int n_col = chi >= clo ? (chi - clo + 1) * SYM_NG : 0;
+        // only the first CTA of a panel can have started its share in an earlier panel (shares are contiguous and ordered)
+        const int slot_lo = n_col > 0 ? ki - T.cta_kf[clo] : 0;
+        const double* cbase = colpart + (size_t)clo * T.nslots * SYM_NG * 1024 + col;
+        int n_dyn = 0;
+        const double* dbase = T.colpart_dyn;
+        if (T.ndyn > 0) {
+            const int d0 = T.panel_dyn0[ki];
+            n_dyn = (T.panel_dyn0[ki + 1] - d0) * SYM_NG;
+            dbase = T.colpart_dyn + (size_t)d0 * SYM_NG * 1024 + col;
+        }
+        const int n_rc = n_row + n_col, total = n_rc + n_dyn;
+        const size_t cstride = (size_t)T.nslots * SYM_NG * 1024;
+        for (int q = j; q < total; q += FOLD_LPB * FOLD_UN) {
+            double v[FOLD_UN];
+#pragma unroll
+            for (int u = 0; u < FOLD_UN; ++u) {
+                const int idx = q + u * FOLD_LPB;
+                const double* p = nullptr;
+                if (idx < n_row) {
+                    p = rbase + (long long)idx * rp_ld;
+                } else if (idx < n_rc) {
+                    const int e = idx - n_row, cc = e / SYM_NG, gg = e % SYM_NG;
+                    p = cbase + (size_t)cc * cstride + ((size_t)(cc == 0 ? slot_lo : 0) * SYM_NG + gg) * 1024;
+                } else if (idx < total) {
+                    p = dbase + (size_t)(idx - n_rc) * 1024;
+                }
+                v[u] = p != nullptr ? __ldcg(p) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < FOLD_UN; ++u) s += v[u];
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < FOLD_LPB; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
 __global__ void __launch_bounds__(256)
 k_sym_fold(int n, int n4, const double* rowpart, const double* colpart, SymTab T, double* __restrict__ t, const int* __restrict__ done) {
     if (done != nullptr && *done) return;
@@ -2309,9 +2370,9 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, bid = blockIdx.x;
     const int L0 = st->matvecs;                       // products completed so far; the partials hold product L0-1
-    // vector phase: a warp takes 4 consecutive bins (8 lanes each, one 32-byte sector of every partial array) and consecutive
-    // quads go to consecutive CTAs, so bins that are expensive to fold (many column partials) are spread over the whole grid
-    constexpr int WPC = SYM_THREADS / 32;
+    // vector phase: a warp takes 32 / FOLD_LPB consecutive bins and consecutive warp-loads go to consecutive CTAs, so bins that are
+    // expensive to fold (many column partials) are spread over the whole grid
+    constexpr int WPC = SYM_THREADS / 32, BPW = 32 / FOLD_LPB;
     const double tol = st->tol;
     const int max_iter = st->max_iter;
     float4* tiles = reinterpret_cast<float4*>(tma_smem);
@@ -2337,6 +2398,7 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
                                                        empty_bar, gred, su0, su1, T.cta_kf[bid], T.cta_kl[bid], false);
     if (stamps != nullptr) stamps[1] = (long long)globaltimer_ns();
     if (it > 0) grid.sync();          // the previous pass's partials are complete (this replaces the kernel boundary)
+    if (stamps != nullptr) stamps[14] = (long long)globaltimer_ns();
     const double alpha = st->alpha, beta = st->beta, phi = st->phi, cc_prev = st->cc;
     if (L > 0) {
         const double* uprev = uring + (long long)((L + 1) & 1) * nv;
@@ -2346,15 +2408,16 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
         const int par = L & 1;
         if (DIST) {
             // ---- P1a: this rank's partial t' of every bin -> all ranks' receive buffers ----
-            for (int q0 = 0; 4 * q0 < n; q0 += WPC * G) {
-                const int i = 4 * (q0 + warp * G + bid) + (lane >> 3);
-                const double pi = sym_fold_group8(i, i < n, n4, rowpart, colpart, T);
-                if (i < n && (tid & 7) == 0) {
+            for (int q0 = 0; BPW * q0 < n; q0 += WPC * G) {
+                const int i = BPW * (q0 + warp * G + bid) + lane / FOLD_LPB;
+                const double pi = sym_fold_mlp(i, i < n, n4, rowpart, colpart, T);
+                if (i < n && (tid & (FOLD_LPB - 1)) == 0) {
                     for (int q = 0; q < X.world; ++q) X.peer_recv[q][((long long)par * X.world + X.rank) * nv + i] = pi;
                 }
             }
             __threadfence_system();
             __syncthreads();
+            if (stamps != nullptr) stamps[12] = (long long)globaltimer_ns();
             if (tid < X.world) {
                 const unsigned int want = X.seq0 + (unsigned int)L;
                 st_release_sys_u32(X.peer_flags[tid] + (long long)X.rank * G + bid, want);
@@ -2368,15 +2431,16 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
                 }
             }
             __syncthreads();
+            if (stamps != nullptr) stamps[13] = (long long)globaltimer_ns();
         }
         // ---- P1: fold, next vector, partial sums ----
         double s = 0.0, c = 0.0, l1 = 0.0;
         int irr = 0;
-        for (int q0 = 0; 4 * q0 < n; q0 += WPC * G) {
-            const int i = 4 * (q0 + warp * G + bid) + (lane >> 3);
+        for (int q0 = 0; BPW * q0 < n; q0 += WPC * G) {
+            const int i = BPW * (q0 + warp * G + bid) + lane / FOLD_LPB;
             double tp = 0.0;
-            if (!DIST) tp = sym_fold_group8(i, i < n, n4, rowpart, colpart, T);
-            if (i < n && (tid & 7) == 0) {
+            if (!DIST) tp = sym_fold_mlp(i, i < n, n4, rowpart, colpart, T);
+            if (i < n && (tid & (FOLD_LPB - 1)) == 0) {
                 if (DIST) {
                     for (int q = 0; q < X.world; ++q) tp += __ldcg(X.recv + ((long long)par * X.world + q) * nv + i);     // rank order
                 }
@@ -2400,6 +2464,7 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
             }
         }
         if (irr) st->irregular = 1;
+        if (stamps != nullptr) stamps[15] = (long long)globaltimer_ns();
         // one block reduction for the three sums (fixed tree)
         s = warp_sum(s); c = warp_sum(c); l1 = warp_sum(l1);
         if (lane == 0) { sm[warp] = s; gred[warp] = c; gred[16 + warp] = l1; }

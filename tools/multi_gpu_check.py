@@ -89,6 +89,7 @@ def main():
             one.swap()
             sd1 = one.stationary()
         res.update(partition=partition, sharded_symmetric_pass=bool(ic["symmetric"]), single_symmetric_pass=bool(ic1["symmetric"]),
+            peer_exchange=bool(ic.get("peer_exchange")), products_launched=(ic.get("products_launched"), ic1.get("products_launched")),
             rowstats_equal=bool(np.array_equal(rs, rs1) and np.array_equal(zc, zc1)),
             ic_passes=(ic["passes"], ic1["passes"]), ic_bias_rel=float(np.max(np.abs(ic["bias"] / ic1["bias"] - 1))),
             kr_counters=((kr["outer"], kr["MVP"]), (kr1["outer"], kr1["MVP"])),

@@ -6,17 +6,36 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from gcmapexplorer_b200 import device as gx, _lib
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 24926
-with gx.DeviceMap(n) as dm:
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:          # under torchrun: the row-sharded pass with the NVLink peer exchange, rank 0 reports
+    import torch, torch.distributed as tdist
+    from gcmapexplorer_b200 import dist as gd
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    tdist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    ctxmgr = gd.sharded_device_map(n, device=int(os.environ["LOCAL_RANK"]), partition="balanced", symmetric=True)
+    if int(os.environ["RANK"]) != 0:
+        sys.stdout = open(os.devnull, "w")
+else:
+    ctxmgr = gx.DeviceMap(n)
+with ctxmgr as dm:
     dm.synth(seed=110)
     dm.set_mask(np.ones(n, dtype=bool))
     for rep in range(2):
         r = dm.ic(1e-4, 500)
+    print("peer exchange:", r.get("peer_exchange"), "world", world)
     buf = (C.c_int64 * (16 * 1024))(); cnt = C.c_int(0)
     _lib.check(_lib.lib().gcx_debug_sym_stamps(dm._ctx, buf, 16 * 1024, C.byref(cnt)))
     G = cnt.value
     st = np.array(buf[:16 * G], dtype=np.int64).reshape(G, 16)
     t0 = st[:, 0].min()
     names = ["entry", "tiles issued", "vector phase done", "past grid barrier", "product starts", "static share done", "all done"]
+    for k, nm in ((14, "past the pass barrier"), (15, "fold + vector update done (thread 0)")):
+        v = (st[:, k] - t0) / 1e3
+        print("%-38s min %8.2f  median %8.2f  max %8.2f us" % (nm, v.min(), np.median(v), v.max()))
+    if world > 1:
+        for k, nm in ((12, "partials stored to peers"), (13, "peers' partials arrived")):
+            v = (st[:, k] - t0) / 1e3
+            print("%-26s min %8.2f  median %8.2f  max %8.2f us" % (nm, v.min(), np.median(v), v.max()))
     print("n", n, "passes", r["passes"], "device ms", r["ms"], "-> us per launch", r["ms"] * 1e3 / r["products_launched"], "G", G)
     for k, nm in enumerate(names):
         v = (st[:, k] - t0) / 1e3
