@@ -238,13 +238,13 @@ def make_map(gx, gd, env, n, partition, seed):
     options = {}
     if env.world > 1 and partition == "balanced":
         # near-equal row blocks (cuts on 1024 rows); each unordered pair of bins is read once, the off-diagonal blocks dealt out
-        # to the ranks in a circulant pattern.  The synthetic map is symmetric by construction, which a rank cannot verify
-        # locally -> assume_symmetric.
+        # to the ranks in a circulant pattern.  Whether the map is symmetric is TESTED across the ranks (k_sym_hash: hash sums of
+        # the entries above / below the diagonal, allreduced) before the first pass -- nothing is assumed.
         row0, nloc = gd.row_partition_aligned(n, env.world, env.rank)
-        options = {"exchange_allreduce": 1, "assume_symmetric": 1}
+        options = {"exchange_allreduce": 1}
     elif env.world > 1 and partition == "equal_area":
         row0, nloc = gd.row_partition_equal_area(n, env.world, env.rank)
-        options = {"exchange_allreduce": 1, "assume_symmetric": 1, "sym_blocks": 0}
+        options = {"exchange_allreduce": 1, "sym_blocks": 0}
     else:
         row0, nloc = gd.row_partition(n, env.world, env.rank)
     dist = (env.rank, env.world, env.unique_id(gx)) if env.world > 1 else None

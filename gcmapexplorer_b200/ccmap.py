@@ -159,6 +159,39 @@ class CCMAP:
         return other
 
 
+def new_like(ccMapObj):
+    """New temporary CCMAP (this module's class) with an uninitialised writable backing file and the metadata of `ccMapObj`,
+    which may be this module's CCMAP *or* the reference's ``gcMapExplorer.lib.ccmap.CCMAP`` (duck-typed on the attribute set
+    of lib/ccmap.py:125-140) -- what ``ccMapObj.copy(fill=0.0)`` gives the reference's normalizers (lib/normalizer.py:308, 561)
+    without the n^2 fill."""
+    if isinstance(ccMapObj, CCMAP):
+        return ccMapObj.new_like()
+    other = CCMAP(dtype=getattr(ccMapObj, "dtype", dtype_npBINarray))
+    for key in _ATTRS:
+        if key in ("matrix", "state", "path2matrix"):
+            continue
+        if hasattr(ccMapObj, key):
+            setattr(other, key, getattr(ccMapObj, key))
+    other.shape = tuple(ccMapObj.shape)
+    other.state = "temporary"
+    other.gen_matrix_file(workDir=os.path.dirname(getattr(ccMapObj, "path2matrix", "") or "") or None)
+    other.make_writable()
+    return other
+
+
+def result_like(dm, which, ccMapObj):
+    """new_like(ccMapObj) filled with a device result (`which`: 0 input buffer, 1 / 2 output buffers of the DeviceMap).  The
+    device map is float32 (lib/ccmap.py:42); a CCMAP of another dtype (gen_from_matrix keeps the dtype of the array it was given,
+    lib/ccmap.py:203) gets the result cast into its own dtype, like the reference's in-place arithmetic would."""
+    out = new_like(ccMapObj)
+    if np.dtype(out.dtype) == np.float32:
+        dm.download(which, out=out.matrix)
+    else:
+        out.matrix[:] = dm.download(which)
+    out.matrix.flush()
+    return out
+
+
 # ---- coarsening (lib/ccmap.py:655-842) ------------------------------------------------------------------
 def getOutputShapeFor2DMapDownsampling(inputShape, level=2):
     """Shape of the map after coarsening by `level` (lib/ccmap.py:712-735)."""

@@ -62,9 +62,7 @@ def calculateCorrMatrixForCCMap(inputCCMap, logspace=False, maskvalue=0.0, vmin=
         with DeviceMap.from_host(ccMapObj.matrix) as dm:
             dm.set_mask(keep)
             dm.corr(maskvalue, logspace, vmin, vmax)
-            corrCCMap = ccMapObj.new_like()
-            dm.download(1, out=corrCCMap.matrix)
-        corrCCMap.matrix.flush()
+            corrCCMap = cmp.result_like(dm, 1, ccMapObj)
         corrCCMap.bNoData = np.asarray(bNoData, dtype=bool).copy()
         corrCCMap.minvalue = -1
         corrCCMap.maxvalue = 1

@@ -49,7 +49,7 @@ static int fail(const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------------------
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclInt32 = 2, ncclUint32 = 3, ncclFloat32 = 7, ncclFloat64 = 8, ncclUint8 = 1 };
+enum { ncclInt32 = 2, ncclUint32 = 3, ncclUint64 = 5, ncclFloat32 = 7, ncclFloat64 = 8, ncclUint8 = 1 };
 enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
 struct NcclApi {
     void* h = nullptr;
@@ -524,6 +524,14 @@ static int map_alloc(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc) {
     c->n = n; c->row0 = row0; c->nloc = nloc;
     c->ld = round_up(n, 32);
     c->rpr = (n + c->world - 1) / c->world;
+    if (c->world > 1 && !c->exchange_allreduce) {
+        // the allgather exchange sends slot `rank` of ceil(n/world) entries: any other row block would be gathered into the wrong place
+        const int64_t want0 = std::min<int64_t>(n, (int64_t)c->rank * c->rpr), wantn = std::max<int64_t>(0, std::min<int64_t>(c->rpr, n - want0));
+        if (row0 != want0 || nloc != wantn)
+            return fail("row block [%lld, +%lld) of rank %d is not the equal ceil(n/world) block [%lld, +%lld) the allgather exchange assumes: "
+                        "set the option \"exchange_allreduce\" on every rank for custom partitions (gcx_partition_rows, equal-area cuts)",
+                        (long long)row0, (long long)nloc, c->rank, (long long)want0, (long long)wantn);
+    }
     c->nv = round_up(std::max<int64_t>(c->ld, c->rpr * c->world), 32) + 32;
     CK(cudaMalloc(&c->A, sizeof(float) * (size_t)nloc * c->ld));
     CK(cudaMemsetAsync(c->A, 0, sizeof(float) * (size_t)nloc * c->ld, c->stream));
@@ -1011,11 +1019,29 @@ extern "C" int gcx_partition_rows(int64_t n, int world, int rank, int64_t* row0,
 static int sym_ready(gcx_ctx* c, bool* ok) {
     *ok = false;
     if (!c->sym_enable || c->n < 2048) return 0;
-    if (c->world > 1 && !(c->assume_symmetric && c->exchange_allreduce && c->row0 % 1024 == 0)) return 0;
+    // sharded: needs the zero-fill + allreduce exchange (an option every rank sets) and panel-aligned cuts; a rank whose block is
+    // not aligned cannot simply return -- the others would wait in the collective of the symmetry test -- it votes "no" there
+    if (c->world > 1 && !c->exchange_allreduce) return 0;
+    const bool aligned = c->world == 1 || c->row0 % 1024 == 0;
+    if (c->world > 1 && c->assume_symmetric && !aligned) return 0;
     if (c->world == 1 && (c->row0 != 0 || c->nloc != c->n)) return 0;
     if (c->sym_state < 0) {
-        if (c->world > 1 || c->assume_symmetric) {
-            c->sym_state = 1;             // a rank cannot see the mirrored block: the caller vouches (gcx_set_option "assume_symmetric")
+        if (c->assume_symmetric) {
+            c->sym_state = 1;             // the caller vouches (gcx_set_option "assume_symmetric"): no test
+        } else if (c->world > 1) {
+            // sharded: hash sums of the entries above / below the diagonal, added over the ranks, must agree (k_sym_hash)
+            unsigned long long* hs = nullptr;
+            CKR(ensure_scratch(c, 256));
+            hs = (unsigned long long*)c->scratch;
+            CK(cudaMemsetAsync(hs, 0, 2 * sizeof(unsigned long long), c->stream));
+            k_sym_hash<<<grid_rows(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, (int)c->n, (int)c->row0, hs);
+            CK(cudaGetLastError());
+            c->launches += 1;
+            if (!aligned) CK(cudaMemsetAsync(hs, 0xff, sizeof(unsigned long long), c->stream));      // poison: the sums cannot agree
+            NK(g_nccl.AllReduce(hs, hs, 2, ncclUint64, ncclSum, c->comm, c->stream));
+            unsigned long long h2[2] = {0, 1};
+            CKR(read_small(c, hs, sizeof h2, h2));
+            c->sym_state = h2[0] == h2[1] ? 1 : 0;
         } else {
             CK(cudaMemsetAsync(c->csum_dev, 0, sizeof(unsigned long long), c->stream));
             k_count_asym<<<c->sm_count * 8, 256, 0, c->stream>>>(c->A, c->ld, (int)c->n, c->csum_dev);

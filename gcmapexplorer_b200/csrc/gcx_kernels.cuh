@@ -963,6 +963,41 @@ k_count_asym(const float* __restrict__ A, long long ld, int n, unsigned long lon
     if (tx == 0 && bad) atomicAdd(count, (unsigned long long)bad);
 }
 
+// Symmetry test for a ROW-SHARDED map, where no rank sees a block and its mirror image: every rank adds, over its own rows, a 64-bit
+// hash of (min(i,j), max(i,j), value bits) for the entries above the diagonal into one sum and for the entries below it into
+// another (+0 == -0: zeros are skipped).  The map is symmetric iff the multiset of (pair, value) above the diagonal equals the one
+// below, so the two sums -- added over the ranks, modulo 2^64 -- agree (and differ with probability 1 - 2^-64 per mismatching
+// entry otherwise).  One read of the block; replaces the caller's promise ("assume_symmetric") of round 1.
+__global__ void __launch_bounds__(MV_THREADS)
+k_sym_hash(const float* __restrict__ A, long long ld, int nloc, int n, int row0, unsigned long long* out /* [2]: upper, lower */) {
+    unsigned long long up = 0, lo = 0;
+    for (int r = blockIdx.x; r < nloc; r += gridDim.x) {
+        const int i = row0 + r;
+        const float4* rp = reinterpret_cast<const float4*>(A + (long long)r * ld);
+        const int n4 = (n + 3) / 4;
+        for (int c4 = threadIdx.x; c4 < n4; c4 += MV_THREADS) {
+            const float4 a = ld_stream_f4(rp + c4);
+            const float e[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = 4 * c4 + k;
+                const unsigned int bits = __float_as_uint(e[k]);
+                if (j < n && j != i && (bits & 0x7fffffffu)) {
+                    const uint64_t a0 = (uint64_t)(i < j ? i : j), a1 = (uint64_t)(i < j ? j : i);
+                    const uint64_t h = mix64(mix64((a0 << 32) | a1) ^ (uint64_t)bits);
+                    if (j > i) up += h; else lo += h;
+                }
+            }
+        }
+    }
+    up = (unsigned long long)warp_sum_ll((long long)up);
+    lo = (unsigned long long)warp_sum_ll((long long)lo);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, up);
+        atomicAdd(out + 1, lo);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K1 row statistics: float64 row sum + int32 count of zeros over the n real columns.
 // Replaces the loop of lib/ccmapHelpers.pyx:190-201.  Algorithmic bytes: 4 * nloc * n.

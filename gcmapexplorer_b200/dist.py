@@ -73,24 +73,26 @@ def broadcast_unique_id(rank, device=None):
     return bytes(t.cpu().tolist())
 
 
-def sharded_device_map(n, device=None, partition="rows", symmetric=False):
+def sharded_device_map(n, device=None, partition="rows", symmetric=False, assume_symmetric=False):
     """DeviceMap for this rank's row block, wired to the other ranks (torch.distributed must be initialised).
 
     partition="rows": equal ceil(n/world) row blocks, n-vectors exchanged by allgather, dense passes.
     partition="balanced" (+ symmetric=True): near-equal row blocks cut on multiples of 1024 rows; IC/KR passes read each
     unordered pair of bins once, the off-diagonal blocks dealt out to the ranks in a circulant pattern; allreduce exchange.
-    partition="equal_area" (+ symmetric=True, the caller vouching that the map is symmetric): row blocks holding equal
-    shares of the upper triangle, n-vectors exchanged by allreduce, IC/KR passes read the upper triangle only."""
+    partition="equal_area": row blocks holding equal shares of the upper triangle, n-vectors exchanged by allreduce, IC/KR
+    passes read the upper triangle only.
+    Whether the sharded map is symmetric is tested across the ranks by the library (k_sym_hash); `symmetric` is kept for
+    callers of round 1 and ignored, assume_symmetric=True skips the test (the caller vouches)."""
     import torch.distributed as tdist
     from .device import DeviceMap
     rank, world = tdist.get_rank(), tdist.get_world_size()
     options = {}
     if partition == "balanced" and world > 1:
         row0, nloc = row_partition_aligned(n, world, rank)
-        options = {"exchange_allreduce": 1, "assume_symmetric": 1 if symmetric else 0}
+        options = {"exchange_allreduce": 1, "assume_symmetric": 1 if assume_symmetric else 0}
     elif partition == "equal_area" and world > 1:
         row0, nloc = row_partition_equal_area(n, world, rank)
-        options = {"exchange_allreduce": 1, "assume_symmetric": 1 if symmetric else 0, "sym_blocks": 0}
+        options = {"exchange_allreduce": 1, "assume_symmetric": 1 if assume_symmetric else 0, "sym_blocks": 0}
     else:
         row0, nloc = row_partition(n, world, rank)
     if nloc == 0:

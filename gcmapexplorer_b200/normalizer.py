@@ -21,6 +21,7 @@ import numpy as np
 
 from . import ccmap as cmp
 from . import ccmapHelpers as cmh
+from . import sharded
 from . import util
 from ._lib import GcxError
 from .device import DeviceMap
@@ -41,7 +42,12 @@ def _upload(ccMapObj, vmin, vmax):
     (lib/normalizer.py:299-301, 567-569, 827-829, 1105-1107)."""
     ccMapObj.make_readable()
     try:
-        dm = DeviceMap.from_host(ccMapObj.matrix)
+        k = sharded.gpus_for_map(int(ccMapObj.shape[0]))
+        if k > 1:
+            # too large for one GPU (or GCX_GPUS=k): row blocks on k GPUs of this node, one host thread each (sharded.py)
+            dm = sharded.ShardedDeviceMap.from_host(ccMapObj.matrix, devices=list(range(k)))
+        else:
+            dm = DeviceMap.from_host(ccMapObj.matrix)
     finally:
         ccMapObj.make_unreadable()
     if vmin is not None or vmax is not None:
@@ -50,10 +56,8 @@ def _upload(ccMapObj, vmin, vmax):
 
 
 def _emit(dm, which, like, bNoData, minvalue, maxvalue):
-    """New temporary CCMAP next to `like`, filled with the device result."""
-    out = like.new_like()
-    dm.download(which, out=out.matrix)
-    out.matrix.flush()
+    """New temporary CCMAP next to `like` (this package's CCMAP or the reference's, duck-typed), filled with the device result."""
+    out = cmp.result_like(dm, which, like)
     out.bNoData = np.asarray(bNoData, dtype=bool)
     out.minvalue = float(minvalue)
     out.maxvalue = float(maxvalue)

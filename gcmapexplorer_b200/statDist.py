@@ -64,9 +64,7 @@ def transitionProbabilityMatrixForCCMap(ccMap, outFile=None, percentile_threshol
             bNoData = np.asarray(ccMapObj.bNoData, dtype=bool)
         dm.set_mask(~bNoData)
         mn, mx = dm.transition(in_place=False)
-        normCCMap = ccMapObj.new_like()
-        dm.download(1, out=normCCMap.matrix)
-        normCCMap.matrix.flush()
+        normCCMap = cmp.result_like(dm, 1, ccMapObj)
     normCCMap.bNoData = bNoData
     normCCMap.minvalue = float(mn)
     normCCMap.maxvalue = float(mx)

@@ -159,3 +159,42 @@ def test_reference_reads_our_ccmap_files(tmp_path):
     o = cmp.load_ccmap(str(tmp_path / "theirs.ccmap"), workDir=str(tmp_path))
     o.make_readable()
     assert np.array_equal(np.array(o.matrix), A) and o.xlabel == "chr2"
+
+
+def test_new_like_accepts_a_reference_ccmap(tmp_path):
+    """ccmap.new_like builds the output carrier from ANY object with the CCMAP attribute set (lib/ccmap.py:125-140): the real
+    reference class where /root/reference exists, and a plain stand-in everywhere."""
+    from gcmapexplorer_b200 import ccmap as cmp
+    A = onp.synth_map(30, seed=4)
+
+    class Duck:                       # the reference's attribute set, nothing else
+        pass
+    d = Duck()
+    src = cmp.CCMAP()
+    src.gen_from_matrix(A, 1000, xlabel="chrD", ylabel="chrD", workDir=str(tmp_path))
+    for k in ("path2matrix", "xticks", "yticks", "binsize", "title", "xlabel", "ylabel", "shape", "minvalue", "maxvalue", "bNoData", "bLog", "dtype", "state"):
+        setattr(d, k, getattr(src, k))
+    d.matrix = None
+    objs = [d]
+    from oracle import ref_loader as rl
+    if rl.have_full():
+        import sys
+        rl.load_full()
+        r = sys.modules["gcMapExplorer.lib.ccmap"].CCMAP()
+        r.gen_from_matrix(A, 1000, xlabel="chrD", ylabel="chrD", workDir=str(tmp_path))
+        objs.append(r)
+    for o in objs:
+        out = cmp.new_like(o)
+        assert isinstance(out, cmp.CCMAP) and out.state == "temporary" and tuple(out.shape) == (30, 30) and out.xlabel == "chrD"
+        assert out.binsize == 1000 and out.path2matrix != o.path2matrix and os.path.dirname(out.path2matrix) == str(tmp_path)
+        assert out.matrix is not None and out.matrix.shape == (30, 30) and np.dtype(out.dtype) == np.float32
+        out.matrix[:] = 1.0                                          # writable
+
+
+def test_float64_ccmap_keeps_its_dtype():
+    """gen_from_matrix keeps the dtype of the array it is given (lib/ccmap.py:203); new_like follows it."""
+    from gcmapexplorer_b200 import ccmap as cmp
+    c = cmp.CCMAP()
+    c.gen_from_matrix(onp.synth_map(20, seed=1).astype(np.float64), 1000)
+    out = cmp.new_like(c)
+    assert np.dtype(out.dtype) == np.float64 and out.matrix.dtype == np.float64

@@ -590,6 +590,38 @@ def test_symmetric_pass_vs_oracle_and_asymmetric_fallback(gx):
     assert not r2["symmetric"]               # dense pass: row sums of the stored matrix, like every other dense run
 
 
+def test_dropin_accepts_foreign_ccmap_objects_and_float64_maps(gx, tmp_path):
+    """The normalizers take any object with the CCMAP attribute set (the reference's own class is one) and maps whose dtype is
+    not float32: results equal the float32 route, the output keeps the input's dtype (no AttributeError / silent None)."""
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz, statDist as sd
+    A = onp.synth_map(150, seed=12)
+    c = cmp.CCMAP()
+    c.gen_from_matrix(A, 100000, xlabel="chrS", ylabel="chrS", workDir=str(tmp_path))
+    c.make_unreadable()
+
+    class Duck:
+        def make_readable(self):
+            self.matrix = np.memmap(self.path2matrix, dtype=self.dtype, mode="r", shape=tuple(self.shape))
+
+        def make_unreadable(self):
+            self.matrix = None
+    d = Duck()
+    for k in ("path2matrix", "xticks", "yticks", "binsize", "title", "xlabel", "ylabel", "shape", "minvalue", "maxvalue", "bNoData", "bLog", "dtype", "state"):
+        setattr(d, k, getattr(c, k))
+    d.matrix = None
+    for fn in (nz.normalizeCCMapByKR, nz.normalizeCCMapByIC, nz.normalizeCCMapByVCNorm, nz.normalizeCCMapByMCFS, sd.transitionProbabilityMatrixForCCMap):
+        a, b = fn(c), fn(d)
+        assert a is not None and b is not None and isinstance(b, cmp.CCMAP)
+        a.make_readable(); b.make_readable()
+        assert np.array_equal(np.array(a.matrix), np.array(b.matrix)) and np.array_equal(a.bNoData, b.bNoData)
+    c64 = cmp.CCMAP()
+    c64.gen_from_matrix(A.astype(np.float64), 100000, xlabel="chrS", ylabel="chrS", workDir=str(tmp_path))
+    o64, o32 = nz.normalizeCCMapByIC(c64), nz.normalizeCCMapByIC(c)
+    assert o64 is not None and o64.matrix.dtype == np.float64
+    o32.make_readable()
+    assert np.array_equal(np.array(o64.matrix), np.array(o32.matrix).astype(np.float64))
+
+
 @pytest.mark.parametrize("n", [2100, 4099, 6145])
 def test_deferred_scalar_pass_matches_literal_order(gx, n):
     """The default upper-triangle IC pass defers the global scalars (k_ic_pass_symd: v_next = kappa / t, one grid barrier);
