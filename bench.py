@@ -98,12 +98,16 @@ class ClockSampler:
 
 
 def recorded_traffic(kernel, n):
-    """DRAM bytes per launch of `kernel` at size n from this round's ncu --set full capture (profiles/r01_traffic.json), else None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return json.load(f).get("%s@%d" % (kernel, n), {}).get("bytes")
-    except Exception:
-        return None
+    """DRAM bytes per pass of `kernel` at size n from an ncu --set full capture (profiles/r02_traffic.json, else r01), else None."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                b = json.load(f).get("%s@%d" % (kernel, n), {}).get("bytes")
+            if b is not None:
+                return b
+        except Exception:
+            pass
+    return None
 
 
 def step_bytes(n, nloc_total, matvecs):

@@ -39,6 +39,10 @@ _PROTOS = {
     "gcx_map_create": (C.c_int, [_ctx, C.c_int64, C.c_int64, C.c_int64]),
     "gcx_map_upload": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "gcx_map_download": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int64]),
+    "gcx_map_upload_rows": (C.c_int, [_ctx, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "gcx_map_upload_finish": (C.c_int, [_ctx]),
+    "gcx_map_upload_file": (C.c_int, [_ctx, C.c_char_p, C.c_int64, C.c_int]),
+    "gcx_map_download_file": (C.c_int, [_ctx, C.c_int, C.c_char_p, C.c_int64]),
     "gcx_map_download_async": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int64]),
     "gcx_download_wait": (C.c_int, [_ctx]),
     "gcx_map_synth": (C.c_int, [_ctx, C.c_uint64, C.c_double, C.c_double, C.c_double]),

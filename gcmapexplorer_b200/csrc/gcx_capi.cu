@@ -8,8 +8,12 @@
 #include <stdio.h>
 #include <string.h>
 #include <unistd.h>
+#include <fcntl.h>
+#include <errno.h>
+#include <sys/stat.h>
 
 #include <algorithm>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -504,6 +508,8 @@ static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 static int map_alloc(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc);
 static int xchg_setup(gcx_ctx* c);
+static int allgather_f64(gcx_ctx* c, double* vec);
+static int allgather_i32(gcx_ctx* c, int32_t* vec);
 
 extern "C" int gcx_map_create(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc) {
     if (!c) return fail("gcx_map_create: null context");
@@ -680,6 +686,190 @@ extern "C" int gcx_map_download(gcx_ctx* c, int which, float* host, int64_t host
         ++it;
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// streaming residency: rows arrive in chunks -- from a .npbin file read by a pool of pread threads, from a
+// gzip stream, from an HDF5 dataset -- and every chunk's row statistics are computed as it lands, so the mask pass overlaps the
+// upload and the map is read from HBM one time less.
+// ---------------------------------------------------------------------------------------------------
+static void par_for(int64_t items, size_t bytes_total, const std::function<void(int64_t, int64_t)>& work) {
+    unsigned hw = std::thread::hardware_concurrency();
+    static const unsigned cap = [] { const char* e = getenv("GCX_COPY_THREADS"); return e ? (unsigned)std::max(1, atoi(e)) : 16u; }();
+    int T = (int)std::min<int64_t>(std::max(1u, std::min(hw, cap)), items);
+    if (bytes_total < (4u << 20)) T = 1;
+    if (T <= 1) { work(0, items); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back([=, &work] { work(items * t / T, items * (t + 1) / T); });
+    work(0, items / T);
+    for (auto& x : th) x.join();
+}
+
+// row statistics of the local rows [r0, r0 + rows) right behind their host-to-device copy on the stream
+static int stats_for_rows(gcx_ctx* c, int64_t r0, int64_t rows) {
+    ProfScope ps(c, 3);
+    const int grid = (int)std::min<int64_t>(rows, (int64_t)c->sm_count * 8);
+    k_row_stats<<<grid, MV_THREADS, 0, c->stream>>>(c->A + r0 * c->ld, c->ld, (int)rows, (int)c->n, c->vrowsum + c->row0 + r0, c->zero_count + c->row0 + r0);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int gcx_map_upload_rows(gcx_ctx* c, const float* host, int64_t host_ld, int64_t row_begin, int64_t nrows, int with_stats) {
+    CKR(need_map(c));
+    if (row_begin < 0 || nrows < 0 || row_begin + nrows > c->nloc) return fail("gcx_map_upload_rows: rows [%lld, +%lld) outside the local block of %lld rows", (long long)row_begin, (long long)nrows, (long long)c->nloc);
+    if (host_ld < c->n) return fail("host_ld < n");
+    if (row_begin == 0) {
+        CKR(fence_copy(c));
+        c->sym_state = -1; c->have_rowsum = false; c->have_scale = false;
+    }
+    if (nrows == 0) return 0;
+    const size_t width = sizeof(float) * (size_t)c->n;
+    if (is_pinned(host)) {
+        CK(cudaMemcpy2DAsync(c->A + row_begin * c->ld, sizeof(float) * c->ld, host, sizeof(float) * host_ld, width, (size_t)nrows, cudaMemcpyHostToDevice, c->stream));
+        if (with_stats) CKR(stats_for_rows(c, row_begin, nrows));
+        CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    CKR(ensure_stage(c));
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t)(c->stage_bytes / width));
+    int64_t r0 = 0;
+    int it = 0;
+    while (r0 < nrows) {
+        const int b = it & 1;
+        const int64_t rows = std::min(rows_per, nrows - r0);
+        if (it >= 2) CK(cudaEventSynchronize(c->stage_ev[b]));
+        par_copy_rows((char*)c->stage[b], width, (const char*)(host + r0 * host_ld), sizeof(float) * host_ld, width, rows);
+        CK(cudaMemcpy2DAsync(c->A + (row_begin + r0) * c->ld, sizeof(float) * c->ld, c->stage[b], width, width, (size_t)rows, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(c->stage_ev[b], c->stream));
+        if (with_stats) CKR(stats_for_rows(c, row_begin + r0, rows));
+        r0 += rows;
+        ++it;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// every row of the local block has been uploaded with with_stats != 0: publish the statistics (allgather when sharded)
+extern "C" int gcx_map_upload_finish(gcx_ctx* c) {
+    CKR(need_map(c));
+    CKR(allgather_f64(c, c->vrowsum));
+    CKR(allgather_i32(c, c->zero_count));
+    c->have_rowsum = true;
+    return 0;
+}
+
+// The local row block straight from a raw float32 row-major file (.npbin, lib/ccmap.py:233: n x n float32, no header): a pool of
+// threads preads row ranges into the two pinned stages while the previous stage travels to the device.  No memmap, no page
+// faults on the critical path, no intermediate copy.
+extern "C" int gcx_map_upload_file(gcx_ctx* c, const char* path, int64_t file_offset, int with_stats) {
+    CKR(need_map(c));
+    CKR(fence_copy(c));
+    c->sym_state = -1; c->have_rowsum = false; c->have_scale = false;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail("gcx_map_upload_file: cannot open %s: %s", path, strerror(errno));
+    struct stat sb;
+    const size_t width = sizeof(float) * (size_t)c->n;
+    const int64_t base = file_offset + (int64_t)c->row0 * (int64_t)width;
+    if (fstat(fd, &sb) != 0 || (int64_t)sb.st_size < base + (int64_t)c->nloc * (int64_t)width) {
+        close(fd);
+        return fail("gcx_map_upload_file: %s is shorter than rows [%lld, +%lld) of a %lld x %lld float32 map", path, (long long)c->row0, (long long)c->nloc, (long long)c->n, (long long)c->n);
+    }
+    int rc = ensure_stage(c);
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t)(c->stage_bytes / width));
+    int64_t r0 = 0;
+    int it = 0;
+    std::string err;
+    std::mutex err_mu;
+    while (rc == 0 && r0 < c->nloc) {
+        const int b = it & 1;
+        const int64_t rows = std::min(rows_per, c->nloc - r0);
+        if (it >= 2 && cudaEventSynchronize(c->stage_ev[b]) != cudaSuccess) { rc = fail("cudaEventSynchronize failed"); break; }
+        char* dst = (char*)c->stage[b];
+        const int64_t off0 = base + r0 * (int64_t)width, total = rows * (int64_t)width;
+        // contiguous in the file and in the stage: split by bytes (4 MB granules), not by rows
+        const int64_t gran = 4ll << 20, items = (total + gran - 1) / gran;
+        par_for(items, (size_t)total, [&](int64_t a, int64_t e) {
+            int64_t p = a * gran;
+            const int64_t pe = std::min(total, e * gran);
+            while (p < pe) {
+                const ssize_t got = pread(fd, dst + p, (size_t)(pe - p), (off_t)(off0 + p));
+                if (got <= 0) {
+                    if (got < 0 && errno == EINTR) continue;
+                    std::lock_guard<std::mutex> g(err_mu);
+                    err = got == 0 ? "unexpected end of file" : strerror(errno);
+                    return;
+                }
+                p += got;
+            }
+        });
+        if (!err.empty()) { rc = fail("gcx_map_upload_file: reading %s: %s", path, err.c_str()); break; }
+        if (cudaMemcpy2DAsync(c->A + r0 * c->ld, sizeof(float) * c->ld, c->stage[b], width, width, (size_t)rows, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaEventRecord(c->stage_ev[b], c->stream) != cudaSuccess) { rc = fail("gcx_map_upload_file: host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        if (with_stats) rc = stats_for_rows(c, r0, rows);
+        r0 += rows;
+        ++it;
+    }
+    close(fd);
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    if (with_stats) CKR(gcx_map_upload_finish(c));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// A result map straight into a raw float32 file (created / extended as needed): device-to-host per stage, parallel pwrite behind it.
+extern "C" int gcx_map_download_file(gcx_ctx* c, int which, const char* path, int64_t file_offset) {
+    CKR(need_map(c));
+    const float* src = which == 0 ? c->A : (which == 2 ? c->Out2 : c->Out);
+    if (!src) return fail("no output map resident");
+    const int fd = open(path, O_WRONLY | O_CREAT, 0644);
+    if (fd < 0) return fail("gcx_map_download_file: cannot open %s: %s", path, strerror(errno));
+    const size_t width = sizeof(float) * (size_t)c->n;
+    const int64_t base = file_offset + (int64_t)c->row0 * (int64_t)width;
+    if (c->world == 1 && ftruncate(fd, (off_t)(file_offset + (int64_t)c->n * (int64_t)width)) != 0) {
+        close(fd);
+        return fail("gcx_map_download_file: cannot size %s: %s", path, strerror(errno));
+    }
+    int rc = ensure_stage(c);
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t)(c->stage_bytes / width));
+    int64_t r0 = 0, prev_r0 = -1, prev_rows = 0;
+    int it = 0;
+    std::string err;
+    std::mutex err_mu;
+    while (rc == 0 && (r0 < c->nloc || prev_r0 >= 0)) {
+        const int b = it & 1;
+        int64_t rows = 0;
+        if (r0 < c->nloc) {
+            rows = std::min(rows_per, c->nloc - r0);
+            if (cudaMemcpy2DAsync(c->stage[b], width, src + r0 * c->ld, sizeof(float) * c->ld, width, (size_t)rows, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaEventRecord(c->stage_ev[b], c->stream) != cudaSuccess) { rc = fail("gcx_map_download_file: device-to-host copy failed"); break; }
+        }
+        if (prev_r0 >= 0) {
+            if (cudaEventSynchronize(c->stage_ev[b ^ 1]) != cudaSuccess) { rc = fail("cudaEventSynchronize failed"); break; }
+            const char* from = (const char*)c->stage[b ^ 1];
+            const int64_t off0 = base + prev_r0 * (int64_t)width, total = prev_rows * (int64_t)width;
+            const int64_t gran = 4ll << 20, items = (total + gran - 1) / gran;
+            par_for(items, (size_t)total, [&](int64_t a, int64_t e) {
+                int64_t p = a * gran;
+                const int64_t pe = std::min(total, e * gran);
+                while (p < pe) {
+                    const ssize_t put = pwrite(fd, from + p, (size_t)(pe - p), (off_t)(off0 + p));
+                    if (put <= 0) {
+                        if (put < 0 && errno == EINTR) continue;
+                        std::lock_guard<std::mutex> g(err_mu);
+                        err = strerror(errno);
+                        return;
+                    }
+                    p += put;
+                }
+            });
+            if (!err.empty()) { rc = fail("gcx_map_download_file: writing %s: %s", path, err.c_str()); break; }
+        }
+        if (rows > 0) { prev_r0 = r0; prev_rows = rows; r0 += rows; } else { prev_r0 = -1; }
+        ++it;
+    }
+    close(fd);
+    if (rc) cudaStreamSynchronize(c->stream);
+    return rc;
 }
 
 extern "C" int gcx_map_download_async(gcx_ctx* c, int which, float* host, int64_t host_ld) {

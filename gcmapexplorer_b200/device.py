@@ -120,6 +120,24 @@ class DeviceMap:
             raise ValueError(f"expected shape {(self.nloc, self.n)}, got {m.shape}")
         check(lib().gcx_map_upload(self._ctx, C.c_void_p(m.ctypes.data), m.strides[0] // 4))
 
+    def upload_rows(self, rows, row_begin, with_stats=True):
+        """A chunk of the local row block (streaming sources: gzip / HDF5 readers); finish with upload_finish()."""
+        m = _as_f32_matrix(rows)
+        if m.ndim != 2 or m.shape[1] != self.n:
+            raise ValueError(f"expected [rows, {self.n}] float32, got {m.shape}")
+        check(lib().gcx_map_upload_rows(self._ctx, C.c_void_p(m.ctypes.data), m.strides[0] // 4, int(row_begin), m.shape[0], int(bool(with_stats))))
+
+    def upload_finish(self):
+        check(lib().gcx_map_upload_finish(self._ctx))
+
+    def upload_file(self, path, offset=0, with_stats=True):
+        """The local row block straight from a raw float32 file (.npbin): parallel pread -> pinned stages -> HBM."""
+        check(lib().gcx_map_upload_file(self._ctx, os.fsencode(path), int(offset), int(bool(with_stats))))
+
+    def download_file(self, which, path, offset=0):
+        """A result map straight into a raw float32 file (created / sized as needed)."""
+        check(lib().gcx_map_download_file(self._ctx, int(which), os.fsencode(path), int(offset)))
+
     def download(self, which=1, out=None):
         if out is None:
             out = np.empty((self.nloc, self.n), dtype=np.float32)

@@ -47,6 +47,19 @@ int gcx_host_free(void* ptr);
 int gcx_map_create(gcx_ctx* ctx, int64_t n, int64_t row0, int64_t nloc);
 int gcx_map_upload(gcx_ctx* ctx, const float* host_rows, int64_t host_ld);          /* host_rows -> first local row */
 int gcx_map_download(gcx_ctx* ctx, int which, float* host_rows, int64_t host_ld);   /* which: 0 input, 1 output, 2 second output */
+/* Streaming residency (SURVEY.md 8f row N1 -- replaces the memmap-to-memmap copies and np.memmap page faults of lib/ccmap.py:264-300,
+ * 404-567 on the way in and out):
+ *   gcx_map_upload_rows    local rows [row_begin, row_begin + nrows) from a host chunk (a gzip / HDF5 reader hands the map over
+ *                          piecewise); with_stats != 0 computes the chunk's row statistics (lib/ccmapHelpers.pyx:190-201) right
+ *                          behind its copy, so the mask pass overlaps the upload and the map is not read again for it;
+ *   gcx_map_upload_finish  after the last chunk: publishes those statistics (gcx_row_stats then returns them without a pass);
+ *   gcx_map_upload_file    the local row block from a raw float32 row-major file (.npbin, lib/ccmap.py:233) at file_offset:
+ *                          a pool of pread threads fills two pinned stages while the previous stage travels to the device;
+ *   gcx_map_download_file  a result map into such a file (created / sized as needed), parallel pwrite behind each stage. */
+int gcx_map_upload_rows(gcx_ctx* ctx, const float* host_rows, int64_t host_ld, int64_t row_begin, int64_t nrows, int with_stats);
+int gcx_map_upload_finish(gcx_ctx* ctx);
+int gcx_map_upload_file(gcx_ctx* ctx, const char* path, int64_t file_offset, int with_stats);
+int gcx_map_download_file(gcx_ctx* ctx, int which, const char* path, int64_t file_offset);
 /* asynchronous download into PINNED host memory on the context's copy stream: returns at once, overlaps with
  * kernels enqueued afterwards (e.g. the VC result streams out while IC iterates); gcx_download_wait blocks until
  * the last async download has landed.  Kernels that later overwrite the source buffer wait for it on the device. */
