@@ -60,6 +60,7 @@ _PROTOS = {
     "gcx_diag_stats": (C.c_int, [_ctx, C.c_int, _c_f64p]),
     "gcx_diag_apply": (C.c_int, [_ctx, _c_f64p, C.c_int, C.c_int, _c_f32p, _c_f32p]),
     "gcx_mcfs_batch": (C.c_int, [C.POINTER(_ctx), C.c_int, C.c_int, C.c_int, _c_f32p, _c_f32p]),
+    "gcx_diag_stats_pooled": (C.c_int, [C.POINTER(_ctx), C.c_int, C.c_int, _c_f64p, C.c_int64]),
     "gcx_diag_avg_read": (C.c_int, [_ctx, _c_f64p]),
     "gcx_compact_f64": (C.c_int, [_ctx, _c_i32p, C.c_int64, _c_f64p]),
     "gcx_downsample": (C.c_int, [_ctx, C.c_int, C.c_int, _c_f32p, C.c_int64, _c_f32p, _c_f32p]),

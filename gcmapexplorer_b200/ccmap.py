@@ -90,6 +90,12 @@ class CCMAP:
 
     def _map(self, mode):
         self.matrix = None
+        if not self.path2matrix and getattr(self, "_gz_source", None):
+            # lazily opened compressed map (load_ccmap(lazy_gz=True)) that somebody wants to look at after all: inflate now
+            self.gen_matrix_file(workDir=getattr(self, "_gz_workdir", None))
+            with gzip.open(self._gz_source, "rb") as f_in, open(self.path2matrix, "wb") as f_out:
+                shutil.copyfileobj(f_in, f_out)
+            self._gz_source = None
         self.matrix = np.memmap(self.path2matrix, dtype=self.dtype, mode=mode, shape=tuple(self.shape))
 
     def make_readable(self):
@@ -134,7 +140,8 @@ class CCMAP:
             other.__dict__[key] = val
         other.matrix = None
         other.state = "temporary"
-        other.gen_matrix_file(workDir=os.path.dirname(self.path2matrix) or None)
+        other._gz_source = None
+        other.gen_matrix_file(workDir=os.path.dirname(self.path2matrix) or getattr(self, "_gz_workdir", None) or None)
         return other
 
     def copy(self, fill=None):
@@ -180,16 +187,83 @@ def new_like(ccMapObj):
 
 
 def result_like(dm, which, ccMapObj):
-    """new_like(ccMapObj) filled with a device result (`which`: 0 input buffer, 1 / 2 output buffers of the DeviceMap).  The
-    device map is float32 (lib/ccmap.py:42); a CCMAP of another dtype (gen_from_matrix keeps the dtype of the array it was given,
-    lib/ccmap.py:203) gets the result cast into its own dtype, like the reference's in-place arithmetic would."""
-    out = new_like(ccMapObj)
-    if np.dtype(out.dtype) == np.float32:
-        dm.download(which, out=out.matrix)
+    """New temporary CCMAP with the metadata of `ccMapObj`, holding a device result (`which`: 0 input buffer, 1 / 2 output buffers
+    of the DeviceMap), returned editable (memmap r+).  float32 maps (lib/ccmap.py:42) are written by the library straight into the
+    new backing file (gcx_map_download_file: device -> pinned stages -> parallel pwrite; no np.memmap page faults on the way);
+    a CCMAP of another dtype (gen_from_matrix keeps the dtype of the array it was given, lib/ccmap.py:203) gets the result cast
+    into its own dtype, like the reference's in-place arithmetic would."""
+    if isinstance(ccMapObj, CCMAP):
+        out = ccMapObj._clone_meta()
     else:
+        out = new_like(ccMapObj)
+        out.matrix = None
+    if np.dtype(out.dtype) == np.float32 and hasattr(dm, "download_file"):
+        out.matrix = None
+        if os.path.exists(out.path2matrix):
+            os.remove(out.path2matrix)
+        dm.download_file(which, out.path2matrix)
+        out.make_editable()
+    else:
+        if out.matrix is None:
+            out.make_writable()
         out.matrix[:] = dm.download(which)
-    out.matrix.flush()
+        out.matrix.flush()
     return out
+
+
+def upload_ccmap(ccMapObj, make_map):
+    """The CCMAP's matrix into HBM by the cheapest route.  `make_map(n)` returns an empty DeviceMap / ShardedDeviceMap.
+    A plain float32 backing file goes through gcx_map_upload_file (parallel pread into pinned stages, row statistics per stage as
+    it lands); a lazily opened `.npbin.gz` (load_ccmap(..., lazy_gz=True)) is inflated chunk by chunk straight into the device --
+    no temporary file (the reference gunzips to a temp file first, lib/ccmap.py:550-563); anything else is uploaded from the memmap."""
+    n = int(ccMapObj.shape[0])
+    dm = make_map(n)
+    try:
+        gz = getattr(ccMapObj, "_gz_source", None)
+        path = getattr(ccMapObj, "path2matrix", "")
+        if gz is not None:
+            _stream_gz(dm, gz, n)
+        elif (np.dtype(ccMapObj.dtype) == np.float32 and path and os.path.isfile(path) and os.path.getsize(path) == 4 * n * n
+              and hasattr(dm, "upload_file")):
+            dm.upload_file(path)
+        else:
+            ccMapObj.make_readable()
+            try:
+                dm.upload(ccMapObj.matrix)
+            finally:
+                ccMapObj.make_unreadable()
+    except Exception:
+        dm.close()
+        raise
+    return dm
+
+
+def _stream_gz(dm, gz_path, n, chunk_bytes=64 << 20):
+    """zlib stream -> row chunks -> device (every chunk's row statistics are taken as it lands)."""
+    import zlib
+    row_bytes = 4 * n
+    rows_per = max(1, chunk_bytes // row_bytes)
+    buf = bytearray()
+    r0 = 0
+    dec = zlib.decompressobj(zlib.MAX_WBITS | 16)          # gzip container
+    with open(gz_path, "rb") as f:
+        while True:
+            raw = f.read(8 << 20)
+            if not raw:
+                break
+            buf += dec.decompress(raw)
+            while len(buf) >= rows_per * row_bytes:
+                take = rows_per * row_bytes
+                dm.upload_rows(np.frombuffer(bytes(buf[:take]), dtype=np.float32).reshape(rows_per, n), r0)
+                del buf[:take]
+                r0 += rows_per
+        buf += dec.flush()
+    if len(buf) % row_bytes or r0 + len(buf) // row_bytes != n:
+        raise ValueError("{0}: {1} bytes do not make a {2} x {2} float32 matrix".format(gz_path, r0 * row_bytes + len(buf), n))
+    if buf:
+        rows = len(buf) // row_bytes
+        dm.upload_rows(np.frombuffer(bytes(buf), dtype=np.float32).reshape(rows, n), r0)
+    dm.upload_finish()
 
 
 # ---- coarsening (lib/ccmap.py:655-842) ------------------------------------------------------------------
@@ -305,6 +379,8 @@ def save_ccmap(ccMapObj, outfile, compress=False, logHandler=None):
         log.propagate = False
         log.addHandler(logHandler)
     log.setLevel(logging.INFO)
+    if getattr(ccMapObj, "_gz_source", None) and not ccMapObj.path2matrix:
+        ccMapObj.make_readable()          # lazily opened compressed map: materialise its matrix first
     ccMapObj.make_unreadable()
     if os.path.splitext(outfile)[1] != ".ccmap":
         outfile = outfile + ".ccmap"
@@ -327,7 +403,7 @@ def save_ccmap(ccMapObj, outfile, compress=False, logHandler=None):
     ccMapObj.state = "compressed" if compress else "saved"
     try:
         with open(outpath, "w") as fout:
-            json.dump(ccMapObj.__dict__, fout, indent=4, separators=(",", ":"))   # matrix is None here
+            json.dump({k: v for k, v in ccMapObj.__dict__.items() if not k.startswith("_")}, fout, indent=4, separators=(",", ":"))   # matrix is None here
         if compress:
             if os.path.exists(npbin + ".gz"):
                 gen_backup(npbin + ".gz")
@@ -342,7 +418,10 @@ def save_ccmap(ccMapObj, outfile, compress=False, logHandler=None):
     log.info("       Finished!!!\n")
 
 
-def load_ccmap(infile, workDir=None):
+def load_ccmap(infile, workDir=None, lazy_gz=False):
+    """lazy_gz=True (used by the normalizers for file inputs): a compressed matrix is NOT inflated into a temporary file; the
+    object carries `_gz_source` and upload_ccmap streams it into the device.  Such an object has no backing file: make_readable
+    inflates it on first use, so code that does look at `.matrix` still works."""
     with open(infile, "r") as fin:
         jd = json.load(fin)
     obj = CCMAP(dtype=np.dtype(jd["dtype"]))
@@ -350,6 +429,12 @@ def load_ccmap(infile, workDir=None):
     obj.matrix = None
     indir = os.path.dirname(os.path.abspath(os.path.expanduser(infile)))
     npbin = os.path.join(indir, obj.path2matrix)
+    if os.path.exists(npbin + ".gz") and lazy_gz and np.dtype(obj.dtype) == np.float32:
+        obj._gz_source = npbin + ".gz"
+        obj._gz_workdir = workDir
+        obj.path2matrix = ""
+        obj.state = "temporary"
+        return obj
     if os.path.exists(npbin + ".gz"):
         obj.gen_matrix_file(workDir=workDir)
         try:
@@ -364,7 +449,7 @@ def load_ccmap(infile, workDir=None):
     return obj
 
 
-def checkCCMapObjectOrFile(ccMap, workDir=None):
+def checkCCMapObjectOrFile(ccMap, workDir=None, lazy_gz=False):
     """(CCMAP, 'Object' | 'File'); a missing file returns a bare None like the reference (ccmap.py:644-647),
     so callers that tuple-unpack raise TypeError."""
     if is_ccmap(ccMap):
@@ -373,4 +458,4 @@ def checkCCMapObjectOrFile(ccMap, workDir=None):
         logger.info(" {0} file not found.".format(ccMap))
         logger.info(" Not able to normalize.")
         return None
-    return load_ccmap(ccMap, workDir=workDir), "File"
+    return load_ccmap(ccMap, workDir=workDir, lazy_gz=lazy_gz), "File"

@@ -2123,6 +2123,115 @@ extern "C" int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtrac
     return 0;
 }
 
+// getAvgContactByDistance for a LIST of maps (lib/cmstats.py:572-578): per distance d the non-zero entries of the d-th diagonal of
+// every map that has one are pooled, then median or mean.  Median: all maps feed ONE set of per-diagonal histograms (radix select
+// as for a single map); mean: per-map sums and counts, added per diagonal.
+extern "C" int gcx_diag_stats_pooled(gcx_ctx** ctxs, int count, int median, double* avg, int64_t nmax) {
+    if (!ctxs || count < 1 || !avg) return fail("gcx_diag_stats_pooled: bad arguments");
+    if (count > 120) return fail("gcx_diag_stats_pooled: at most 120 maps per call");
+    gcx_ctx* c0 = ctxs[0];
+    int64_t nm = 0;
+    for (int m = 0; m < count; ++m) {
+        gcx_ctx* c = ctxs[m];
+        if (!c || !c->A) return fail("gcx_diag_stats_pooled: map %d has no resident matrix", m);
+        if (c->device != c0->device) return fail("gcx_diag_stats_pooled: all maps must be resident on one device");
+        if (c->world != 1 || c->row0 != 0 || c->nloc != c->n) return fail("gcx_diag_stats_pooled: sharded maps are not pooled");
+        nm = std::max(nm, c->n);
+    }
+    if (nmax != nm) return fail("gcx_diag_stats_pooled: the output needs %lld entries (the largest map)", (long long)nm);
+    CKR(set_dev(c0));
+    std::vector<BMap> tab((size_t)count + 1);
+    size_t off = align256(sizeof(BMap) * ((size_t)count + 1));
+    const size_t o_hist = off; off += median ? align256(sizeof(unsigned int) * 256 * (size_t)nm) : 0;
+    const size_t o_small = off; off += median ? align256(sizeof(unsigned int) * 5 * (size_t)nm) : 0;
+    const size_t o_avg = off; off += align256(sizeof(double) * (size_t)nm);
+    std::vector<size_t> o_psum((size_t)count), o_pcnt((size_t)count), o_sc((size_t)count);
+    long long blk = 0, red = 0;
+    for (int m = 0; m < count; ++m) {
+        gcx_ctx* c = ctxs[m];
+        const int n = (int)c->n;
+        BMap& M = tab[m];
+        memset(&M, 0, sizeof M);
+        M.ld = c->ld; M.n = n;
+        M.gx = (n + MV_THREADS - 1) / MV_THREADS;
+        M.gy = (n + DIAG_RB - 1) / DIAG_RB;
+        M.blk0 = (int)blk; M.red0 = (int)red;
+        blk += (long long)M.gx * M.gy;
+        red += (n + 63) / 64;
+        if (!median) {
+            o_psum[m] = off; off += align256(sizeof(double) * (size_t)M.gy * n);
+            o_pcnt[m] = off; off += align256(sizeof(int) * (size_t)M.gy * n);
+            o_sc[m] = off; off += align256(sizeof(double) * 2 * (size_t)n);
+        }
+    }
+    if (blk > 0x7fffffffLL) return fail("gcx_diag_stats_pooled: batch too large");
+    for (int m = 1; m < count; ++m) {
+        CK(cudaEventRecord(ctxs[m]->ev_ready, ctxs[m]->stream));
+        CK(cudaStreamWaitEvent(c0->stream, ctxs[m]->ev_ready, 0));
+    }
+    CKR(ensure_scratch(c0, off));
+    char* base = (char*)c0->scratch;
+    DiagSel S{};
+    if (median) {
+        S.hist = (unsigned int*)(base + o_hist);
+        unsigned int* small = (unsigned int*)(base + o_small);
+        S.prefix = small; S.krem = small + nm; S.cnt = small + 2 * nm; S.need = small + 3 * nm; S.next = small + 4 * nm;
+    }
+    double* davg = (double*)(base + o_avg);
+    for (int m = 0; m < count; ++m) {
+        gcx_ctx* c = ctxs[m];
+        BMap& M = tab[m];
+        M.A = c->A; M.S = S;
+        if (!median) {
+            M.psum = (double*)(base + o_psum[m]);
+            M.pcnt = (int*)(base + o_pcnt[m]);
+            M.sum = (double*)(base + o_sc[m]);
+            M.cnt = M.sum + c->n;
+        }
+    }
+    // one pseudo-map of nmax diagonals for the stages that run once for the pool (selection, final)
+    BMap& P = tab[(size_t)count];
+    memset(&P, 0, sizeof P);
+    P.n = (int)nm; P.S = S; P.avg = davg;
+    cudaStream_t st = c0->stream;
+    CK(cudaMemcpyAsync(base, tab.data(), sizeof(BMap) * ((size_t)count + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    const BMap* dt = (const BMap*)base;
+    const BMap* dp = dt + count;
+    if (median) {
+        CK(cudaMemsetAsync(base + o_hist, 0, o_avg - o_hist, st));
+        const unsigned sel = (unsigned)(((long long)nm * 32 + MV_THREADS - 1) / MV_THREADS);
+        for (int pass = 0; pass < 4; ++pass) {
+            {
+                ProfScope ps(c0, 4);
+                k_diag_hist_b<<<(unsigned)blk, MV_THREADS, 0, st>>>(dt, count, pass);
+            }
+            k_diag_select_b<<<sel, MV_THREADS, 0, st>>>(dp, 1, pass);
+            c0->launches += 1;
+        }
+        {
+            ProfScope ps(c0, 4);
+            k_diag_next_b<<<(unsigned)blk, MV_THREADS, 0, st>>>(dt, count);
+        }
+        k_diag_median_final_b<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(dp, 1);
+        c0->launches += 1;
+    } else {
+        {
+            ProfScope ps(c0, 4);
+            k_diag_mean_partial_b<<<(unsigned)blk, MV_THREADS, 0, st>>>(dt, count);
+        }
+        k_diag_mean_reduce_b<<<(unsigned)red, 64 * DIAG_RED_SL, 0, st>>>(dt, count);
+        k_diag_pool_mean_final<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(dt, count, (int)nm, davg);
+        c0->launches += 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(avg, davg, sizeof(double) * (size_t)nm, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c0->ev_ready, st));
+    for (int m = 1; m < count; ++m) CK(cudaStreamWaitEvent(ctxs[m]->stream, c0->ev_ready, 0));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 /* the per-diagonal statistic left resident by the last gcx_diag_stats / gcx_mcfs_batch (n doubles) */
 extern "C" int gcx_diag_avg_read(gcx_ctx* c, double* avg) {
     CKR(need_map(c));

@@ -1647,6 +1647,18 @@ k_diag_mean_final_b(const BMap* __restrict__ maps, int count) {
     if (d < M.n) M.avg[d] = M.cnt[d] > 0.0 ? M.sum[d] / M.cnt[d] : 0.0;
 }
 
+// pooled mean over several maps (lib/cmstats.py:572-578 with a list of maps): sum of the maps' per-diagonal sums / counts
+__global__ void __launch_bounds__(256)
+k_diag_pool_mean_final(const BMap* __restrict__ maps, int count, int nmax, double* __restrict__ avg) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= nmax) return;
+    double s = 0.0, c = 0.0;
+    for (int m = 0; m < count; ++m) {
+        if (d < maps[m].n) { s += maps[m].sum[d]; c += maps[m].cnt[d]; }
+    }
+    avg[d] = c > 0.0 ? s / c : 0.0;
+}
+
 __global__ void k_mm_init_b(const BMap* __restrict__ maps, int count) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m < count) { maps[m].mm->min_nz = 0xffffffffu; maps[m].mm->max_all = 0u; }

@@ -389,6 +389,13 @@ class MapBatch:
             raise ValueError("empty batch")
         self._arr = (C.c_void_p * len(self.maps))(*[m._ctx for m in self.maps])
 
+    def diag_stats_pooled(self, stats="median"):
+        """Per-diagonal statistic of the POOLED non-zero entries of all maps (lib/cmstats.py:572-578); length = largest map."""
+        nmax = max(m.n for m in self.maps)
+        avg = np.empty(nmax, dtype=np.float64)
+        check(lib().gcx_diag_stats_pooled(self._arr, len(self.maps), 1 if stats == "median" else 0, avg.ctypes.data_as(_lib._c_f64p), nmax))
+        return avg
+
     def mcfs(self, stats="median", subtract=False):
         """diag_stats + diag_apply (into output 1) for every map; returns [(min non-zero, max)] per map."""
         k = len(self.maps)

@@ -38,18 +38,16 @@ def _label(ccMapObj):
 
 
 def _upload(ccMapObj, vmin, vmax):
-    """Stream the CCMAP's float32 memmap into HBM once and apply the vmin/vmax clamp there
-    (lib/normalizer.py:299-301, 567-569, 827-829, 1105-1107)."""
-    ccMapObj.make_readable()
-    try:
-        k = sharded.gpus_for_map(int(ccMapObj.shape[0]))
+    """Stream the CCMAP's float32 matrix into HBM once -- straight from its backing file (parallel pread), from its gzip stream,
+    or from the memmap (ccmap.upload_ccmap) -- on one GPU, or row-sharded over several when it does not fit (sharded.py), and
+    apply the vmin/vmax clamp there (lib/normalizer.py:299-301, 567-569, 827-829, 1105-1107)."""
+    def make_map(n):
+        k = sharded.gpus_for_map(n)
         if k > 1:
-            # too large for one GPU (or GCX_GPUS=k): row blocks on k GPUs of this node, one host thread each (sharded.py)
-            dm = sharded.ShardedDeviceMap.from_host(ccMapObj.matrix, devices=list(range(k)))
-        else:
-            dm = DeviceMap.from_host(ccMapObj.matrix)
-    finally:
-        ccMapObj.make_unreadable()
+            # too large for one GPU (or GCX_GPUS=k): row blocks on k GPUs of this node, one host thread each
+            return sharded.ShardedDeviceMap(n, devices=list(range(k)))
+        return DeviceMap(n)
+    dm = cmp.upload_ccmap(ccMapObj, make_map)
     if vmin is not None or vmax is not None:
         dm.clamp(vmin, vmax)
     return dm
@@ -78,7 +76,7 @@ def normalizeCCMapByKR(ccMap, memory='RAM', tol=1e-12, outFile=None, vmin=None, 
     """Knight-Ruiz matrix balancing (lib/normalizer.py:228-395).  Returns the normalized CCMAP, or None when
     ``outFile`` is given.  Errors are logged and re-raised, like the reference (:390-395).
     ``memory`` accepts 'RAM' and 'HDD' (both run on the GPU); anything else raises ValueError (:353-354)."""
-    ccMapObj, ccmapType = cmp.checkCCMapObjectOrFile(ccMap, workDir=workDir)
+    ccMapObj, ccmapType = cmp.checkCCMapObjectOrFile(ccMap, workDir=workDir, lazy_gz=True)
     logger.info(' KR Normalization will be done through {0}.'.format(memory))
     logger.info(' KR Normalization is in process for {0}...'.format(_label(ccMapObj)))
     delta, Delta = 0.1, 3           # :319-320
@@ -113,7 +111,7 @@ def normalizeCCMapByIC(ccMap, tol=1e-4, vmin=None, vmax=None, outFile=None, iter
     """Iterative correction (lib/normalizer.py:505-647).  Returns the normalized CCMAP (matrix left open
     r+, :583), None when ``outFile`` is given, and -- like the reference (:642-647) -- None after logging when
     anything but a device error goes wrong."""
-    ccMapObj, ccmapType = cmp.checkCCMapObjectOrFile(ccMap, workDir=workDir)
+    ccMapObj, ccmapType = cmp.checkCCMapObjectOrFile(ccMap, workDir=workDir, lazy_gz=True)
     logger.info(' Iterative Correction is in process for {0}...'.format(_label(ccMapObj)))
     applyFilter = not (percentile_threshold_no_data is None and threshold_data_occup is None)   # :577-580
     try:
@@ -154,7 +152,7 @@ def normalizeCCMapByMCFS(ccMap, stats='median', vmin=None, vmax=None, stype='o/e
     if stype not in ['o/e', 'o-e']:
         logger.warning('Wrong value {0} for stype: {1}.'.format(stype, ['o/e', 'o-e']))
         return None
-    ccMapObj, ccmapType = cmp.checkCCMapObjectOrFile(ccMap, workDir=workDir)
+    ccMapObj, ccmapType = cmp.checkCCMapObjectOrFile(ccMap, workDir=workDir, lazy_gz=True)
     logger.info(' Median Contact Frequency Scaling is in process for {0}...'.format(_label(ccMapObj)))
     try:
         with _upload(ccMapObj, vmin, vmax) as dm:
@@ -166,7 +164,8 @@ def normalizeCCMapByMCFS(ccMap, stats='median', vmin=None, vmax=None, stype='o/e
             mn, mx = dm.diag_apply(None, subtract=(stype == 'o-e'), in_place=False)              # :860-864
             normCCMap = _emit(dm, 1, ccMapObj, ~keep, mn, mx)
         normCCMap.make_editable()
-        ccMapObj.make_readable()
+        if ccmapType == 'Object':           # a map loaded from a file inside this call is dropped on return: nothing to re-open
+            ccMapObj.make_readable()
         last_run_info.clear()
         last_run_info.update(method='MCFS', n=int(keep.size), stats=stats, stype=stype, avg=avg)
         logger.info(' 	...Finished Median Contact Frequency Scaling for {0}...'.format(_label(ccMapObj)))
@@ -184,7 +183,7 @@ def normalizeCCMapByVCNorm(ccMap, sqroot=False, vmin=None, vmax=None, outFile=No
                            percentile_threshold_no_data=None, threshold_data_occup=None, workDir=None):
     """Vanilla-coverage normalization (lib/normalizer.py:1041-1168).  Returns the normalized CCMAP (readable),
     None with ``outFile``; non-device errors are printed and give None (:1160-1168)."""
-    ccMapObj, ccmapType = cmp.checkCCMapObjectOrFile(ccMap, workDir=workDir)
+    ccMapObj, ccmapType = cmp.checkCCMapObjectOrFile(ccMap, workDir=workDir, lazy_gz=True)
     try:
         with _upload(ccMapObj, vmin, vmax) as dm:
             keep = cmh.device_mask(dm, percentile_threshold_no_data, threshold_data_occup)       # :1123
@@ -192,7 +191,8 @@ def normalizeCCMapByVCNorm(ccMap, sqroot=False, vmin=None, vmax=None, outFile=No
             mn, mx, csum = dm.vc(sqroot=sqroot, in_place=False)                                  # :1128
             normCCMap = _emit(dm, 1, ccMapObj, ~keep, mn, mx)
         normCCMap.make_readable()
-        ccMapObj.make_readable()
+        if ccmapType == 'Object':
+            ccMapObj.make_readable()
         last_run_info.clear()
         last_run_info.update(method='VC', n=int(keep.size), kept=int(keep.sum()), sqroot=bool(sqroot))
         return _finish(normCCMap, outFile)
@@ -204,17 +204,77 @@ def normalizeCCMapByVCNorm(ccMap, sqroot=False, vmin=None, vmax=None, outFile=No
 
 
 # ---------------------------------------------------------------------------------------------------
-def _gcmap_unavailable(name):
-    def f(*args, **kwargs):
-        raise NotImplementedError(
-            name + ": the HDF5 .gcmap container (gcMapExplorer/lib/gcmap.py) is outside the accelerated hot path "
-            "(SURVEY.md section 8f, row N1) and h5py is not available in this image; convert with the reference's "
-            "gcmap tools and call the normalizeCCMapBy* functions per map.")
-    f.__name__ = name
-    return f
+# Batch drivers (lib/normalizer.py:397-503, 649-740, 904-1039, 1170-1290): every map of a set, smallest first.
+# The set is the HDF5 .gcmap file when h5py is importable, or a map-set directory / list of .ccmap files (mapset.py).
+# ---------------------------------------------------------------------------------------------------
+def normalizeGCMapByKR(gcMapInputFile, gcMapOutFile, mapSizeCeilingForMemory=20000, vmin=None, vmax=None, tol=1e-12,
+                       percentile_threshold_no_data=None, threshold_data_occup=None, compression='lzf', workDir=None, logHandler=None):
+    """KR-balance every map of a set (lib/normalizer.py:397-503): maps in ascending size; each result is stored with its
+    coarser levels (x2, 'sum', until below 500 bins).  ``mapSizeCeilingForMemory`` picks 'RAM' or 'HDD' in the reference
+    (:479-482); both run on the GPU(s) here -- a map too large for one GPU is row-sharded instead."""
+    from . import mapset
+    ms = mapset.MapSet(gcMapInputFile)
+    for mapName in ms.names_smallest_first():
+        ccMap = ms.load(mapName, workDir=workDir)
+        memory = 'HDD' if ccMap.shape[0] > mapSizeCeilingForMemory else 'RAM'                    # :479-482
+        norm_ccmap = normalizeCCMapByKR(ccMap, memory=memory, tol=tol, vmin=vmin, vmax=vmax,
+                                        percentile_threshold_no_data=percentile_threshold_no_data,
+                                        threshold_data_occup=threshold_data_occup, workDir=workDir)
+        if norm_ccmap is not None:
+            mapset.add_map(norm_ccmap, gcMapOutFile, compression=compression, generateCoarse=True, coarseningMethod='sum')
+        del ccMap
+        del norm_ccmap
 
 
-normalizeGCMapByKR = _gcmap_unavailable('normalizeGCMapByKR')
-normalizeGCMapByIC = _gcmap_unavailable('normalizeGCMapByIC')
-normalizeGCMapByMCFS = _gcmap_unavailable('normalizeGCMapByMCFS')
-normalizeGCMapByVCNorm = _gcmap_unavailable('normalizeGCMapByVCNorm')
+def normalizeGCMapByIC(gcMapInputFile, gcMapOutFile, vmin=None, vmax=None, tol=1e-12, iteration=500,
+                       percentile_threshold_no_data=None, threshold_data_occup=None, compression='lzf', workDir=None, logHandler=None):
+    """Iterative correction of every map of a set (lib/normalizer.py:649-740; note the driver's own default tol=1e-12).  A map whose
+    normalization fails is skipped with the warnings of normalizeCCMapByIC, like the reference (norm_ccmap is None, :718)."""
+    from . import mapset
+    ms = mapset.MapSet(gcMapInputFile)
+    for mapName in ms.names_smallest_first():
+        ccMap = ms.load(mapName, workDir=workDir)
+        norm_ccmap = normalizeCCMapByIC(ccMap, tol=tol, iteration=iteration, vmin=vmin, vmax=vmax,
+                                        percentile_threshold_no_data=percentile_threshold_no_data,
+                                        threshold_data_occup=threshold_data_occup, workDir=workDir)
+        if norm_ccmap is not None:
+            mapset.add_map(norm_ccmap, gcMapOutFile, compression=compression, generateCoarse=True, coarseningMethod='sum')
+        del ccMap
+        del norm_ccmap
+
+
+def _walk_resolutions(ms, gcMapOutFile, compression, workDir, norm_one):
+    """MCFS and VC normalize EVERY stored resolution of every map, finest first, and add each without coarsening
+    (lib/normalizer.py:1003-1030, 1247-1283); the walk of a map stops at the first resolution that fails."""
+    from . import mapset
+    for mapName in ms.names_smallest_first():
+        for resolution in ms.resolutions(mapName):
+            ccMap = ms.load(mapName, resolution=resolution, workDir=workDir)
+            norm_ccmap = norm_one(ccMap)
+            del ccMap
+            if norm_ccmap is None:
+                break
+            mapset.add_map(norm_ccmap, gcMapOutFile, compression=compression, generateCoarse=False, replaceCMap=False)
+            del norm_ccmap
+
+
+def normalizeGCMapByMCFS(gcMapInputFile, gcMapOutFile, stats='median', vmin=None, vmax=None, stype='o/e', scaleUpInput=False,
+                         percentile_threshold_no_data=None, threshold_data_occup=None, compression='lzf', workDir=None, logHandler=None):
+    """Distance-frequency scaling of every map of a set at every stored resolution (lib/normalizer.py:904-1039)."""
+    from . import mapset
+    ms = mapset.MapSet(gcMapInputFile)
+    _walk_resolutions(ms, gcMapOutFile, compression, workDir,
+                      lambda c: normalizeCCMapByMCFS(c, stats=stats, stype=stype, vmin=vmin, vmax=vmax, scaleUpInput=scaleUpInput,
+                                                     percentile_threshold_no_data=percentile_threshold_no_data,
+                                                     threshold_data_occup=threshold_data_occup, workDir=workDir))
+
+
+def normalizeGCMapByVCNorm(gcMapInputFile, gcMapOutFile, sqroot=False, vmin=None, vmax=None, percentile_threshold_no_data=None,
+                           threshold_data_occup=None, compression='lzf', workDir=None, logHandler=None):
+    """Vanilla-coverage normalization of every map of a set at every stored resolution (lib/normalizer.py:1170-1290)."""
+    from . import mapset
+    ms = mapset.MapSet(gcMapInputFile)
+    _walk_resolutions(ms, gcMapOutFile, compression, workDir,
+                      lambda c: normalizeCCMapByVCNorm(c, sqroot=sqroot, vmin=vmin, vmax=vmax,
+                                                       percentile_threshold_no_data=percentile_threshold_no_data,
+                                                       threshold_data_occup=threshold_data_occup, workDir=workDir))

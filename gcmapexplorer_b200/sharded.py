@@ -95,6 +95,28 @@ class ShardedDeviceMap:
             raise ValueError(f"expected shape {(self.n, self.n)}, got {tuple(matrix.shape)}")
         self._all(lambda r, m: m.upload(matrix[self.parts[r][0]:self.parts[r][0] + self.parts[r][1]]))
 
+    def upload_file(self, path, offset=0, with_stats=True):
+        """Every rank reads its own row block of the raw float32 file (parallel pread per rank)."""
+        self._all(lambda r, m: m.upload_file(path, offset, with_stats))
+
+    def upload_rows(self, rows, row_begin, with_stats=True):
+        """A chunk of GLOBAL rows [row_begin, row_begin + len(rows)): every rank takes the part inside its block."""
+        def part(r, m):
+            r0, nl = self.parts[r]
+            a, b = max(row_begin, r0), min(row_begin + rows.shape[0], r0 + nl)
+            if a < b:
+                m.upload_rows(rows[a - row_begin:b - row_begin], a - r0, with_stats)
+        self._all(part)
+
+    def upload_finish(self):
+        self._all(lambda r, m: m.upload_finish())
+
+    def download_file(self, which, path, offset=0):
+        """Every rank writes its rows into the shared raw float32 file (sized first)."""
+        with open(path, "wb") as f:
+            f.truncate(4 * self.n * self.n + int(offset))
+        self._all(lambda r, m: m.download_file(which, path, offset))
+
     def download(self, which=1, out=None):
         if out is None:
             out = np.empty((self.n, self.n), dtype=np.float32)

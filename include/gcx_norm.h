@@ -130,6 +130,10 @@ int gcx_diag_apply(gcx_ctx* ctx, const double* avg, int subtract, int in_place, 
  * to the per-map calls. */
 int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtract, float* minv, float* maxv);
 int gcx_diag_avg_read(gcx_ctx* ctx, double* avg);
+/* getAvgContactByDistance for a LIST of maps (lib/cmstats.py:572-578): per distance the non-zero entries of that diagonal of every
+ * map that is large enough are pooled, then median (one radix selection fed by all maps) or mean.  avg: nmax doubles, nmax = bins of
+ * the largest map. */
+int gcx_diag_stats_pooled(gcx_ctx** ctxs, int count, int median, double* avg, int64_t nmax);
 
 /* ---- compaction ---------------------------------------------------------------------------------
  * Replaces the element loop of ccmapHelpers.remove_zeros (lib/ccmapHelpers.pyx:286-299): host_out[ci][cj] =

@@ -362,7 +362,23 @@ def test_mcfs_bad_stype_and_inner_seam(gx):
     assert core.normalizeByAvgContactBySubtraction(A, avg, Out=out) is None
     assert rel_err(out, onp.mcfs_subtract(A, avg)) < MAT_RTOL
     with pytest.raises(NotImplementedError):
-        cmstats.getAvgContactByDistance([c, c])
+        cmstats.getAvgContactByDistance(c, removeOutliers=True)
+    # pooled list (lib/cmstats.py:572-578): maps of different sizes, the d-th diagonals pooled
+    B = onp.synth_map(A.shape[0] + 37, seed=77, scale=30.0)
+    c2 = cmp.CCMAP()
+    c2.gen_from_matrix(B, 100000)
+    c2.make_readable()
+    for st in ("median", "mean"):
+        got = cmstats.getAvgContactByDistance([c, c2, c], stats=st)
+        exp = np.zeros(B.shape[0])
+        for d in range(B.shape[0]):
+            vals = np.concatenate([np.diagonal(M, -d)[np.diagonal(M, -d) != 0] for M in (A, B, A) if d < M.shape[0]]).astype(np.float64)
+            if vals.size:
+                exp[d] = np.median(vals) if st == "median" else np.mean(vals)
+        if st == "median":
+            assert np.array_equal(got, exp)
+        else:
+            np.testing.assert_allclose(got, exp, rtol=1e-13)
     with pytest.raises(TypeError):
         cmstats.getAvgContactByDistance(A)
 
@@ -434,8 +450,111 @@ def test_error_conventions(gx, caplog):
         nz.normalizeCCMapByKR(c, memory="TAPE")
     assert nz.normalizeCCMapByVCNorm(c, threshold_data_occup=1.5) is None
     assert nz.normalizeCCMapByMCFS(c, threshold_data_occup=1.5) is None
-    with pytest.raises(NotImplementedError):
-        nz.normalizeGCMapByIC("in.gcmap", "out.gcmap")
+    with pytest.raises((ImportError, OSError)):
+        nz.normalizeGCMapByIC("in.gcmap", "out.gcmap")        # HDF5 container: needs h5py at call time (absent here) / an existing file
+
+
+def test_streaming_residency_file_rows_and_gzip(gx, tmp_path):
+    """the three streaming routes into HBM (raw .npbin through parallel pread, row chunks, a gzip stream) leave
+    the same map and the same row statistics as a plain upload, the statistics arrive with the upload (no extra pass), and
+    gcx_map_download_file writes the bytes np.memmap would."""
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz
+    n = 1237
+    A = onp.synth_map(n, seed=5)
+    raw = tmp_path / "a.npbin"
+    A.tofile(raw)
+    with gx.DeviceMap.from_host(A) as ref:
+        rs0, zc0 = ref.row_stats()
+        c0 = ref.checksum(0)
+    with gx.DeviceMap(n) as dm:
+        dm.upload_file(str(raw))
+        l0 = dm.launch_count()
+        rs, zc = dm.row_stats()
+        assert dm.launch_count() == l0                      # statistics came with the upload
+        assert dm.checksum(0) == c0 and np.array_equal(rs, rs0) and np.array_equal(zc, zc0)
+        dm.download_file(0, str(tmp_path / "b.npbin"))
+        assert np.array_equal(np.fromfile(tmp_path / "b.npbin", dtype=np.float32).reshape(n, n), A)
+        for r0 in range(0, n, 300):                           # row chunks, as a gzip / HDF5 reader hands them over
+            dm.upload_rows(A[r0:r0 + 300] * 2.0, r0)
+        dm.upload_finish()
+        rs2, zc2 = dm.row_stats()
+        assert np.array_equal(rs2, 2.0 * rs0) and np.array_equal(zc2, zc0)
+    # a compressed .ccmap given by file name is inflated straight into the device: same result as the CCMAP object route
+    c = cmp.CCMAP()
+    c.gen_from_matrix(A, 10000, xlabel="chrZ", ylabel="chrZ", workDir=str(tmp_path))
+    cmp.save_ccmap(c, str(tmp_path / "z.ccmap"), compress=True)
+    lazy = cmp.load_ccmap(str(tmp_path / "z.ccmap"), workDir=str(tmp_path), lazy_gz=True)
+    assert lazy._gz_source.endswith("z.npbin.gz") and lazy.path2matrix == ""
+    a = nz.normalizeCCMapByIC(str(tmp_path / "z.ccmap"), workDir=str(tmp_path))
+    b = nz.normalizeCCMapByIC(c)
+    assert np.array_equal(np.array(a.matrix), np.array(b.matrix)) and np.array_equal(a.bNoData, b.bNoData)
+    lazy.make_readable()                                      # and a lazily opened map can still be looked at
+    assert np.array_equal(np.array(lazy.matrix), A)
+
+
+def test_batch_driver_over_a_map_set(gx, tmp_path):
+    """normalizeGCMapByIC / ByKR / ByMCFS over a map-set directory (the HDF5-free carrier of a .gcmap, mapset.py): maps are
+    processed smallest first (lib/gcmap.py:219-262), each result equals the per-map oracle, IC / KR results are stored with their
+    x2 'sum' pyramid down to < 500 bins (lib/gcmap.py:582-604), MCFS normalizes every stored resolution without coarsening."""
+    from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz, mapset
+    inputs = {"chrB": onp.synth_map(482, seed=3), "chrA": onp.synth_map(1101, seed=4), "chrC": load_golden("s97_ic")["input"]}
+    src = tmp_path / "in"
+    for name, A in inputs.items():
+        c = cmp.CCMAP()
+        c.gen_from_matrix(A, 10000, xlabel=name, ylabel=name, workDir=str(tmp_path))
+        c.bNoData = ~onp.get_nonzeros_index(A)
+        mapset.add_map(c, str(src), generateCoarse=(name == "chrA"), compress_files=(name != "chrB"))
+    ms = mapset.MapSet(str(src))
+    assert ms.names_smallest_first() == ["chrC", "chrB", "chrA"]
+    assert ms.resolutions("chrA") == ["10kb", "20kb", "40kb"] and ms.resolutions("chrB") == ["10kb"]
+    order = []
+    real_add = mapset.add_map
+
+    def spy(cm, dest, **kw):
+        order.append(cm.xlabel)
+        return real_add(cm, dest, **kw)
+    mapset.add_map = spy
+    try:
+        nz.normalizeGCMapByIC(str(src), str(tmp_path / "out_ic"), tol=1e-4, workDir=str(tmp_path))
+        nz.normalizeGCMapByKR(str(src), str(tmp_path / "out_kr"), workDir=str(tmp_path))
+        nz.normalizeGCMapByMCFS(str(src), str(tmp_path / "out_mcfs"), workDir=str(tmp_path))
+    finally:
+        mapset.add_map = real_add
+    assert order[:3] == ["chrC", "chrB", "chrA"] and order[3:6] == ["chrC", "chrB", "chrA"]
+    assert order[6:] == ["chrC", "chrB", "chrA", "chrA", "chrA"]             # MCFS: every stored resolution of chrA
+    out_ic, out_kr, out_m = (mapset.MapSet(str(tmp_path / d)) for d in ("out_ic", "out_kr", "out_mcfs"))
+    for name, A in inputs.items():
+        got = out_ic.load(name, workDir=str(tmp_path))
+        got.make_readable()
+        ref = onp.normalize_ic(A, tol=1e-4, fp64=True)
+        assert rel_err(np.array(got.matrix), ref["matrix"]) < MAT_RTOL and np.array_equal(got.bNoData, ref["bNoData"])
+        gk = out_kr.load(name, workDir=str(tmp_path))
+        gk.make_readable()
+        rk = onp.normalize_kr(A)
+        assert rel_err(np.array(gk.matrix), rk["matrix"]) < MAT_RTOL and np.array_equal(gk.bNoData, rk["bNoData"])
+    # pyramid of the largest map: 1101 -> 551 -> 276 bins, each level the 'sum' coarsening of the level before
+    assert out_ic.resolutions("chrA") == ["10kb", "20kb", "40kb"] and out_ic.resolutions("chrB") == ["10kb"]
+    fine = out_ic.load("chrA", workDir=str(tmp_path))
+    fine.make_readable()
+    lvl = np.array(fine.matrix)
+    for res in ("20kb", "40kb"):
+        cm = out_ic.load("chrA", resolution=res, workDir=str(tmp_path))
+        cm.make_readable()
+        lvl = onp.downsample_2d(lvl, 2, "sum")
+        assert cm.shape == lvl.shape and np.array_equal(np.array(cm.matrix), lvl) and cm.binsize == util_res(res)
+    # MCFS walked the stored resolutions of chrA itself (no coarsening of the result)
+    for res in ("10kb", "20kb", "40kb"):
+        a_in = ms.load("chrA", resolution=res, workDir=str(tmp_path))
+        a_in.make_readable()
+        m = out_m.load("chrA", resolution=res, workDir=str(tmp_path))
+        m.make_readable()
+        refm = onp.normalize_mcfs(np.array(a_in.matrix))
+        assert rel_err(np.array(m.matrix), refm["matrix"]) < MAT_RTOL
+
+
+def util_res(res):
+    from gcmapexplorer_b200 import util
+    return util.resolutionToBinsize(res)
 
 
 def test_reupload_invalidates_cached_row_statistics(gx):

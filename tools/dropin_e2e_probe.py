@@ -24,4 +24,17 @@ for name, fn in (("IC", lambda: nz.normalizeCCMapByIC(c)), ("KR", lambda: nz.nor
     res[name + "_s"] = round(time.perf_counter() - t0, 3)
     res[name + "_info"] = {k: v for k, v in nz.last_run_info.items() if k in ("passes", "outer", "MVP", "device_ms")}
     del out
+# plain-copy floor on the same file system: read the 4 n^2-byte input once, write a 4 n^2-byte output once (what any implementation must do)
+raw = np.empty(n * n, dtype=np.float32)
+t0 = time.perf_counter()
+with open(c.path2matrix, "rb") as f:
+    f.readinto(raw)
+t_read = time.perf_counter() - t0
+t0 = time.perf_counter()
+with open(os.path.join(work, "floor.out"), "wb") as f:
+    f.write(raw)
+t_write = time.perf_counter() - t0
+os.remove(os.path.join(work, "floor.out"))
+res["plain_copy_floor_s"] = {"read_input_single_thread": round(t_read, 3), "write_output_single_thread": round(t_write, 3),
+                             "note": "single-threaded read() / write() of one 4 n^2-byte file each on the same file system; the library uses 16 pread / pwrite threads"}
 print(json.dumps(res))
