@@ -55,6 +55,7 @@ _PROTOS = {
     "gcx_ic_run": (C.c_int, [_ctx, C.c_double, C.c_int, _c_f64p, C.POINTER(C.c_int), _c_f64p, C.POINTER(C.c_int)]),
     "gcx_kr_run": (C.c_int, [_ctx, C.c_double, C.c_double, C.c_double, _c_f64p, C.POINTER(C.c_int), C.POINTER(C.c_int), _c_f64p]),
     "gcx_apply_sym_scale": (C.c_int, [_ctx, _c_f64p, C.c_int, C.c_int, _c_f32p, _c_f32p]),
+    "gcx_apply_norm_vectors": (C.c_int, [_ctx, _c_f64p, _c_f64p, C.c_int, _c_f32p, _c_f32p]),
     "gcx_apply_sym_vc": (C.c_int, [_ctx, _c_u8p, C.c_int, C.c_int, _c_f32p, _c_f32p, _c_f32p, _c_f32p]),
     "gcx_vc_run": (C.c_int, [_ctx, C.c_int, C.c_int, _c_f32p, _c_f32p, _c_f32p]),
     "gcx_diag_stats": (C.c_int, [_ctx, C.c_int, _c_f64p]),

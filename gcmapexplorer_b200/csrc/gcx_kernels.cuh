@@ -1187,6 +1187,57 @@ k_vc_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld, i
     mm_commit(mn, mx, mm);
 }
 
+// .hic import with a precomputed norm vector pair (second half): every stored count becomes
+// count / (c1[bin_x] * c2[bin_y]), +inf where that product is zero (lib/hic2gcmap.py:88-95, the vectors of
+// lib/hicparser.py:358-412); the arithmetic is Python's float64, the map float32.  Bins without a record (zeros of the dense map)
+// stay zero.  Algorithmic bytes: 8 * nloc * n.
+template <int R, int OCC>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
+k_apply_norm_vectors(const float* __restrict__ A, float* __restrict__ Out, long long ld, int nloc, int n4, int n, int row0,
+                     const double* __restrict__ c1, const double* __restrict__ c2, MinMax* mm) {
+    const int tid = threadIdx.x;
+    const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
+    const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
+    float mn = GCX_PINF, mx = GCX_NINF;
+    const double2* __restrict__ c22 = reinterpret_cast<const double2*>(c2);
+    for (long long u = u0; u < u1; ++u) {
+        const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
+        const int c4 = k * MV_THREADS + tid;
+        if (c4 >= n4) continue;
+        float4 a[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r < nloc) a[rr] = ld_stream_f4(reinterpret_cast<const float4*>(A + (long long)r * ld) + c4);
+        }
+        const double2 ca = __ldg(c22 + 2 * c4), cb = __ldg(c22 + 2 * c4 + 1);
+        const double cj[4] = {ca.x, ca.y, cb.x, cb.y};
+        const int j0 = 4 * c4;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = b * R + rr;
+            if (r >= nloc) break;
+            const double ci = __ldg(c1 + row0 + r);
+            const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float v = in[e];
+                if (v != 0.f && j0 + e < n) {
+                    const double norm = ci * cj[e];                                   // lib/hic2gcmap.py:89
+                    v = norm != 0.0 ? (float)((double)in[e] / norm) : GCX_PINF;       // :90-93
+                }
+                o[e] = v;
+                if (j0 + e < n) mm_update(v, mn, mx);
+            }
+            st_stream_f4(reinterpret_cast<float4*>(Out + (long long)r * ld) + c4, make_float4(o[0], o[1], o[2], o[3]));
+        }
+    }
+    mm_commit(mn, mx, mm);
+}
+
 // K4 + K5 fused: one read of the map, two results -- the IC (or KR) scaled map of k_apply_sym into OutS and the vanilla-coverage
 // map of k_vc_apply into OutV, each with its own mask and its own min/max.  Same arithmetic per element as the two kernels
 // (bit-identical outputs); algorithmic bytes 12 * nloc * n instead of 16 * nloc * n for the pair.

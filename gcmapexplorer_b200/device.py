@@ -275,6 +275,18 @@ class DeviceMap:
         check(lib().gcx_apply_sym_scale(self._ctx, sp, int(masked_mode), int(bool(in_place)), C.byref(mn), C.byref(mx)))
         return mn.value, mx.value
 
+    def apply_norm_vectors(self, c1, c2, in_place=False):
+        """count / (c1[row] * c2[col]) with +inf on a zero product (.hic import with KR / VC vectors, lib/hic2gcmap.py:82-98).
+        Returns (min non-zero, max)."""
+        c1 = np.ascontiguousarray(c1, dtype=np.float64)
+        c2 = np.ascontiguousarray(c2, dtype=np.float64)
+        if c1.shape != (self.n,) or c2.shape != (self.n,):
+            raise ValueError("norm vectors must have n entries")
+        mn, mx = C.c_float(0), C.c_float(0)
+        check(lib().gcx_apply_norm_vectors(self._ctx, c1.ctypes.data_as(_lib._c_f64p), c2.ctypes.data_as(_lib._c_f64p), int(bool(in_place)),
+                                           C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
     def apply_sym_vc(self, keep_vc, masked_mode=0, sqroot=False):
         """Fused tail: scaled map (resident scale + mask) -> output 1, vanilla-coverage map under `keep_vc` -> output 2, one read
         of the input.  Returns ((min, max) of the scaled map, (min, max) of the VC map)."""

@@ -27,6 +27,8 @@ from . import util
 def _h5py():
     try:
         import h5py
+        if not hasattr(h5py, "File") or not hasattr(h5py, "Dataset") or not getattr(h5py, "__version__", None):
+            raise ImportError("the module named h5py that is loaded is a stub, not the HDF5 binding")
         return h5py
     except ImportError as e:
         raise ImportError("reading or writing the HDF5 .gcmap container needs h5py, which is not installed here; pass a map-set "

@@ -75,3 +75,18 @@ def normalizeByAvgContactByDivision(A, avgContacts, Out=None):
 def normalizeByAvgContactBySubtraction(A, avgContacts, Out=None):
     """normalizeCore.pyx:123-170: A_ij - avg[|i-j|]; negative -> 1; zero input -> 0; avg 0 -> A_ij."""
     return _diag_apply(A, avgContacts, Out, True)
+
+
+def applyNormVectors(A, c1_norm, c2_norm, Out=None):
+    """The norm-vector step of the .hic importer on a dense map (lib/hic2gcmap.py:82-98): every stored count divided by
+    ``c1_norm[bin_x] * c2_norm[bin_y]`` in float64, ``inf`` where that product is zero, bins without a record (zeros) untouched.
+    Same calling convention as the other cores: fills `Out` when given, else returns the new array."""
+    with DeviceMap.from_host(A) as dm:
+        dm.apply_norm_vectors(c1_norm, c2_norm, in_place=False)
+        if Out is None:
+            return dm.download(1)
+        if isinstance(Out, np.ndarray) and Out.dtype == np.float32 and Out.shape == tuple(A.shape):
+            dm.download(1, out=Out)
+        else:
+            Out[:] = dm.download(1)
+    return None

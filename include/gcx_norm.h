@@ -108,6 +108,12 @@ int gcx_apply_sym_scale(gcx_ctx* ctx, const double* s, int masked_mode, int in_p
  * Needs gcx_row_stats + gcx_set_mask first.  csum: n floats out (may be NULL). */
 int gcx_vc_run(gcx_ctx* ctx, int sqroot, int in_place, float* minv, float* maxv, float* csum);
 
+/* ---- .hic import: precomputed norm vectors (second half) ---------------------
+ * Replaces the per-record arithmetic of lib/hic2gcmap.py:82-98 on a resident map: out_ij = f32(f64(A_ij) / (c1[i] * c2[j])), +inf
+ * where c1[i] * c2[j] == 0, zeros (bins without a record) untouched; c1 / c2 are the KR / VC / VC_SQRT vectors a .hic file stores
+ * per chromosome and resolution (lib/hicparser.py:358-412), n doubles each (c1 indexes rows, c2 columns). */
+int gcx_apply_norm_vectors(gcx_ctx* ctx, const double* c1, const double* c2, int in_place, float* minv, float* maxv);
+
 /* ---- fused tail: symmetric scale + vanilla coverage from ONE read of the map ----------------------
  * For callers that want both normalizations of a map (bench.py's step, the batch driver): the result of gcx_apply_sym_scale
  * (resident scale and mask of the last gcx_ic_run / gcx_kr_run, not in place) goes to output 1 and the result of gcx_vc_run under

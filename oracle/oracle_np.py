@@ -428,6 +428,20 @@ def normalize_mcfs(A, stats="median", stype="o/e", vmin=None, vmax=None, scaleUp
     return dict(matrix=out, bNoData=~keep, minvalue=mn, maxvalue=float(np.amax(out)), avg=avg)
 
 
+def hic_norm_apply(A, c1, c2):
+    """lib/hic2gcmap.py:82-98 on a dense map: a stored count (non-zero entry) becomes count / (c1[bin_x] * c2[bin_y]) in Python
+    float64 arithmetic, inf where the product is 0.0 (:89-93); the matrix is float32.  Zeros are bins without a record."""
+    out = np.array(A, dtype=np.float32, copy=True)
+    n = A.shape[0]
+    for i in range(n):
+        for j in range(n):
+            count = float(A[i, j])
+            if count != 0.0:
+                norm = float(c1[i]) * float(c2[j])
+                out[i, j] = np.float32(count / norm) if norm != 0.0 else np.float32(np.inf)
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # synthetic maps for CPU-side tests (SURVEY.md section 8d definition; host RNG, small n only)
 # --------------------------------------------------------------------------------------------------

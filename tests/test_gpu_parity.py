@@ -454,6 +454,28 @@ def test_error_conventions(gx, caplog):
         nz.normalizeGCMapByIC("in.gcmap", "out.gcmap")        # HDF5 container: needs h5py at call time (absent here) / an existing file
 
 
+def test_hic_norm_vector_application(gx):
+    """SURVEY.md 8f row N4, second half: the norm-vector arithmetic of the .hic importer (lib/hic2gcmap.py:82-98) on a resident map,
+    bit-identical to the reference's per-record Python arithmetic incl. inf on zero norms and NaN vectors entries."""
+    from gcmapexplorer_b200 import normalizeCore as core
+    n = 131
+    A = onp.synth_map(n, seed=8, scale=25.0)
+    rng = np.random.default_rng(3)
+    c1 = rng.uniform(0.3, 2.5, n)
+    c2 = rng.uniform(0.3, 2.5, n)
+    c1[[5, 40]] = 0.0                      # zero norm -> inf for the stored counts of that bin
+    c2[17] = np.nan                        # .hic files mark unusable bins with NaN
+    with np.errstate(invalid="ignore"):
+        exp = onp.hic_norm_apply(A, c1, c2)
+    got = core.applyNormVectors(A, c1, c2)
+    assert np.array_equal(got, exp, equal_nan=True)
+    assert np.isinf(got[5][A[5] != 0]).all() and np.isnan(got[:, 17][A[:, 17] != 0]).all() and (got[A == 0] == 0).all()
+    out = np.zeros_like(A)
+    assert core.applyNormVectors(A, c1, c1, Out=out) is None            # symmetric use: KR / VC vectors of an intra-chromosomal map
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(out, onp.hic_norm_apply(A, c1, c1), equal_nan=True)
+
+
 def test_streaming_residency_file_rows_and_gzip(gx, tmp_path):
     """the three streaming routes into HBM (raw .npbin through parallel pread, row chunks, a gzip stream) leave
     the same map and the same row statistics as a plain upload, the statistics arrive with the upload (no extra pass), and
