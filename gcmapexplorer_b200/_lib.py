@@ -51,6 +51,9 @@ _PROTOS = {
     "gcx_map_swap": (C.c_int, [_ctx]),
     "gcx_map_checksum": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_uint64)]),
     "gcx_row_stats": (C.c_int, [_ctx, _c_f64p, _c_i32p]),
+    "gcx_row_negative_flags": (C.c_int, [_ctx, _c_i32p]),
+    "gcx_map_adopt_device": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
+    "gcx_map_export_device": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int64]),
     "gcx_set_mask": (C.c_int, [_ctx, _c_u8p]),
     "gcx_ic_run": (C.c_int, [_ctx, C.c_double, C.c_int, _c_f64p, C.POINTER(C.c_int), _c_f64p, C.POINTER(C.c_int)]),
     "gcx_kr_run": (C.c_int, [_ctx, C.c_double, C.c_double, C.c_double, _c_f64p, C.POINTER(C.c_int), C.POINTER(C.c_int), _c_f64p]),

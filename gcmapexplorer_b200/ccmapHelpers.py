@@ -70,9 +70,27 @@ def mask_from_row_stats(rowsum, raw_zero_count, n, threshold_percentile=None, th
     return np.asarray(bData, dtype=bool)
 
 
-def device_mask(dm, threshold_percentile=None, threshold_data_occup=None):
+def float32_empty_rows(dm, rowsum, host_rows=None):
+    """The reference calls a row empty when ``np.sum(row) == 0.0`` in FLOAT32 (lib/ccmapHelpers.pyx:192).  On rows without negative
+    entries that is "all entries zero", which the device's float64 row sum decides exactly.  A row WITH negative entries (o-e
+    output, correlation maps) can have a float32 sum that cancels to exactly 0 while the float64 sum does not: those rows -- flagged
+    by the device -- are re-checked with NumPy's own float32 sum when the host copy is at hand (`host_rows(i)` returns row i as the
+    device holds it); without one the float64 rule stands (documented divergence)."""
+    empty = np.asarray(rowsum) == 0.0
+    if not hasattr(dm, "row_negative_flags"):
+        return empty
+    suspect = np.nonzero(dm.row_negative_flags() != 0)[0]
+    if suspect.size and host_rows is not None:
+        for i in suspect:
+            empty[i] = bool(np.sum(np.asarray(host_rows(int(i)), dtype=np.float32)) == 0.0)
+    return empty
+
+
+def device_mask(dm, threshold_percentile=None, threshold_data_occup=None, host_rows=None):
     """get_nonzeros_index for a map that is already resident (used by the orchestrators)."""
     rowsum, zc = dm.row_stats()
+    if host_rows is not None:
+        rowsum = np.where(float32_empty_rows(dm, rowsum, host_rows), 0.0, np.where(np.asarray(rowsum) == 0.0, 1.0, rowsum))
     return mask_from_row_stats(rowsum, zc, dm.n, threshold_percentile, threshold_data_occup)
 
 
@@ -80,6 +98,8 @@ def get_nonzeros_index(matrix, threshold_percentile=None, threshold_data_occup=N
     """Drop-in for ccmapHelpers.get_nonzeros_index (same signature, same errors, bit-identical result)."""
     with DeviceMap.from_host(matrix) as dm:
         rowsum, zc = dm.row_stats()
+        empty = float32_empty_rows(dm, rowsum, lambda i: matrix[i])
+        rowsum = np.where(empty, 0.0, np.where(np.asarray(rowsum) == 0.0, 1.0, rowsum))     # carry the float32 verdict
     diag0 = (np.diagonal(matrix) == 0) if filterByDiagonal else None
     return mask_from_row_stats(rowsum, zc, matrix.shape[0], threshold_percentile, threshold_data_occup, diag0)
 

@@ -162,6 +162,7 @@ struct gcx_ctx {
     KrVecs kr{};
     float* csum32 = nullptr;
     int32_t* zero_count = nullptr;
+    int32_t* neg_flag = nullptr;           // 1: the row has negative entries (its float32 emptiness test is re-checked on the host)
     uint8_t* keep = nullptr;
     bool have_mask = false, have_rowsum = false, have_scale = false;
     // matvec workspace
@@ -170,7 +171,7 @@ struct gcx_ctx {
     // symmetric (upper-triangle) passes: single rank, exactly symmetric map
     int sym_enable = 1;          // GCX_SYM=0 disables
     int sym_state = -1;          // -1 unknown, 0 not symmetric, 1 symmetric
-    double* rowpart = nullptr;   // [nch * SYM_NG][ld]
+    double* rowpart = nullptr;   // [nch][ld]: one partial per (panel, row)
     double* colpart = nullptr;   // [grid][nslots][SYM_NG][1024]
     long long* sym_tab_ll = nullptr;      // panel_u0 [nch+1] | cta_u0 [G+1]
     int* sym_tab_i = nullptr;             // cta_kf [G] | cta_kl [G] | panel_cta [nch] | panel_cta_hi [nch]
@@ -321,6 +322,7 @@ extern "C" int gcx_device_count(int* count) {
 }
 
 extern "C" int gcx_ctx_destroy(gcx_ctx* c);
+static void stage_give(void* p);
 
 static int ctx_init(gcx_ctx* c, int device) {
     c->device = device;
@@ -446,6 +448,7 @@ static void free_map(gcx_ctx* c) {
     cudaFree(c->slab); c->slab = nullptr;
     cudaFree(c->csum32); c->csum32 = nullptr;
     cudaFree(c->zero_count); c->zero_count = nullptr;
+    cudaFree(c->neg_flag); c->neg_flag = nullptr;
     cudaFree(c->keep); c->keep = nullptr;
     c->have_mask = c->have_rowsum = c->have_scale = false;
 }
@@ -462,7 +465,7 @@ extern "C" int gcx_ctx_destroy(gcx_ctx* c) {
     cudaFree(c->ic_state); cudaFree(c->kr_state); cudaFree(c->sd_state); cudaFree(c->mm); cudaFree(c->mm2); cudaFree(c->csum_dev); cudaFree(c->ticket); cudaFree(c->ws); cudaFree(c->part); cudaFree(c->scratch);
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int i = 0; i < 2; ++i) {
-        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+        if (c->stage[i]) stage_give(c->stage[i]);
         if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
     }
     for (cudaEvent_t e : {c->run_a, c->run_b, c->tm_a, c->tm_b})
@@ -554,6 +557,8 @@ static int map_alloc(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc) {
     CK(cudaMemsetAsync(c->csum32, 0, sizeof(float) * (size_t)c->nv, c->stream));
     CK(cudaMalloc(&c->zero_count, sizeof(int32_t) * (size_t)c->nv));
     CK(cudaMemsetAsync(c->zero_count, 0, sizeof(int32_t) * (size_t)c->nv, c->stream));
+    CK(cudaMalloc(&c->neg_flag, sizeof(int32_t) * (size_t)c->nv));
+    CK(cudaMemsetAsync(c->neg_flag, 0, sizeof(int32_t) * (size_t)c->nv, c->stream));
     CK(cudaMalloc(&c->keep, (size_t)c->nv));
     CK(cudaMemsetAsync(c->keep, 0, (size_t)c->nv, c->stream));
     CK(cudaMalloc(&c->ic_ring, sizeof(double) * (size_t)c->nv * 5));
@@ -586,11 +591,29 @@ static int ensure_scratch(gcx_ctx* c, size_t bytes) {
     return 0;
 }
 
+// Pinned staging buffers are expensive to create (cudaHostAlloc of 64 MB: tens of milliseconds) and every drop-in call makes a
+// fresh context, so released stages are parked in a small process-wide pool (cudaHostAllocPortable: usable from any device).
+static std::mutex g_stage_mutex;
+static std::vector<void*> g_stage_pool;
+static int stage_take(void** p) {
+    {
+        std::lock_guard<std::mutex> lock(g_stage_mutex);
+        if (!g_stage_pool.empty()) { *p = g_stage_pool.back(); g_stage_pool.pop_back(); return 0; }
+    }
+    CK(cudaHostAlloc(p, STAGE_BYTES, cudaHostAllocPortable));
+    return 0;
+}
+static void stage_give(void* p) {
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    if (g_stage_pool.size() < 16) g_stage_pool.push_back(p);
+    else cudaFreeHost(p);
+}
+
 static int ensure_stage(gcx_ctx* c) {
     if (c->stage[0]) return 0;
     c->stage_bytes = STAGE_BYTES;
     for (int i = 0; i < 2; ++i) {
-        CK(cudaHostAlloc(&c->stage[i], c->stage_bytes, cudaHostAllocDefault));
+        CKR(stage_take(&c->stage[i]));
         CK(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
     }
     return 0;
@@ -710,7 +733,8 @@ static void par_for(int64_t items, size_t bytes_total, const std::function<void(
 static int stats_for_rows(gcx_ctx* c, int64_t r0, int64_t rows) {
     ProfScope ps(c, 3);
     const int grid = (int)std::min<int64_t>(rows, (int64_t)c->sm_count * 8);
-    k_row_stats<<<grid, MV_THREADS, 0, c->stream>>>(c->A + r0 * c->ld, c->ld, (int)rows, (int)c->n, c->vrowsum + c->row0 + r0, c->zero_count + c->row0 + r0);
+    k_row_stats<<<grid, MV_THREADS, 0, c->stream>>>(c->A + r0 * c->ld, c->ld, (int)rows, (int)c->n, c->vrowsum + c->row0 + r0, c->zero_count + c->row0 + r0,
+                                                      c->neg_flag + c->row0 + r0);
     CK(cudaGetLastError());
     return 0;
 }
@@ -755,6 +779,7 @@ extern "C" int gcx_map_upload_finish(gcx_ctx* c) {
     CKR(need_map(c));
     CKR(allgather_f64(c, c->vrowsum));
     CKR(allgather_i32(c, c->zero_count));
+    CKR(allgather_i32(c, c->neg_flag));
     c->have_rowsum = true;
     return 0;
 }
@@ -867,6 +892,30 @@ extern "C" int gcx_map_download_file(gcx_ctx* c, int which, const char* path, in
     munmap(map, (size_t)file_bytes);
     if (rc) cudaStreamSynchronize(c->stream);
     return rc;
+}
+
+// Device-resident twin of upload / download (SURVEY.md 8b "when data is already resident"): the map comes from / goes to memory of
+// THIS device owned by another producer (a torch tensor, an importer kernel) -- one device-to-device copy, no PCIe trip.
+extern "C" int gcx_map_adopt_device(gcx_ctx* c, const float* dev_rows, int64_t dev_ld) {
+    CKR(need_map(c));
+    CKR(fence_copy(c));
+    if (!dev_rows || dev_ld < c->n) return fail("gcx_map_adopt_device: bad pointer / pitch");
+    c->sym_state = -1; c->have_rowsum = false; c->have_scale = false;
+    CK(cudaMemcpy2DAsync(c->A, sizeof(float) * c->ld, dev_rows, sizeof(float) * dev_ld, sizeof(float) * (size_t)c->n, (size_t)c->nloc,
+                         cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gcx_map_export_device(gcx_ctx* c, int which, float* dev_rows, int64_t dev_ld) {
+    CKR(need_map(c));
+    const float* src = which == 0 ? c->A : (which == 2 ? c->Out2 : c->Out);
+    if (!src) return fail("no output map resident");
+    if (!dev_rows || dev_ld < c->n) return fail("gcx_map_export_device: bad pointer / pitch");
+    CK(cudaMemcpy2DAsync(dev_rows, sizeof(float) * dev_ld, src, sizeof(float) * c->ld, sizeof(float) * (size_t)c->n, (size_t)c->nloc,
+                         cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 extern "C" int gcx_map_download_async(gcx_ctx* c, int which, float* host, int64_t host_ld) {
@@ -1150,12 +1199,25 @@ static int run_row_stats(gcx_ctx* c) {
     if (c->have_rowsum) return 0;
     {
         ProfScope ps(c, 3);
-        k_row_stats<<<grid_rows(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, (int)c->n, c->vrowsum + c->row0, c->zero_count + c->row0);
+        k_row_stats<<<grid_rows(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, (int)c->n, c->vrowsum + c->row0, c->zero_count + c->row0,
+                                                                  c->neg_flag + c->row0);
     }
     CK(cudaGetLastError());
     CKR(allgather_f64(c, c->vrowsum));
     CKR(allgather_i32(c, c->zero_count));
+    CKR(allgather_i32(c, c->neg_flag));
     c->have_rowsum = true;
+    return 0;
+}
+
+/* 1 per row that holds negative entries (n int32; computed with gcx_row_stats): lib/ccmapHelpers.pyx:192 tests emptiness with a
+ * float32 sum, which only differs from "all entries zero" on such rows -- the caller re-checks them in NumPy's float32 arithmetic */
+extern "C" int gcx_row_negative_flags(gcx_ctx* c, int32_t* flags) {
+    CKR(need_map(c));
+    CKR(run_row_stats(c));
+    if (!flags) return fail("gcx_row_negative_flags: null output");
+    CK(cudaMemcpyAsync(flags, c->neg_flag, sizeof(int32_t) * c->n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -1388,7 +1450,7 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         CK(cudaMalloc(&c->sym_tab_i, sizeof(int) * ti.size()));
         CK(cudaMemcpy(c->sym_tab_ll, tll.data(), sizeof(long long) * tll.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->sym_tab_i, ti.data(), sizeof(int) * ti.size(), cudaMemcpyHostToDevice));
-        const size_t rp_bytes = sizeof(double) * (size_t)nch * SYM_NG * c->ld;
+        const size_t rp_bytes = sizeof(double) * (size_t)nch * c->ld;
         const size_t cp_bytes = sizeof(double) * (size_t)G * slots * SYM_NG * 1024;
         CK(cudaMalloc(&c->rowpart, rp_bytes));
         CK(cudaMalloc(&c->colpart, cp_bytes));
@@ -1405,7 +1467,7 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
             CK(cudaMemset(c->sym_stamps, 0, sizeof(long long) * 16 * (size_t)G));
             if (const char* e = getenv("GCX_SYM_DEBUG_LAUNCH")) c->sym_dbg_launch = atoi(e);
         }
-        // rowpart must start from zero: a (panel, band) is written by one consumer group only, the fold adds both
+        // rowpart must start from zero: (panel, row) pairs this rank never walks are read by the fold
         CK(cudaMemsetAsync(c->rowpart, 0, rp_bytes, c->stream));
         CK(cudaMemsetAsync(c->colpart, 0, cp_bytes, c->stream));
     }

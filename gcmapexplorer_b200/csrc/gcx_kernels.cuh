@@ -757,7 +757,8 @@ __device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, lo
                 double ssum = 0.0;
 #pragma unroll
                 for (int w = 0; w < WPG; ++w) ssum += gred[((par * NG + g) * WPG + w) * R + lane];
-                if (l0 + lane < nloc) rowpart[((long long)k * NG + g) * rp_ld + i0 + lane] = ssum;
+                // one partial per (panel, row): a band is walked by exactly one group, once per pass
+                if (l0 + lane < nloc) rowpart[(long long)k * rp_ld + i0 + lane] = ssum;
             }
         }
     }
@@ -830,7 +831,7 @@ __device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n4, con
             // entries of panels (or bands) this rank never walks keep their initial zero, so the loop may cover them
             const int kstart = T.kfold_lo < 0 ? ki : T.kfold_lo;
 #pragma unroll 4
-            for (int k = kstart + j / SYM_NG; k < nch; k += 8 / SYM_NG) s += __ldcg(rowpart + ((long long)k * SYM_NG + (j % SYM_NG)) * rp_ld + i);
+            for (int k = kstart + j; k < nch; k += 8) s += __ldcg(rowpart + (long long)k * rp_ld + i);
         }
         const int clo = T.panel_cta[ki], chi = T.panel_cta_hi[ki];
 #pragma unroll 2
@@ -874,7 +875,8 @@ __device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n4, con
 // partials (CTA, group) of the static shares; column partials (chunk, group) of the dynamic pool), loads them in batches of
 // FOLD_UN independent loads and adds them in a fixed order.  One round of the grid covers 16 x 2664 bins, so the vector phase
 // of a pass is a handful of L2 round trips instead of three latency-bound rounds.  Every lane of the group returns the sum.
-constexpr int FOLD_LPB = 2, FOLD_UN = 16;
+constexpr int FOLD_UN = 16;
+template <int FOLD_LPB>
 __device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const double* rowpart, const double* colpart, const SymTab& T) {
     const int j = threadIdx.x & (FOLD_LPB - 1);
     const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
@@ -887,8 +889,8 @@ __device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const 
         const double* rbase = rowpart;
         if (i >= T.row0 && i < T.row0 + T.nloc) {
             const int kstart = T.kfold_lo < 0 ? ki : T.kfold_lo;
-            n_row = (nch - kstart) * SYM_NG;
-            rbase = rowpart + (long long)kstart * SYM_NG * rp_ld + i;
+            n_row = nch - kstart;
+            rbase = rowpart + (long long)kstart * rp_ld + i;
         }
         const int clo = T.panel_cta[ki], chi = T.panel_cta_hi[ki];
         const int n_col = chi >= clo ? (chi - clo + 1) * SYM_NG : 0;
@@ -1004,14 +1006,14 @@ k_sym_hash(const float* __restrict__ A, long long ld, int nloc, int n, int row0,
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MV_THREADS)
 k_row_stats(const float* __restrict__ A, long long ld, int nloc, int n, double* __restrict__ rowsum,
-            int* __restrict__ zero_count) {
+            int* __restrict__ zero_count, int* __restrict__ neg_count = nullptr) {
     __shared__ double sm[32];
     const int n4 = (int)(ld / 4);
     const int pad = (int)ld - n;
     for (int r = blockIdx.x; r < nloc; r += gridDim.x) {
         const float4* rp = reinterpret_cast<const float4*>(A + (long long)r * ld);
         double s = 0.0;
-        int zc = 0;
+        int zc = 0, ng = 0;
         for (int c4 = threadIdx.x; c4 < n4; c4 += 4 * MV_THREADS) {
             float4 a[4];
 #pragma unroll
@@ -1025,11 +1027,16 @@ k_row_stats(const float* __restrict__ A, long long ld, int nloc, int n, double* 
                 if (cc < n4) {
                     s += ((double)a[k].x + (double)a[k].y) + ((double)a[k].z + (double)a[k].w);
                     zc += (a[k].x == 0.f) + (a[k].y == 0.f) + (a[k].z == 0.f) + (a[k].w == 0.f);
+                    ng += (a[k].x < 0.f) + (a[k].y < 0.f) + (a[k].z < 0.f) + (a[k].w < 0.f);
                 }
             }
         }
         const double S = block_reduce<RED_SUM>(s, sm);
         const double Z = block_reduce<RED_SUM>((double)zc, sm);   // exact: counts < 2^53
+        // rows with negative entries: the reference's emptiness test is a FLOAT32 sum (lib/ccmapHelpers.pyx:192), which can cancel to
+        // exactly 0 where the float64 sum does not; the host re-checks just those rows in NumPy's float32 arithmetic
+        const int any_neg = __syncthreads_or(ng);
+        if (neg_count != nullptr && threadIdx.x == 0) neg_count[r] = any_neg ? 1 : 0;
         if (threadIdx.x == 0) {
             rowsum[r] = S;
             // raw count of zeros among the n real columns; the host applies lib/ccmapHelpers.pyx:192-195
@@ -2449,6 +2456,74 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p
     return v;
 }
 
+// Vector phase of the deferred-scalar pass for one launch: [DIST: this rank's partial t' of every bin -> every rank's receive
+// buffer, per-CTA flags] fold, next vector u, partial sums.  LPB = lanes that share a bin.
+template <int LPB, bool DIST>
+__device__ __forceinline__ void symd_vector_phase(int n, int n4, long long nv, int L, const uint8_t* __restrict__ keep, double* tcur, const double* tm2,
+                                                  const double* tm3, const double* uprev, double* ucur, double* B, const double* rowpart,
+                                                  const double* colpart, const SymTab& T, IcState* st, const IcXchg& X, double beta, double phi,
+                                                  long long* stamps, double& s, double& c, double& l1, int& irr) {
+    constexpr int WPC = SYM_THREADS / 32, BPW = 32 / LPB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int par = L & 1;
+    if (DIST) {
+        // ---- P1a: this rank's partial t' of every bin -> all ranks' receive buffers ----
+        for (int q0 = 0; BPW * q0 < n; q0 += WPC * G) {
+            const int i = BPW * (q0 + warp * G + bid) + lane / LPB;
+            const double pi = sym_fold_mlp<LPB>(i, i < n, n4, rowpart, colpart, T);
+            if (i < n && (tid & (LPB - 1)) == 0) {
+                for (int q = 0; q < X.world; ++q) X.peer_recv[q][((long long)par * X.world + X.rank) * nv + i] = pi;
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (stamps != nullptr) stamps[12] = (long long)globaltimer_ns();
+        if (tid < X.world) {
+            const unsigned int want = X.seq0 + (unsigned int)L;
+            st_release_sys_u32(X.peer_flags[tid] + (long long)X.rank * G + bid, want);
+            const unsigned int* f = X.flags + (long long)tid * G + bid;
+            const unsigned long long t0 = globaltimer_ns();
+            while ((int)(ld_acquire_sys_u32(f) - want) < 0) {
+                if (globaltimer_ns() - t0 > 20000000000ull) {       // 20 s: a peer died -- fail instead of hanging the box
+                    st->error = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        if (stamps != nullptr) stamps[13] = (long long)globaltimer_ns();
+    }
+    // ---- P1: fold, next vector, partial sums ----
+    for (int q0 = 0; BPW * q0 < n; q0 += WPC * G) {
+        const int i = BPW * (q0 + warp * G + bid) + lane / LPB;
+        double tp = 0.0;
+        if (!DIST) tp = sym_fold_mlp<LPB>(i, i < n, n4, rowpart, colpart, T);
+        if (i < n && (tid & (LPB - 1)) == 0) {
+            if (DIST) {
+                for (int q = 0; q < X.world; ++q) tp += __ldcg(X.recv + ((long long)par * X.world + q) * nv + i);     // rank order
+            }
+            tcur[i] = tp;
+            double un = 0.0;
+            if (keep[i]) {
+                const double p = uprev[i] * tp;
+                s += p;
+                c += (p != 0.0) ? 1.0 : 0.0;
+                const bool ne = tp != 0.0;
+                un = ne ? 1.0 / tp : 0.0;
+                if (L >= 2 && ((tm2[i] != 0.0) != ne)) irr = 1;
+                if (L >= 3) {
+                    const double w = tm3[i];
+                    const double bn = (w != 0.0) ? beta * w : phi;       // f / v (:51-52); empty kept bin: f_1 ... f_m
+                    l1 += fabs(B[i] - bn);                               // :56
+                    B[i] = bn;
+                }
+            }
+            ucur[i] = un;
+        }
+    }
+}
+
 template <int STAGES, int OCC, bool DIST>
 __global__ void __launch_bounds__(SYM_THREADS, OCC)
 k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long long nv, const uint8_t* __restrict__ keep, double* tring,
@@ -2468,9 +2543,9 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, bid = blockIdx.x;
     const int L0 = st->matvecs;                       // products completed so far; the partials hold product L0-1
-    // vector phase: a warp takes 32 / FOLD_LPB consecutive bins and consecutive warp-loads go to consecutive CTAs, so bins that are
+    // vector phase: a warp takes 32 / LPB consecutive bins and consecutive warp-loads go to consecutive CTAs, so bins that are
     // expensive to fold (many column partials) are spread over the whole grid
-    constexpr int WPC = SYM_THREADS / 32, BPW = 32 / FOLD_LPB;
+    constexpr int WPC = SYM_THREADS / 32;
     const double tol = st->tol;
     const int max_iter = st->max_iter;
     float4* tiles = reinterpret_cast<float4*>(tma_smem);
@@ -2503,64 +2578,14 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
         double* tcur = tring + (long long)((L + 2) % 3) * nv;            // t'_{L-1}
         const double* tm2 = tring + (long long)((L + 1) % 3) * nv;       // t'_{L-2}
         const double* tm3 = tring + (long long)(L % 3) * nv;             // t'_{L-3} = 1 / u_{L-2}
-        const int par = L & 1;
-        if (DIST) {
-            // ---- P1a: this rank's partial t' of every bin -> all ranks' receive buffers ----
-            for (int q0 = 0; BPW * q0 < n; q0 += WPC * G) {
-                const int i = BPW * (q0 + warp * G + bid) + lane / FOLD_LPB;
-                const double pi = sym_fold_mlp(i, i < n, n4, rowpart, colpart, T);
-                if (i < n && (tid & (FOLD_LPB - 1)) == 0) {
-                    for (int q = 0; q < X.world; ++q) X.peer_recv[q][((long long)par * X.world + X.rank) * nv + i] = pi;
-                }
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (stamps != nullptr) stamps[12] = (long long)globaltimer_ns();
-            if (tid < X.world) {
-                const unsigned int want = X.seq0 + (unsigned int)L;
-                st_release_sys_u32(X.peer_flags[tid] + (long long)X.rank * G + bid, want);
-                const unsigned int* f = X.flags + (long long)tid * G + bid;
-                const unsigned long long t0 = globaltimer_ns();
-                while ((int)(ld_acquire_sys_u32(f) - want) < 0) {
-                    if (globaltimer_ns() - t0 > 20000000000ull) {       // 20 s: a peer died -- fail instead of hanging the box
-                        st->error = 1;
-                        break;
-                    }
-                }
-            }
-            __syncthreads();
-            if (stamps != nullptr) stamps[13] = (long long)globaltimer_ns();
-        }
-        // ---- P1: fold, next vector, partial sums ----
         double s = 0.0, c = 0.0, l1 = 0.0;
         int irr = 0;
-        for (int q0 = 0; BPW * q0 < n; q0 += WPC * G) {
-            const int i = BPW * (q0 + warp * G + bid) + lane / FOLD_LPB;
-            double tp = 0.0;
-            if (!DIST) tp = sym_fold_mlp(i, i < n, n4, rowpart, colpart, T);
-            if (i < n && (tid & (FOLD_LPB - 1)) == 0) {
-                if (DIST) {
-                    for (int q = 0; q < X.world; ++q) tp += __ldcg(X.recv + ((long long)par * X.world + q) * nv + i);     // rank order
-                }
-                tcur[i] = tp;
-                double un = 0.0;
-                if (keep[i]) {
-                    const double p = uprev[i] * tp;
-                    s += p;
-                    c += (p != 0.0) ? 1.0 : 0.0;
-                    const bool ne = tp != 0.0;
-                    un = ne ? 1.0 / tp : 0.0;
-                    if (L >= 2 && ((tm2[i] != 0.0) != ne)) irr = 1;
-                    if (L >= 3) {
-                        const double w = tm3[i];
-                        const double bn = (w != 0.0) ? beta * w : phi;       // f / v (:51-52); empty kept bin: f_1 ... f_m
-                        l1 += fabs(B[i] - bn);                               // :56
-                        B[i] = bn;
-                    }
-                }
-                ucur[i] = un;
-            }
-        }
+        // lanes per bin: 2 while one round of the grid covers the map (16 bins per warp, short source chains), 1 beyond that
+        // (32 bins per warp: half the rounds) -- the same choice on every rank (it depends on n only)
+        if (n <= 16 * WPC * G)
+            symd_vector_phase<2, DIST>(n, n4, nv, L, keep, tcur, tm2, tm3, uprev, ucur, B, rowpart, colpart, T, st, X, beta, phi, stamps, s, c, l1, irr);
+        else
+            symd_vector_phase<1, DIST>(n, n4, nv, L, keep, tcur, tm2, tm3, uprev, ucur, B, rowpart, colpart, T, st, X, beta, phi, stamps, s, c, l1, irr);
         if (irr) st->irregular = 1;
         if (stamps != nullptr) stamps[15] = (long long)globaltimer_ns();
         // one block reduction for the three sums (fixed tree)

@@ -120,6 +120,26 @@ class DeviceMap:
             raise ValueError(f"expected shape {(self.nloc, self.n)}, got {m.shape}")
         check(lib().gcx_map_upload(self._ctx, C.c_void_p(m.ctypes.data), m.strides[0] // 4))
 
+    # ---- device-resident twin: torch tensors (or any CUDA pointer) on this device ---------------------------------
+    def adopt_tensor(self, t):
+        """Make a float32 CUDA tensor [nloc, n] of this device the resident map: one device-to-device copy, no host trip."""
+        if not t.is_cuda or t.device.index != self.device or str(t.dtype) != "torch.float32" or tuple(t.shape) != (self.nloc, self.n) or t.stride(1) != 1:
+            raise ValueError("expected a float32 CUDA tensor [%d, %d] on device %d with unit column stride" % (self.nloc, self.n, self.device))
+        import torch
+        torch.cuda.current_stream(t.device).synchronize()
+        check(lib().gcx_map_adopt_device(self._ctx, C.c_void_p(t.data_ptr()), int(t.stride(0))))
+
+    def export_tensor(self, which=1, out=None):
+        """A result map as a float32 CUDA tensor of this device (device-to-device copy)."""
+        import torch
+        if out is None:
+            out = torch.empty((self.nloc, self.n), dtype=torch.float32, device=torch.device("cuda", self.device))
+        if not out.is_cuda or out.device.index != self.device or out.dtype != torch.float32 or tuple(out.shape) != (self.nloc, self.n) or out.stride(1) != 1:
+            raise ValueError("out must be a float32 CUDA tensor [nloc, n] on this device")
+        torch.cuda.current_stream(out.device).synchronize()
+        check(lib().gcx_map_export_device(self._ctx, int(which), C.c_void_p(out.data_ptr()), int(out.stride(0))))
+        return out
+
     def upload_rows(self, rows, row_begin, with_stats=True):
         """A chunk of the local row block (streaming sources: gzip / HDF5 readers); finish with upload_finish()."""
         m = _as_f32_matrix(rows)
@@ -195,6 +215,12 @@ class DeviceMap:
         zc = np.empty(self.n, dtype=np.int32)
         check(lib().gcx_row_stats(self._ctx, rs.ctypes.data_as(_lib._c_f64p), zc.ctypes.data_as(_lib._c_i32p)))
         return rs, zc
+
+    def row_negative_flags(self):
+        """int32[n], 1 where the row holds negative entries (their float32 emptiness test is re-checked on the host)."""
+        f = np.empty(self.n, dtype=np.int32)
+        check(lib().gcx_row_negative_flags(self._ctx, f.ctypes.data_as(_lib._c_i32p)))
+        return f
 
     def set_mask(self, keep):
         k = np.ascontiguousarray(np.asarray(keep, dtype=bool).astype(np.uint8))

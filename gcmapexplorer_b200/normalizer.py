@@ -53,6 +53,28 @@ def _upload(ccMapObj, vmin, vmax):
     return dm
 
 
+def _host_rows(ccMapObj, vmin=None, vmax=None, factor=None):
+    """Row i of the map as the device holds it (clamped / scaled), read from the CCMAP's own file -- only ever called for rows with
+    negative entries, whose float32 emptiness test (lib/ccmapHelpers.pyx:192) the host repeats in NumPy (ccmapHelpers.float32_empty_rows)."""
+    def row(i):
+        opened = ccMapObj.matrix is None
+        if opened:
+            ccMapObj.make_readable()
+        try:
+            r = np.array(ccMapObj.matrix[i], dtype=np.float32)
+        finally:
+            if opened:
+                ccMapObj.make_unreadable()
+        if vmin is not None:
+            r[r <= vmin] = 0.0
+        if vmax is not None:
+            r[r >= vmax] = 0.0
+        if factor is not None:
+            r = r * np.float32(factor)
+        return r
+    return row
+
+
 def _emit(dm, which, like, bNoData, minvalue, maxvalue):
     """New temporary CCMAP next to `like` (this package's CCMAP or the reference's, duck-typed), filled with the device result."""
     out = cmp.result_like(dm, which, like)
@@ -84,7 +106,7 @@ def normalizeCCMapByKR(ccMap, memory='RAM', tol=1e-12, outFile=None, vmin=None, 
         if memory not in ('RAM', 'HDD'):
             raise ValueError('This memory={0} is not is not understandable.. Please use \'RAM\' or \'HDD\'.'.format(memory))
         with _upload(ccMapObj, vmin, vmax) as dm:
-            keep = cmh.device_mask(dm, percentile_threshold_no_data, threshold_data_occup)     # :327
+            keep = cmh.device_mask(dm, percentile_threshold_no_data, threshold_data_occup, _host_rows(ccMapObj, vmin, vmax))     # :327
             dm.set_mask(keep)
             r = dm.kr(tol, delta, Delta)                                                       # :335-336
             mn, mx = dm.apply_sym(None, masked_mode=0, in_place=False)
@@ -118,7 +140,7 @@ def normalizeCCMapByIC(ccMap, tol=1e-4, vmin=None, vmax=None, outFile=None, iter
         with _upload(ccMapObj, vmin, vmax) as dm:
             rowsum, zc = dm.row_stats()
             if applyFilter:
-                keep = cmh.mask_from_row_stats(rowsum, zc, dm.n, percentile_threshold_no_data, threshold_data_occup)  # :588
+                keep = cmh.device_mask(dm, percentile_threshold_no_data, threshold_data_occup, _host_rows(ccMapObj, vmin, vmax))  # :588
                 solve_mask = keep
             else:
                 # :592-594 -- IC runs on the whole matrix; bNoData = columns that are entirely zero
@@ -156,10 +178,12 @@ def normalizeCCMapByMCFS(ccMap, stats='median', vmin=None, vmax=None, stype='o/e
     logger.info(' Median Contact Frequency Scaling is in process for {0}...'.format(_label(ccMapObj)))
     try:
         with _upload(ccMapObj, vmin, vmax) as dm:
+            factor = None
             if scaleUpInput:                                                                     # :832-834
                 toScale = util.locate_significant_digit_after_decimal(ccMapObj.minvalue) + 1
-                dm.scale(10 ** toScale)
-            keep = cmh.device_mask(dm, percentile_threshold_no_data, threshold_data_occup)       # :854-855
+                factor = 10 ** toScale
+                dm.scale(factor)
+            keep = cmh.device_mask(dm, percentile_threshold_no_data, threshold_data_occup, _host_rows(ccMapObj, vmin, vmax, factor))       # :854-855
             avg = dm.diag_stats(stats)                                                           # :858
             mn, mx = dm.diag_apply(None, subtract=(stype == 'o-e'), in_place=False)              # :860-864
             normCCMap = _emit(dm, 1, ccMapObj, ~keep, mn, mx)
@@ -186,7 +210,7 @@ def normalizeCCMapByVCNorm(ccMap, sqroot=False, vmin=None, vmax=None, outFile=No
     ccMapObj, ccmapType = cmp.checkCCMapObjectOrFile(ccMap, workDir=workDir, lazy_gz=True)
     try:
         with _upload(ccMapObj, vmin, vmax) as dm:
-            keep = cmh.device_mask(dm, percentile_threshold_no_data, threshold_data_occup)       # :1123
+            keep = cmh.device_mask(dm, percentile_threshold_no_data, threshold_data_occup, _host_rows(ccMapObj, vmin, vmax))       # :1123
             dm.set_mask(keep)
             mn, mx, csum = dm.vc(sqroot=sqroot, in_place=False)                                  # :1128
             normCCMap = _emit(dm, 1, ccMapObj, ~keep, mn, mx)

@@ -60,6 +60,10 @@ int gcx_map_upload_rows(gcx_ctx* ctx, const float* host_rows, int64_t host_ld, i
 int gcx_map_upload_finish(gcx_ctx* ctx);
 int gcx_map_upload_file(gcx_ctx* ctx, const char* path, int64_t file_offset, int with_stats);
 int gcx_map_download_file(gcx_ctx* ctx, int which, const char* path, int64_t file_offset);
+/* Device-resident twin: dev_rows points to memory of the context's device owned by the caller (another library's
+ * tensor, an importer kernel): nloc rows of n floats, row pitch dev_ld floats; one device-to-device copy, no host round trip. */
+int gcx_map_adopt_device(gcx_ctx* ctx, const float* dev_rows, int64_t dev_ld);
+int gcx_map_export_device(gcx_ctx* ctx, int which, float* dev_rows, int64_t dev_ld);
 /* asynchronous download into PINNED host memory on the context's copy stream: returns at once, overlaps with
  * kernels enqueued afterwards (e.g. the VC result streams out while IC iterates); gcx_download_wait blocks until
  * the last async download has landed.  Kernels that later overwrite the source buffer wait for it on the device. */
@@ -81,6 +85,10 @@ int gcx_map_swap(gcx_ctx* ctx);
  * integer work on n values and stay on the host (NumPy itself) so the mask is bit-exact. */
 int gcx_row_stats(gcx_ctx* ctx, double* rowsum /* n, may be NULL */, int32_t* zero_count /* n, may be NULL */);
 int gcx_set_mask(gcx_ctx* ctx, const uint8_t* keep /* n; 1 = bin takes part */);
+/* flags[n]: 1 where the row holds negative entries.  lib/ccmapHelpers.pyx:192 calls a row empty when its FLOAT32 sum is 0.0; on a
+ * non-negative map that is "all entries zero" = (rowsum == 0), on a signed map (o-e output, correlation map) the float32 sum of a
+ * row can cancel exactly where the float64 sum does not -- the caller re-checks the flagged rows with NumPy's float32 sum. */
+int gcx_row_negative_flags(gcx_ctx* ctx, int32_t* flags);
 
 /* ---- Iterative correction ---------------------------------------------------------------------
  * Replaces normalizeCore.performIterativeCorrection(matrix, tol, iteration) (lib/normalizeCore.pyx:34-60).

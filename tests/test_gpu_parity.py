@@ -454,6 +454,52 @@ def test_error_conventions(gx, caplog):
         nz.normalizeGCMapByIC("in.gcmap", "out.gcmap")        # HDF5 container: needs h5py at call time (absent here) / an existing file
 
 
+def test_signed_map_float32_emptiness_rule(gx):
+    """lib/ccmapHelpers.pyx:192 calls a row empty when its FLOAT32 sum is 0.0.  On a signed map (o-e output, correlation map) a
+    row can cancel in float32 but not in float64 (2^24 + 1 - 2^24): the reference masks it; so does the drop-in (the device flags rows
+    with negative entries, the host repeats NumPy's float32 sum on those); and a row that cancels exactly in both is masked too."""
+    from gcmapexplorer_b200 import ccmapHelpers as cmh
+    n = 64
+    A = onp.synth_map(n, seed=2, scale=50.0, empty_frac=0.0)
+    A[7, :] = 0; A[:, 7] = 0
+    A[7, 0], A[7, 8], A[7, 16] = 16777216.0, 1.0, -16777216.0         # NumPy's float32 sum (8 interleaved accumulators): 0.0 ; float64 sum: 1.0
+    A[9, :] = 0; A[:, 9] = 0
+    A[9, 4], A[9, 5] = 3.0, -3.0                                       # cancels exactly in any precision
+    exp = onp.get_nonzeros_index(A)                                    # NumPy float32 row sums, like the reference
+    assert not exp[7] and not exp[9]
+    got = cmh.get_nonzeros_index(A)
+    assert np.array_equal(got, exp)
+    with gx.DeviceMap.from_host(A) as dm:
+        rs, _ = dm.row_stats()
+        flags = dm.row_negative_flags()
+        assert rs[7] == 1.0 and flags[7] == 1 and flags[9] == 1 and flags.sum() == 2
+        assert np.array_equal(cmh.device_mask(dm, host_rows=lambda i: A[i]), exp)
+        assert cmh.device_mask(dm)[7]                                  # without the host copy the float64 rule stands (documented)
+
+
+def test_device_resident_twin_adopt_and_export(gx):
+    """when the map is already in HBM (a torch tensor) it is adopted / exported device to device -- same results as
+    the host route, no PCIe trip."""
+    import torch
+    n = 1500
+    A = onp.synth_map(n, seed=6)
+    t = torch.from_numpy(A).cuda()
+    with gx.DeviceMap(n) as dm, gx.DeviceMap.from_host(A) as ref:
+        dm.adopt_tensor(t)
+        assert dm.checksum(0) == ref.checksum(0)
+        keep = onp.get_nonzeros_index(A)
+        for d in (dm, ref):
+            d.set_mask(keep)
+            d.kr(1e-12, 0.1, 3.0)
+            d.apply_sym(None, masked_mode=0, in_place=False)
+        out = dm.export_tensor(1)
+        assert out.is_cuda and np.array_equal(out.cpu().numpy(), ref.download(1))
+        pitched = torch.zeros((n, n + 12), dtype=torch.float32, device="cuda")          # strided views work too
+        pitched[:, :n] = t
+        dm.adopt_tensor(pitched[:, :n])
+        assert dm.checksum(0) == ref.checksum(0)
+
+
 def test_hic_norm_vector_application(gx):
     """SURVEY.md 8f row N4, second half: the norm-vector arithmetic of the .hic importer (lib/hic2gcmap.py:82-98) on a resident map,
     bit-identical to the reference's per-record Python arithmetic incl. inf on zero norms and NaN vectors entries."""
@@ -785,7 +831,7 @@ def test_deferred_scalar_pass_matches_literal_order(gx, n):
         assert a["passes"] == b["passes"] and a["matvecs"] == b["matvecs"] == a["passes"] + 1
         assert a["products_launched"] == a["passes"] + 2 and b["products_launched"] == b["passes"] + 1
         np.testing.assert_allclose(a["bias"], b["bias"], rtol=1e-12)
-        assert abs(a["l1"] - b["l1"]) <= 1e-9 * b["l1"] + 1e-18
+        assert abs(a["l1"] - b["l1"]) <= 1e-7 * b["l1"] + 1e-18      # a sum of differences of nearly equal numbers: rounding is amplified
     assert res[(1, "cap")]["passes"] == 5 and res[(1, "cap0")]["passes"] == 2
 
 
