@@ -71,6 +71,7 @@ _PROTOS = {
     "gcx_transition_run": (C.c_int, [_ctx, C.c_int, _c_f32p, _c_f32p]),
     "gcx_corr_run": (C.c_int, [_ctx, C.c_int, C.c_double, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float]),
     "gcx_corr_matrix_f64": (C.c_int, [_ctx, _c_f64p, C.c_int64, C.c_int, C.c_double, C.c_int, _c_f64p]),
+    "gcx_debug_i8gemm": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "gcx_corr_last_route": (C.c_int, [_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gcx_stationary_run": (C.c_int, [_ctx, C.c_double, C.c_int, _c_f64p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "gcx_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_double]),

@@ -22,6 +22,7 @@
 
 #include "../../include/gcx_norm.h"
 #include "gcx_kernels.cuh"
+#include "gcx_i8gemm.cuh"
 
 using namespace gcx;
 
@@ -205,6 +206,8 @@ struct gcx_ctx {
     bool xchg_ipc[8] = {false};
     unsigned int xchg_seq = 1;   // flag value of the next run's launch 0 (same on every rank: SPMD call sequence)
     int ic_grid = 0, ic_grid_tma = 0;
+    int corr_own_gemm = 1;  // int8 slice / indicator products on this library's tcgen05 kernel (k_i8gemm_nt); 0: cublasGemmEx (option "corr_own_gemm", GCX_CORR_OWN_GEMM)
+    bool i8_ready = false;
     int corr_int_path = 1;  // variant 1: exact int8 slice products for Sx and Sxy when the map is integer-valued (option "corr_int_path")
     int corr_last_int = 0;
     int corr_variant = 1;   // correlation: 1 = bf16 tensor-core counts + DSYRK + DGEMM, 0 = three DGEMMs (GCX_CORR_VARIANT / option "corr_variant")
@@ -373,6 +376,7 @@ static int ctx_init(gcx_ctx* c, int device) {
     if (v) c->mv_variant = atoi(v);
     if (const char* sv = getenv("GCX_SD_VARIANT")) c->sd_variant = atoi(sv);
     if (const char* cv = getenv("GCX_CORR_VARIANT")) c->corr_variant = atoi(cv);
+    if (const char* cv = getenv("GCX_CORR_OWN_GEMM")) c->corr_own_gemm = atoi(cv);
     const char* sy = getenv("GCX_SYM");
     if (sy) c->sym_enable = atoi(sy);
     if (c->ic_fused != 2) c->sym_enable = c->sym_enable && (c->ic_fused != 1);   // the fused LDG pass has no symmetric twin
@@ -1165,6 +1169,7 @@ extern "C" int gcx_set_option(gcx_ctx* c, const char* key, double value) {
     else if (k == "sd_variant") c->sd_variant = (int)value;
     else if (k == "corr_variant") c->corr_variant = (int)value;
     else if (k == "corr_int_path") c->corr_int_path = (int)value;
+    else if (k == "corr_own_gemm") c->corr_own_gemm = (int)value;
     else return fail("gcx_set_option: unknown key '%s'", key);
     return 0;
 }
@@ -2559,7 +2564,7 @@ struct CorrBufs {
 
 static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
     const size_t mm = align256(sizeof(double) * (size_t)m * m), bv = align256(sizeof(double) * (size_t)m), bi = align256(sizeof(int) * (size_t)m);
-    const int64_t mb = round_up(m, 64);
+    const int64_t mb = round_up(m, 256);       // every tile of k_i8gemm_nt (128 x 256 x 128) is full; also satisfies cuBLAS' 64-element alignment
     const size_t bb = align256(sizeof(unsigned short) * (size_t)mb * mb);
     const size_t nn = std::max(mm, align256(sizeof(float) * (size_t)mb * mb));      // N (float64 m x m) doubles as Nf (float32 mb x mb)
     const size_t tt = align256(sizeof(int) * (size_t)mb * mb), b8 = align256((size_t)mb * mb);
@@ -2587,6 +2592,46 @@ static int corr_bufs(gcx_ctx* c, int64_t m, CorrBufs* B) {
     return 0;
 }
 
+// ---- this library's int8 tensor-core product: row-major T32 = L R^T on k_i8gemm_nt (tcgen05 + TMEM + TMA) ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode_tiled = nullptr;
+static int i8_tensor_map(CUtensorMap* tm, const signed char* base, int mb, int box_rows) {
+    if (!g_encode_tiled) {
+        std::lock_guard<std::mutex> lock(g_loader_mutex);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available in this driver");
+        g_encode_tiled = (PFN_encodeTiled)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)mb, (cuuint64_t)mb};          // innermost first: K (bytes), rows
+    const cuuint64_t strides[1] = {(cuuint64_t)mb};                        // bytes between rows
+    const cuuint32_t box[2] = {(cuuint32_t)I8_BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with status %d", (int)r);
+    return 0;
+}
+
+static int i8gemm_nt(gcx_ctx* c, const signed char* L, const signed char* R, int* T32, int mb, int symmetric) {
+    if (mb % I8_BN != 0) return fail("i8gemm_nt: the padded size %d is not a multiple of %d", mb, I8_BN);
+    if (!c->i8_ready) {
+        CK(cudaFuncSetAttribute(k_i8gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+        c->i8_ready = true;
+    }
+    CUtensorMap tmL, tmR;
+    CKR(i8_tensor_map(&tmL, L, mb, I8_BM));
+    CKR(i8_tensor_map(&tmR, R, mb, I8_BN));
+    {
+        ProfScope ps(c, 7);
+        k_i8gemm_nt<<<c->sm_count, I8_THREADS, I8_SMEM, c->stream>>>(tmL, tmR, T32, mb, symmetric);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // the three products and the row variances, from X0 / I.  corr_variant 1 (default): counts on the bf16 tensor cores + SYRK for
 // the symmetric sum; 0: three float64 GEMMs.  Returns which count buffer the epilogue must read.
 static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
@@ -2603,10 +2648,11 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
         };
         auto counts_int8 = [&]() -> int {   // the sliced routes have the int8 indicator at hand: same product at twice the rate, int32 counts
             const int i1 = 1, i0 = 0;
+            *counts_mode = 2;
+            if (c->corr_own_gemm) return i8gemm_nt(c, B.I8, B.I8, (int*)B.Nf, B.mb, 0);
             ProfScope ps(c, 7);
             BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &i1, B.I8, 3 /* CUDA_R_8I */, B.mb, B.I8, 3, B.mb, &i0, B.Nf,
                                10 /* CUDA_R_32I */, B.mb, 72 /* CUBLAS_COMPUTE_32I */, -1));
-            *counts_mode = 2;
             return 0;
         };
         // integer-valued map: Sx and Sxy from exact int8 slice products (int32 accumulation) instead of the float64 GEMM / SYRK
@@ -2631,6 +2677,7 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
             CK(cudaGetLastError());
             c->launches += 1;
             auto imma = [&](const signed char* L, const signed char* R) -> int {        // row-major T32 = L R^T
+                if (c->corr_own_gemm) return i8gemm_nt(c, L, R, B.T32, B.mb, 0);
                 ProfScope ps(c, 7);
                 return g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &ione, R, 3 /* CUDA_R_8I */, B.mb, L, 3, B.mb, &izero,
                                        B.T32, 10 /* CUDA_R_32I */, B.mb, 72 /* CUBLAS_COMPUTE_32I */, -1);
@@ -2687,7 +2734,9 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
                 c->launches += 1;
                 CKR(counts_int8());
                 for (int t = 0; t < K; ++t) {
-                    {
+                    if (c->corr_own_gemm) {
+                        CKR(i8gemm_nt(c, B.S8 + t * plane, B.I8, B.T32, B.mb, 0));
+                    } else {
                         ProfScope ps(c, 7);      // row-major T32 = S_t I^T
                         BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &ione, B.I8, 3 /* CUDA_R_8I */, B.mb,
                                            B.S8 + t * plane, 3, B.mb, &izero, B.T32, 10 /* CUDA_R_32I */, B.mb, 72 /* CUBLAS_COMPUTE_32I */, -1));
@@ -2709,7 +2758,9 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
                 bool first = true;
                 for (int a = 0; a < K; ++a)
                     for (int b = a; b < K; ++b) {
-                        {
+                        if (c->corr_own_gemm) {
+                            CKR(i8gemm_nt(c, B.S8 + a * plane, B.S8 + b * plane, B.T32, B.mb, 0));
+                        } else {
                             ProfScope ps(c, 7);      // row-major T32 = S_a S_b^T
                             BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &ione, B.S8 + b * plane, 3, B.mb,
                                                B.S8 + a * plane, 3, B.mb, &izero, B.T32, 10, B.mb, 72, -1));
@@ -2775,6 +2826,34 @@ extern "C" int gcx_corr_run(gcx_ctx* c, int has_mask, double maskvalue, int logs
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+/* measurement / test hook for the library's own int8 tensor-core product (k_i8gemm_nt): T = L R^T for host int8 matrices (mb x mb,
+ * row-major, mb a multiple of 256); T_host may be NULL (timing only); reps >= 1 launches, ms = mean device time of one */
+extern "C" int gcx_debug_i8gemm(gcx_ctx* c, const signed char* L, const signed char* R, int mb, int32_t* T_host, int symmetric, int reps, double* ms) {
+    if (!c) return fail("null context");
+    CKR(set_dev(c));
+    if (mb < I8_BN || mb % I8_BN) return fail("gcx_debug_i8gemm: mb must be a positive multiple of %d", I8_BN);
+    const size_t plane = (size_t)mb * mb;
+    CKR(ensure_scratch(c, align256(plane) * 2 + sizeof(int) * plane));
+    signed char* dL = (signed char*)c->scratch;
+    signed char* dR = dL + align256(plane);
+    int* dT = (int*)(dR + align256(plane));
+    if (L) CK(cudaMemcpyAsync(dL, L, plane, cudaMemcpyHostToDevice, c->stream));
+    else CK(cudaMemsetAsync(dL, 1, plane, c->stream));
+    if (R) CK(cudaMemcpyAsync(dR, R, plane, cudaMemcpyHostToDevice, c->stream));
+    else CK(cudaMemsetAsync(dR, 1, plane, c->stream));
+    CK(cudaMemsetAsync(dT, 0xff, sizeof(int) * plane, c->stream));
+    CKR(i8gemm_nt(c, dL, dR, dT, mb, symmetric));          // warm
+    CK(cudaEventRecord(c->run_a, c->stream));
+    for (int i = 0; i < std::max(1, reps); ++i) CKR(i8gemm_nt(c, dL, dR, dT, mb, symmetric));
+    CK(cudaEventRecord(c->run_b, c->stream));
+    if (T_host) CK(cudaMemcpyAsync(T_host, dT, sizeof(int) * plane, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, c->run_a, c->run_b));
+    if (ms) *ms = t / std::max(1, reps);
     return 0;
 }
 

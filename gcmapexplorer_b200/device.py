@@ -276,6 +276,19 @@ class DeviceMap:
         check(lib().gcx_corr_last_route(self._ctx, C.byref(a), C.byref(b)))
         return a.value, bool(b.value)
 
+    def i8gemm(self, L=None, R=None, mb=None, symmetric=False, reps=1, want_result=True):
+        """T = L R^T on the library's own int8 tensor-core kernel (test / measurement hook).  Returns (T int32 or None, ms per launch)."""
+        if L is not None:
+            L = np.ascontiguousarray(L, dtype=np.int8)
+            mb = L.shape[0]
+        if R is not None:
+            R = np.ascontiguousarray(R, dtype=np.int8)
+        T = np.empty((mb, mb), dtype=np.int32) if want_result else None
+        ms = C.c_double(0)
+        check(lib().gcx_debug_i8gemm(self._ctx, None if L is None else C.c_void_p(L.ctypes.data), None if R is None else C.c_void_p(R.ctypes.data), int(mb),
+                                     None if T is None else C.c_void_p(T.ctypes.data), int(bool(symmetric)), int(reps), C.byref(ms)))
+        return T, ms.value
+
     def corr_f64(self, in_array, maskvalue=None, covariance=False, out=None):
         """Correlation (or covariance) matrix of the rows of a square float64 array, float64 result
         (lib/_corrMatrixCore.pyx:49-146).  Needs no resident map."""

@@ -188,6 +188,12 @@ int gcx_corr_matrix_f64(gcx_ctx* ctx, const double* in, int64_t m, int has_mask,
  * slices > 0: integer-valued map, that many exact 7-bit int8 slices; slices < 0: float32-valued map, -slices exact slices with one
  * exponent per row; 0: float64 GEMM.  sxy_sliced: 1 when Sxy came from slice products too, 0 when it came from the float64 SYRK/GEMM. */
 int gcx_corr_last_route(gcx_ctx* ctx, int* slices, int* sxy_sliced);
+/* The int8 products of the correlation path run on this library's own tensor-core kernel (k_i8gemm_nt in csrc/gcx_i8gemm.cuh:
+ * tcgen05.mma kind::i8 with TMEM accumulators, TMA-staged 128-byte-swizzled tiles, 128 x 256 x 128 per stage; option
+ * "corr_own_gemm" = 0 routes them through cublasGemmEx instead, for cross-checks).  Test / measurement hook: T = L R^T for host
+ * int8 matrices mb x mb (row-major, mb a multiple of 256; NULL operands = all ones), T_host mb x mb int32 or NULL, mean device
+ * milliseconds of `reps` launches. */
+int gcx_debug_i8gemm(gcx_ctx* ctx, const signed char* L, const signed char* R, int mb, int32_t* T_host, int symmetric, int reps, double* ms);
 
 /* ---- multi-GPU (row-block sharding; one context per rank) ------------------------------------
  * nccl_unique_id: the 128-byte ncclUniqueId from gcx_dist_unique_id on rank 0, broadcast by the host
@@ -207,6 +213,7 @@ int gcx_corr_last_route(gcx_ctx* ctx, int* slices, int* sxy_sliced);
  *   "matvec_variant"     kernel variant for sweeps
  *   "sd_variant"         stationary distribution: 1 TMA-bulk transposed product (default), 0 per-thread loads
  *   "corr_variant"       correlation: 1 counts on the bf16 tensor cores + DSYRK + DGEMM (default), 0 three DGEMMs
+ *   "corr_own_gemm"      0/1  int8 products on the library's own tcgen05 kernel (default 1) or through cublasGemmEx (0)
  *   "corr_int_path"      0/1  variant 1 on an integer-valued map (raw counts): Sx and Sxy from exact 7-bit-slice products on the
  *                             int8 tensor cores (int32 accumulation) instead of the float64 GEMM / SYRK (default 1) */
 int gcx_set_option(gcx_ctx* ctx, const char* key, double value);
