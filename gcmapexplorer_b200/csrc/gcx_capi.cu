@@ -207,7 +207,8 @@ struct gcx_ctx {
     unsigned int xchg_seq = 1;   // flag value of the next run's launch 0 (same on every rank: SPMD call sequence)
     int ic_grid = 0, ic_grid_tma = 0;
     int corr_own_gemm = 1;  // int8 slice / indicator products on this library's tcgen05 kernel (k_i8gemm_nt); 0: cublasGemmEx (option "corr_own_gemm", GCX_CORR_OWN_GEMM)
-    bool i8_ready = false;
+    unsigned int i8_cfg_mask = 0;
+    bool selfvar_ready = false;
     int corr_int_path = 1;  // variant 1: exact int8 slice products for Sx and Sxy when the map is integer-valued (option "corr_int_path")
     int corr_last_int = 0;
     int corr_variant = 1;   // correlation: 1 = bf16 tensor-core counts + DSYRK + DGEMM, 0 = three DGEMMs (GCX_CORR_VARIANT / option "corr_variant")
@@ -2615,21 +2616,51 @@ static int i8_tensor_map(CUtensorMap* tm, const signed char* base, int mb, int b
     return 0;
 }
 
-static int i8gemm_nt(gcx_ctx* c, const signed char* L, const signed char* R, int* T32, int mb, int symmetric) {
-    if (mb % I8_BN != 0) return fail("i8gemm_nt: the padded size %d is not a multiple of %d", mb, I8_BN);
-    if (!c->i8_ready) {
-        CK(cudaFuncSetAttribute(k_i8gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-        c->i8_ready = true;
+template <int BN, int STAGES>
+static int i8gemm_launch(gcx_ctx* c, const signed char* L, const signed char* R, int* T32, int mb, int symmetric, unsigned int bit) {
+    constexpr int smem = i8_smem_bytes(BN, STAGES);
+    if (!(c->i8_cfg_mask & bit)) {
+        CK(cudaFuncSetAttribute(k_i8gemm_nt<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        c->i8_cfg_mask |= bit;
     }
     CUtensorMap tmL, tmR;
     CKR(i8_tensor_map(&tmL, L, mb, I8_BM));
-    CKR(i8_tensor_map(&tmR, R, mb, I8_BN));
+    CKR(i8_tensor_map(&tmR, R, mb, BN));
     {
         ProfScope ps(c, 7);
-        k_i8gemm_nt<<<c->sm_count, I8_THREADS, I8_SMEM, c->stream>>>(tmL, tmR, T32, mb, symmetric);
+        k_i8gemm_nt<BN, STAGES><<<c->sm_count, I8_THREADS, smem, c->stream>>>(tmL, tmR, T32, mb, symmetric);
     }
     CK(cudaGetLastError());
     return 0;
+}
+
+static int i8gemm_launch_pair(gcx_ctx* c, const signed char* L, const signed char* R, int* T32, int mb, int symmetric) {
+    if (!(c->i8_cfg_mask & 16u)) {
+        CK(cudaFuncSetAttribute(k_i8gemm_nt_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, I8P_SMEM));
+        c->i8_cfg_mask |= 16u;
+    }
+    CUtensorMap tmL, tmR;
+    CKR(i8_tensor_map(&tmL, L, mb, 128));
+    CKR(i8_tensor_map(&tmR, R, mb, 128));
+    {
+        ProfScope ps(c, 7);
+        k_i8gemm_nt_pair<<<c->sm_count & ~1, I8_THREADS, I8P_SMEM, c->stream>>>(tmL, tmR, T32, mb, symmetric);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int i8gemm_nt(gcx_ctx* c, const signed char* L, const signed char* R, int* T32, int mb, int symmetric) {
+    if (mb % 256 != 0) return fail("i8gemm_nt: the padded size %d is not a multiple of 256", mb);
+    // default: the CTA-pair kernel (cta_group::2, 256 x 256 tiles; 3.0-3.5 POP/s); 0: one CTA per 128 x 256 tile (2.7 POP/s); 1-3: sweeps
+    static const int variant = [] { const char* e = getenv("GCX_I8_VARIANT"); return e ? atoi(e) : 4; }();
+    switch (variant) {
+        case 4: return i8gemm_launch_pair(c, L, R, T32, mb, symmetric);
+        case 1: return i8gemm_launch<256, 3>(c, L, R, T32, mb, symmetric, 2u);
+        case 2: return i8gemm_launch<128, 6>(c, L, R, T32, mb, symmetric, 4u);
+        case 3: return i8gemm_launch<128, 4>(c, L, R, T32, mb, symmetric, 8u);
+        default: return i8gemm_launch<256, 4>(c, L, R, T32, mb, symmetric, 1u);
+    }
 }
 
 // the three products and the row variances, from X0 / I.  corr_variant 1 (default): counts on the bf16 tensor cores + SYRK for
@@ -2649,7 +2680,7 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
         auto counts_int8 = [&]() -> int {   // the sliced routes have the int8 indicator at hand: same product at twice the rate, int32 counts
             const int i1 = 1, i0 = 0;
             *counts_mode = 2;
-            if (c->corr_own_gemm) return i8gemm_nt(c, B.I8, B.I8, (int*)B.Nf, B.mb, 0);
+            if (c->corr_own_gemm) return i8gemm_nt(c, B.I8, B.I8, (int*)B.Nf, B.mb, 1);      // symmetric: the consumers read j <= i only
             ProfScope ps(c, 7);
             BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &i1, B.I8, 3 /* CUDA_R_8I */, B.mb, B.I8, 3, B.mb, &i0, B.Nf,
                                10 /* CUDA_R_32I */, B.mb, 72 /* CUBLAS_COMPUTE_32I */, -1));
@@ -2677,7 +2708,7 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
             CK(cudaGetLastError());
             c->launches += 1;
             auto imma = [&](const signed char* L, const signed char* R) -> int {        // row-major T32 = L R^T
-                if (c->corr_own_gemm) return i8gemm_nt(c, L, R, B.T32, B.mb, 0);
+                if (c->corr_own_gemm) return i8gemm_nt(c, L, R, B.T32, B.mb, L == R ? 1 : 0);     // S_a S_a^T: lower triangle only
                 ProfScope ps(c, 7);
                 return g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &ione, R, 3 /* CUDA_R_8I */, B.mb, L, 3, B.mb, &izero,
                                        B.T32, 10 /* CUDA_R_32I */, B.mb, 72 /* CUBLAS_COMPUTE_32I */, -1);
@@ -2759,7 +2790,7 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
                 for (int a = 0; a < K; ++a)
                     for (int b = a; b < K; ++b) {
                         if (c->corr_own_gemm) {
-                            CKR(i8gemm_nt(c, B.S8 + a * plane, B.S8 + b * plane, B.T32, B.mb, 0));
+                            CKR(i8gemm_nt(c, B.S8 + a * plane, B.S8 + b * plane, B.T32, B.mb, a == b ? 1 : 0));
                         } else {
                             ProfScope ps(c, 7);      // row-major T32 = S_a S_b^T
                             BK(g_cublas.GemmEx(c->blas, CUBLAS_OP_T_, CUBLAS_OP_N_, B.mb, B.mb, B.mb, &ione, B.S8 + b * plane, 3, B.mb,
@@ -2781,7 +2812,19 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
         CKR(gemm_nt(c, m, B.X0, B.I, B.Sx));
         CKR(gemm_nt(c, m, B.X0, B.X0, B.Sxy));
     }
-    k_corr_selfvar<<<(m + 127) / 128, 128, 0, c->stream>>>(B.X0, B.I, m, B.var);
+    {
+        static const int sv = [] { const char* e = getenv("GCX_CORR_SELFVAR"); return e ? atoi(e) : 1; }();
+        if (sv == 1) {
+            const int smem = SV_WARPS * SV_STAGES * 2 * 32 * SV_PITCH * (int)sizeof(double);
+            if (!c->selfvar_ready) {
+                CK(cudaFuncSetAttribute(k_corr_selfvar_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                c->selfvar_ready = true;
+            }
+            k_corr_selfvar_tiled<<<(m + SV_WARPS * 32 - 1) / (SV_WARPS * 32), SV_WARPS * 32, smem, c->stream>>>(B.X0, B.I, m, B.var);
+        } else {
+            k_corr_selfvar<<<(m + 127) / 128, 128, 0, c->stream>>>(B.X0, B.I, m, B.var);
+        }
+    }
     CK(cudaGetLastError());
     c->launches += 1;
     return 0;

@@ -500,6 +500,41 @@ def test_device_resident_twin_adopt_and_export(gx):
         assert dm.checksum(0) == ref.checksum(0)
 
 
+@pytest.mark.parametrize("mb", [256, 768])
+def test_own_int8_tensor_core_product_is_exact(gx, mb):
+    """k_i8gemm_nt (tcgen05 kind::i8, TMEM accumulators, TMA-staged swizzled tiles) against NumPy integer arithmetic: every entry
+    of T = L R^T exact, full int8 range, and the lower-triangle-only mode of a symmetric product."""
+    rng = np.random.default_rng(mb)
+    L = rng.integers(-128, 128, size=(mb, mb), dtype=np.int8)
+    R = rng.integers(-128, 128, size=(mb, mb), dtype=np.int8)
+    with gx.DeviceMap(8) as dm:
+        T, _ = dm.i8gemm(L, R)
+        assert np.array_equal(T, L.astype(np.int32) @ R.astype(np.int32).T)
+        S, _ = dm.i8gemm(L, L, symmetric=True)
+        il = np.tril_indices(mb)
+        assert np.array_equal(S[il], (L.astype(np.int32) @ L.astype(np.int32).T)[il])
+
+
+def test_correlation_own_product_equals_cublas_route(gx):
+    """The correlation matrix with the int8 products on the library's own kernel (default) is bit-identical to the cuBLAS route."""
+    n = 700
+    A = onp.synth_map(n, seed=12)
+    keep = onp.get_nonzeros_index(A)
+    outs = []
+    for own in (1, 0):
+        with gx.DeviceMap(n, options={"corr_own_gemm": own}) as dm:
+            dm.upload(A)
+            dm.set_mask(keep)
+            dm.corr(0.0)
+            outs.append((dm.download(1), dm.corr_last_route()))
+            dm.scale(0.37)                                   # float32-valued map: the per-row-exponent slices
+            dm.corr(0.0)
+            outs.append((dm.download(1), dm.corr_last_route()))
+    assert outs[0][1][0] > 0 and outs[1][1][0] < 0           # integer slices / float slices were taken
+    assert np.array_equal(outs[0][0], outs[2][0]) and np.array_equal(outs[1][0], outs[3][0])
+    assert outs[0][1] == outs[2][1] and outs[1][1] == outs[3][1]
+
+
 def test_hic_norm_vector_application(gx):
     """SURVEY.md 8f row N4, second half: the norm-vector arithmetic of the .hic importer (lib/hic2gcmap.py:82-98) on a resident map,
     bit-identical to the reference's per-record Python arithmetic incl. inf on zero norms and NaN vectors entries."""

@@ -18,8 +18,8 @@ with gx.DeviceMap(8) as dm:
             print("   rows with errors:", np.unique(idx[:, 0])[:10], "cols:", np.unique(idx[:, 1])[:10])
         T2, _ = dm.i8gemm(L, L, symmetric=True)
         e2 = L.astype(np.int32) @ L.astype(np.int32).T
-        iu = np.triu_indices(mb)
-        print("   symmetric (upper triangle): mismatches %d" % int((T2[iu] != e2[iu]).sum()), flush=True)
+        il = np.tril_indices(mb)
+        print("   symmetric (lower triangle): mismatches %d" % int((T2[il] != e2[il]).sum()), flush=True)
     for mb in (8192, 24832):
         _, ms = dm.i8gemm(None, None, mb=mb, reps=3, want_result=False)
         print("mb %5d: %.3f ms per product = %.2f POP/s (nominal int8 dense 4.5)" % (mb, ms, 2.0 * mb ** 3 / (ms * 1e-3) / 1e15), flush=True)
