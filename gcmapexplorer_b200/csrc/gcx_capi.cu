@@ -2634,7 +2634,7 @@ static int i8gemm_launch(gcx_ctx* c, const signed char* L, const signed char* R,
     return 0;
 }
 
-static int i8gemm_launch_pair(gcx_ctx* c, const signed char* L, const signed char* R, int* T32, int mb, int symmetric) {
+static int i8gemm_launch_pair(gcx_ctx* c, const signed char* L, const signed char* R, int* T32, int mb, int symmetric, const I8Epilogue& E) {
     if (!(c->i8_cfg_mask & 16u)) {
         CK(cudaFuncSetAttribute(k_i8gemm_nt_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, I8P_SMEM));
         c->i8_cfg_mask |= 16u;
@@ -2644,18 +2644,38 @@ static int i8gemm_launch_pair(gcx_ctx* c, const signed char* L, const signed cha
     CKR(i8_tensor_map(&tmR, R, mb, 128));
     {
         ProfScope ps(c, 7);
-        k_i8gemm_nt_pair<<<c->sm_count & ~1, I8_THREADS, I8P_SMEM, c->stream>>>(tmL, tmR, T32, mb, symmetric);
+        k_i8gemm_nt_pair<<<c->sm_count & ~1, I8_THREADS, I8P_SMEM, c->stream>>>(tmL, tmR, T32, mb, symmetric, E);
     }
     CK(cudaGetLastError());
     return 0;
 }
 
-static int i8gemm_nt(gcx_ctx* c, const signed char* L, const signed char* R, int* T32, int mb, int symmetric) {
-    if (mb % 256 != 0) return fail("i8gemm_nt: the padded size %d is not a multiple of 256", mb);
+static int i8_variant() {
     // default: the CTA-pair kernel (cta_group::2, 256 x 256 tiles; 3.0-3.5 POP/s); 0: one CTA per 128 x 256 tile (2.7 POP/s); 1-3: sweeps
     static const int variant = [] { const char* e = getenv("GCX_I8_VARIANT"); return e ? atoi(e) : 4; }();
-    switch (variant) {
-        case 4: return i8gemm_launch_pair(c, L, R, T32, mb, symmetric);
+    return variant;
+}
+
+// product with the accumulation fused into the epilogue (pair kernel only; the caller checks i8_variant() == 4)
+// The fused accumulation is correct (tests) but SLOWER today (72.8 ms vs 63.3 ms per correlation at n = 24,926): a thread owns one row of
+// the tile, so its float64 read-modify-writes touch 32 different rows per instruction (8 useful bytes per 32-byte sector) and the
+// epilogue stalls the MMA pipeline.  Off by default (GCX_I8_FUSED=1 enables it) until the epilogue stages the tile through shared
+// memory for coalesced row segments.
+static bool i8_fused_epilogue() {
+    static const bool on = [] { const char* e = getenv("GCX_I8_FUSED"); return e && atoi(e) != 0; }();
+    return on && i8_variant() == 4;
+}
+
+static int i8gemm_nt_fused(gcx_ctx* c, const signed char* L, const signed char* R, int mb, int symmetric, const I8Epilogue& E) {
+    if (mb % 256 != 0) return fail("i8gemm_nt: the padded size %d is not a multiple of 256", mb);
+    return i8gemm_launch_pair(c, L, R, nullptr, mb, symmetric, E);
+}
+
+static int i8gemm_nt(gcx_ctx* c, const signed char* L, const signed char* R, int* T32, int mb, int symmetric) {
+    if (mb % 256 != 0) return fail("i8gemm_nt: the padded size %d is not a multiple of 256", mb);
+    const I8Epilogue store{0, 0, nullptr, nullptr, 0, 0, 0};
+    switch (i8_variant()) {
+        case 4: return i8gemm_launch_pair(c, L, R, T32, mb, symmetric, store);
         case 1: return i8gemm_launch<256, 3>(c, L, R, T32, mb, symmetric, 2u);
         case 2: return i8gemm_launch<128, 6>(c, L, R, T32, mb, symmetric, 4u);
         case 3: return i8gemm_launch<128, 4>(c, L, R, T32, mb, symmetric, 8u);
@@ -2719,16 +2739,22 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
                 c->launches += 1;
                 return 0;
             };
-            const int st = imma(B.S8, B.I8);
+            const bool fused = c->corr_own_gemm && i8_fused_epilogue();      // accumulate in the product's epilogue: no int32 round trip
+            const int st = fused ? i8gemm_nt_fused(c, B.S8, B.I8, B.mb, 0, I8Epilogue{1, m, B.Sx, nullptr, 0, 1, 0}) : imma(B.S8, B.I8);
+            if (st != 0 && fused) return st;
             if (st != 0) {
                 ns = 0;                       // this cuBLAS build has no int8 path for the shape: float64 products from now on
                 c->corr_int_path = 0;
             } else {
-                CKR(accum(1.0, 1, B.Sx));
+                if (!fused) CKR(accum(1.0, 1, B.Sx));
                 CKR(counts_int8());
                 for (int t = 1; t < ns; ++t) {
-                    BK(imma(B.S8 + t * plane, B.I8));
-                    CKR(accum((double)(1ull << (7 * t)), 0, B.Sx));
+                    if (fused) {
+                        CKR(i8gemm_nt_fused(c, B.S8 + t * plane, B.I8, B.mb, 0, I8Epilogue{1, m, B.Sx, nullptr, -7 * t, 0, 0}));
+                    } else {
+                        BK(imma(B.S8 + t * plane, B.I8));
+                        CKR(accum((double)(1ull << (7 * t)), 0, B.Sx));
+                    }
                 }
                 // S_b S_a^T is the transpose of S_a S_b^T: multiply a <= b only, add T + T^T on the lower triangle (exponents all 0)
                 CK(cudaMemsetAsync(B.rhi, 0, sizeof(int) * (size_t)m, c->stream));
@@ -2736,10 +2762,15 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
                 bool first = true;
                 for (int a = 0; a < ns; ++a)
                     for (int b = a; b < ns; ++b) {
-                        BK(imma(B.S8 + a * plane, B.S8 + b * plane));
-                        k_corr_faccum_sxy<<<tg, 256, 0, c->stream>>>(B.T32, m, B.mb, B.rhi, -7 * (a + b), a != b, first ? 1 : 0, B.Sxy);
-                        CK(cudaGetLastError());
-                        c->launches += 1;
+                        if (fused && a == b) {
+                            // S_a S_a^T: lower triangle, accumulated into Sxy by the epilogue (k_corr_faccum_sxy with sym = 0)
+                            CKR(i8gemm_nt_fused(c, B.S8 + a * plane, B.S8 + a * plane, B.mb, 1, I8Epilogue{1, m, B.Sxy, B.rhi, -7 * (a + b), first ? 1 : 0, 1}));
+                        } else {
+                            BK(imma(B.S8 + a * plane, B.S8 + b * plane));
+                            k_corr_faccum_sxy<<<tg, 256, 0, c->stream>>>(B.T32, m, B.mb, B.rhi, -7 * (a + b), a != b, first ? 1 : 0, B.Sxy);
+                            CK(cudaGetLastError());
+                            c->launches += 1;
+                        }
                         first = false;
                     }
             }
@@ -2764,7 +2795,12 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
                 CK(cudaGetLastError());
                 c->launches += 1;
                 CKR(counts_int8());
+                const bool fusedf = c->corr_own_gemm && i8_fused_epilogue();
                 for (int t = 0; t < K; ++t) {
+                    if (fusedf) {          // Sx += 2^(rhi_i - 7 (t + 1)) S_t I^T in the product's epilogue
+                        CKR(i8gemm_nt_fused(c, B.S8 + t * plane, B.I8, B.mb, 0, I8Epilogue{1, m, B.Sx, B.rhi, 7 * (t + 1), t == 0 ? 1 : 0, 0}));
+                        continue;
+                    }
                     if (c->corr_own_gemm) {
                         CKR(i8gemm_nt(c, B.S8 + t * plane, B.I8, B.T32, B.mb, 0));
                     } else {
@@ -2789,6 +2825,11 @@ static int corr_core(gcx_ctx* c, int m, const CorrBufs& B, int* counts_mode) {
                 bool first = true;
                 for (int a = 0; a < K; ++a)
                     for (int b = a; b < K; ++b) {
+                        if (c->corr_own_gemm && i8_fused_epilogue() && a == b) {
+                            CKR(i8gemm_nt_fused(c, B.S8 + a * plane, B.S8 + a * plane, B.mb, 1, I8Epilogue{1, m, B.Sxy, B.rhi, 7 * (a + b + 2), first ? 1 : 0, 1}));
+                            first = false;
+                            continue;
+                        }
                         if (c->corr_own_gemm) {
                             CKR(i8gemm_nt(c, B.S8 + a * plane, B.S8 + b * plane, B.T32, B.mb, a == b ? 1 : 0));
                         } else {

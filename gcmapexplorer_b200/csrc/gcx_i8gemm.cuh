@@ -235,6 +235,17 @@ k_i8gemm_nt(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUt
 // multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive remotely (mapa) on
 // the leader's "accumulator drained" barrier.
 // ---------------------------------------------------------------------------------------------------
+// What the epilogue does with the int32 tile.  mode 0: store it (T, pitch mb).  mode 1: fused accumulation of the correlation path --
+// dst[i][j] (= | +=) ldexp((double) t_ij, rhi[i] + (col_exp ? rhi[j] : 0) - shift) for i, j < m (dst: float64 m x m; a symmetric product
+// only touches j <= i) -- the arithmetic of k_corr_accum32 / k_corr_faccum / k_corr_faccum_sxy(sym = 0) without the int32 round trip.
+struct I8Epilogue {
+    int mode;
+    int m;
+    double* dst;
+    const int* rhi;       // per-row exponents (nullptr: all zero)
+    int shift, first, col_exp;
+};
+
 constexpr int I8P_STAGES = 6;
 constexpr int I8P_STAGE_BYTES = 2 * 128 * I8_BK;            // 32 KB per CTA per k-block
 constexpr int I8P_SMEM = I8P_STAGES * I8P_STAGE_BYTES + 1024;
@@ -266,7 +277,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
-k_i8gemm_nt_pair(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR, int* __restrict__ T, int mb, int symmetric) {
+k_i8gemm_nt_pair(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR, int* __restrict__ T, int mb, int symmetric,
+                 I8Epilogue E) {
     extern __shared__ unsigned char i8_smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * I8P_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
@@ -379,9 +391,24 @@ k_i8gemm_nt_pair(const __grid_constant__ CUtensorMap tmL, const __grid_constant_
                     : "r"(taddr)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (E.mode == 0) {
 #pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    dst[c * 8 + v] = make_int4((int)r[4 * v], (int)r[4 * v + 1], (int)r[4 * v + 2], (int)r[4 * v + 3]);
+                    for (int v = 0; v < 8; ++v)
+                        dst[c * 8 + v] = make_int4((int)r[4 * v], (int)r[4 * v + 1], (int)r[4 * v + 2], (int)r[4 * v + 3]);
+                } else if (row < E.m) {
+                    const int j0 = nblk * 256 + c * 32;
+                    const int ei = (E.rhi != nullptr ? E.rhi[row] : 0) - E.shift;
+                    double* d = E.dst + (long long)row * E.m + j0;
+                    const int jend = min(32, (symmetric ? min(E.m, row + 1) : E.m) - j0);
+#pragma unroll
+                    for (int v = 0; v < 32; ++v) {
+                        if (v < jend) {
+                            const int e = ei + (E.col_exp ? E.rhi[j0 + v] : 0);
+                            const double val = ldexp((double)(int)r[v], e);
+                            d[v] = E.first ? val : d[v] + val;
+                        }
+                    }
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
