@@ -955,9 +955,14 @@ def run_corr(args):
         # exact 7-bit slices of X0 (integer map: plain digits; float32-valued map: one exponent per row): K products for Sx and, when Sxy is
         # sliced too, K (K + 1) / 2 for Sxy (pairs a <= b) -- all int8 x int8 -> int32 -- plus the bf16 counts product
         nprod = K + (K * (K + 1) // 2 if sxy_sliced else 0)
-        kind = "cublasGemmEx int8 x%d (%d seven-bit slices of X0: Sx%s) + bf16 x1 (N = I I^T)%s" % (
-            nprod, K, ", Sxy" if sxy_sliced else "", "" if sxy_sliced else " + cublasDsyrk (Sxy)")
-        ops, peak, unit = (nprod + 1) * 2.0 * mb ** 3, 4500.0, "TOP/s"
+        own = int(os.environ.get("GCX_CORR_OWN_GEMM", "1")) != 0
+        mb = (m + 255) // 256 * 256
+        engine = "k_i8gemm_nt_pair (this library's tcgen05 kind::i8 CTA-pair kernel)" if own else "cublasGemmEx int8"
+        kind = "%s x%d (%d seven-bit slices of X0: Sx%s; counts N = I I^T)%s" % (
+            engine, nprod + 1, K, ", Sxy" if sxy_sliced else "", "" if sxy_sliced else " + cublasDsyrk (Sxy)")
+        # symmetric products (counts, S_a S_a^T) only compute the lower-triangle tiles: count them as half
+        nsym = 1 + (K if sxy_sliced else 0)
+        ops, peak, unit = ((nprod + 1 - nsym) + 0.5 * nsym if own else (nprod + 1)) * 2.0 * mb ** 3, 4500.0, "TOP/s"
     line = {"metric": "correlation matrix time (s), chr1 @ 10 kb", "value": round(t, 4), "unit": "s", "n_gpus": 1, "steps": args.steps,
             "warmup": max(1, args.warmup), "ms_per_step": round(t * 1e3, 2), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if (variant != 1 or slices == 0) else "int8/int32 exact slice products, f64 accumulation and epilogue",
