@@ -1365,9 +1365,11 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         // GCX_SYM_POOL=1 (default): the LAST bands of every large full-width panel -- a bin's fold then adds a handful of chunk
         // partials whichever panel it lies in; =0: whole panels, largest first (round 1: the ~2000 bins of the pooled panels each
         // folded ~400 chunk partials and held the whole grid at the barrier, profiles/r02_phase_stamps.md).
-        int DYN_CHUNK = 32;
+        // defaults from the sweeps in profiles/r02_ic_variants_*.txt: 30 % of the units in guided chunks of 64 / 32 / 16 / 8 bands at
+        // chr1 @ 10 kb and above; smaller maps (fewer units per CTA) do better with 20 % in 32 / 16 / 8 / 4
+        int DYN_CHUNK = c->n >= 20000 ? 64 : 32;
         if (const char* e = getenv("GCX_SYM_DYN_CHUNK")) DYN_CHUNK = std::max(4, atoi(e));
-        double dyn_frac = 0.20;
+        double dyn_frac = c->n >= 20000 ? 0.30 : 0.20;
         if (const char* e = getenv("GCX_SYM_DYN")) dyn_frac = atof(e) / 100.0;
         int pool_mode = 1;
         if (const char* e = getenv("GCX_SYM_POOL")) pool_mode = atoi(e);
@@ -1396,18 +1398,42 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
                 pooled += pool_bands[k];
             }
         }
-        std::vector<int> dk, db0, dcnt, pdyn0((size_t)nch + 1, 0);
+        // Guided chunk sizes: most of the pool goes out in DYN_CHUNK-band chunks, the last part in chunks of a half, a quarter and an
+        // eighth of that, handed out LAST -- the chunk in flight when the pool runs dry bounds every CTA's idle time at the end of a
+        // pass (a 32-band chunk is ~23 us of one CTA's bandwidth; the per-CTA throughput varies +-15 % at random).
+        // GCX_SYM_GUIDED=0: equal chunks (round 1).
+        int guided = 1;
+        if (const char* e = getenv("GCX_SYM_GUIDED")) guided = atoi(e);
+        std::vector<int> dk, db0, dcnt, dorder, pdyn0((size_t)nch + 1, 0);
+        std::vector<std::vector<int>> by_class(4);
         for (int k = 0; k < nch; ++k) {
             pdyn0[k] = (int)dk.size();
             const long long stat = nbk[k] - pool_bands[k];
-            for (long long b = stat; b < nbk[k]; b += DYN_CHUNK) {
-                dk.push_back(k);
-                db0.push_back((int)b);
-                dcnt.push_back((int)std::min<long long>((long long)DYN_CHUNK, nbk[k] - b));
+            long long b = stat;
+            const long long pb = pool_bands[k];
+            // shares of this panel's pool per size class (bands): 60 % full chunks, then 22 % / 12 % / 6 % in halves
+            const double share[4] = {guided ? 0.60 : 1.0, 0.22, 0.12, 0.06};
+            long long class_end[4];
+            double acc = 0.0;
+            for (int cl = 0; cl < 4; ++cl) {
+                acc += share[cl];
+                class_end[cl] = cl == 3 || !guided ? nbk[k] : stat + (long long)(acc * (double)pb) / DYN_CHUNK * DYN_CHUNK;
+            }
+            for (int cl = 0; cl < 4 && b < nbk[k]; ++cl) {
+                const int size = std::max(4, DYN_CHUNK >> cl);
+                while (b < class_end[cl]) {
+                    const int cnt = (int)std::min<long long>((long long)size, class_end[cl] - b);
+                    by_class[cl].push_back((int)dk.size());
+                    dk.push_back(k);
+                    db0.push_back((int)b);
+                    dcnt.push_back(cnt);
+                    b += cnt;
+                }
             }
             pu[k + 1] = pu[k] + stat;
         }
         pdyn0[nch] = (int)dk.size();
+        for (int cl = 0; cl < 4; ++cl) dorder.insert(dorder.end(), by_class[cl].begin(), by_class[cl].end());     // hand-out order: large first
         const int ndyn = (int)dk.size();
         const long long U = pu[nch];
         if (U < G) return 0;          // tiny share: keep the dense pass
@@ -1451,6 +1477,7 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         ti.insert(ti.end(), db0.begin(), db0.end());
         ti.insert(ti.end(), dcnt.begin(), dcnt.end());
         ti.insert(ti.end(), pdyn0.begin(), pdyn0.end());
+        ti.insert(ti.end(), dorder.begin(), dorder.end());
         c->sym_ndyn = ndyn;
         CK(cudaMalloc(&c->sym_tab_ll, sizeof(long long) * tll.size()));
         CK(cudaMalloc(&c->sym_tab_i, sizeof(int) * ti.size()));
@@ -1501,6 +1528,7 @@ static SymTab sym_tab(gcx_ctx* c) {
     T.dyn_b0 = T.dyn_k + c->sym_ndyn;
     T.dyn_cnt = T.dyn_b0 + c->sym_ndyn;
     T.panel_dyn0 = T.dyn_cnt + c->sym_ndyn;
+    T.dyn_order = T.panel_dyn0 + nch + 1;
     T.colpart_dyn = c->colpart_dyn;
     T.dyn_counter = c->sym_dyn_counter;
     T.nslots = c->sym_slots;

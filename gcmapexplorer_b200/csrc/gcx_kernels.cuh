@@ -569,6 +569,7 @@ struct SymTab {
     const int* dyn_k;          // [ndyn] panel of the chunk
     const int* dyn_b0;         // [ndyn] first local band
     const int* dyn_cnt;        // [ndyn] number of bands
+    const int* dyn_order;      // [ndyn] hand-out order: ticket -> chunk (large chunks first, the small ones close the pass)
     const int* panel_dyn0;     // [nch + 1] first chunk of every panel
     double* colpart_dyn;       // [ndyn][NG][1024]
     unsigned int* dyn_counter; // zeroed by the host before every launch
@@ -583,7 +584,7 @@ enum { SYM_ALL = 0, SYM_BEGIN = 1, SYM_CONT = 2 };
 template <int NG, int STAGES, bool ZNC, int MODE = SYM_ALL>
 __device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, long long ld, int n4, const double* z, double* rowpart,
                                                  double* colslots, const SymTab& T, float4* tiles, uint64_t* full_bar, uint64_t* empty_bar,
-                                                 double* gred, long long u0, long long u1, int kfirst, int klast, bool single_panel) {
+                                                 double* gred, double* cred, long long u0, long long u1, int kfirst, int klast, bool single_panel) {
     // Walks the units [u0, u1).  Static share: unit numbers of the panel-major list (panel_u0 maps them to (panel, band)),
     // panels kfirst..klast, column partials to colslots[(panel - kfirst)][group].  Dynamic chunk (single_panel): the units are the
     // bands u0..u1-1 of panel kfirst.  Every thread of the CTA must call this; it starts and ends with a CTA-wide barrier.
@@ -665,14 +666,37 @@ __device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, lo
             zc[q][0] = za.x; zc[q][1] = za.y; zc[q][2] = zb.x; zc[q][3] = zb.y;
         }
     };
+    // Column partials leave the CTA as ONE vector per (share or chunk, panel): the groups g > 0 hand theirs to group 0 through shared
+    // memory (every group flushes the same panels in the same order, so the two consumer-wide barriers pair up), group 0 adds them
+    // in group order and stores -- half the partials for the next launch's fold to read.
     auto flush = [&](int kk) {
+        if (g > 0) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            double2* dst = reinterpret_cast<double2*>(colslots + ((size_t)(kk - kfirst) * NG + g) * 1024) + 2 * (q * TG + tig);
-            dst[0] = make_double2(cacc[q][0], cacc[q][1]);
-            dst[1] = make_double2(cacc[q][2], cacc[q][3]);
-            cacc[q][0] = cacc[q][1] = cacc[q][2] = cacc[q][3] = 0.0;
+            for (int q = 0; q < NQ; ++q) {
+                double2* st = reinterpret_cast<double2*>(cred + (size_t)(g - 1) * 1024) + 2 * (q * TG + tig);
+                st[0] = make_double2(cacc[q][0], cacc[q][1]);
+                st[1] = make_double2(cacc[q][2], cacc[q][3]);
+            }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(SYM_CW * 32) : "memory");
+        if (g == 0) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                double a0 = cacc[q][0], a1 = cacc[q][1], a2 = cacc[q][2], a3 = cacc[q][3];
+#pragma unroll
+                for (int gg = 1; gg < NG; ++gg) {
+                    const double2* ld2 = reinterpret_cast<const double2*>(cred + (size_t)(gg - 1) * 1024) + 2 * (q * TG + tig);
+                    const double2 x = ld2[0], y = ld2[1];
+                    a0 += x.x; a1 += x.y; a2 += y.x; a3 += y.y;
+                }
+                double2* dst = reinterpret_cast<double2*>(colslots + ((size_t)(kk - kfirst) * NG) * 1024) + 2 * (q * TG + tig);
+                dst[0] = make_double2(a0, a1);
+                dst[1] = make_double2(a2, a3);
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(SYM_CW * 32) : "memory");
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) cacc[q][0] = cacc[q][1] = cacc[q][2] = cacc[q][3] = 0.0;
     };
 #pragma unroll
     for (int q = 0; q < NQ; ++q) cacc[q][0] = cacc[q][1] = cacc[q][2] = cacc[q][3] = 0.0;
@@ -777,22 +801,22 @@ __device__ __forceinline__ void matvec_sym_range(const float* __restrict__ A, lo
 template <int NG, int STAGES, bool ZNC, bool BEGUN = false>
 __device__ __forceinline__ void matvec_sym_core(const float* __restrict__ A, long long ld, int n4, const double* z, double* rowpart,
                                                 double* colpart, const SymTab& T, float4* tiles, uint64_t* full_bar, uint64_t* empty_bar,
-                                                double* gred) {
+                                                double* gred, double* cred) {
     __shared__ int s_chunk;
     const long long c = blockIdx.x;
     const long long t_start = (T.dbg_cycles != nullptr && threadIdx.x == 0) ? clock64() : 0;
     matvec_sym_range<NG, STAGES, ZNC, BEGUN ? SYM_CONT : SYM_ALL>(A, ld, n4, z, rowpart, colpart + (size_t)c * T.nslots * NG * 1024, T, tiles, full_bar,
-                                                                  empty_bar, gred, T.cta_u0[c], T.cta_u0[c + 1], T.cta_kf[c], T.cta_kl[c], false);
+                                                                  empty_bar, gred, cred, T.cta_u0[c], T.cta_u0[c + 1], T.cta_kf[c], T.cta_kl[c], false);
     if (BEGUN && T.dbg_stamps != nullptr && threadIdx.x == 0 && T.dbg_stamps[c * 16 + 8] != 0) T.dbg_stamps[c * 16 + 5] = (long long)globaltimer_ns();
     int nchunks = 0;
     while (T.ndyn > 0) {
         if (threadIdx.x == 0) s_chunk = (int)atomicAdd(T.dyn_counter, 1u);
         __syncthreads();
-        const int ch = s_chunk;
-        if (ch >= T.ndyn) break;
+        if (s_chunk >= T.ndyn) break;
+        const int ch = T.dyn_order[s_chunk];
         const int k = T.dyn_k[ch], b0 = T.dyn_b0[ch], cnt = T.dyn_cnt[ch];
         // (the range function's leading barrier also protects s_chunk against the next fetch)
-        matvec_sym_range<NG, STAGES, ZNC>(A, ld, n4, z, rowpart, T.colpart_dyn + (size_t)ch * NG * 1024, T, tiles, full_bar, empty_bar, gred,
+        matvec_sym_range<NG, STAGES, ZNC>(A, ld, n4, z, rowpart, T.colpart_dyn + (size_t)ch * NG * 1024, T, tiles, full_bar, empty_bar, gred, cred,
                                           b0, b0 + cnt, k, k, true);
         ++nchunks;
     }
@@ -812,7 +836,8 @@ k_matvec_sym_tma(const float* __restrict__ A, long long ld, int n4, const double
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ double gred[2 * SYM_CW * SYM_R];
-    matvec_sym_core<SYM_NG, STAGES, true>(A, ld, n4, z, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred);
+    __shared__ __align__(16) double cred[(SYM_NG - 1) * 1024];       // column partials of the groups g > 0 on their way to group 0
+    matvec_sym_core<SYM_NG, STAGES, true>(A, ld, n4, z, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred, cred);
 }
 
 // This rank's contribution to t_i, computed by 8 cooperating lanes: lane j sums the row partials of consumer group
@@ -837,8 +862,7 @@ __device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n4, con
 #pragma unroll 2
         for (int c = clo + j; c <= chi; c += 8) {
             const double* cp = colpart + ((size_t)c * T.nslots + (ki - T.cta_kf[c])) * SYM_NG * 1024 + (i & 1023);
-#pragma unroll
-            for (int gg = 0; gg < SYM_NG; ++gg) s += __ldcg(cp + gg * 1024);
+            s += __ldcg(cp);            // the groups' partials were combined at the flush: slot 0 holds the CTA's sum
         }
         if (T.ndyn > 0) {
             // column partials of the dynamic chunks of panel ki, in chunk order; two independent chains (fixed order) keep
@@ -849,17 +873,10 @@ __device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n4, con
 #pragma unroll 2
             for (; ch + 8 < d1; ch += 16) {
                 const double* cp = T.colpart_dyn + (size_t)ch * SYM_NG * 1024 + (i & 1023);
-#pragma unroll
-                for (int gg = 0; gg < SYM_NG; ++gg) {
-                    s += __ldcg(cp + gg * 1024);
-                    s2 += __ldcg(cp + (size_t)8 * SYM_NG * 1024 + gg * 1024);
-                }
+                s += __ldcg(cp);
+                s2 += __ldcg(cp + (size_t)8 * SYM_NG * 1024);
             }
-            if (ch < d1) {
-                const double* cp = T.colpart_dyn + (size_t)ch * SYM_NG * 1024 + (i & 1023);
-#pragma unroll
-                for (int gg = 0; gg < SYM_NG; ++gg) s += __ldcg(cp + gg * 1024);
-            }
+            if (ch < d1) s += __ldcg(T.colpart_dyn + (size_t)ch * SYM_NG * 1024 + (i & 1023));
             s += s2;
         }
     }
@@ -893,7 +910,7 @@ __device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const 
             rbase = rowpart + (long long)kstart * rp_ld + i;
         }
         const int clo = T.panel_cta[ki], chi = T.panel_cta_hi[ki];
-        const int n_col = chi >= clo ? (chi - clo + 1) * SYM_NG : 0;
+        const int n_col = chi >= clo ? (chi - clo + 1) : 0;            // one combined partial per CTA (slot of group 0)
         // only the first CTA of a panel can have started its share in an earlier panel (shares are contiguous and ordered)
         const int slot_lo = n_col > 0 ? ki - T.cta_kf[clo] : 0;
         const double* cbase = colpart + (size_t)clo * T.nslots * SYM_NG * 1024 + col;
@@ -901,7 +918,7 @@ __device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const 
         const double* dbase = T.colpart_dyn;
         if (T.ndyn > 0) {
             const int d0 = T.panel_dyn0[ki];
-            n_dyn = (T.panel_dyn0[ki + 1] - d0) * SYM_NG;
+            n_dyn = T.panel_dyn0[ki + 1] - d0;
             dbase = T.colpart_dyn + (size_t)d0 * SYM_NG * 1024 + col;
         }
         const int n_rc = n_row + n_col, total = n_rc + n_dyn;
@@ -915,10 +932,10 @@ __device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const 
                 if (idx < n_row) {
                     p = rbase + (long long)idx * rp_ld;
                 } else if (idx < n_rc) {
-                    const int e = idx - n_row, cc = e / SYM_NG, gg = e % SYM_NG;
-                    p = cbase + (size_t)cc * cstride + ((size_t)(cc == 0 ? slot_lo : 0) * SYM_NG + gg) * 1024;
+                    const int cc = idx - n_row;
+                    p = cbase + (size_t)cc * cstride + (size_t)(cc == 0 ? slot_lo : 0) * SYM_NG * 1024;
                 } else if (idx < total) {
-                    p = dbase + (size_t)(idx - n_rc) * 1024;
+                    p = dbase + (size_t)(idx - n_rc) * SYM_NG * 1024;
                 }
                 v[u] = p != nullptr ? __ldcg(p) : 0.0;
             }
@@ -2324,6 +2341,7 @@ k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, cons
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ double sm[32];
     __shared__ double gred[2 * SYM_CW * SYM_R];
+    __shared__ __align__(16) double cred[(SYM_NG - 1) * 1024];       // column partials of the groups g > 0 on their way to group 0
     const int tid = threadIdx.x;
     const int G = gridDim.x, bid = blockIdx.x;
     const int m = st->matvecs;
@@ -2403,7 +2421,7 @@ k_ic_pass_sym_tma(const float* __restrict__ A, long long ld, int n, int n4, cons
         if (done) return;
     }
     // the previous launch's partials have been consumed by every CTA (grid barriers above, or m == 0)
-    matvec_sym_core<SYM_NG, STAGES, false>(A, ld, n4, v, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred);
+    matvec_sym_core<SYM_NG, STAGES, false>(A, ld, n4, v, rowpart, colpart, T, reinterpret_cast<float4*>(tma_smem), full_bar, empty_bar, gred, cred);
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(ticket, 1u) == (unsigned int)(G - 1)) {       // last CTA to issue its work: safe to bump the counter
@@ -2540,6 +2558,7 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ double sm[32];
     __shared__ double gred[2 * SYM_CW * SYM_R];
+    __shared__ __align__(16) double cred[(SYM_NG - 1) * 1024];       // column partials of the groups g > 0 on their way to group 0
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, bid = blockIdx.x;
     const int L0 = st->matvecs;                       // products completed so far; the partials hold product L0-1
@@ -2568,7 +2587,7 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
     }
     // ---- P0: barriers + the first tiles of this CTA's static share ----
     matvec_sym_range<SYM_NG, STAGES, false, SYM_BEGIN>(A, ld, n4, ucur, rowpart, colpart + (size_t)bid * T.nslots * SYM_NG * 1024, T, tiles, full_bar,
-                                                       empty_bar, gred, su0, su1, T.cta_kf[bid], T.cta_kl[bid], false);
+                                                       empty_bar, gred, cred, su0, su1, T.cta_kf[bid], T.cta_kl[bid], false);
     if (stamps != nullptr) stamps[1] = (long long)globaltimer_ns();
     if (it > 0) grid.sync();          // the previous pass's partials are complete (this replaces the kernel boundary)
     if (stamps != nullptr) stamps[14] = (long long)globaltimer_ns();
@@ -2641,7 +2660,7 @@ k_ic_pass_symd(const float* __restrict__ A, long long ld, int n, int n4, long lo
         }
     }
     if (stamps != nullptr) stamps[4] = (long long)globaltimer_ns();
-    matvec_sym_core<SYM_NG, STAGES, false, true>(A, ld, n4, ucur, rowpart, colpart, T, tiles, full_bar, empty_bar, gred);
+    matvec_sym_core<SYM_NG, STAGES, false, true>(A, ld, n4, ucur, rowpart, colpart, T, tiles, full_bar, empty_bar, gred, cred);
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(ticket, 1u) == (unsigned int)(G - 1)) {       // last CTA: every CTA is past its chunk fetches
