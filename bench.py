@@ -666,66 +666,27 @@ WG_25KB_BINS = [9971, 9728, 7921, 7647, 7237, 6845, 6366, 5855, 5649, 5422, 5401
 
 def run_mcfs_wg(args):
     """BASELINE configs[3]: distance-frequency (MCFS o/e) over the 24 whole-genome maps at 25 kb on one GPU.
-    Maps are device-generated and resident; a step = per-diagonal stats + apply for all 24 maps."""
+    Maps are device-generated and resident; a step = per-diagonal stats + apply for all 24 maps, each stage ONE grid over all maps
+    (gcx_mcfs_batch), one host thread."""
     from gcmapexplorer_b200 import device as gx
-    stats = args.mcfs_stats
-    maps = []
-    for k, n in enumerate(WG_25KB_BINS):
-        dm = gx.DeviceMap(n, device=int(os.environ.get("LOCAL_RANK", "0")))
-        dm.synth(seed=25000 + k, scale=200.0, alpha=1.0, empty_frac=0.01)
-        maps.append(dm)
     peak, peak_kind = measured_peak()
-
-    def one(dm):
-        dm.diag_stats(stats)
-        dm.diag_apply(None, subtract=False, in_place=False)
-
-    pool = None
-    if args.mcfs_threads > 1:
-        # the 24 maps are independent and every DeviceMap has its own context + stream; ctypes releases the GIL, so a few host
-        # threads keep several maps' (launch-latency-bound) kernels in flight at once
-        from concurrent.futures import ThreadPoolExecutor
-        pool = ThreadPoolExecutor(max_workers=args.mcfs_threads)
-
-    def step():
-        if pool is None:
-            for dm in maps:
-                one(dm)
-        else:
-            list(pool.map(one, maps))
-    for _ in range(args.warmup):
-        step()
-    for dm in maps:
-        dm.profile(True); dm.profile_read(True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    for dm in maps:
-        dm.sync()
-    sec = (time.perf_counter() - t0) / args.steps
-    red_ms = app_ms = 0.0
-    launches = 0
-    for dm in maps:
-        p = dm.profile_read(True)
-        red_ms += p["diag_reduce"]["ms"] / args.steps
-        app_ms += p["diag_apply"]["ms"] / args.steps
+    stats = args.mcfs_stats
+    sec = mcfs_section(gx, int(os.environ.get("LOCAL_RANK", "0")), stats, args.steps, args.warmup, peak)
     nn = float(sum(n * n for n in WG_25KB_BINS))
     traversals = 5 if stats == "median" else 1
     bytes_step = (2.0 * traversals + 8.0) * nn
     line = {"metric": "MCFS (distance-frequency o/e, stats=%s) throughput, whole genome @ 25 kb, 24 maps (algorithmic GB/s)" % stats,
-            "value": round(bytes_step / sec / 1e9, 1), "unit": "GB/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 stats / f32 storage",
-            "data": "synthetic (device-generated)", "config": {"workload": "24 maps, sum n^2*4 = %.3f GB" % (4 * nn / 1e9), "stats": stats, "host_threads": args.mcfs_threads},
-            "kernel_ms_per_step": {"diag_reduce": round(red_ms, 3), "diag_apply": round(app_ms, 3)},
-            "roofline": {"kernel": "k_diag_apply", "bound": "hbm", "achieved": round(8.0 * nn / (app_ms * 1e-3) / 1e9, 1), "peak": peak, "peak_kind": peak_kind,
-                         "unit": "GB/s", "frac": round(8.0 * nn / (app_ms * 1e-3) / 1e9 / peak, 4), "traffic": None}}
+            "value": sec["algorithmic_gbs"], "unit": "GB/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 stats / f32 storage",
+            "data": "synthetic (device-generated)", "config": {"workload": sec["workload"], "stats": stats, "host_threads": 1, "batched_launches": sec["batched_launches"]},
+            "roofline": {"kernel": "gcx_mcfs_batch (k_diag_hist_b x4 + k_diag_next_b + k_diag_apply_b)", "bound": "hbm", "achieved": sec["algorithmic_gbs"], "peak": peak,
+                         "peak_kind": peak_kind, "unit": "GB/s", "frac": sec["frac"], "traffic": None,
+                         "note": "whole step (all stages of all 24 maps) against the algorithmic bytes (2 n^2 per traversal of the lower triangle, 8 n^2 for the apply)"}}
     if not args.no_cpu_baseline:
         cpu = cpu_reference_sample_mcfs(stats, nn)
         cpu["value"] = round(bytes_step / cpu["seconds_per_step"] / 1e9, 4)
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
-    for dm in maps:
-        dm.close()
 
 
 def run_host_copy_floor(args):
