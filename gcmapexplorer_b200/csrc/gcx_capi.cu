@@ -186,6 +186,7 @@ struct gcx_ctx {
     int sym_ndyn = 0;
     int sym_blocks = 1;                   // sharded: circulant assignment of off-diagonal blocks (needs the aligned row partition)
     int sym_kfold_lo = -1;
+    int sym_nfoldk = 0;
     int assume_symmetric = 0;             // sharded runs cannot test symmetry locally: the caller vouches for it
     int exchange_allreduce = 0;           // custom (unequal) row partition: vectors are exchanged by zero-fill + allreduce
     int sym_slots = 0, sym_grid = 0;
@@ -1478,6 +1479,13 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         ti.insert(ti.end(), dcnt.begin(), dcnt.end());
         ti.insert(ti.end(), pdyn0.begin(), pdyn0.end());
         ti.insert(ti.end(), dorder.begin(), dorder.end());
+        // sharded: the row partials of a bin can only be non-zero in the panels this rank walks (about W/2 + 1 of W column blocks)
+        std::vector<int> foldk;
+        if (blocks)
+            for (int k = 0; k < nch; ++k)
+                if (nbk[k] > 0) foldk.push_back(k);
+        ti.insert(ti.end(), foldk.begin(), foldk.end());
+        c->sym_nfoldk = (int)foldk.size();
         c->sym_ndyn = ndyn;
         CK(cudaMalloc(&c->sym_tab_ll, sizeof(long long) * tll.size()));
         CK(cudaMalloc(&c->sym_tab_i, sizeof(int) * ti.size()));
@@ -1503,6 +1511,16 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         // rowpart must start from zero: (panel, row) pairs this rank never walks are read by the fold
         CK(cudaMemsetAsync(c->rowpart, 0, rp_bytes, c->stream));
         CK(cudaMemsetAsync(c->colpart, 0, cp_bytes, c->stream));
+        if (c->world > 1 && c->xchg_ok) {
+            // the sharded pass does not send the bins a rank never contributes to: the receive slots must hold zeros for THESE
+            // tables (they may differ from an earlier build's).  All ranks build together; the collective keeps any rank from
+            // starting a pass -- and storing into a peer -- before that peer's slots are cleared.
+            const size_t fb = xchg_flag_bytes(c);
+            CK(cudaMemsetAsync((char*)c->xchg_buf + fb, 0, sizeof(double) * 2 * (size_t)W * c->nv, c->stream));
+            CKR(ensure_scratch(c, 256));
+            CK(cudaMemsetAsync(c->scratch, 0, sizeof(int), c->stream));
+            NK(g_nccl.AllReduce(c->scratch, c->scratch, 1, ncclInt32, ncclSum, c->comm, c->stream));
+        }
     }
     *ok = true;
     return 0;
@@ -1529,6 +1547,8 @@ static SymTab sym_tab(gcx_ctx* c) {
     T.dyn_cnt = T.dyn_b0 + c->sym_ndyn;
     T.panel_dyn0 = T.dyn_cnt + c->sym_ndyn;
     T.dyn_order = T.panel_dyn0 + nch + 1;
+    T.fold_k = T.dyn_order + c->sym_ndyn;
+    T.n_fold_k = c->sym_nfoldk;
     T.colpart_dyn = c->colpart_dyn;
     T.dyn_counter = c->sym_dyn_counter;
     T.nslots = c->sym_slots;

@@ -558,6 +558,8 @@ struct SymTab {
     const int* panel_full;     // [nch] 1: the panel is an off-diagonal block assigned to this rank (every element counts for
                                //      the row AND the column part); 0: the rank's own diagonal region (j >= i / j > i rules)
     int kfold_lo;              // first panel with units on this rank (row-partial fold starts here)
+    const int* fold_k;         // sharded: the panels this rank walks (ascending) -- the only row partials that can be non-zero
+    int n_fold_k;              // 0: every panel from kfold_lo (or the bin's own panel) on
     long long* dbg_cycles;     // optional [G]: cycles every CTA spent in the main loop (GCX_SYM_DEBUG=1), else nullptr
     long long* dbg_stamps;     // optional [G][16]: globaltimer (ns) at the phases of launch dbg_launch of k_ic_pass_symd
     int dbg_launch;
@@ -894,7 +896,8 @@ __device__ __forceinline__ double sym_fold_group8(int i, bool valid, int n4, con
 // of a pass is a handful of L2 round trips instead of three latency-bound rounds.  Every lane of the group returns the sum.
 constexpr int FOLD_UN = 16;
 template <int FOLD_LPB>
-__device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const double* rowpart, const double* colpart, const SymTab& T) {
+__device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const double* rowpart, const double* colpart, const SymTab& T,
+                                               bool* has_sources = nullptr) {
     const int j = threadIdx.x & (FOLD_LPB - 1);
     const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
     const long long rp_ld = (long long)n4 * 4;
@@ -904,10 +907,11 @@ __device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const 
         // the three source lists, flattened into one index range so that every batch of loads is full
         int n_row = 0;
         const double* rbase = rowpart;
+        const bool listed = T.n_fold_k > 0;
         if (i >= T.row0 && i < T.row0 + T.nloc) {
             const int kstart = T.kfold_lo < 0 ? ki : T.kfold_lo;
-            n_row = nch - kstart;
-            rbase = rowpart + (long long)kstart * rp_ld + i;
+            n_row = listed ? T.n_fold_k : nch - kstart;
+            rbase = rowpart + (long long)(listed ? 0 : kstart) * rp_ld + i;
         }
         const int clo = T.panel_cta[ki], chi = T.panel_cta_hi[ki];
         const int n_col = chi >= clo ? (chi - clo + 1) : 0;            // one combined partial per CTA (slot of group 0)
@@ -922,6 +926,7 @@ __device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const 
             dbase = T.colpart_dyn + (size_t)d0 * SYM_NG * 1024 + col;
         }
         const int n_rc = n_row + n_col, total = n_rc + n_dyn;
+        if (has_sources != nullptr) *has_sources = total > 0;        // a static property of (rank, bin): the same in every pass
         const size_t cstride = (size_t)T.nslots * SYM_NG * 1024;
         for (int q = j; q < total; q += FOLD_LPB * FOLD_UN) {
             double v[FOLD_UN];
@@ -930,7 +935,7 @@ __device__ __forceinline__ double sym_fold_mlp(int i, bool valid, int n4, const 
                 const int idx = q + u * FOLD_LPB;
                 const double* p = nullptr;
                 if (idx < n_row) {
-                    p = rbase + (long long)idx * rp_ld;
+                    p = rbase + (long long)(listed ? T.fold_k[idx] : idx) * rp_ld;
                 } else if (idx < n_rc) {
                     const int cc = idx - n_row;
                     p = cbase + (size_t)cc * cstride + (size_t)(cc == 0 ? slot_lo : 0) * SYM_NG * 1024;
@@ -2489,8 +2494,11 @@ __device__ __forceinline__ void symd_vector_phase(int n, int n4, long long nv, i
         // ---- P1a: this rank's partial t' of every bin -> all ranks' receive buffers ----
         for (int q0 = 0; BPW * q0 < n; q0 += WPC * G) {
             const int i = BPW * (q0 + warp * G + bid) + lane / LPB;
-            const double pi = sym_fold_mlp<LPB>(i, i < n, n4, rowpart, colpart, T);
-            if (i < n && (tid & (LPB - 1)) == 0) {
+            bool mine = false;
+            const double pi = sym_fold_mlp<LPB>(i, i < n, n4, rowpart, colpart, T, &mine);
+            // bins this rank never contributes to (columns of blocks it does not walk, outside its own rows) are not sent: the
+            // peers' slots for them keep the zeros they were created with
+            if (i < n && mine && (tid & (LPB - 1)) == 0) {
                 for (int q = 0; q < X.world; ++q) X.peer_recv[q][((long long)par * X.world + X.rank) * nv + i] = pi;
             }
         }
@@ -2519,7 +2527,12 @@ __device__ __forceinline__ void symd_vector_phase(int n, int n4, long long nv, i
         if (!DIST) tp = sym_fold_mlp<LPB>(i, i < n, n4, rowpart, colpart, T);
         if (i < n && (tid & (LPB - 1)) == 0) {
             if (DIST) {
-                for (int q = 0; q < X.world; ++q) tp += __ldcg(X.recv + ((long long)par * X.world + q) * nv + i);     // rank order
+                double r[XCHG_MAX_WORLD];
+#pragma unroll
+                for (int q = 0; q < XCHG_MAX_WORLD; ++q)                  // independent loads, then the sum in rank order
+                    r[q] = q < X.world ? __ldcg(X.recv + ((long long)par * X.world + q) * nv + i) : 0.0;
+#pragma unroll
+                for (int q = 0; q < XCHG_MAX_WORLD; ++q) tp += r[q];
             }
             tcur[i] = tp;
             double un = 0.0;
