@@ -160,6 +160,7 @@ struct gcx_ctx {
     // vectors (float64, nv each) carved from one slab
     double* slab = nullptr;
     double *vz = nullptr, *vq = nullptr, *vB = nullptr, *vscale = nullptr, *vrowsum = nullptr, *vavg = nullptr;
+    double2* vavr = nullptr;             // (vavg, 1 / vavg) per distance, rebuilt before every distance-frequency apply
     KrVecs kr{};
     float* csum32 = nullptr;
     int32_t* zero_count = nullptr;
@@ -559,6 +560,8 @@ static int map_alloc(gcx_ctx* c, int64_t n, int64_t row0, int64_t nloc) {
     c->vz = take(); c->vq = take(); c->vB = take(); c->vscale = take(); c->vrowsum = take(); c->vavg = take();
     c->kr.x = take(); c->kr.v = take(); c->kr.rk = take(); c->kr.y = take(); c->kr.Z = take(); c->kr.p = take(); c->kr.w = take();
     c->kr.z = c->vz;
+    c->vavr = reinterpret_cast<double2*>(take());      // two slots
+    take();
     CK(cudaMalloc(&c->csum32, sizeof(float) * (size_t)c->nv));
     CK(cudaMemsetAsync(c->csum32, 0, sizeof(float) * (size_t)c->nv, c->stream));
     CK(cudaMalloc(&c->zero_count, sizeof(int32_t) * (size_t)c->nv));
@@ -2047,6 +2050,10 @@ static dim3 diag_grid(gcx_ctx* c) {
     return dim3((unsigned)((c->n + MV_THREADS - 1) / MV_THREADS), (unsigned)((c->nloc + DIAG_RB - 1) / DIAG_RB));
 }
 
+static dim3 diag_hist_grid(gcx_ctx* c) {
+    return dim3((unsigned)((c->n + MV_THREADS - 1) / MV_THREADS), (unsigned)((c->nloc + DIAG_HB - 1) / DIAG_HB));
+}
+
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 static int diag_mean(gcx_ctx* c) {
@@ -2074,29 +2081,33 @@ static int diag_mean(gcx_ctx* c) {
 
 static int diag_median(gcx_ctx* c) {
     const int n = (int)c->n;
-    const size_t b_hist = align256(sizeof(unsigned int) * 256 * (size_t)n), b_small = align256(sizeof(unsigned int) * 5 * (size_t)n);
+    const size_t b_hist = align256(sizeof(unsigned int) * DIAG_NBIN * (size_t)n),
+                 b_small = align256(sizeof(unsigned int) * (DIAG_SEL_ARRAYS * (size_t)n + 1));
     CKR(ensure_scratch(c, b_hist + b_small));
     DiagSel S{};
-    S.hist = (unsigned int*)c->scratch;
-    unsigned int* small = (unsigned int*)((char*)c->scratch + b_hist);     // prefix, krem, cnt, need, next
-    S.prefix = small; S.krem = small + n; S.cnt = small + 2 * (size_t)n; S.need = small + 3 * (size_t)n; S.next = small + 4 * (size_t)n;
+    unsigned int* small = (unsigned int*)((char*)c->scratch + b_hist);     // prefix, krem, cnt, need, next, nbp, dirty, done | pending
+    diag_sel_bind(S, (unsigned int*)c->scratch, small, (size_t)n, small + DIAG_SEL_ARRAYS * (size_t)n);
     CK(cudaMemsetAsync(c->scratch, 0, b_hist + b_small, c->stream));
+    const int sel_grid = (int)(((long long)n * 32 + MV_THREADS - 1) / MV_THREADS);
     for (int pass = 0; pass < 4; ++pass) {
         {
             ProfScope ps(c, 4);
-            k_diag_hist<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, pass, S);
+            const dim3 g = diag_hist_grid(c);
+            if (pass == 0) k_diag_hist<0><<<g, MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, S);
+            else if (pass == 1) k_diag_hist<1><<<g, MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, S);
+            else if (pass == 2) k_diag_hist<2><<<g, MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, S);
+            else k_diag_hist<3><<<g, MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, S);
         }
         CK(cudaGetLastError());
-        if (c->world > 1) NK(g_nccl.AllReduce(S.hist, S.hist, 256 * (size_t)n, ncclUint32, ncclSum, c->comm, c->stream));
-        k_diag_select<<<(int)(((long long)n * 32 + MV_THREADS - 1) / MV_THREADS), MV_THREADS, 0, c->stream>>>(n, pass, S);
+        if (c->world > 1) {
+            // sharded: the histograms add up over the ranks; every rank then makes the same selection
+            NK(g_nccl.AllReduce(S.hist, S.hist, DIAG_NBIN * (size_t)n, ncclUint32, ncclSum, c->comm, c->stream));
+            if (pass == 1) NK(g_nccl.AllReduce(S.dirty, S.dirty, (size_t)n, ncclUint32, ncclMax, c->comm, c->stream));
+        }
+        k_diag_select<<<sel_grid, MV_THREADS, 0, c->stream>>>(n, pass, S);
         CK(cudaGetLastError());
         c->launches += 1;
     }
-    {
-        ProfScope ps(c, 4);
-        k_diag_next<<<diag_grid(c), MV_THREADS, 0, c->stream>>>(c->A, c->ld, (int)c->nloc, n, (int)c->row0, S);
-    }
-    CK(cudaGetLastError());
     if (c->world > 1) NK(g_nccl.AllReduce(S.next, S.next, (size_t)n, ncclUint32, ncclMin, c->comm, c->stream));
     k_diag_median_final<<<(n + 255) / 256, 256, 0, c->stream>>>(n, S, c->vavg);
     CK(cudaGetLastError());
@@ -2125,7 +2136,8 @@ extern "C" int gcx_diag_apply(gcx_ctx* c, const double* avg, int subtract, int i
     CKR(mm_begin(c));
     {
         ProfScope ps(c, 5);
-        EW_DISPATCH(k_diag_apply, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->vavg, subtract, c->mm)
+        k_diag_recip<<<(int)((c->n + 255) / 256), 256, 0, c->stream>>>((int)c->n, c->vavg, c->vavr);
+        EW_DISPATCH(k_diag_apply, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->vavr, subtract, c->mm)
     }
     CK(cudaGetLastError());
     if (in_place) { c->have_rowsum = false; c->sym_state = -1; }
@@ -2135,6 +2147,13 @@ extern "C" int gcx_diag_apply(gcx_ctx* c, const double* avg, int subtract, int i
 // ---------------------------------------------------------------------------------------------------
 // batched distance-frequency normalization over many resident maps (one grid per stage for the whole set)
 // ---------------------------------------------------------------------------------------------------
+static void launch_diag_hist_b(int pass, unsigned grid, cudaStream_t st, const BMap* dt, int count, int nblocks) {
+    if (pass == 0) k_diag_hist_b<0><<<grid, MV_THREADS, 0, st>>>(dt, count, nblocks);
+    else if (pass == 1) k_diag_hist_b<1><<<grid, MV_THREADS, 0, st>>>(dt, count, nblocks);
+    else if (pass == 2) k_diag_hist_b<2><<<grid, MV_THREADS, 0, st>>>(dt, count, nblocks);
+    else k_diag_hist_b<3><<<grid, MV_THREADS, 0, st>>>(dt, count, nblocks);
+}
+
 extern "C" int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtract, float* minv, float* maxv) {
     if (!ctxs || count < 1) return fail("gcx_mcfs_batch: no maps");
     if (count > 120) return fail("gcx_mcfs_batch: at most 120 maps per call");
@@ -2151,7 +2170,9 @@ extern "C" int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtrac
     size_t off = align256(sizeof(BMap) * (size_t)count), zero_from = off;
     std::vector<size_t> o_hist((size_t)count), o_small((size_t)count), o_psum((size_t)count), o_pcnt((size_t)count), o_sc((size_t)count);
     long long blk = 0, sel = 0, red = 0, fin = 0, units = 0;
-    constexpr int R = 4;
+    int apply_variant = 3;                   // rows per unit / CTAs per SM of the batched apply: 0 = 4 / 4, 1 = 8 / 3, 2 = 8 / 2
+    if (const char* e = getenv("GCX_DIAG_APPLY_VARIANT")) apply_variant = atoi(e);
+    const int R = (apply_variant == 0 || apply_variant == 3) ? 4 : 8;       // 3, 4: lane-strided columns, 4 / 4 and 8 / 3
     for (int m = 0; m < count; ++m) {
         gcx_ctx* c = ctxs[m];
         const int n = (int)c->n;
@@ -2159,7 +2180,7 @@ extern "C" int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtrac
         memset(&M, 0, sizeof M);
         M.ld = c->ld; M.n = n;
         M.gx = (n + MV_THREADS - 1) / MV_THREADS;
-        M.gy = (n + DIAG_RB - 1) / DIAG_RB;
+        M.gy = median ? (n + DIAG_HB - 1) / DIAG_HB : (n + DIAG_RB - 1) / DIAG_RB;      // row bands of the histogram / the mean-partial grid
         M.blk0 = (int)blk; M.sel0 = (int)sel; M.red0 = (int)red; M.fin0 = (int)fin; M.u0 = units;
         blk += (long long)M.gx * M.gy;
         sel += ((long long)n * 32 + MV_THREADS - 1) / MV_THREADS;
@@ -2167,8 +2188,8 @@ extern "C" int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtrac
         fin += (n + 255) / 256;
         units += (long long)((n + R - 1) / R) * (((int)(c->ld / 4) + MV_THREADS - 1) / MV_THREADS);
         if (median) {
-            o_hist[m] = off; off += align256(sizeof(unsigned int) * 256 * (size_t)n);
-            o_small[m] = off; off += align256(sizeof(unsigned int) * 5 * (size_t)n);
+            o_hist[m] = off; off += align256(sizeof(unsigned int) * DIAG_NBIN * (size_t)n);
+            o_small[m] = off; off += align256(sizeof(unsigned int) * DIAG_SEL_ARRAYS * (size_t)n);
         } else {
             o_psum[m] = off; off += align256(sizeof(double) * (size_t)M.gy * n);
             o_pcnt[m] = off; off += align256(sizeof(int) * (size_t)M.gy * n);
@@ -2176,6 +2197,8 @@ extern "C" int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtrac
         }
     }
     if (blk > 0x7fffffffLL || sel > 0x7fffffffLL) return fail("gcx_mcfs_batch: batch too large");
+    const size_t o_pending = off;             // one word for the whole batch: diagonals that need the two narrow passes
+    off += 256;
     const size_t o_mm = off;
     off += align256(sizeof(MinMax) * (size_t)count);
     // the batch runs on the first context's stream: it waits for whatever the other contexts have in flight ...
@@ -2190,12 +2213,10 @@ extern "C" int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtrac
         CKR(fence_copy(c));
         CKR(ensure_out(c));
         BMap& M = tab[m];
-        M.A = c->A; M.Out = c->Out; M.avg = c->vavg; M.mm = c->mm;
+        M.A = c->A; M.Out = c->Out; M.avg = c->vavg; M.avr = c->vavr; M.mm = c->mm;
         if (median) {
             const size_t n = (size_t)c->n;
-            M.S.hist = (unsigned int*)(base + o_hist[m]);
-            unsigned int* small = (unsigned int*)(base + o_small[m]);
-            M.S.prefix = small; M.S.krem = small + n; M.S.cnt = small + 2 * n; M.S.need = small + 3 * n; M.S.next = small + 4 * n;
+            diag_sel_bind(M.S, (unsigned int*)(base + o_hist[m]), (unsigned int*)(base + o_small[m]), n, (unsigned int*)(base + o_pending));
         } else {
             M.psum = (double*)(base + o_psum[m]);
             M.pcnt = (int*)(base + o_pcnt[m]);
@@ -2211,17 +2232,15 @@ extern "C" int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtrac
     if (median) CK(cudaMemsetAsync(base + zero_from, 0, o_mm - zero_from, st));
     k_mm_init_b<<<1, 128, 0, st>>>(dt, count);
     if (median) {
+        const long long cap = (long long)c0->sm_count * 16;
         for (int pass = 0; pass < 4; ++pass) {
+            const unsigned gh = (unsigned)(pass < 2 ? blk : std::min(blk, cap)), gs = (unsigned)(pass < 2 ? sel : std::min(sel, cap));
             {
                 ProfScope ps(c0, 4);
-                k_diag_hist_b<<<(unsigned)blk, MV_THREADS, 0, st>>>(dt, count, pass);
+                launch_diag_hist_b(pass, gh, st, dt, count, (int)blk);
             }
-            k_diag_select_b<<<(unsigned)sel, MV_THREADS, 0, st>>>(dt, count, pass);
+            k_diag_select_b<<<gs, MV_THREADS, 0, st>>>(dt, count, pass, (int)sel);
             c0->launches += 1;
-        }
-        {
-            ProfScope ps(c0, 4);
-            k_diag_next_b<<<(unsigned)blk, MV_THREADS, 0, st>>>(dt, count);
         }
         k_diag_median_final_b<<<(unsigned)fin, 256, 0, st>>>(dt, count);
         c0->launches += 1;
@@ -2235,9 +2254,19 @@ extern "C" int gcx_mcfs_batch(gcx_ctx** ctxs, int count, int median, int subtrac
         c0->launches += 2;
     }
     CK(cudaGetLastError());
+    k_diag_recip_b<<<(unsigned)fin, 256, 0, st>>>(dt, count);
     {
         ProfScope ps(c0, 5);
-        k_diag_apply_b<R, 4><<<c0->sm_count * 4, MV_THREADS, 0, st>>>(dt, count, units, subtract);
+        if (apply_variant == 0) k_diag_apply_b<4, 4><<<c0->sm_count * 4, MV_THREADS, 0, st>>>(dt, count, units, subtract);
+        else if (apply_variant == 1) k_diag_apply_b<8, 3><<<c0->sm_count * 3, MV_THREADS, 0, st>>>(dt, count, units, subtract);
+        else if (apply_variant == 2) k_diag_apply_b<8, 2><<<c0->sm_count * 2, MV_THREADS, 0, st>>>(dt, count, units, subtract);
+        else if (apply_variant == 3) {
+            if (subtract) k_diag_apply_lane_b<4, 4, true><<<c0->sm_count * 4, MV_THREADS, 0, st>>>(dt, count, units);
+            else k_diag_apply_lane_b<4, 4, false><<<c0->sm_count * 4, MV_THREADS, 0, st>>>(dt, count, units);
+        } else {
+            if (subtract) k_diag_apply_lane_b<8, 3, true><<<c0->sm_count * 3, MV_THREADS, 0, st>>>(dt, count, units);
+            else k_diag_apply_lane_b<8, 3, false><<<c0->sm_count * 3, MV_THREADS, 0, st>>>(dt, count, units);
+        }
     }
     CK(cudaGetLastError());
     MinMax* gathered = (MinMax*)(base + o_mm);
@@ -2279,8 +2308,8 @@ extern "C" int gcx_diag_stats_pooled(gcx_ctx** ctxs, int count, int median, doub
     CKR(set_dev(c0));
     std::vector<BMap> tab((size_t)count + 1);
     size_t off = align256(sizeof(BMap) * ((size_t)count + 1));
-    const size_t o_hist = off; off += median ? align256(sizeof(unsigned int) * 256 * (size_t)nm) : 0;
-    const size_t o_small = off; off += median ? align256(sizeof(unsigned int) * 5 * (size_t)nm) : 0;
+    const size_t o_hist = off; off += median ? align256(sizeof(unsigned int) * DIAG_NBIN * (size_t)nm) : 0;
+    const size_t o_small = off; off += median ? align256(sizeof(unsigned int) * (DIAG_SEL_ARRAYS * (size_t)nm + 1)) : 0;
     const size_t o_avg = off; off += align256(sizeof(double) * (size_t)nm);
     std::vector<size_t> o_psum((size_t)count), o_pcnt((size_t)count), o_sc((size_t)count);
     long long blk = 0, red = 0;
@@ -2291,7 +2320,7 @@ extern "C" int gcx_diag_stats_pooled(gcx_ctx** ctxs, int count, int median, doub
         memset(&M, 0, sizeof M);
         M.ld = c->ld; M.n = n;
         M.gx = (n + MV_THREADS - 1) / MV_THREADS;
-        M.gy = (n + DIAG_RB - 1) / DIAG_RB;
+        M.gy = median ? (n + DIAG_HB - 1) / DIAG_HB : (n + DIAG_RB - 1) / DIAG_RB;      // row bands of the histogram / the mean-partial grid
         M.blk0 = (int)blk; M.red0 = (int)red;
         blk += (long long)M.gx * M.gy;
         red += (n + 63) / 64;
@@ -2310,9 +2339,8 @@ extern "C" int gcx_diag_stats_pooled(gcx_ctx** ctxs, int count, int median, doub
     char* base = (char*)c0->scratch;
     DiagSel S{};
     if (median) {
-        S.hist = (unsigned int*)(base + o_hist);
         unsigned int* small = (unsigned int*)(base + o_small);
-        S.prefix = small; S.krem = small + nm; S.cnt = small + 2 * nm; S.need = small + 3 * nm; S.next = small + 4 * nm;
+        diag_sel_bind(S, (unsigned int*)(base + o_hist), small, (size_t)nm, small + DIAG_SEL_ARRAYS * (size_t)nm);
     }
     double* davg = (double*)(base + o_avg);
     for (int m = 0; m < count; ++m) {
@@ -2338,17 +2366,14 @@ extern "C" int gcx_diag_stats_pooled(gcx_ctx** ctxs, int count, int median, doub
     if (median) {
         CK(cudaMemsetAsync(base + o_hist, 0, o_avg - o_hist, st));
         const unsigned sel = (unsigned)(((long long)nm * 32 + MV_THREADS - 1) / MV_THREADS);
+        const long long cap = (long long)c0->sm_count * 16;
         for (int pass = 0; pass < 4; ++pass) {
             {
                 ProfScope ps(c0, 4);
-                k_diag_hist_b<<<(unsigned)blk, MV_THREADS, 0, st>>>(dt, count, pass);
+                launch_diag_hist_b(pass, (unsigned)(pass < 2 ? blk : std::min(blk, cap)), st, dt, count, (int)blk);
             }
-            k_diag_select_b<<<sel, MV_THREADS, 0, st>>>(dp, 1, pass);
+            k_diag_select_b<<<sel, MV_THREADS, 0, st>>>(dp, 1, pass, (int)sel);
             c0->launches += 1;
-        }
-        {
-            ProfScope ps(c0, 4);
-            k_diag_next_b<<<(unsigned)blk, MV_THREADS, 0, st>>>(dt, count);
         }
         k_diag_median_final_b<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(dp, 1);
         c0->launches += 1;

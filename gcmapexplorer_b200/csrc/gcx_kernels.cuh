@@ -1348,10 +1348,74 @@ k_apply_sym_vc(const float* __restrict__ A, float* __restrict__ OutS, float* __r
 
 // K7: distance-frequency apply (lib/normalizeCore.pyx:91-170): divide or subtract by avg[|i-j|].
 // Algorithmic bytes: 8 * nloc * n.
+//
+// The reference divides in float64 and stores float32: out = f32(RN64(x / av)).  A float64 division is ~30 instructions with
+// its special cases, and on a sparse map nearly every warp has a few non-zero lanes, so the whole warp pays it for every entry
+// (the first version of the batched kernel ran 47 instructions per entry at 17 of 32 lanes active).  Here every entry takes the
+// same branch-free path: with r = RN64(1 / av) tabulated per distance next to av,
+//     q0 = x r,  e = fma(-q0, av, x),  q = fma(e, r, q0)
+// is RN64(x / av) or its neighbour (|q - x/av| < 2^-104 |x/av| before the last rounding).  The two can only round to different
+// float32 values when q sits within one float64 ulp of the midpoint between two floats; those entries (29 low mantissa bits within
+// 0x10000000 +- 1: about one in 10^8), results below the float32 normal range and non-finite intermediates take the exact
+// division.  The stored float is therefore the reference's, bit for bit (tests/test_gpu_parity.py::test_diag_apply_exactness).
+__global__ void k_diag_recip(int n, const double* __restrict__ avg, double2* __restrict__ avr) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) {
+        const double a = avg[d];
+        avr[d] = make_double2(a, a != 0.0 ? 1.0 / a : 0.0);
+    }
+}
+
+// out of line on purpose: inlined, the compiler hoists the division above the test and every entry pays it again
+__device__ __noinline__ double diag_exact_quotient(double x, double av) { return x / av; }
+
+// Four adjacent entries of row i (columns j0 .. j0 + 3): one test for the rare exact-division path instead of one per entry.
+// CS: column stride between the four entries, 1 (a float4 of the row) or 32 (lane-strided, see k_diag_apply_lane_b); SUB: o - e
+// instead of o / e; GUARD: some of the four columns may lie in the padding (j >= n).
+template <int CS, bool SUB, bool GUARD>
+__device__ __forceinline__ void diag_apply_quad(const float (&x)[4], float (&o)[4], int i, int j0, int n, const double2* __restrict__ avr,
+                                                float& mn, float& mx) {
+    double q[4];
+    bool live[4];
+    unsigned int risky = 0u;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int j = j0 + e * CS;
+        const int d = GUARD ? min(abs(i - j), n - 1) : abs(i - j);       // padding columns read a valid slot; they hold zeros
+        const double2 ar = __ldg(avr + d);
+        const double xd = (double)x[e];
+        live[e] = x[e] != 0.f && ar.x != 0.0;                 // a zero entry stays zero in both modes (0/avg = 0; :142-144 forces 0 for o-e)
+        if (!SUB) {
+            const double q0 = xd * ar.y;
+            const double r = fma(-q0, ar.x, xd);
+            q[e] = fma(r, ar.y, q0);                                                   // :105-108, :114-117
+            const unsigned int lo = (unsigned int)__double2loint(q[e]), ex = ((unsigned int)__double2hiint(q[e]) >> 20) & 0x7ffu;
+            const bool rk = ((lo & 0x1fffffffu) - 0x0fffffffu) <= 2u || (ex - 899u) >= (0x7ffu - 899u);
+            risky |= (live[e] && rk) ? (1u << e) : 0u;
+        } else {
+            const double t = xd - ar.x;                                                // :138
+            q[e] = t < 0.0 ? 1.0 : t;                                                  // :139-141
+        }
+    }
+    if (!SUB && risky) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (risky & (1u << e)) q[e] = diag_exact_quotient((double)x[e], __ldg(avr + min(abs(i - j0 - e * CS), n - 1)).x);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float v = live[e] ? (float)q[e] : x[e];
+        o[e] = v;
+        const bool in = !GUARD || j0 + e * CS < n;
+        mn = (in && v != 0.f) ? fminf(mn, v) : mn;
+        mx = in ? fmaxf(mx, v) : mx;
+    }
+}
+
 template <int R, int OCC>
 __global__ void __launch_bounds__(MV_THREADS, OCC)
 k_diag_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld, int nloc, int n4, int n, int row0,
-             const double* __restrict__ avg, int subtract, MinMax* mm) {
+             const double2* __restrict__ avr, int subtract, MinMax* mm) {
     const int tid = threadIdx.x;
     const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
     const int nb = (nloc + R - 1) / R;
@@ -1376,28 +1440,8 @@ k_diag_apply(const float* __restrict__ A, float* __restrict__ Out, long long ld,
             const int i = row0 + r;
             const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
             float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = j0 + e;
-                float v = in[e];
-                if (j < n) {
-                    // a zero entry stays zero in both modes (0/avg = 0; :142-144 forces 0 for o-e): skip the lookup
-                    const int d = i > j ? i - j : j - i;
-                    const double av = in[e] != 0.f ? __ldg(avg + d) : 0.0;
-                    if (av != 0.0) {
-                        if (!subtract) {
-                            v = (float)((double)in[e] / av);                       // :105-108, :114-117
-                        } else {
-                            double t = (double)in[e] - av;                         // :138
-                            if (t < 0.0) t = 1.0;                                  // :139-141
-                            if (in[e] == 0.f) t = 0.0;                             // :142-144
-                            v = (float)t;
-                        }
-                    }
-                    mm_update(v, mn, mx);
-                }
-                o[e] = v;
-            }
+            if (subtract) diag_apply_quad<1, true, true>(in, o, i, j0, n, avr, mn, mx);
+            else diag_apply_quad<1, false, true>(in, o, i, j0, n, avr, mn, mx);
             st_stream_f4(reinterpret_cast<float4*>(Out + (long long)r * ld) + c4, make_float4(o[0], o[1], o[2], o[3]));
         }
     }
@@ -1483,145 +1527,268 @@ __global__ void k_diag_mean_final(int n, const double* __restrict__ sum, const d
     if (d < n) avg[d] = cnt[d] > 0.0 ? sum[d] / cnt[d] : 0.0;      // lib/cmstats.py:598, :602-603
 }
 
-// median: 4-pass MSB-first radix select on the order-preserving uint32 encoding of the floats, one
-// 256-bin histogram per diagonal (global atomics; lanes of a warp hit 32 different diagonals).
+// median: MSB-first radix select on the order-preserving uint32 encoding of the floats, one histogram row per diagonal (global
+// atomics; lanes of a warp hit 32 different diagonals).  Digits of 9 + 9 + 7 + 7 bits: the first two passes fix the sign, the
+// exponent and nine mantissa bits -- every integer count up to 1023 exactly.  While pass 1 runs, the low 14 bits of the candidates
+// (the entries inside the bucket pass 0 selected) are OR-ed per diagonal; when they are all zero the second selection is final and
+// the diagonal leaves the search: on count maps the median costs TWO reads of the triangle, and passes 2 / 3 return at once when
+// no diagonal is pending.  np.median of an even count needs the next larger value as well: every pass also tracks (atomicMin) the
+// entries of the bucket next to the selected one at the level above, the last selection adds the next occupied bin of its own
+// histogram -- no extra pass over the map.  A thread adds its entries of a band into a 4-entry (bin, count) cache in registers
+// before it touches the histogram (count data repeats a handful of values along a diagonal).
+constexpr int DIAG_NBIN = 512;                 // histogram row (passes 2, 3 use the first 128 bins)
+constexpr int DIAG_HB = 256;                   // rows per CTA of the histogram passes: long enough that filling the slots is rare
+constexpr int DIAG_SEL_ARRAYS = 8;
+__host__ __device__ __forceinline__ int diag_digit_bits(int pass) { return pass < 2 ? 9 : 7; }
+__host__ __device__ __forceinline__ int diag_digit_shift(int pass) { return pass == 0 ? 23 : (pass == 1 ? 14 : (pass == 2 ? 7 : 0)); }
 struct DiagSel {
-    unsigned int* hist;     // [n][256]
-    unsigned int* prefix;   // [n] high bytes fixed so far
+    unsigned int* hist;     // [n][DIAG_NBIN]
+    unsigned int* prefix;   // [n] high bits fixed so far (right-aligned); the full key once the diagonal is done
     unsigned int* krem;     // [n] rank still to skip inside the current prefix group
     unsigned int* cnt;      // [n] number of non-zero entries
     unsigned int* need;     // [n] 1 if the upper middle value is the next distinct key
-    unsigned int* next;     // [n] min key > vlo
+    unsigned int* next;     // [n] min key > the selected one seen so far
+    unsigned int* nbp;      // [n] prefix (at the width of the last selection) of the bucket to track for `next`; 0xffffffff: none
+    unsigned int* dirty;    // [n] 1 if a candidate of pass 1 has non-zero low 14 bits
+    unsigned int* done;     // [n] 1 once the lower middle key is known
+    unsigned int* pending;  // [1] diagonals that need passes 2 and 3
 };
 
-__device__ __forceinline__ void diag_hist_body(const float* __restrict__ A, long long ld, int nloc, int n, int row0, int pass, const DiagSel& S, int bx, int by) {
-    const int band = by, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
+__host__ __forceinline__ void diag_sel_bind(DiagSel& S, unsigned int* hist, unsigned int* small, size_t n, unsigned int* pending) {
+    S.hist = hist;
+    S.prefix = small; S.krem = small + n; S.cnt = small + 2 * n; S.need = small + 3 * n; S.next = small + 4 * n;
+    S.nbp = small + 5 * n; S.dirty = small + 6 * n; S.done = small + 7 * n;
+    S.pending = pending;
+}
+
+template <int PASS>
+__device__ __forceinline__ void diag_hist_body(const float* __restrict__ A, long long ld, int nloc, int n, int row0, const DiagSel& S, int bx, int by) {
+    const int band = by, r0 = band * DIAG_HB, r1 = min(r0 + DIAG_HB, nloc);
     const int imax = row0 + r1 - 1;
     if ((int)(bx * MV_THREADS) > imax) return;
     const int d = bx * MV_THREADS + threadIdx.x;
     if (d > imax || d >= n) return;
-    const unsigned int pre = pass ? S.prefix[d] : 0u;
-    const int sh_hi = 32 - 8 * pass, sh = 24 - 8 * pass;
-    unsigned int* h = S.hist + (long long)d * 256;
+    if (PASS >= 2 && S.done[d]) return;
+    const unsigned int pre = PASS ? S.prefix[d] : 0u;
+    const unsigned int nbpre = PASS ? S.nbp[d] : 0xffffffffu;
+    constexpr int sh = PASS == 0 ? 23 : (PASS == 1 ? 14 : (PASS == 2 ? 7 : 0)), bits = PASS < 2 ? 9 : 7, sh_hi = sh + bits;
+    constexpr unsigned int mask = (1u << bits) - 1u;
+    unsigned int* h = S.hist + (long long)d * DIAG_NBIN;
     const int rs = max(r0, d - row0);
-    int run_bin = -1;
-    unsigned int run = 0;
-    // the loads of a batch are issued before any atomic (an atomic inside the loop keeps the compiler from hoisting them)
-    const long long off = (long long)row0 - d;
-    auto take = [&](float v) {
-        if (v != 0.f) {
-            const unsigned int key = f2ord(v);
-            if (pass == 0 || (key >> sh_hi) == pre) {
-                const int bin = (key >> sh) & 255;
-                if (bin == run_bin) {
-                    ++run;
-                } else {
-                    if (run) atomicAdd(h + run_bin, run);
-                    run_bin = bin;
-                    run = 1;
-                }
-            }
-        }
+    // Four (bin, count) slots in registers.  A batch of entries is first counted against the slots WITHOUT branches (nearly every
+    // warp-row of a sparse map has both zero and non-zero lanes: a branch per entry runs both sides for everyone, and any slot
+    // update inside the unrolled batch makes the compiler shuffle the slots through moves -- the first two versions of this loop
+    // were issue-bound at 73 and 49 instructions per entry, profiles/r02_ncu_mcfs_batch.txt); entries that found no slot leave
+    // a bit in `missed` and are handled after the batch: the slot whose turn it is goes to the histogram and is taken over.
+    // The slots start on the bins short counts fall into -- pass 0: the exponents of 1, 2..3, 4..7, 8..15; pass 1: the mantissas
+    // of the integers below 8 -- so a thread of a sparse count map never takes the slow path (a thread that starts cold misses
+    // two or three times per band, and then nearly every batch of the warp has a lane in the slow path).  Any other data only
+    // pays the misses it would pay anyway.
+    unsigned int t0 = PASS == 0 ? 127u : 0u, t1 = PASS == 0 ? 128u : (PASS == 1 ? 128u : 1u), t2 = PASS == 0 ? 129u : (PASS == 1 ? 256u : 2u),
+                 t3 = PASS == 0 ? 130u : (PASS == 1 ? 384u : 3u), c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    unsigned int low = 0u, tmin = 0xffffffffu;
+    int vic = 0;
+    // Pass 0 counts on the RAW sign + exponent field (float bits >> 23): the order-preserving encoding only permutes the bins, so
+    // it is applied when a slot goes to the histogram (`ordered`), not per entry.
+    auto bin_of = [&](float v) -> unsigned int {     // the entry's bin, 0xfffffffe (a value no slot ever holds) if it does not count
+        const unsigned int u = __float_as_uint(v);
+        const bool nz = v != 0.f;
+        if (PASS == 0) return nz ? (u >> 23) : 0xfffffffeu;
+        const unsigned int key = u ^ ((unsigned int)((int)u >> 31) | 0x80000000u);        // f2ord
+        const unsigned int hi = key >> (sh_hi & 31);
+        const bool m = nz && hi == pre;
+        if (PASS == 1) low |= m ? (key & 0x3fffu) : 0u;
+        tmin = min(tmin, (nz && hi == nbpre) ? key : 0xffffffffu);
+        return m ? ((key >> sh) & mask) : 0xfffffffeu;
     };
+    auto ordered = [&](unsigned int bin) -> unsigned int {
+        return PASS == 0 ? ((bin & 256u) ? 511u - bin : (bin | 256u)) : bin;
+    };
+    auto insert = [&](unsigned int bin) {            // rare: an entry whose bin is in no slot
+        if (bin == t0) { ++c0; return; }
+        if (bin == t1) { ++c1; return; }
+        if (bin == t2) { ++c2; return; }
+        if (bin == t3) { ++c3; return; }
+        if (vic == 0) { if (c0) atomicAdd(h + ordered(t0), c0); t0 = bin; c0 = 1u; }
+        else if (vic == 1) { if (c1) atomicAdd(h + ordered(t1), c1); t1 = bin; c1 = 1u; }
+        else if (vic == 2) { if (c2) atomicAdd(h + ordered(t2), c2); t2 = bin; c2 = 1u; }
+        else { if (c3) atomicAdd(h + ordered(t3), c3); t3 = bin; c3 = 1u; }
+        vic = (vic + 1) & 3;
+    };
+    // the address walks down the diagonal by one row and one column per entry; the loads of the NEXT batch are in flight while
+    // this one is counted (without it every warp alternated between waiting for 16 loads and ~600 instructions of counting)
+    const long long stride = ld + 1;
+    const float* __restrict__ p = A + ((long long)rs * stride + ((long long)row0 - d));
     int r = rs;
-    for (; r + DIAG_BATCH <= r1; r += DIAG_BATCH) {
-        float v[DIAG_BATCH];
+    float v[DIAG_BATCH];
+    if (r + DIAG_BATCH <= r1) {
 #pragma unroll
-        for (int k = 0; k < DIAG_BATCH; ++k) v[k] = __ldg(A + ((long long)(r + k) * (ld + 1) + off));
-#pragma unroll
-        for (int k = 0; k < DIAG_BATCH; ++k) take(v[k]);
+        for (int k = 0; k < DIAG_BATCH; ++k) { v[k] = __ldg(p); p += stride; }
     }
-    for (; r < r1; ++r) take(__ldg(A + ((long long)r * (ld + 1) + off)));
-    if (run) atomicAdd(h + run_bin, run);
+    for (; r + DIAG_BATCH <= r1; r += DIAG_BATCH) {
+        float nv[DIAG_BATCH];
+        const bool more = r + 2 * DIAG_BATCH <= r1;
+        if (more) {
+#pragma unroll
+            for (int k = 0; k < DIAG_BATCH; ++k) { nv[k] = __ldg(p); p += stride; }
+        }
+        unsigned int b[DIAG_BATCH], missed = 0u;
+#pragma unroll
+        for (int k = 0; k < DIAG_BATCH; ++k) {
+            b[k] = bin_of(v[k]);
+            const bool h0 = b[k] == t0, h1 = b[k] == t1, h2 = b[k] == t2, h3 = b[k] == t3;
+            c0 += h0; c1 += h1; c2 += h2; c3 += h3;
+            missed |= (b[k] != 0xfffffffeu && !(h0 || h1 || h2 || h3)) ? (1u << k) : 0u;
+        }
+        if (missed) {
+#pragma unroll
+            for (int k = 0; k < DIAG_BATCH; ++k)
+                if (missed & (1u << k)) insert(b[k]);
+        }
+        if (more) {
+#pragma unroll
+            for (int k = 0; k < DIAG_BATCH; ++k) v[k] = nv[k];
+        }
+    }
+    for (; r < r1; ++r) {
+        const unsigned int bb = bin_of(__ldg(p));
+        p += stride;
+        if (bb != 0xfffffffeu) insert(bb);
+    }
+    if (c0) atomicAdd(h + ordered(t0), c0);
+    if (c1) atomicAdd(h + ordered(t1), c1);
+    if (c2) atomicAdd(h + ordered(t2), c2);
+    if (c3) atomicAdd(h + ordered(t3), c3);
+    if (PASS == 1 && low) S.dirty[d] = 1u;          // every writer stores the same value
+    if (PASS >= 1 && tmin != 0xffffffffu) atomicMin(S.next + d, tmin);
 }
 
-__global__ void __launch_bounds__(MV_THREADS)
-k_diag_hist(const float* __restrict__ A, long long ld, int nloc, int n, int row0, int pass, DiagSel S) {
-    diag_hist_body(A, ld, nloc, n, row0, pass, S, blockIdx.x, blockIdx.y);
+template <int PASS>
+__global__ void __launch_bounds__(MV_THREADS, 3)
+k_diag_hist(const float* __restrict__ A, long long ld, int nloc, int n, int row0, DiagSel S) {
+    if (PASS >= 2 && *S.pending == 0u) return;
+    diag_hist_body<PASS>(A, ld, nloc, n, row0, S, blockIdx.x, blockIdx.y);
 }
 
-// one warp per diagonal: find the bin holding rank krem, descend into it, clear the histogram row
+// one warp per diagonal: find the bin holding rank krem and the next occupied bin, descend, clear the histogram row.
+// The row is read as uint4 groups of four bins, group j * 32 + lane by lane `lane` in round j: every request of the warp is one
+// contiguous 512 bytes (lane-major bins made every load touch 32 sectors; the kernel sat on the L1 queue).  Groups that are
+// already zero are not written back.
 __device__ __forceinline__ void diag_select_body(int n, int pass, const DiagSel& S, int bx) {
     const int d = (bx * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (d >= n) return;
-    unsigned int* h = S.hist + (long long)d * 256;
-    unsigned int c[8], tot = 0;
+    if (pass >= 2 && S.done[d]) return;            // its histogram row was not touched in this pass
+    uint4* h4 = reinterpret_cast<uint4*>(S.hist + (long long)d * DIAG_NBIN);
+    constexpr int NJ = DIAG_NBIN / 128;            // rounds in the wide passes
+    const int nj = (1 << diag_digit_bits(pass)) / 128;
+    uint4 q[NJ];
+    unsigned int gs[NJ], excl[NJ], nzm[NJ];
+    unsigned int carry = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        c[k] = h[lane * 8 + k];
-        tot += c[k];
-        h[lane * 8 + k] = 0u;
+    for (int j = 0; j < NJ; ++j) {
+        q[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (j < nj) q[j] = h4[j * 32 + lane];
     }
-    unsigned int incl = tot;     // inclusive prefix over lanes
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+    for (int j = 0; j < NJ; ++j) {
+        gs[j] = q[j].x + q[j].y + q[j].z + q[j].w;
+        if (j < nj && gs[j]) h4[j * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+        unsigned int incl = gs[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        excl[j] = carry + incl - gs[j];
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        nzm[j] = __ballot_sync(0xffffffffu, gs[j] != 0u);
     }
-    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned int total = carry;
     unsigned int kr;
     if (pass == 0) {
-        if (lane == 0) S.cnt[d] = total;
+        if (lane == 0) { S.cnt[d] = total; S.next[d] = 0xffffffffu; }
         kr = total ? (total - 1) / 2 : 0;      // lower middle rank (np.median: mean of the two middles when even)
     } else {
         kr = S.krem[d];
     }
     if (total == 0) {
-        if (lane == 0) { S.prefix[d] = 0u; S.krem[d] = 0u; S.need[d] = 0u; }
+        if (lane == 0) { S.prefix[d] = 0u; S.krem[d] = 0u; S.need[d] = 0u; S.nbp[d] = 0xffffffffu; S.done[d] = 1u; }
         return;
     }
-    const unsigned int excl = incl - tot;
-    const bool mine = kr >= excl && kr < incl;
-    if (mine) {
-        unsigned int run = excl;
-        int bin = 0;
-        unsigned int hb = 0;
+    // the group that holds rank kr (exactly one (round, lane)), known to every lane
+    int jo = 0, lo = 0;
+    bool mine = false;
+    int first[NJ];                                 // first occupied bin of the lane's group in round j
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (kr >= run && kr < run + c[k]) { bin = lane * 8 + k; hb = c[k]; break; }
-            run += c[k];
+    for (int j = 0; j < NJ; ++j) {
+        const bool mj = gs[j] != 0u && kr >= excl[j] && kr < excl[j] + gs[j];
+        const unsigned int bm = __ballot_sync(0xffffffffu, mj);
+        if (bm) { jo = j; lo = __ffs(bm) - 1; }
+        mine = mine || mj;
+        const int g4 = 4 * (j * 32 + lane);
+        first[j] = q[j].x ? g4 : (q[j].y ? g4 + 1 : (q[j].z ? g4 + 2 : (q[j].w ? g4 + 3 : -1)));
+    }
+    // the next occupied group after the owner's: later lanes of the same round, then the following rounds
+    int jt = -1, lt = 0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        if (jt < 0 && j >= jo) {
+            const unsigned int msk = (j == jo) ? (lo < 31 ? (nzm[j] & (0xffffffffu << (lo + 1))) : 0u) : nzm[j];
+            if (msk) { jt = j; lt = __ffs(msk) - 1; }
         }
+    }
+    int nb_far = -1;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int f = __shfl_sync(0xffffffffu, first[j], lt);
+        if (j == jt) nb_far = f;
+    }
+    if (mine) {
+        unsigned int cq[4] = {0u, 0u, 0u, 0u};
+        unsigned int run = 0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+            if (j == jo) { cq[0] = q[j].x; cq[1] = q[j].y; cq[2] = q[j].z; cq[3] = q[j].w; run = excl[j]; }
+        const int g4 = 4 * (jo * 32 + lane);
+        int bin = 0, nb = -1;
+        unsigned int hb = 0;
+        bool found = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!found) {
+                if (kr < run + cq[k]) { bin = g4 + k; hb = cq[k]; found = true; }
+                else run += cq[k];
+            } else if (nb < 0 && cq[k]) {
+                nb = g4 + k;
+            }
+        }
+        if (nb < 0) nb = nb_far;
+        const int w = diag_digit_bits(pass), sh = diag_digit_shift(pass);
         const unsigned int pre = pass ? S.prefix[d] : 0u;
-        S.prefix[d] = (pre << 8) | (unsigned int)bin;
+        const unsigned int sel = (pre << w) | (unsigned int)bin;
         const unsigned int kin = kr - run;      // rank inside the chosen bin
-        S.krem[d] = kin;
-        if (pass == 3) {
+        const unsigned int nbsel = nb >= 0 ? ((pre << w) | (unsigned int)nb) : 0xffffffffu;
+        const bool fin = pass == 3 || (pass == 1 && S.dirty[d] == 0u);
+        if (fin) {
+            S.prefix[d] = sel << sh;            // every candidate has zeros below the digits fixed so far
             const unsigned int cn = S.cnt[d];
             S.need[d] = ((cn & 1u) == 0u && kin + 1 >= hb) ? 1u : 0u;
-            S.next[d] = 0xffffffffu;
+            if (nb >= 0) S.next[d] = min(S.next[d], nbsel << sh);
+            S.done[d] = 1u;
+        } else {
+            S.prefix[d] = sel;
+            S.krem[d] = kin;
+            S.nbp[d] = nbsel;
+            if (pass == 0) S.done[d] = 0u;
+            if (pass == 1) atomicAdd(S.pending, 1u);
         }
     }
 }
 
 __global__ void __launch_bounds__(MV_THREADS)
 k_diag_select(int n, int pass, DiagSel S) {
+    if (pass >= 2 && *S.pending == 0u) return;
     diag_select_body(n, pass, S, blockIdx.x);
-}
-
-__device__ __forceinline__ void diag_next_body(const float* __restrict__ A, long long ld, int nloc, int n, int row0, const DiagSel& S, int bx, int by) {
-    const int band = by, r0 = band * DIAG_RB, r1 = min(r0 + DIAG_RB, nloc);
-    const int imax = row0 + r1 - 1;
-    if ((int)(bx * MV_THREADS) > imax) return;
-    const int d = bx * MV_THREADS + threadIdx.x;
-    if (d > imax || d >= n) return;
-    if (!S.need[d]) return;
-    const unsigned int vlo = S.prefix[d];
-    unsigned int best = 0xffffffffu;
-    const int rs = max(r0, d - row0);
-#pragma unroll 8
-    for (int r = rs; r < r1; ++r) {
-        const float v = __ldg(A + (long long)r * ld + (row0 + r - d));
-        if (v != 0.f) {
-            const unsigned int key = f2ord(v);
-            if (key > vlo && key < best) best = key;
-        }
-    }
-    if (best != 0xffffffffu) atomicMin(S.next + d, best);
-}
-
-__global__ void __launch_bounds__(MV_THREADS)
-k_diag_next(const float* __restrict__ A, long long ld, int nloc, int n, int row0, DiagSel S) {
-    diag_next_body(A, ld, nloc, n, row0, S, blockIdx.x, blockIdx.y);
 }
 
 __global__ void k_diag_median_final(int n, DiagSel S, double* __restrict__ avg) {
@@ -1645,6 +1812,7 @@ struct BMap {
     long long ld;
     int n, gx, gy, pad;
     double* avg;                 // [>= n] the map's per-diagonal statistic
+    double2* avr;                // [>= n] (statistic, its reciprocal) for the apply pass
     DiagSel S;                   // median: histogram / selection state of this map
     double *psum, *sum, *cnt;    // mean: per-band partials and their reduction
     int* pcnt;
@@ -1669,27 +1837,35 @@ __device__ __forceinline__ int bmap_find(const BMap* __restrict__ maps, int coun
     return m;
 }
 
-__global__ void __launch_bounds__(MV_THREADS)
-k_diag_hist_b(const BMap* __restrict__ maps, int count, int pass) {
-    const int m = bmap_find<0>(maps, count, blockIdx.x);
-    const BMap M = maps[m];
-    const int local = (int)blockIdx.x - M.blk0;
-    diag_hist_body(M.A, M.ld, M.n, M.n, 0, pass, M.S, local % M.gx, local / M.gx);
+template <int PASS>
+__device__ __forceinline__ void diag_hist_block_b(const BMap* __restrict__ maps, int count, int b) {
+    const int m = bmap_find<0>(maps, count, b);
+    const BMap& M = maps[m];                   // fields are read where they are used: the whole table entry in registers cost occupancy
+    const int local = b - M.blk0, gx = M.gx;
+    diag_hist_body<PASS>(M.A, M.ld, M.n, M.n, 0, M.S, local % gx, local / gx);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(MV_THREADS, 3)
+k_diag_hist_b(const BMap* __restrict__ maps, int count, int nblocks) {
+    if (PASS < 2) {
+        diag_hist_block_b<PASS>(maps, count, blockIdx.x);          // one CTA per block of the list
+    } else {
+        // passes 2 and 3 run on a capped grid that strides over the block list: when no diagonal is pending (count maps) they
+        // cost one wave of empty CTAs
+        if (*maps[0].S.pending == 0u) return;
+        for (int b = blockIdx.x; b < nblocks; b += gridDim.x) diag_hist_block_b<PASS>(maps, count, b);
+    }
 }
 
 __global__ void __launch_bounds__(MV_THREADS)
-k_diag_select_b(const BMap* __restrict__ maps, int count, int pass) {
-    const int m = bmap_find<1>(maps, count, blockIdx.x);
-    const BMap M = maps[m];
-    diag_select_body(M.n, pass, M.S, (int)blockIdx.x - M.sel0);
-}
-
-__global__ void __launch_bounds__(MV_THREADS)
-k_diag_next_b(const BMap* __restrict__ maps, int count) {
-    const int m = bmap_find<0>(maps, count, blockIdx.x);
-    const BMap M = maps[m];
-    const int local = (int)blockIdx.x - M.blk0;
-    diag_next_body(M.A, M.ld, M.n, M.n, 0, M.S, local % M.gx, local / M.gx);
+k_diag_select_b(const BMap* __restrict__ maps, int count, int pass, int nblocks) {
+    if (pass >= 2 && *maps[0].S.pending == 0u) return;
+    for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const int m = bmap_find<1>(maps, count, b);
+        const BMap& M = maps[m];
+        diag_select_body(M.n, pass, M.S, b - M.sel0);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1748,6 +1924,17 @@ __global__ void k_mm_gather_b(const BMap* __restrict__ maps, int count, MinMax* 
     if (m < count) out[m] = *maps[m].mm;
 }
 
+__global__ void __launch_bounds__(256)
+k_diag_recip_b(const BMap* __restrict__ maps, int count) {
+    const int m = bmap_find<3>(maps, count, blockIdx.x);
+    const BMap& M = maps[m];
+    const int d = ((int)blockIdx.x - M.fin0) * 256 + threadIdx.x;
+    if (d < M.n) {
+        const double a = M.avg[d];
+        M.avr[d] = make_double2(a, a != 0.0 ? 1.0 / a : 0.0);
+    }
+}
+
 // the apply pass of all maps: the (band, chunk) units of every map in one list, split evenly over a persistent grid
 template <int R, int OCC>
 __global__ void __launch_bounds__(MV_THREADS, OCC)
@@ -1764,7 +1951,7 @@ k_diag_apply_b(const BMap* __restrict__ maps, int count, long long U, int subtra
         const long long ue = uend < ub ? uend : ub;
         const int n = M.n, n4 = (int)(M.ld / 4);
         const int nch = (n4 + MV_THREADS - 1) / MV_THREADS;
-        const double* __restrict__ avg = M.avg;
+        const double2* __restrict__ avr = M.avr;
         float mn = GCX_PINF, mx = GCX_NINF;
         for (; u < ue; ++u) {
             const long long lu = u - M.u0;
@@ -1784,28 +1971,83 @@ k_diag_apply_b(const BMap* __restrict__ maps, int count, long long U, int subtra
                 if (i >= n) break;
                 const float in[4] = {a[rr].x, a[rr].y, a[rr].z, a[rr].w};
                 float o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = j0 + e;
-                    float v = in[e];
-                    if (j < n) {
-                        const int d = i > j ? i - j : j - i;
-                        const double av = in[e] != 0.f ? __ldg(avg + d) : 0.0;
-                        if (av != 0.0) {
-                            if (!subtract) {
-                                v = (float)((double)in[e] / av);                       // lib/normalizeCore.pyx:105-108, :114-117
-                            } else {
-                                double t = (double)in[e] - av;                         // :138
-                                if (t < 0.0) t = 1.0;                                  // :139-141
-                                if (in[e] == 0.f) t = 0.0;                             // :142-144
-                                v = (float)t;
-                            }
-                        }
-                        mm_update(v, mn, mx);
-                    }
-                    o[e] = v;
-                }
+                if (subtract) diag_apply_quad<1, true, true>(in, o, i, j0, n, avr, mn, mx);      // lib/normalizeCore.pyx:138-144
+                else diag_apply_quad<1, false, true>(in, o, i, j0, n, avr, mn, mx);              // :105-117
                 st_stream_f4(reinterpret_cast<float4*>(M.Out + (long long)i * M.ld) + c4, make_float4(o[0], o[1], o[2], o[3]));
+            }
+        }
+        mm_commit(mn, mx, M.mm);
+        ++m;
+    }
+}
+
+// The same pass with lane-strided columns: lane l of warp w takes columns 128 w + l, + 32, + 64, + 96 of the unit's 1024.  Every
+// load, store and table lookup of a warp then covers CONSECUTIVE addresses (128 bytes of the map, 512 bytes of the (avg, 1/avg)
+// table); with a float4 per thread the four lookups of a warp each touched all 16 lines of a 2 KB window and the L1 ran at 87 %
+// (profiles/r02_ncu_mcfs_batch.txt).
+__device__ __forceinline__ float ld_stream_f1(const float* p) {
+    float r;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_f1(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+template <int R, int OCC, bool SUB>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
+k_diag_apply_lane_b(const BMap* __restrict__ maps, int count, long long U) {
+    const int tid = threadIdx.x, cl = (tid >> 5) * 128 + (tid & 31);
+    const long long G = gridDim.x, c = blockIdx.x;
+    const long long ua = unit_begin(c, U, G), ub = unit_begin(c + 1, U, G);
+    if (ua >= ub) return;
+    int m = bmap_find<4>(maps, count, ua);
+    long long u = ua;
+    while (u < ub) {
+        const BMap& M = maps[m];
+        const long long uend = (m + 1 < count) ? maps[m + 1].u0 : U, mu0 = M.u0;
+        const long long ue = uend < ub ? uend : ub;
+        const int n = M.n;
+        const long long ld = M.ld;
+        const int nch = ((int)(ld / 4) + MV_THREADS - 1) / MV_THREADS;
+        const double2* __restrict__ avr = M.avr;
+        const float* __restrict__ A = M.A;
+        float* __restrict__ Out = M.Out;
+        float mn = GCX_PINF, mx = GCX_NINF;
+        for (; u < ue; ++u) {
+            const long long lu = u - mu0;
+            const int b = (int)(lu / nch), k = (int)(lu - (long long)b * nch);
+            const int j0 = k * 1024 + cl, i0 = b * R;
+            const float* __restrict__ ap = A + (long long)i0 * ld + j0;
+            float* __restrict__ op = Out + (long long)i0 * ld + j0;
+            float a[R][4];
+            if (k * 1024 + 1024 <= n && i0 + R <= n) {
+                // interior unit: every row and column exists
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) a[rr][e] = ld_stream_f1(ap + rr * ld + 32 * e);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    float o[4];
+                    diag_apply_quad<32, SUB, false>(a[rr], o, i0 + rr, j0, n, avr, mn, mx);       // lib/normalizeCore.pyx:105-117, :138-144
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) st_stream_f1(op + rr * ld + 32 * e, o[e]);
+                }
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) a[rr][e] = (i0 + rr < n && j0 + 32 * e < (int)ld) ? ld_stream_f1(ap + rr * ld + 32 * e) : 0.f;
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    if (i0 + rr >= n) break;
+                    float o[4];
+                    diag_apply_quad<32, SUB, true>(a[rr], o, i0 + rr, j0, n, avr, mn, mx);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (j0 + 32 * e < (int)ld) st_stream_f1(op + rr * ld + 32 * e, o[e]);
+                }
             }
         }
         mm_commit(mn, mx, M.mm);

@@ -327,6 +327,78 @@ def test_diag_median_non_integer_and_negative(gx):
     assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_diag_median_early_exit_levels(gx, seed):
+    """The radix select ends after two passes on diagonals whose candidates are short integers and runs all four on the others;
+    the upper middle of an even count comes from the selected bin, the next bin of the same histogram, or the next bucket one,
+    two or three levels up.  Few entries per diagonal and values spread over many exponents hit every one of those cases."""
+    rng = np.random.default_rng(100 + seed)
+    n = 96 if seed < 2 else 333
+    pools = [np.array([1, 2, 3, 4, 7, 8], np.float32), np.array([1, 100, 1000, 1023, 1024, 1025], np.float32),
+             np.array([5000, 65537, 3, 16777215], np.float32), np.array([0.5, 1e-3, 2.0, 1536.0, 1536.25], np.float32),
+             np.array([-3, -1, 2, 1024, -1025.5], np.float32)]
+    L = np.zeros((n, n), np.float32)
+    for d in range(n):
+        pool = pools[rng.integers(len(pools))] if seed % 2 else np.concatenate(pools)
+        vals = rng.choice(pool, size=n - d)
+        vals[rng.random(n - d) < 0.35] = 0.0
+        L[np.arange(d, n), np.arange(0, n - d)] = vals
+    A = np.tril(L) + np.tril(L, -1).T
+    exp = onp.avg_contact_by_distance(A, "median")
+    with gx.DeviceMap.from_host(A) as dm:
+        got = dm.diag_stats("median")
+    assert np.array_equal(got, exp)
+    # the same through the batched and the pooled entry points (one word of "pending" state for the whole batch)
+    B = onp.synth_map(200, seed=seed)
+    with gx.DeviceMap.from_host(A) as da, gx.DeviceMap.from_host(B) as db:
+        gx.MapBatch([da, db]).mcfs("median", subtract=False)
+        assert np.array_equal(da.diag_avg(), exp)
+        assert np.array_equal(db.diag_avg(), onp.avg_contact_by_distance(B, "median"))
+
+
+@pytest.mark.parametrize("subtract", [False, True])
+def test_diag_apply_exactness(gx, subtract):
+    """o/e divides in float64 and stores float32 (lib/normalizeCore.pyx:105-117); the kernel reaches the same bits through a tabulated
+    reciprocal and one correction step, falling back to the division where the two could round differently.  Adversarial input:
+    per distance d a value x_d and a divisor chosen so that x_d / av_d lands within an ulp of the MIDPOINT between two floats
+    (the only place a last-bit error of the float64 quotient can change the float32 result), besides random values, huge and tiny
+    quotients and zero divisors."""
+    rng = np.random.default_rng(77)
+    n = 1536
+    x = np.ldexp(rng.integers(1 << 23, 1 << 24, size=n).astype(np.float64), rng.integers(-30, 8, size=n)).astype(np.float32)
+    f = np.ldexp(rng.integers(1 << 23, 1 << 24, size=n).astype(np.float64), rng.integers(-24, 0, size=n)).astype(np.float32)
+    mid = f.astype(np.float64) + 0.5 * np.spacing(f).astype(np.float64)          # exactly representable in float64
+    av = x.astype(np.float64) / mid
+    av[::7] = rng.uniform(0.1, 900.0, size=av[::7].size)                           # ordinary divisors
+    av[5::97] = 0.0                                                                # distances without data
+    av[11::101] = 1e-300                                                           # reciprocal overflows
+    av[13::103] = 1e300                                                            # quotient below the float32 range
+    i, j = np.indices((n, n))
+    d = np.abs(i - j)
+    A = x[d].copy()
+    flip = rng.random((n, n)) < 0.3
+    A[flip] = rng.integers(1, 2000, size=int(flip.sum())).astype(np.float32)
+    A[rng.random((n, n)) < 0.4] = 0.0
+    A = np.tril(A) + np.tril(A, -1).T
+    with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+        if subtract:
+            t = A.astype(np.float64) - av[d]
+            t[t < 0.0] = 1.0
+            exp = t.astype(np.float32)
+        else:
+            exp = (A.astype(np.float64) / av[d]).astype(np.float32)
+    keep = (A == 0) | (av[d] == 0.0)
+    exp[keep] = A[keep]
+    with gx.DeviceMap.from_host(A) as dm:
+        dm.diag_apply(av, subtract=subtract, in_place=False)
+        got = dm.download(1)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+    if not subtract:
+        q = A.astype(np.float64) / np.where(av[d] == 0.0, 1.0, av[d])
+        near = np.abs((q.view(np.uint64) & np.uint64(0x1fffffff)).astype(np.int64) - 0x10000000) <= 2
+        assert near[~keep].sum() > 1000                     # the fallback really ran
+
+
 @pytest.mark.parametrize("name", golden_names("MCFS"))
 def test_mcfs_golden_dropin(gx, name):
     from gcmapexplorer_b200 import ccmap as cmp, normalizer as nz
