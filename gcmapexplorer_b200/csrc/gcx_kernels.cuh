@@ -1569,51 +1569,65 @@ __device__ __forceinline__ void diag_hist_body(const float* __restrict__ A, long
     const int d = bx * MV_THREADS + threadIdx.x;
     if (d > imax || d >= n) return;
     if (PASS >= 2 && S.done[d]) return;
-    const unsigned int pre = PASS ? S.prefix[d] : 0u;
-    const unsigned int nbpre = PASS ? S.nbp[d] : 0xffffffffu;
     constexpr int sh = PASS == 0 ? 23 : (PASS == 1 ? 14 : (PASS == 2 ? 7 : 0)), bits = PASS < 2 ? 9 : 7, sh_hi = sh + bits;
     constexpr unsigned int mask = (1u << bits) - 1u;
+    // Everything per entry happens on the RAW float bits u: the order-preserving key is u ^ 0x80000000 for a positive and ~u for a
+    // negative value, so "the high bits of the key equal the prefix" is "the high bits of u equal the prefix mapped back" (the
+    // prefix fixes the sign), and the digit of the key is the digit of u, complemented for a negative prefix -- applied when a
+    // slot goes to the histogram (`ordered`), not per entry.
+    const unsigned int pre = PASS ? S.prefix[d] : 0u;
+    const unsigned int nbpre = PASS ? S.nbp[d] : 0xffffffffu;
+    constexpr unsigned int top = PASS ? (1u << ((32 - sh_hi - 1) & 31)) : 0u;           // the sign position inside a prefix
+    const bool neg = PASS && !(pre & top), nbneg = PASS && !(nbpre & top);
+    const unsigned int pre_raw = PASS ? (neg ? (~pre & (2u * top - 1u)) : (pre ^ top)) : 0u;
+    const unsigned int nb_raw = nbpre == 0xffffffffu ? 0xffffffffu : (nbneg ? (~nbpre & (2u * top - 1u)) : (nbpre ^ top));
+    const unsigned int nb_flip = nbneg ? 0xffffffffu : 0x80000000u;
     unsigned int* h = S.hist + (long long)d * DIAG_NBIN;
     const int rs = max(r0, d - row0);
-    // Four (bin, count) slots in registers.  A batch of entries is first counted against the slots WITHOUT branches (nearly every
+    // (bin, count) slots in registers.  A batch of entries is first counted against the slots WITHOUT branches (nearly every
     // warp-row of a sparse map has both zero and non-zero lanes: a branch per entry runs both sides for everyone, and any slot
     // update inside the unrolled batch makes the compiler shuffle the slots through moves -- the first two versions of this loop
     // were issue-bound at 73 and 49 instructions per entry, profiles/r02_ncu_mcfs_batch.txt); entries that found no slot leave
     // a bit in `missed` and are handled after the batch: the slot whose turn it is goes to the histogram and is taken over.
-    // The slots start on the bins short counts fall into -- pass 0: the exponents of 1, 2..3, 4..7, 8..15; pass 1: the mantissas
-    // of the integers below 8 -- so a thread of a sparse count map never takes the slow path (a thread that starts cold misses
-    // two or three times per band, and then nearly every batch of the warp has a lane in the slow path).  Any other data only
-    // pays the misses it would pay anyway.
-    unsigned int t0 = PASS == 0 ? 127u : 0u, t1 = PASS == 0 ? 128u : (PASS == 1 ? 128u : 1u), t2 = PASS == 0 ? 129u : (PASS == 1 ? 256u : 2u),
-                 t3 = PASS == 0 ? 130u : (PASS == 1 ? 384u : 3u), c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    // The slots start on the bins short counts fall into -- pass 0: the exponents of 1, 2..3, 4..7; later passes: the digits of
+    // 2^k and 3 * 2^(k-1) -- so a thread of a sparse count map never takes the slow path (a thread that starts cold misses two
+    // or three times per band, and then nearly every batch of the warp has a lane in the slow path).  Any other data only pays
+    // the misses it would pay anyway.
+    constexpr int NS = PASS == 0 ? 3 : 2;
+    unsigned int t[NS], c[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        t[k] = PASS == 0 ? 127u + k : (k == 0 ? 0u : (mask + 1u) / 2u);
+        c[k] = 0u;
+    }
     unsigned int low = 0u, tmin = 0xffffffffu;
     int vic = 0;
-    // Pass 0 counts on the RAW sign + exponent field (float bits >> 23): the order-preserving encoding only permutes the bins, so
-    // it is applied when a slot goes to the histogram (`ordered`), not per entry.
-    auto bin_of = [&](float v) -> unsigned int {     // the entry's bin, 0xfffffffe (a value no slot ever holds) if it does not count
+    auto bin_of = [&](float v) -> unsigned int {     // the entry's (raw) bin, 0xfffffffe (a value no slot ever holds) if it does not count
         const unsigned int u = __float_as_uint(v);
         const bool nz = v != 0.f;
         if (PASS == 0) return nz ? (u >> 23) : 0xfffffffeu;
-        const unsigned int key = u ^ ((unsigned int)((int)u >> 31) | 0x80000000u);        // f2ord
-        const unsigned int hi = key >> (sh_hi & 31);
-        const bool m = nz && hi == pre;
-        if (PASS == 1) low |= m ? (key & 0x3fffu) : 0u;
-        tmin = min(tmin, (nz && hi == nbpre) ? key : 0xffffffffu);
-        return m ? ((key >> sh) & mask) : 0xfffffffeu;
+        const unsigned int hi = u >> (sh_hi & 31);
+        const bool m = nz && hi == pre_raw;
+        if (PASS == 1) low |= m ? u : 0u;
+        tmin = min(tmin, (nz && hi == nb_raw) ? (u ^ nb_flip) : 0xffffffffu);
+        return m ? ((u >> sh) & mask) : 0xfffffffeu;
     };
     auto ordered = [&](unsigned int bin) -> unsigned int {
-        return PASS == 0 ? ((bin & 256u) ? 511u - bin : (bin | 256u)) : bin;
+        if (PASS == 0) return (bin & 256u) ? 511u - bin : (bin | 256u);
+        return neg ? (bin ^ mask) : bin;
     };
     auto insert = [&](unsigned int bin) {            // rare: an entry whose bin is in no slot
-        if (bin == t0) { ++c0; return; }
-        if (bin == t1) { ++c1; return; }
-        if (bin == t2) { ++c2; return; }
-        if (bin == t3) { ++c3; return; }
-        if (vic == 0) { if (c0) atomicAdd(h + ordered(t0), c0); t0 = bin; c0 = 1u; }
-        else if (vic == 1) { if (c1) atomicAdd(h + ordered(t1), c1); t1 = bin; c1 = 1u; }
-        else if (vic == 2) { if (c2) atomicAdd(h + ordered(t2), c2); t2 = bin; c2 = 1u; }
-        else { if (c3) atomicAdd(h + ordered(t3), c3); t3 = bin; c3 = 1u; }
-        vic = (vic + 1) & 3;
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            if (bin == t[k]) { ++c[k]; return; }
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            if (vic == k) {
+                if (c[k]) atomicAdd(h + ordered(t[k]), c[k]);
+                t[k] = bin;
+                c[k] = 1u;
+            }
+        vic = vic + 1 == NS ? 0 : vic + 1;
     };
     // the address walks down the diagonal by one row and one column per entry; the loads of the NEXT batch are in flight while
     // this one is counted (without it every warp alternated between waiting for 16 loads and ~600 instructions of counting)
@@ -1636,9 +1650,14 @@ __device__ __forceinline__ void diag_hist_body(const float* __restrict__ A, long
 #pragma unroll
         for (int k = 0; k < DIAG_BATCH; ++k) {
             b[k] = bin_of(v[k]);
-            const bool h0 = b[k] == t0, h1 = b[k] == t1, h2 = b[k] == t2, h3 = b[k] == t3;
-            c0 += h0; c1 += h1; c2 += h2; c3 += h3;
-            missed |= (b[k] != 0xfffffffeu && !(h0 || h1 || h2 || h3)) ? (1u << k) : 0u;
+            bool hit = false;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                const bool hq = b[k] == t[q];
+                c[q] += hq;
+                hit = hit || hq;
+            }
+            missed |= (b[k] != 0xfffffffeu && !hit) ? (1u << k) : 0u;
         }
         if (missed) {
 #pragma unroll
@@ -1655,11 +1674,12 @@ __device__ __forceinline__ void diag_hist_body(const float* __restrict__ A, long
         p += stride;
         if (bb != 0xfffffffeu) insert(bb);
     }
-    if (c0) atomicAdd(h + ordered(t0), c0);
-    if (c1) atomicAdd(h + ordered(t1), c1);
-    if (c2) atomicAdd(h + ordered(t2), c2);
-    if (c3) atomicAdd(h + ordered(t3), c3);
-    if (PASS == 1 && low) S.dirty[d] = 1u;          // every writer stores the same value
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+        if (c[k]) atomicAdd(h + ordered(t[k]), c[k]);
+    // early exit needs "all candidates have zeros in the low 14 bits of the KEY": for a positive prefix that is the low bits of
+    // u; a negative prefix (its keys are ~u) simply takes all four passes
+    if (PASS == 1 && (neg ? low != 0u : (low & 0x3fffu) != 0u)) S.dirty[d] = 1u;          // every writer stores the same value
     if (PASS >= 1 && tmin != 0xffffffffu) atomicMin(S.next + d, tmin);
 }
 
