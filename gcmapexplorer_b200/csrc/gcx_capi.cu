@@ -2137,7 +2137,14 @@ extern "C" int gcx_diag_apply(gcx_ctx* c, const double* avg, int subtract, int i
     {
         ProfScope ps(c, 5);
         k_diag_recip<<<(int)((c->n + 255) / 256), 256, 0, c->stream>>>((int)c->n, c->vavg, c->vavr);
-        EW_DISPATCH(k_diag_apply, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->vavr, subtract, c->mm)
+        static const int lane = getenv("GCX_DIAG_APPLY_LANE") ? atoi(getenv("GCX_DIAG_APPLY_LANE")) : 1;
+        if (!lane) {
+            EW_DISPATCH(k_diag_apply, c->A, out, c->ld, (int)c->nloc, (int)(c->ld / 4), (int)c->n, (int)c->row0, c->vavr, subtract, c->mm)
+        } else if (subtract) {
+            k_diag_apply_lane<4, 4, true><<<c->sm_count * 4, MV_THREADS, 0, c->stream>>>(c->A, out, c->ld, (int)c->nloc, (int)c->n, (int)c->row0, c->vavr, c->mm);
+        } else {
+            k_diag_apply_lane<4, 4, false><<<c->sm_count * 4, MV_THREADS, 0, c->stream>>>(c->A, out, c->ld, (int)c->nloc, (int)c->n, (int)c->row0, c->vavr, c->mm);
+        }
     }
     CK(cudaGetLastError());
     if (in_place) { c->have_rowsum = false; c->sym_state = -1; }

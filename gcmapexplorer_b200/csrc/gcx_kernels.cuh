@@ -2014,6 +2014,54 @@ __device__ __forceinline__ void st_stream_f1(float* p, float v) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// one map (possibly a row block [row0, row0 + nloc) of a sharded one)
+template <int R, int OCC, bool SUB>
+__global__ void __launch_bounds__(MV_THREADS, OCC)
+k_diag_apply_lane(const float* __restrict__ A, float* __restrict__ Out, long long ld, int nloc, int n, int row0,
+                  const double2* __restrict__ avr, MinMax* mm) {
+    const int tid = threadIdx.x, cl = (tid >> 5) * 128 + (tid & 31);
+    const int nch = ((int)(ld / 4) + MV_THREADS - 1) / MV_THREADS;
+    const int nb = (nloc + R - 1) / R;
+    const long long U = (long long)nb * nch, G = gridDim.x, c = blockIdx.x;
+    const long long u0 = unit_begin(c, U, G), u1 = unit_begin(c + 1, U, G);
+    float mn = GCX_PINF, mx = GCX_NINF;
+    for (long long u = u0; u < u1; ++u) {
+        const int b = (int)(u / nch), k = (int)(u - (long long)b * nch);
+        const int j0 = k * 1024 + cl, r0 = b * R;
+        const float* __restrict__ ap = A + (long long)r0 * ld + j0;
+        float* __restrict__ op = Out + (long long)r0 * ld + j0;
+        float a[R][4];
+        if (k * 1024 + 1024 <= n && r0 + R <= nloc) {
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[rr][e] = ld_stream_f1(ap + rr * ld + 32 * e);
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                float o[4];
+                diag_apply_quad<32, SUB, false>(a[rr], o, row0 + r0 + rr, j0, n, avr, mn, mx);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) st_stream_f1(op + rr * ld + 32 * e, o[e]);
+            }
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[rr][e] = (r0 + rr < nloc && j0 + 32 * e < (int)ld) ? ld_stream_f1(ap + rr * ld + 32 * e) : 0.f;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                if (r0 + rr >= nloc) break;
+                float o[4];
+                diag_apply_quad<32, SUB, true>(a[rr], o, row0 + r0 + rr, j0, n, avr, mn, mx);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (j0 + 32 * e < (int)ld) st_stream_f1(op + rr * ld + 32 * e, o[e]);
+            }
+        }
+    }
+    mm_commit(mn, mx, mm);
+}
+
 template <int R, int OCC, bool SUB>
 __global__ void __launch_bounds__(MV_THREADS, OCC)
 k_diag_apply_lane_b(const BMap* __restrict__ maps, int count, long long U) {

@@ -25,6 +25,13 @@ def main():
             wall = (time.perf_counter() - t0) / reps * 1e3
             print(f"n={n} {stats}: {ms:.3f} ms device, {wall:.3f} ms wall, lower-triangle bytes {2.0 * n * n / 1e9:.3f} GB"
                   f" -> {2.0 * n * n / 1e9 / (ms * 1e-3):.0f} GB/s per traversal-equivalent, checksum {float(np.sum(avg)):.6e}")
+        for sub in (False, True):
+            dm.diag_apply(None, subtract=sub, in_place=False)
+            dm.timer_start()
+            for _ in range(5):
+                dm.diag_apply(None, subtract=sub, in_place=False)
+            ms = dm.timer_stop() / 5
+            print(f"n={n} apply ({'o-e' if sub else 'o/e'}): {ms:.3f} ms device -> {8.0 * n * n / 1e9 / (ms * 1e-3):.0f} GB/s on 8 n^2 bytes")
         del dm
 
 
