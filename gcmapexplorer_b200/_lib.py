@@ -85,6 +85,7 @@ _PROTOS = {
     "gcx_map_invalidate": (C.c_int, [_ctx]),
     "gcx_debug_sym_cycles": (C.c_int, [_ctx, _c_i64p, C.c_int, C.POINTER(C.c_int)]),
     "gcx_debug_sym_stamps": (C.c_int, [_ctx, _c_i64p, C.c_int, C.POINTER(C.c_int)]),
+    "gcx_debug_sym_plan": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, _c_i64p, C.POINTER(C.c_int32), C.c_int, _c_i64p]),
     "gcx_pass_bytes": (C.c_int, [_ctx, _c_i64p, C.POINTER(C.c_int)]),
     "gcx_last_run_ms": (C.c_int, [_ctx, _c_f64p]),
     "gcx_last_run_products": (C.c_int, [_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

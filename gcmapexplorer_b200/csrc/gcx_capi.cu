@@ -187,6 +187,7 @@ struct gcx_ctx {
     int sym_ndyn = 0;
     int sym_blocks = 1;                   // sharded: circulant assignment of off-diagonal blocks (needs the aligned row partition)
     int sym_kfold_lo = -1;
+    int sym_balance = 1;                 // move the cuts of the block pairs until the ranks' shares of a pass are level
     int sym_nfoldk = 0;
     int assume_symmetric = 0;             // sharded runs cannot test symmetry locally: the caller vouches for it
     int exchange_allreduce = 0;           // custom (unequal) row partition: vectors are exchanged by zero-fill + allreduce
@@ -1170,6 +1171,14 @@ extern "C" int gcx_set_option(gcx_ctx* c, const char* key, double value) {
         }
         c->sym_blocks = (int)value;
     }
+    else if (k == "sym_balance") {       // before the first solve, on every rank (the tables are built once)
+        if (c->sym_balance != (int)value && c->stream) {
+            cudaSetDevice(c->device);
+            cudaStreamSynchronize(c->stream);
+            free_sym(c);
+        }
+        c->sym_balance = (int)value;
+    }
     else if (k == "matvec_variant") c->mv_variant = (int)value;
     else if (k == "sd_variant") c->sd_variant = (int)value;
     else if (k == "corr_variant") c->corr_variant = (int)value;
@@ -1274,6 +1283,129 @@ extern "C" int gcx_partition_rows(int64_t n, int world, int rank, int64_t* row0,
     return 0;
 }
 
+// ---- which rows of which column panels a rank walks in the upper-triangle pass (pure host logic, shared by the table builder
+// and by gcx_debug_sym_plan, which the CPU tests use to check that every unordered pair of bins is visited exactly once) ----
+//
+// Sharded + aligned partition: rank r owns the triangle of its diagonal block; every off-diagonal block pair {lo, hi} (lo < hi)
+// is shared by its two ranks through a panel-aligned cut inside lo's rows: rank lo walks rows [a_lo, cut) of block (lo, hi) from
+// its own rows, rank hi walks ALL its rows against the columns [cut, b_lo) of the mirrored block (hi, lo).  cut = b_lo gives the
+// whole pair to lo, cut = a_lo to hi.  The start is the circulant deal (lo takes the pair if hi - lo < W/2, hi if > W/2, the
+// antipodal pair is halved); the cuts are then moved panel by panel from the most loaded rank to a partner while that lowers
+// the maximum -- the aligned row blocks differ by a panel (8 vs 9 at chr1-like sizes on 8 GPUs: +-5 % of a pass, which every
+// other rank spent waiting in the exchange, profiles/r02_stamps_g_8gpu_final.txt).
+struct SymPlan {
+    std::vector<long long> nb;     // bands of SYM_R rows walked in panel k (from the rank's first row)
+    std::vector<int> full;         // 1: off-diagonal block (no triangle mask)
+    int64_t bytes = 0;
+};
+
+static bool sym_blocks_possible(int64_t n, int W) {
+    for (int r = 0; r < W; ++r)
+        if (aligned_cut(n, W, r + 1) - aligned_cut(n, W, r) < 2048) return false;
+    return W > 1;
+}
+
+static void sym_panel_plan(int64_t n, int64_t ld, int W, int me, int64_t r0, int64_t r1, bool blocks, const std::vector<int64_t>& cut, SymPlan* P) {
+    const int nch = (int)((ld / 4 + MV_THREADS - 1) / MV_THREADS);
+    const long long all_bands = (r1 - r0 + SYM_R - 1) / SYM_R;
+    P->nb.assign((size_t)nch, 0);
+    P->full.assign((size_t)nch, 0);
+    P->bytes = 0;
+    for (int k = 0; k < nch; ++k) {
+        long long nb = 0;
+        int full = 0;
+        const long long col0 = (long long)k * 1024;
+        int s_blk = 0;
+        if (blocks) {
+            while (s_blk + 1 < W && aligned_cut(n, W, s_blk + 1) <= col0) ++s_blk;
+        }
+        if (!blocks || s_blk == me) {
+            // own diagonal region (or the whole upper triangle of the rank's rows when blocks are off)
+            const long long rows_end = std::min<long long>(r1, (k < nch - 1) ? (long long)(k + 1) * 1024 : (long long)n);
+            nb = rows_end > r0 ? (rows_end - r0 + SYM_R - 1) / SYM_R : 0;
+            if (blocks && col0 >= r1) nb = 0;
+        } else {
+            full = 1;
+            const int lo = std::min(me, s_blk), hi = std::max(me, s_blk);
+            const int64_t ct = cut[(size_t)lo * W + hi];
+            if (me == lo) nb = (ct - r0) / SYM_R;                          // first rows of the block, up to the cut
+            else nb = (col0 >= ct) ? all_bands : 0;                       // all rows against the partner's columns from the cut on
+        }
+        P->full[k] = full;
+        P->nb[k] = nb;
+        P->bytes += nb * SYM_R * std::min<int64_t>(1024, ld - (int64_t)k * 1024) * 4;
+    }
+}
+
+static void sym_pair_cuts(int64_t n, int64_t ld, int W, bool balance, std::vector<int64_t>* cut) {
+    cut->assign((size_t)W * W, 0);
+    for (int lo = 0; lo < W; ++lo)
+        for (int hi = lo + 1; hi < W; ++hi) {
+            const int64_t a = aligned_cut(n, W, lo), b = aligned_cut(n, W, lo + 1);
+            const int d = hi - lo;
+            (*cut)[(size_t)lo * W + hi] = 2 * d < W ? b : (2 * d > W ? a : a + ((b - a) / 2 + 512) / 1024 * 1024);
+        }
+    if (!balance || W < 3) return;
+    std::vector<int64_t> work((size_t)W);
+    SymPlan P;
+    auto measure = [&]() {
+        for (int r = 0; r < W; ++r) {
+            sym_panel_plan(n, ld, W, r, aligned_cut(n, W, r), aligned_cut(n, W, r + 1), true, *cut, &P);
+            work[r] = P.bytes;
+        }
+    };
+    // steepest descent on (max, sum of squares): try every one-panel move of every pair, keep the best, stop when none helps
+    auto score = [&](int64_t* mx, double* sq) {
+        measure();
+        *mx = *std::max_element(work.begin(), work.end());
+        *sq = 0.0;
+        for (int r = 0; r < W; ++r) *sq += (double)work[r] * (double)work[r];
+    };
+    int64_t cur_max;
+    double cur_sq;
+    score(&cur_max, &cur_sq);
+    for (int iter = 0; iter < 16 * W * W; ++iter) {
+        int best_lo = -1, best_hi = -1;
+        int64_t best_step = 0, best_max = cur_max;
+        double best_sq = cur_sq;
+        for (int lo = 0; lo < W; ++lo)
+            for (int hi = lo + 1; hi < W; ++hi)
+                for (int64_t step = -1024; step <= 1024; step += 2048) {
+                    int64_t& ct = (*cut)[(size_t)lo * W + hi];
+                    const int64_t a = aligned_cut(n, W, lo), b = aligned_cut(n, W, lo + 1);
+                    if (ct + step < a || ct + step > b) continue;
+                    ct += step;
+                    int64_t m;
+                    double q;
+                    score(&m, &q);
+                    ct -= step;
+                    if (m < best_max || (m == best_max && q < best_sq)) { best_max = m; best_sq = q; best_lo = lo; best_hi = hi; best_step = step; }
+                }
+        if (best_lo < 0) break;
+        (*cut)[(size_t)best_lo * W + best_hi] += best_step;
+        cur_max = best_max;
+        cur_sq = best_sq;
+    }
+}
+
+/* Testing hook (no GPU needed): the panel plan of `rank` for a map of n bins row-sharded over `world` ranks with the library's
+   aligned partition -- nb[k] bands of 4 rows from the rank's first row in column panel k (1024 columns), full[k] = 1 for an
+   off-diagonal block.  nch = number of panels = ceil(round_up(n, 32) / 1024); both arrays hold nch entries. */
+extern "C" int gcx_debug_sym_plan(int64_t n, int world, int rank, int balance, int64_t* nb, int32_t* full, int nch, int64_t* bytes) {
+    if (n < 1 || world < 1 || rank < 0 || rank >= world || !nb || !full) return fail("gcx_debug_sym_plan: bad arguments");
+    const int64_t ld = round_up(n, 32);
+    const int want = (int)((ld / 4 + MV_THREADS - 1) / MV_THREADS);
+    if (nch != want) return fail("gcx_debug_sym_plan: a map of %lld bins has %d panels", (long long)n, want);
+    const bool blocks = sym_blocks_possible(n, world);
+    std::vector<int64_t> cut;
+    if (blocks) sym_pair_cuts(n, ld, world, balance != 0, &cut);
+    SymPlan P;
+    sym_panel_plan(n, ld, world, rank, aligned_cut(n, world, rank), aligned_cut(n, world, rank + 1), blocks, cut, &P);
+    for (int k = 0; k < nch; ++k) { nb[k] = P.nb[k]; full[k] = P.full[k]; }
+    if (bytes) *bytes = P.bytes;
+    return 0;
+}
+
 // decides (and caches) whether the resident map can use the upper-triangle passes, and tabulates the geometry
 static int sym_ready(gcx_ctx* c, bool* ok) {
     *ok = false;
@@ -1320,49 +1452,19 @@ static int sym_ready(gcx_ctx* c, bool* ok) {
         std::vector<long long> pu((size_t)nch + 1, 0);
         std::vector<int> pfull((size_t)nch, 0);
         const int W = c->world, me = c->rank;
-        // sharded + aligned partition: off-diagonal blocks are dealt out in a circulant pattern -- rank r takes the blocks
-        // (r, r+1) ... (r, r+floor((W-1)/2)) from its own rows (the mirrored blocks belong to nobody else), and for even W the
-        // antipodal pair {r, r+W/2} is split: the lower rank walks the first half of its rows, the upper rank the remaining
-        // columns of the mirrored block.  Every unordered pair of bins is then visited exactly once, W/2 blocks per rank.
-        bool blocks = W > 1 && c->sym_blocks;
-        if (blocks) {
-            blocks = (r0 == aligned_cut(n, W, me) && r1 == aligned_cut(n, W, me + 1));
-            for (int r = 0; r < W && blocks; ++r) blocks = aligned_cut(n, W, r + 1) - aligned_cut(n, W, r) >= 2048;
-        }
-        auto half_cut = [&](int r) {           // panel-aligned middle of rank r's rows
-            const int64_t a = aligned_cut(n, W, r), b = aligned_cut(n, W, r + 1);
-            return a + ((b - a) / 2 + 512) / 1024 * 1024;
-        };
-        const long long all_bands = (c->nloc + SYM_R - 1) / SYM_R;
-        int64_t bytes = 0;
+        // sharded + aligned partition: the diagonal block plus a share of every off-diagonal block pair (sym_panel_plan above)
+        bool blocks = W > 1 && c->sym_blocks && sym_blocks_possible(n, W);
+        if (blocks) blocks = (r0 == aligned_cut(n, W, me) && r1 == aligned_cut(n, W, me + 1));
+        std::vector<int64_t> cuts;
+        if (blocks) sym_pair_cuts(n, c->ld, W, c->sym_balance != 0, &cuts);
+        SymPlan plan;
+        sym_panel_plan(n, c->ld, W, me, r0, r1, blocks, cuts, &plan);
+        const int64_t bytes = plan.bytes;
         int kfold_lo = -1;
-        std::vector<long long> nbk((size_t)nch, 0);
+        std::vector<long long> nbk(plan.nb);
         for (int k = 0; k < nch; ++k) {
-            long long nb = 0;
-            int full = 0;
-            const long long col0 = (long long)k * 1024;
-            int s_blk = 0;
-            if (blocks) {
-                while (s_blk + 1 < W && aligned_cut(n, W, s_blk + 1) <= col0) ++s_blk;
-            }
-            if (!blocks || s_blk == me) {
-                // own diagonal region (or the whole upper triangle of the rank's rows when blocks are off)
-                const long long rows_end = std::min<long long>(r1, (k < nch - 1) ? (long long)(k + 1) * 1024 : (long long)n);
-                nb = rows_end > r0 ? (rows_end - r0 + SYM_R - 1) / SYM_R : 0;
-                if (blocks && col0 >= r1) nb = 0;
-            } else {
-                const int d = ((s_blk - me) % W + W) % W;
-                if (2 * d < W) { nb = all_bands; full = 1; }
-                else if (2 * d == W) {
-                    full = 1;
-                    if (me < s_blk) nb = (half_cut(me) - r0) / SYM_R;                 // lower rank: first half of its rows
-                    else nb = (col0 >= half_cut(s_blk)) ? all_bands : 0;              // upper rank: columns of the partner's second half
-                }
-            }
-            if (nb > 0 && kfold_lo < 0) kfold_lo = k;
-            pfull[k] = full;
-            nbk[k] = nb;
-            bytes += nb * SYM_R * std::min<int64_t>(1024, c->ld - (int64_t)k * 1024) * 4;
+            pfull[k] = plan.full[k];
+            if (nbk[k] > 0 && kfold_lo < 0) kfold_lo = k;
         }
         c->sym_kfold_lo = blocks ? kfold_lo : -1;
         // dynamic pool: ~GCX_SYM_DYN percent of the units, cut into chunks of DYN_CHUNK consecutive bands of one panel.

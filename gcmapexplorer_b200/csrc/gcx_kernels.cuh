@@ -2812,11 +2812,14 @@ __device__ __forceinline__ void symd_vector_phase(int n, int n4, long long nv, i
                 for (int q = 0; q < X.world; ++q) X.peer_recv[q][((long long)par * X.world + X.rank) * nv + i] = pi;
             }
         }
-        __threadfence_system();
+        // The CTA barrier orders every thread's peer stores before the flag threads; their release store at system scope then
+        // publishes all of them (release is cumulative over what happened before it through the barrier -- the pattern of
+        // NCCL's post step and of grid.sync).  A system fence by all 256 threads here cost several microseconds per pass.
         __syncthreads();
         if (stamps != nullptr) stamps[12] = (long long)globaltimer_ns();
         if (tid < X.world) {
             const unsigned int want = X.seq0 + (unsigned int)L;
+            __threadfence_system();
             st_release_sys_u32(X.peer_flags[tid] + (long long)X.rank * G + bid, want);
             const unsigned int* f = X.flags + (long long)tid * G + bid;
             const unsigned long long t0 = globaltimer_ns();

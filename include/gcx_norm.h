@@ -243,6 +243,13 @@ int gcx_pass_bytes(gcx_ctx* ctx, int64_t* bytes, int* symmetric);
 int gcx_debug_sym_cycles(gcx_ctx* ctx, int64_t* cycles, int capacity, int* count);
 /* diagnostics: per-CTA phase timestamps (ns) of one launch of the deferred-scalar IC pass, [grid][16] (needs GCX_SYM_DEBUG=1) */
 int gcx_debug_sym_stamps(gcx_ctx* ctx, int64_t* stamps, int capacity, int* count);
+
+/* Testing hook, no GPU needed: the panel plan of `rank` in the sharded upper-triangle pass of a map of n bins over `world` ranks
+   (aligned partition of gcx_partition_rows).  nb[k] = bands of 4 rows, counted from the rank's first row, that it walks in
+   column panel k (1024 columns); full[k] = 1 for an off-diagonal block (no triangle mask).  nch must be
+   ceil(round_up(n, 32) / 1024).  balance != 0: with the cuts of the block pairs levelled as gcx_ic_run / gcx_kr_run do by default
+   (option "sym_balance").  tests/test_abi_cpu.py checks that the plans of all ranks visit every unordered pair of bins once. */
+int gcx_debug_sym_plan(int64_t n, int world, int rank, int balance, int64_t* nb, int32_t* full, int nch, int64_t* bytes);
 /* device time (ms, CUDA events) of the last ic/kr run: matrix resident -> final vector */
 int gcx_last_run_ms(gcx_ctx* ctx, double* ms);
 /* matrix-vector products the last ic/kr run really launched: the deferred-scalar IC pass sees convergence one launch late and
