@@ -264,6 +264,6 @@ def test_sharded_triangle_plan_balance(n, world):
     level, _ = _sym_plans(n, world, 1)
     b0 = np.array([p[2] for p in plain], float)
     b1 = np.array([p[2] for p in level], float)
-    assert b0.sum() == b1.sum()                            # the same cells, dealt differently
+    assert abs(b0.sum() - b1.sum()) < 1e-4 * b0.sum()      # the same cells, dealt differently (the last panel is padded to 32 columns)
     assert b1.max() <= b0.max()
     assert b1.max() / b1.mean() < 1.03, (b0.max() / b0.mean(), b1.max() / b1.mean())
