@@ -205,7 +205,9 @@ int gcx_debug_i8gemm(gcx_ctx* ctx, const signed char* L, const signed char* R, i
  *                             cannot see the mirrored block (the caller vouches that the map is symmetric)
  *   "exchange_allreduce" 0/1  the row blocks are not the equal ceil(n/world) blocks: exchange n-vectors by zero-fill +
  *                             allreduce instead of allgather (set it on every rank, before gcx_map_create)
- *   "sym_blocks"         0/1  sharded upper-triangle pass: deal the off-diagonal blocks out in the circulant pattern (default 1)
+ *   "sym_blocks"         0/1  sharded upper-triangle pass: share the off-diagonal block pairs between their two ranks (default 1)
+ *   "sym_balance"        0/1  ... and move the pairs' cuts until the ranks' bytes per pass are level (default 1; 0 = the plain
+ *                             circulant deal; set it on every rank)
  *   "peer_exchange"      0/1  sharded upper-triangle IC pass: exchange the partial vectors by NVLink stores into peer-mapped
  *                             buffers with per-CTA flags inside the fused launch (default 1; set before gcx_map_create on every
  *                             rank; falls back to the NCCL allreduce when peer mapping is unavailable; env GCX_PEER_EXCHANGE)
